@@ -1,0 +1,132 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+// CPU restatement of the three in-scope `module mcmod_mass` plugins:
+//   mcmod_1d.f90:8-58, mcmod_2dtest.f90:11-61, mcmod_waterdimer_ccpol.f90:9-77.
+// x and grad are Fortran (ndim,natom) column-major: index = (atom)*ndim + dim.
+#pragma once
+#include <cmath>
+#include <stdexcept>
+
+#include "ccpol_impl.hpp"
+#include "tables.hpp"
+
+namespace oracle {
+
+enum PesKind { PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3 };
+
+struct Pes {
+  PesKind kind = PES_1D;
+  int ndim = 1, natom = 1;
+  double V0 = 0.0;
+  // 1D (mcmod_1d.f90:9-12)
+  double Vheight = 1.0, x0_1d = 1.0;
+  // 2D (mcmod_2dtest.f90:16-24)
+  int m = 6;
+  double a0 = 2.0, b0 = 0.2, rho0 = 3.0;
+  double wx[6], wy[6];
+  // CCpol
+  const CcpolTables* tab = nullptr;
+  long potcount = 0;
+
+  void init_1d() {
+    kind = PES_1D;
+    Vheight = 1.0;
+    x0_1d = 1.0;
+  }
+  void init_2d() {
+    kind = PES_2DTEST;
+    ndim = 2;
+    natom = 1;
+    const double pi = 3.14159265358979;  // mcmod_2dtest.f90:14 (truncated literal)
+    m = 6;
+    a0 = 2.0;
+    b0 = 0.2;
+    rho0 = 3.0;
+    for (int k = 1; k <= m; ++k) {
+      wx[k - 1] = rho0 * std::cos((double)k * 2.0 * pi / (double)m);
+      wy[k - 1] = rho0 * std::sin((double)k * 2.0 * pi / (double)m);
+    }
+    V0 = 0.0;  // never initialised by the reference: static storage -> 0
+  }
+  void init_ccpol(const CcpolTables* t) {
+    kind = PES_CCPOL;
+    ndim = 3;
+    natom = 6;
+    tab = t;
+    V0 = 0.0;  // mcmod_waterdimer_ccpol.f90:14
+  }
+
+  // function V(x)
+  double V(const double* x) const {
+    switch (kind) {
+      case PES_1D: {  // mcmod_1d.f90:20   (ignores V0)
+        double s = 0.0;
+        for (int i = 0; i < ndim * natom; ++i) {
+          double u = (x[i] / x0_1d) * (x[i] / x0_1d) - 1.0;
+          s += Vheight * (u * u);
+        }
+        return s;
+      }
+      case PES_2DTEST: {  // mcmod_2dtest.f90:33-39
+        double answer = 0.0;
+        for (int k = 0; k < m; ++k) {
+          double dx = x[0] - wx[k], dy = x[1] - wy[k];
+          answer = answer - 0.5 * std::exp(-a0 * (dx * dx + dy * dy));
+          answer = answer - 0.5 * std::exp(-b0 * (dx * dx + dy * dy));
+        }
+        return answer - V0;
+      }
+      case PES_CCPOL: {  // mcmod_waterdimer_ccpol.f90:18-37
+        const double ang = 0.529177;
+        double xtemp[18];
+        for (int i = 0; i < 18; ++i) xtemp[i] = x[i] * ang;
+        double Etot = ccpol<double>(*tab, xtemp);
+        return (Etot / 627.510) - V0;
+      }
+    }
+    throw std::runtime_error("bad PES kind");
+  }
+
+  // subroutine Vprime(x, grad).  CCpol: x is perturbed in place and NOT restored bit-exactly.
+  void Vprime(double* x, double* grad) {
+    switch (kind) {
+      case PES_1D: {  // mcmod_1d.f90:31-32
+        for (int i = 0; i < ndim * natom; ++i) {
+          double g = ((x[i] / x0_1d) * (x[i] / x0_1d) - 1.0);
+          grad[i] = g * 4.0 * Vheight * x[i] / (x0_1d * x0_1d);
+        }
+        return;
+      }
+      case PES_2DTEST: {  // mcmod_2dtest.f90:48-58 (24 exp, no CSE in the source)
+        potcount++;
+        double g1 = 0.0, g2 = 0.0;
+        for (int k = 0; k < m; ++k) {
+          double dx = x[0] - wx[k], dy = x[1] - wy[k];
+          double u = dx * dx + dy * dy;
+          g1 = g1 + a0 * dx * std::exp(-a0 * u);
+          g1 = g1 + b0 * dx * std::exp(-b0 * u);
+          g2 = g2 + a0 * dy * std::exp(-a0 * u);
+          g2 = g2 + b0 * dy * std::exp(-b0 * u);
+        }
+        grad[0] = g1;
+        grad[1] = g2;
+        return;
+      }
+      case PES_CCPOL: {  // mcmod_waterdimer_ccpol.f90:40-58
+        const double eps = 1e-4;
+        for (int i = 0; i < ndim; ++i)
+          for (int j = 0; j < natom; ++j) {
+            double& xij = x[j * ndim + i];
+            xij = xij + eps;
+            double potplus = V(x);
+            xij = xij - 2.0 * eps;
+            double potminus = V(x);
+            xij = xij + eps;
+            grad[j * ndim + i] = (potplus - potminus) / (2.0 * eps);
+          }
+        return;
+      }
+    }
+  }
+};
+
+}  // namespace oracle
