@@ -13,25 +13,30 @@
 // The reference is compiled -r8 -i8 (makefile:5): every real literal is FP64.
 //
 // Choices where the Fortran leaves the bits to the compiler (documented in DESIGN.md):
+//  * exp/pow/sin/cos/acos/tanh come from include/pimdk_detmath.h (see its header for why).
 //  * x**k with integer k: binary powering (ipow below);  x**2.d0 -> x*x.
 //  * `rin` passed to dipind is never assigned in driver_potss_sapt5sf
 //    (proc_sapt5sf_new_ncd.f:43-46) -> restated as 0.
 #pragma once
 #include <cmath>
 
+#include "../include/pimdk_detmath.h"
 #include "tables.hpp"
 
 namespace oracle {
 
-using std::acos;
+// Elementary functions: the shared deterministic math policy (include/pimdk_detmath.h) stands in
+// for the reference's (unknown) Intel libm; sqrt, fabs are IEEE; atan is used by the Eckart
+// embedding only (surfaces other than 3/10, oracle-side golden check only).
 using std::atan;
-using std::cos;
-using std::exp;
 using std::fabs;
-using std::pow;
-using std::sin;
 using std::sqrt;
-using std::tanh;
+inline double exp(double x) { return pimdk_exp(x); }
+inline double pow(double x, double y) { return pimdk_pow(x, y); }
+inline double sin(double x) { return pimdk_sin(x); }
+inline double cos(double x) { return pimdk_cos(x); }
+inline double acos(double x) { return pimdk_acos(x); }
+inline double tanh(double x) { return pimdk_tanh(x); }
 
 template <class R>
 inline R ipow(R x, int n) {

@@ -5,6 +5,8 @@
 #pragma once
 #include <cmath>
 
+#include "../include/pimdk_detmath.h"
+
 namespace oracle {
 
 struct Counted {
@@ -30,13 +32,13 @@ inline bool operator>(Counted a, Counted b) { return a.v > b.v; }
 inline bool operator==(Counted a, Counted b) { return a.v == b.v; }
 inline bool operator!=(Counted a, Counted b) { return a.v != b.v; }
 inline Counted sqrt(Counted a) { Counted::cnt[Counted::SQRT]++; return Counted(std::sqrt(a.v)); }
-inline Counted exp(Counted a) { Counted::cnt[Counted::EXP]++; return Counted(std::exp(a.v)); }
-inline Counted pow(Counted a, Counted b) { Counted::cnt[Counted::POW]++; return Counted(std::pow(a.v, b.v)); }
+inline Counted exp(Counted a) { Counted::cnt[Counted::EXP]++; return Counted(pimdk_exp(a.v)); }
+inline Counted pow(Counted a, Counted b) { Counted::cnt[Counted::POW]++; return Counted(pimdk_pow(a.v, b.v)); }
 inline Counted fabs(Counted a) { return Counted(std::fabs(a.v)); }
-inline Counted sin(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(std::sin(a.v)); }
-inline Counted cos(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(std::cos(a.v)); }
-inline Counted acos(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(std::acos(a.v)); }
+inline Counted sin(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_sin(a.v)); }
+inline Counted cos(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_cos(a.v)); }
+inline Counted acos(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_acos(a.v)); }
 inline Counted atan(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(std::atan(a.v)); }
-inline Counted tanh(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(std::tanh(a.v)); }
+inline Counted tanh(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_tanh(a.v)); }
 
 }  // namespace oracle

@@ -70,8 +70,8 @@ struct Pes {
         double answer = 0.0;
         for (int k = 0; k < m; ++k) {
           double dx = x[0] - wx[k], dy = x[1] - wy[k];
-          answer = answer - 0.5 * std::exp(-a0 * (dx * dx + dy * dy));
-          answer = answer - 0.5 * std::exp(-b0 * (dx * dx + dy * dy));
+          answer = answer - 0.5 * pimdk_exp(-a0 * (dx * dx + dy * dy));
+          answer = answer - 0.5 * pimdk_exp(-b0 * (dx * dx + dy * dy));
         }
         return answer - V0;
       }
@@ -102,10 +102,10 @@ struct Pes {
         for (int k = 0; k < m; ++k) {
           double dx = x[0] - wx[k], dy = x[1] - wy[k];
           double u = dx * dx + dy * dy;
-          g1 = g1 + a0 * dx * std::exp(-a0 * u);
-          g1 = g1 + b0 * dx * std::exp(-b0 * u);
-          g2 = g2 + a0 * dy * std::exp(-a0 * u);
-          g2 = g2 + b0 * dy * std::exp(-b0 * u);
+          g1 = g1 + a0 * dx * pimdk_exp(-a0 * u);
+          g1 = g1 + b0 * dx * pimdk_exp(-b0 * u);
+          g2 = g2 + a0 * dy * pimdk_exp(-a0 * u);
+          g2 = g2 + b0 * dy * pimdk_exp(-b0 * u);
         }
         grad[0] = g1;
         grad[1] = g2;

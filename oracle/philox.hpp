@@ -10,12 +10,15 @@
 //   key       : (seed & 0xffffffff, seed >> 32)
 //   counter   : (pair, step & 0xffffffff, traj_gid, (stream << 24) | ((step >> 32) & 0xffffff))
 //   uniforms  : u1 = ((r0<<32 | r1) >> 11 + 0.5) * 2^-53,  u2 likewise from r2,r3
+//   log/sin/cos: include/pimdk_detmath.h (bit-identical on host and device)
 //   normals   : Box-Muller  z0 = sqrt(-2 ln u1) cos(2 pi u2),  z1 = sqrt(-2 ln u1) sin(2 pi u2)
 //   normal #idx of a (stream, step, traj) lives in pair idx>>1, slot idx&1
 //   streams   : 0 init_path momenta, 1 Langevin O-step, 2 Andersen resample, 3 Poisson interval
 #pragma once
 #include <cmath>
 #include <cstdint>
+
+#include "../include/pimdk_detmath.h"
 
 namespace oracle {
 
@@ -46,10 +49,12 @@ inline void normal_pair(uint64_t seed, int stream, uint64_t step, uint32_t traj_
   const double two53 = 1.0 / 9007199254740992.0;
   double u1 = ((double)((((uint64_t)r[0] << 32) | r[1]) >> 11) + 0.5) * two53;
   double u2 = ((double)((((uint64_t)r[2] << 32) | r[3]) >> 11) + 0.5) * two53;
-  double rad = std::sqrt(-2.0 * std::log(u1));
+  double rad = std::sqrt(-2.0 * pimdk_log(u1));
   double ang = 6.283185307179586 * u2;
-  z0 = rad * std::cos(ang);
-  z1 = rad * std::sin(ang);
+  double sn, cs;
+  pimdk_sincos(ang, &sn, &cs);
+  z0 = rad * cs;
+  z1 = rad * sn;
 }
 
 inline double normal_at(uint64_t seed, int stream, uint64_t step, uint32_t traj_gid, uint64_t idx) {
