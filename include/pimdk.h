@@ -1,0 +1,146 @@
+/* pimdk.h — C ABI of the B200-native ring-polymer hot path.
+ *
+ * This is the drop-in boundary for christophevaillant/pimd-tunneling: every entry point replaces
+ * a piece of the reference's Fortran (file:line cited per function) and is what the reference's
+ * ISO_C_BINDING shim (fortran/pimdk_mod.f90) binds.  Conventions follow the
+ * reference build (`ifort -i8 -r8`, makefile:5): all integers are 64-bit, all reals FP64, all
+ * arrays are Fortran column-major exactly as the reference declares them:
+ *     x(n, ndim, natom [, ntraj])     bead index fastest, trajectory slowest
+ *     a(ndim, natom), b/dbdl(ndim, natom [, ntraj])
+ * Host-pointer calls borrow the caller's arrays for the duration of the call only.  The `_dev`
+ * variants take device pointers on the library's device (same layouts) and enqueue on the
+ * library stream without synchronising.  Every call returns 0 on success or a PIMDK_E* code;
+ * pimdk_last_error() gives the text.  The library never calls exit(); the Fortran shim turns a
+ * non-zero code into the reference's `write(*,*) msg; stop`.  Not thread-safe (neither is the
+ * reference: module globals and COMMON /ddaattaa/).
+ *
+ * There is no CPU fallback: without a CUDA device every compute call fails with PIMDK_ENODEV.
+ */
+#ifndef PIMDK_H
+#define PIMDK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t pimdk_int;
+
+enum {
+  PIMDK_OK = 0,
+  PIMDK_EINVAL = 1,   /* bad argument / call order */
+  PIMDK_ENODEV = 2,   /* no usable CUDA device */
+  PIMDK_ECUDA = 3,    /* CUDA runtime error */
+  PIMDK_EDATA = 4,    /* PES data files missing or malformed (reference: stop 010..040) */
+  PIMDK_ENAN = 5,     /* NaN trap (verletmodule.f90:533-536,577-580 "NaN in pot propagation") */
+  PIMDK_ENOCONV = 6   /* "No convergence in indN_iter" (proc_ccpol8s-dimer_xyz_ncd.f:364-369) */
+};
+
+enum { PIMDK_THERMOSTAT_ANDERSEN = 1, PIMDK_THERMOSTAT_PILE = 2 }; /* namelist `thermostat`, pimd_par.f90:68,371-378 */
+enum { PIMDK_MODE_STRICT = 0, PIMDK_MODE_FAST = 1 };
+
+/* Library / device lifetime.  device < 0 keeps the current CUDA device.  data_dir is where the
+ * CCpol-8sf parameter files live: either the reference's own data_SAPT5spfIR_2006 / data_CCpol8s /
+ * data_ccdata (which the reference opens from its CWD: main_CCpol-8sf.f:49,115;
+ * proc_ccpol8s-dimer_xyz_ncd.f:41; main_CCpol-8sf.f:872) or the packed *.tbl files shipped with
+ * this package.  NULL = "." like the reference. */
+int pimdk_init(pimdk_int device, const char* data_dir);
+int pimdk_finalize(void);
+const char* pimdk_last_error(void);
+/* Launch everything on this cudaStream_t (default: the legacy default stream). */
+int pimdk_set_stream(void* cuda_stream);
+/* PIMDK_MODE_STRICT (default): CCpol arithmetic in the reference's operation order without FMA
+ * contraction; PIMDK_MODE_FAST: same kernels with contraction. */
+int pimdk_set_mode(pimdk_int mode);
+
+/* ---- PES plugin: module mcmod_mass -------------------------------------------------------
+ * pimdk_pes_select  = V_init  (mcmod_1d.f90:8, mcmod_2dtest.f90:11, mcmod_waterdimer_ccpol.f90:9
+ *                     -> init_ccpol(3,1,1,0), main_CCpol-8sf.f:1-173)
+ *   name: "1d" | "2dtest" | "ccpol8sf".  pes_params (optional): "1d": {Vheight, x0};
+ *   "2dtest": {a0, b0, rho0}; "ccpol8sf": {iemonomer (default 1)}.
+ * pimdk_pes_set_v0  = assignment to module variable V0 (pimd_par.f90:166, rpi_ser.f90:95)
+ * pimdk_pes_eval    = V (function) and Vprime (subroutine) over a batch x(ndim,natom,nbatch);
+ *                     v (nbatch) and/or grad (ndim,natom,nbatch) may be NULL.  grad = +dV/dx.
+ * pimdk_pes_vprime_inplace = literal Vprime(x,grad) semantics: for ccpol8sf x is perturbed in
+ *                     place and left where the reference leaves it (x+eps-2eps+eps,
+ *                     mcmod_waterdimer_ccpol.f90:48-52). */
+int pimdk_pes_select(const char* name, const double* pes_params, pimdk_int nparams);
+int pimdk_pes_info(pimdk_int* ndim, pimdk_int* natom);
+int pimdk_pes_set_v0(double v0);
+int pimdk_pes_eval(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, const double* x, double* v, double* grad);
+int pimdk_pes_vprime_inplace(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, double* x, double* grad);
+int pimdk_pes_eval_dev(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, const double* x, double* v, double* grad);
+
+/* ---- ring-polymer potential: instantonmod.f90:17-151 (UM, UMprime, UMforceenergy) ----------
+ * x, g: (n,ndim,natom); a,b: (ndim,natom), used when fixedends != 0; f or g may be NULL.
+ * This is the f/g evaluation `instanton` hands to setulb on task 'FG' (instantonmod.f90:748-765). */
+int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x, const double* a,
+                         const double* b, const double* mass, double betan, pimdk_int fixedends, double* f, double* g);
+
+/* ---- module verletint -----------------------------------------------------------------------
+ * pimdk_nm_setup = alloc_nm + the a,b-independent part of init_nm (verletmodule.f90:306-338):
+ *   lam, beadmass, transmatrix.  beadvec (which depends on a and each trajectory's b) is formed
+ *   inside the kernels from the same expression. */
+int pimdk_nm_setup(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* mass, double betan, double tau);
+/* Read back the module arrays (any pointer may be NULL): transmatrix(n,n), lam(n), beadmass(natom,n). */
+int pimdk_nm_get(double* transmatrix, double* lam, double* beadmass);
+/* nmtransform_forward / nmtransform_backward (verletmodule.f90:254-286) over a batch of nvec
+ * bead vectors v(n,nvec).  beadvec == NULL is the reference's bead=0; otherwise beadvec(n,nvec)
+ * is subtracted after (forward) / added before (backward) the transform. */
+int pimdk_nm_transform(pimdk_int forward, pimdk_int nvec, const double* vin, const double* beadvec, double* vout);
+
+/* init_path (verletmodule.f90:32-119, readhess=.false.): beads on the spline at
+ * (k-1)*xi/(n-1), momenta ~ N(0,sqrt(1/betan))*sqrt(beadmass) in normal-mode space, transformed
+ * back.  path/splinepath: (npath,ndim,natom); xi: (ntraj); x,p: (n,ndim,natom,ntraj) out. */
+int pimdk_init_path(pimdk_int ntraj, pimdk_int npath, const double* lampath, const double* path,
+                    const double* splinepath, const double* xi, uint64_t seed, const pimdk_int* traj_gid, double* x,
+                    double* p);
+
+/* propagate_pimd_nm (thermostat 1, verletmodule.f90:190-250) / propagate_pimd_pile (thermostat 2,
+ * :372-416) for ntraj independent ring polymers = the (lambda x repetition) task loop of
+ * pimd_par.f90:321-381 in one call.
+ *   x, p      (n,ndim,natom,ntraj) in/out
+ *   a         (ndim,natom)           startpoint
+ *   b, dbdl   (ndim,natom,ntraj)     endpoints(ii,:,:), gradpoints(ii,:,:)
+ *   dHdr      (ntraj) out: mean over steps > imin of sum mass*(-x(n,:,:))*dbdl, i.e. what the
+ *             reference returns before the driver divides by betan**2 (pimd_par.f90:379)
+ *   Noutput   Andersen: mean collision interval (Poisson); PILE: unused (print cadence)
+ *   seed, traj_gid: RNG contract: Philox4x32-10 keyed by seed, counter carries the
+ *             global trajectory id so results do not depend on how trajectories are sharded.
+ *             traj_gid == NULL means 0..ntraj-1.
+ * Requires pimdk_pes_select and pimdk_nm_setup with matching n, ndim, natom. */
+int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p, const double* a, const double* b,
+                    const double* dbdl, double dt, double gamma, pimdk_int NMC, pimdk_int imin, pimdk_int Noutput,
+                    pimdk_int cayley, uint64_t seed, const pimdk_int* traj_gid, double* dHdr);
+int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p, const double* a, const double* b,
+                        const double* dbdl, double dt, double gamma, pimdk_int NMC, pimdk_int imin, pimdk_int Noutput,
+                        pimdk_int cayley, uint64_t seed, const pimdk_int* traj_gid, double* dHdr);
+/* index (0-based, into the last call's batch) of the first trajectory that tripped the NaN trap, or -1 */
+pimdk_int pimdk_last_nan_trajectory(void);
+
+/* Per-lambda statistics of pimd_par.f90:397-409 for the local shard:
+ * sums(3,nintegral) = {sum I, sum I**2, count} with I = dHdr/betan**2 and lambda index
+ * traj_gid/nrep.  Summing `sums` over ranks (one NCCL all-reduce) and calling pimdk_ti_finish
+ * reproduces the root's mean/variance/answer (pimd_par.f90:410-424). */
+int pimdk_ti_partial_sums(pimdk_int ntraj, const double* dHdr, const pimdk_int* traj_gid, pimdk_int nrep,
+                          pimdk_int nintegral, double betan, double* sums);
+int pimdk_ti_finish(pimdk_int nintegral, const double* sums, const double* weights, double betan, double* mean,
+                    double* var, double* deltaA, double* sigmaA, double* q_over_q0);
+/* gauleg (verletmodule.f90:124-160) */
+int pimdk_gauleg(double x1, double x2, pimdk_int nintegral, double* x, double* w);
+
+/* ---- measurement helpers ---------------------------------------------------------------------
+ * pimdk_profile(1) makes propagate/pes_eval bracket each kernel family with CUDA events on the
+ * library stream; pimdk_profile_get returns accumulated milliseconds and launch counts for
+ * family = "pes", "gemm", "update", "estimator".  pimdk_fp64_peak measures the DFMA pipe. */
+int pimdk_profile(pimdk_int enable);
+int pimdk_profile_get(const char* family, double* ms, pimdk_int* launches);
+int pimdk_profile_reset(void);
+int pimdk_fp64_peak(double* tflops);
+pimdk_int pimdk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIMDK_H */

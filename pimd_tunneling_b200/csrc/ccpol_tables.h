@@ -1,0 +1,58 @@
+// Device image of the CCpol-8sf parameter tables (what the reference keeps in COMMON /ddaattaa/,
+// main_CCpol-8sf.f:6-11), trimmed to what the hot path reads and laid out for shared-memory
+// staging: every access in the kernels is warp-uniform, so a table read is one broadcast LDS.
+#pragma once
+#include <cstdint>
+
+namespace pimdk {
+
+constexpr int kNType = 5;      // SAPT-5s'f site types actually used (1..5; type 6 never occurs)
+constexpr int kNParab = 84;
+constexpr int kNParam = 18;
+
+struct CcpolDev {
+  double param[kNParam * kNType];            // param(k,t)         -> [(t-1)*18 + k-1]
+  double parab[kNParab * kNType * kNType];   // parab(k,ta,tb)     -> [((tb-1)*5+(ta-1))*84 + k-1]
+  double c[568];                             // SAPT-5s'f linear coefficients
+  double cc[144];                            // CCpol-8s linear coefficients
+  double params[134];                        // CCpol-8s nonlinear parameters (1-based in the file)
+  double sites[75];                          // sites(3,25) body-frame coordinates
+  double chrg[5];                            // induction charges of sites 1..5
+  double V0;                                 // module variable V0 of mcmod_mass
+  // static image of poten's first-encounter index map itypus (proc_sapt5sf_new_ncd.f:181-203):
+  // first linear coefficient (1-based) of the symmetric / antisymmetric block of a type pair,
+  // 0 when the pair type carries no exponential.
+  int16_t itu_s[kNType * kNType];
+  int16_t itu_a[kNType * kNType];
+  uint8_t ind_beta[625];                     // ind_beta(nsA,nsB) -> [nsB*25 + nsA] (0-based)
+  uint8_t ind_charge[5];
+  uint8_t ind_d1[25];                        // 5x5, [b*5+a]
+  uint8_t ind_d6[9], ind_d8[9], ind_d10[9], ind_c6[9], ind_c8[9], ind_c10[9];  // 3x3, [b*3+a]
+  int32_t iemonomer;
+  int32_t pad_;
+};
+
+// Host-side full tables (same content as the reference's COMMON block) and loaders.
+struct CcpolHost {
+  double param[18 * 6];
+  double parab[84 * 6 * 6];
+  double c[1000];
+  int numlin;
+  double cc[2000];
+  int nlin0;
+  double params[1000];
+  int nparsall;
+  double chrg[25];
+  double sites[75];
+  int ind_charge[25];
+  int ind_beta[625], ind_d1[625], ind_d6[625], ind_d8[625], ind_d10[625], ind_c6[625], ind_c8[625], ind_c10[625];
+};
+
+// Loads from `dir`: first the reference's own text files (data_SAPT5spfIR_2006, data_CCpol8s,
+// data_ccdata — the names the reference opens from its CWD), else the packed *.tbl files shipped
+// in pimd_tunneling_b200/data.  Returns empty string on success, else an error message.
+const char* load_ccpol_tables(const char* dir, CcpolHost* out);
+// Builds the device image (static index map, byte-sized index tables).  Returns error or "".
+const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* out);
+
+}  // namespace pimdk

@@ -1,0 +1,52 @@
+// FP64 pipe probe: dependent-free DFMA chains, enough warps to saturate every SM sub-partition.
+// MEASURED_PEAKS.json carries no FP64 number, so bench.py measures the denominator of the PES
+// kernel's roofline here, on the same device and clocks as the timed run.
+#include "kernels.h"
+
+namespace pimdk {
+namespace {
+
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  out[(long)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace
+
+cudaError_t fp64_peak_probe(int num_sms, double* tflops, cudaStream_t st) {
+  const int blocks = num_sms * 4, threads = 256, iters = 4096;
+  double* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(double) * blocks * threads);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(t0, st);
+    dfma_kernel<<<blocks, threads, 0, st>>>(out, iters, 1.0 + rep);
+    cudaEventRecord(t1, st);
+    e = cudaEventSynchronize(t1);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(out);
+  *tflops = best;
+  return e;
+}
+
+}  // namespace pimdk

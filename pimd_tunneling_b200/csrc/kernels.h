@@ -1,0 +1,108 @@
+// Internal launch interface between the C ABI (pimdk_api.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ccpol_tables.h"
+
+namespace pimdk {
+
+enum { PIMDK_FLAG_NAN = 1, PIMDK_FLAG_NOCONV = 2 };
+
+// Where geometry g (one bead of one ring polymer, or one batch entry) lives in a coordinate array.
+//   ABI batch   x(ndim,natom,nbatch):          n_inner=1, stride_outer=ndof, stride_dof=1
+//   state       x(n,ndim,natom,ntraj) (device): n_inner=n, stride_outer=ndof*n, stride_inner=1, stride_dof=n
+// dof index = atom*ndim + dim in both.
+struct GeomLayout {
+  long n_inner, stride_outer, stride_inner, stride_dof;
+  __host__ __device__ __forceinline__ long base(long g) const {
+    const long o = g / n_inner;
+    return o * stride_outer + (g - o * n_inner) * stride_inner;
+  }
+};
+
+enum PesKind { PES_NONE = 0, PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3 };
+
+struct SimplePesParams {  // mcmod_1d.f90:9-12, mcmod_2dtest.f90:16-24
+  double Vheight, x0;
+  double a0, b0;
+  double wx[6], wy[6];
+  double V0;
+  int ndof;
+};
+
+// ---- CCpol (ccpol_kernels.cu, built twice) ----
+#define PIMDK_DECL_CCPOL(sfx)                                                                                        \
+  size_t ccpol_smem_bytes_##sfx();                                                                                   \
+  cudaError_t launch_ccpol_energy_##sfx(const CcpolDev* tab, GeomLayout L, const double* x, double* v, long ngeom,   \
+                                        int* flags, int num_sms, cudaStream_t st);                                   \
+  cudaError_t launch_ccpol_grad_##sfx(const CcpolDev* tab, GeomLayout L, double* x, double* grad, long ngeom,        \
+                                      int write_drift, int* flags, int num_sms, cudaStream_t st);
+PIMDK_DECL_CCPOL(strict)
+PIMDK_DECL_CCPOL(fast)
+#undef PIMDK_DECL_CCPOL
+
+// ---- 1D / 2D model surfaces (pes_simple.cu) ----
+cudaError_t launch_simple_pes(PesKind kind, const SimplePesParams& P, GeomLayout L, const double* x, double* v,
+                              double* grad, long ngeom, int* flags, cudaStream_t st);
+
+// ---- normal-mode machinery (nm_kernels.cu) ----
+struct NmTables {       // device pointers, built once per pimdk_nm_setup / propagate call
+  const double* T;      // transmatrix(n,n), symmetric
+  const double* sA;     // sin(k pi/(n+1)),      k=1..n     (beadvec pieces, verletmodule.f90:328-333)
+  const double* sB;     // sin(n k pi/(n+1))
+  const double* lamb2;  // (lam_k*betan)**2
+  const double* cosw;   // [atom][k] cos(time*omegak)      (step_nm :528-531), time = dt/2
+  const double* sinw;   // [atom][k] sin(omegak*time)
+  const double* omega;  // [atom][k] omegak
+  const double* bmass;  // [atom][k] beadmass(atom,k)
+  const double* wbm;    // [atom][k] omegak*beadmass
+  const double* c1sq;   // [atom][k] c1**2                  (step_langevin :651-652)
+  const double* cnoise; // [atom][k] sqrt(beadmass/betan)*c2*sqrt(1+c1**2)
+  const double* sigp;   // [atom][k] sqrt(beadmass) (momentum resampling :218, init_path :107)
+  const double* mass;   // [atom]
+  double norm;          // sqrt(2/(n+1))
+  double stdev;         // sqrt(1/betan)
+  int n, ndim, natom, ndof;
+  int cayley;
+  double time;          // dt/2
+};
+
+// Y[r][k] = sum_j f(A)[r][j] * T[j][k]  for r in [0,rows): FP64 tile GEMM with fused prologue/epilogue.
+enum GemmMode {
+  GEMM_PLAIN = 0,       // Y = A T
+  GEMM_SUB_BEADVEC = 1, // Y = A T - beadvec            (nmtransform_forward, bead>0)
+  GEMM_ADD_BEADVEC = 2, // Y = (A + beadvec) T          (nmtransform_backward, bead>0)
+};
+cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, double* Y, long rows,
+                           const double* a /*(ndof)*/, const double* b /*(ndof,ntraj)*/, cudaStream_t st);
+
+// P <- P - dt*G ; then rotate(dt/2) . O-step(Philox) . rotate(dt/2) on (P,Q) in normal-mode space (PILE), or
+// rotate only (thermostat handled by the caller for Andersen).
+cudaError_t launch_nm_update(const NmTables& nm, double* P, double* Q, const double* G, double dt, long ntraj,
+                             int do_kick, int nrot, int do_langevin, uint64_t seed, uint64_t step,
+                             const int64_t* gid, int* flags, cudaStream_t st);
+// Andersen: P <- N(0, sqrt(1/betan))*sqrt(beadmass) for trajectories whose counter fired; updates counters.
+cudaError_t launch_andersen(const NmTables& nm, double* P, long ntraj, uint64_t seed, uint64_t step, double lambda,
+                            const int64_t* gid, int* count, int* rkick, cudaStream_t st);
+cudaError_t launch_andersen_init(long ntraj, uint64_t seed, double lambda, const int64_t* gid, int* count, int* rkick,
+                                 cudaStream_t st);
+// init_path momenta directly in normal-mode space (stream 0)
+cudaError_t launch_sample_momenta(const NmTables& nm, double* P, long ntraj, uint64_t seed, int stream, uint64_t step,
+                                  const int64_t* gid, cudaStream_t st);
+// estimator: dHdr[traj] += sum_{dim,atom} mass*(-x(n,dim,atom))*dbdl(dim,atom,traj)   (verletmodule.f90:397-403)
+cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* dbdl, double* dHdr, long ntraj,
+                             cudaStream_t st);
+cudaError_t launch_scale(double* v, double s, long n, cudaStream_t st);
+
+// ---- ring-polymer potential (um_kernels.cu): instantonmod.f90:17-151 ----
+cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double* a, const double* b,
+                      const double* mass, double betan, int fixedends, const double* vbead /*n or NULL*/,
+                      const double* gbead /*(n,ndim,natom) or NULL*/, double* um_out /*1, may be NULL*/,
+                      double* grad_out /*(n,ndim,natom) or NULL*/, cudaStream_t st);
+
+// FP64 pipe peak probe (fp64_peak.cu): returns achieved DFMA TFLOP/s
+cudaError_t fp64_peak_probe(int num_sms, double* tflops, cudaStream_t st);
+
+}  // namespace pimdk

@@ -1,0 +1,898 @@
+// C ABI of the hot path (include/pimdk.h): context, table upload, workspace, step loop.
+// Host-side arithmetic that feeds device tables (lam, beadmass, transmatrix, cos/sin of the free
+// ring-polymer rotation, PILE coefficients) uses the reference's own expressions
+// (verletmodule.f90:306-338, 381-386, 515-531) evaluated once per call in FP64 on the host.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pimdk.h"
+#include "kernels.h"
+
+using namespace pimdk;
+
+namespace {
+
+const double PI_TRUNC = 3.14159265358979;  // instantonmod.f90:4 (truncated literal, used by init_nm and gauleg)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Prof {
+  double ms = 0.0;
+  long launches = 0;
+};
+
+struct Ctx {
+  bool inited = false;
+  int device = 0, num_sms = 148;
+  cudaStream_t stream = 0;
+  std::string data_dir = ".";
+  std::string err;
+  int mode = PIMDK_MODE_STRICT;
+  // PES
+  PesKind pes = PES_NONE;
+  int ndim = 0, natom = 0;
+  SimplePesParams sp{};
+  bool tab_loaded = false;
+  CcpolHost htab;
+  CcpolDev hdev;
+  DevBuf dtab;
+  // normal modes
+  bool nm_ready = false;
+  int n = 0, nm_ndim = 0, nm_natom = 0;
+  double betan = 0.0, tau = 1.0;
+  std::vector<double> mass, lam, beadmass, T;
+  DevBuf dT, dsA, dsB, dlamb2, dmass, dtabs;  // dtabs: 8 per-call (natom,n) tables
+  // workspaces
+  DevBuf wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc;
+  // profiling
+  bool profiling = false;
+  std::map<std::string, Prof> prof;
+  struct Span { std::string fam; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  long launch_count = 0;
+  long last_nan_traj = -1;
+};
+
+Ctx g;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g.err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(PIMDK_ECUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), \
+                                        __FILE__, __LINE__, cudaGetErrorString(e__));              \
+  } while (0)
+#define NEED_INIT()                                                          \
+  do {                                                                       \
+    if (!g.inited) return fail(PIMDK_EINVAL, "pimdk_init has not been called"); \
+  } while (0)
+
+// profiling spans: events on the library stream around a kernel family
+struct Scope {
+  const char* fam;
+  bool on;
+  cudaEvent_t a{}, b{};
+  int nlaunch;
+  Scope(const char* f, int nl = 1) : fam(f), on(g.profiling), nlaunch(nl) {
+    g.launch_count += nl;
+    if (on) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, g.stream);
+    }
+  }
+  ~Scope() {
+    if (on) {
+      cudaEventRecord(b, g.stream);
+      g.spans.push_back({fam, a, b});
+      g.prof[fam].launches += nlaunch;
+    }
+  }
+};
+
+void resolve_spans() {
+  for (auto& s : g.spans) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess)
+      g.prof[s.fam].ms += ms;
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  g.spans.clear();
+}
+
+int check_flags(bool sync_first) {
+  int fl = 0;
+  if (sync_first) CU(cudaStreamSynchronize(g.stream));
+  CU(cudaMemcpyAsync(&fl, g.wFlags.p, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  if (fl & PIMDK_FLAG_NOCONV) return fail(PIMDK_ENOCONV, "No convergence in indN_iter");
+  if (fl & PIMDK_FLAG_NAN) return fail(PIMDK_ENAN, "NaN in pot propagation");
+  return PIMDK_OK;
+}
+
+int clear_flags() {
+  CU(g.wFlags.ensure(sizeof(int)));
+  CU(cudaMemsetAsync(g.wFlags.p, 0, sizeof(int), g.stream));
+  return PIMDK_OK;
+}
+
+int ensure_ccpol_tables() {
+  if (g.tab_loaded) return PIMDK_OK;
+  const char* m = load_ccpol_tables(g.data_dir.c_str(), &g.htab);
+  if (m[0]) return fail(PIMDK_EDATA, "%s", m);
+  g.tab_loaded = true;
+  return PIMDK_OK;
+}
+
+int upload_ccpol_dev() {
+  CU(g.dtab.ensure(sizeof(CcpolDev)));
+  CU(cudaMemcpyAsync(g.dtab.p, &g.hdev, sizeof(CcpolDev), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return PIMDK_OK;
+}
+
+// energy and/or gradient of `ngeom` geometries laid out per L (device pointers)
+int pes_eval_dev(GeomLayout L, double* x, double* v, double* grad, long ngeom, int write_drift) {
+  if (g.pes == PES_NONE) return fail(PIMDK_EINVAL, "no PES selected (pimdk_pes_select)");
+  if (ngeom <= 0) return PIMDK_OK;
+  int* flags = g.wFlags.as<int>();
+  if (g.pes == PES_CCPOL) {
+    const CcpolDev* tab = g.dtab.as<CcpolDev>();
+    if (v) {
+      Scope s("pes");
+      CU(g.mode == PIMDK_MODE_FAST ? launch_ccpol_energy_fast(tab, L, x, v, ngeom, flags, g.num_sms, g.stream)
+                                   : launch_ccpol_energy_strict(tab, L, x, v, ngeom, flags, g.num_sms, g.stream));
+    }
+    if (grad) {
+      Scope s("pes");
+      CU(g.mode == PIMDK_MODE_FAST
+             ? launch_ccpol_grad_fast(tab, L, x, grad, ngeom, write_drift, flags, g.num_sms, g.stream)
+             : launch_ccpol_grad_strict(tab, L, x, grad, ngeom, write_drift, flags, g.num_sms, g.stream));
+    }
+  } else {
+    Scope s("pes");
+    CU(launch_simple_pes(g.pes, g.sp, L, x, v, grad, ngeom, flags, g.stream));
+  }
+  return PIMDK_OK;
+}
+
+NmTables nm_tables_base() {
+  NmTables nm{};
+  nm.T = g.dT.as<double>();
+  nm.sA = g.dsA.as<double>();
+  nm.sB = g.dsB.as<double>();
+  nm.lamb2 = g.dlamb2.as<double>();
+  nm.mass = g.dmass.as<double>();
+  nm.n = g.n;
+  nm.ndim = g.nm_ndim;
+  nm.natom = g.nm_natom;
+  nm.ndof = g.nm_ndim * g.nm_natom;
+  nm.norm = std::sqrt(2.0 / (double)(g.n + 1));
+  nm.stdev = std::sqrt(1.0 / g.betan);
+  return nm;
+}
+
+// per-call (natom,n) tables that depend on dt, gamma, cayley
+int build_step_tables(NmTables* nm, double dt, double gamma, int cayley) {
+  const int n = g.n, natom = g.nm_natom;
+  const size_t cnt = (size_t)natom * n;
+  std::vector<double> h(8 * cnt);
+  double *cosw = &h[0], *sinw = &h[cnt], *omega = &h[2 * cnt], *bmass = &h[3 * cnt], *wbm = &h[4 * cnt],
+         *c1sq = &h[5 * cnt], *cnoise = &h[6 * cnt], *sigp = &h[7 * cnt];
+  const double time = 0.5 * dt;
+  for (int a = 0; a < natom; ++a)
+    for (int k = 0; k < n; ++k) {
+      const size_t i = (size_t)a * n + k;
+      const double bm = g.beadmass[(size_t)k * natom + a];  // beadmass(atom,k)
+      const double om = std::sqrt(g.mass[a] / bm) * g.lam[k];  // step_nm :519
+      omega[i] = om;
+      bmass[i] = bm;
+      cosw[i] = std::cos(time * om);
+      sinw[i] = std::sin(om * time);
+      wbm[i] = om * bm;
+      const double c1 = std::exp(-gamma * dt * g.lam[k] * std::sqrt(g.mass[a] / bm));  // :383
+      const double c2 = std::sqrt(1.0 - c1 * c1);                                       // :384
+      c1sq[i] = c1 * c1;
+      cnoise[i] = std::sqrt(bm / g.betan) * c2 * std::sqrt(1.0 + c1 * c1);  // :651-652
+      sigp[i] = std::sqrt(bm);
+    }
+  CU(g.dtabs.ensure(h.size() * sizeof(double)));
+  CU(cudaMemcpyAsync(g.dtabs.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  double* d = g.dtabs.as<double>();
+  nm->cosw = d;
+  nm->sinw = d + cnt;
+  nm->omega = d + 2 * cnt;
+  nm->bmass = d + 3 * cnt;
+  nm->wbm = d + 4 * cnt;
+  nm->c1sq = d + 5 * cnt;
+  nm->cnoise = d + 6 * cnt;
+  nm->sigp = d + 7 * cnt;
+  nm->cayley = cayley;
+  nm->time = time;
+  return PIMDK_OK;
+}
+
+__global__ void first_nan_kernel(const double* __restrict__ p, long per_traj, long ntraj, long long* out) {
+  const long total = per_traj * ntraj;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
+    if (p[e] != p[e]) atomicMin(out, (long long)(e / per_traj));
+}
+
+// init_path positions: x(k,dof,traj) = splint(lampath, path(:,dof), splinepath(:,dof), (k-1)*xi/(n-1))
+// (verletmodule.f90:39-48; splint/locate instantonmod.f90:500-524, 560-596)
+__global__ void init_path_kernel(int n, int ndof, int npath, const double* __restrict__ lampath,
+                                 const double* __restrict__ path, const double* __restrict__ spl,
+                                 const double* __restrict__ xi, long ntraj, double* __restrict__ x) {
+  const long total = ntraj * (long)ndof * n;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % n);
+    const long r = e / n;
+    const int dof = (int)(r % ndof);
+    const long traj = r / ndof;
+    const double xv = (double)k * xi[traj] / (double)(n - 1);
+    // locate
+    const bool ascnd = lampath[npath - 1] >= lampath[0];
+    int jl = 0, ju = npath + 1;
+    while (ju - jl > 1) {
+      const int jm = (ju + jl) / 2;
+      if (ascnd == (xv >= lampath[jm - 1])) jl = jm;
+      else ju = jm;
+    }
+    int loc = jl;
+    if (xv == lampath[0]) loc = 1;
+    else if (xv == lampath[npath - 1]) loc = npath - 1;
+    int klo = loc < npath - 1 ? loc : npath - 1;
+    if (klo < 1) klo = 1;
+    const int khi = klo + 1;
+    const double* ya = path + (long)dof * npath;
+    const double* y2 = spl + (long)dof * npath;
+    const double h = lampath[khi - 1] - lampath[klo - 1];
+    const double aa = (lampath[khi - 1] - xv) / h, bb = (xv - lampath[klo - 1]) / h;
+    x[e] = aa * ya[klo - 1] + bb * ya[khi - 1] +
+           ((aa * aa * aa - aa) * y2[klo - 1] + (bb * bb * bb - bb) * y2[khi - 1]) * (h * h) / 6.0;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pimdk_last_error(void) { return g.err.c_str(); }
+
+int pimdk_init(pimdk_int device, const char* data_dir) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PIMDK_ENODEV, "no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device >= 0) {
+    if (device >= ndev) return fail(PIMDK_EINVAL, "device %lld out of range (%d devices)", (long long)device, ndev);
+    CU(cudaSetDevice((int)device));
+  }
+  CU(cudaGetDevice(&g.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, g.device));
+  g.num_sms = prop.multiProcessorCount;
+  if (prop.major < 10)
+    return fail(PIMDK_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", g.device, prop.major,
+                prop.minor);
+  g.data_dir = data_dir ? data_dir : ".";
+  g.inited = true;
+  g.err.clear();
+  return clear_flags();
+}
+
+int pimdk_finalize(void) {
+  if (!g.inited) return PIMDK_OK;
+  cudaStreamSynchronize(g.stream);
+  resolve_spans();
+  DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wP, &g.wQ, &g.wG, &g.wGn,
+                    &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
+                    &g.wDhdr, &g.wPp, &g.wMisc};
+  for (DevBuf* b : bufs) b->release();
+  g.inited = false;
+  g.nm_ready = false;
+  g.pes = PES_NONE;
+  g.tab_loaded = false;
+  g.stream = 0;
+  return PIMDK_OK;
+}
+
+int pimdk_set_stream(void* s) {
+  g.stream = reinterpret_cast<cudaStream_t>(s);
+  return PIMDK_OK;
+}
+
+int pimdk_set_mode(pimdk_int mode) {
+  if (mode != PIMDK_MODE_STRICT && mode != PIMDK_MODE_FAST) return fail(PIMDK_EINVAL, "unknown mode");
+  g.mode = (int)mode;
+  return PIMDK_OK;
+}
+
+int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
+  NEED_INIT();
+  std::string s(name ? name : "");
+  if (s == "1d") {  // mcmod_1d.f90:8-12
+    g.pes = PES_1D;
+    g.ndim = 1;
+    g.natom = 1;
+    g.sp = SimplePesParams{};
+    g.sp.Vheight = np > 0 ? pp[0] : 1.0;
+    g.sp.x0 = np > 1 ? pp[1] : 1.0;
+    g.sp.ndof = 1;
+    return PIMDK_OK;
+  }
+  if (s == "2dtest") {  // mcmod_2dtest.f90:11-27
+    g.pes = PES_2DTEST;
+    g.ndim = 2;
+    g.natom = 1;
+    g.sp = SimplePesParams{};
+    g.sp.a0 = np > 0 ? pp[0] : 2.0;
+    g.sp.b0 = np > 1 ? pp[1] : 0.2;
+    const double rho0 = np > 2 ? pp[2] : 3.0;
+    const int m = 6;
+    for (int k = 1; k <= m; ++k) {
+      g.sp.wx[k - 1] = rho0 * std::cos((double)k * 2.0 * PI_TRUNC / (double)m);
+      g.sp.wy[k - 1] = rho0 * std::sin((double)k * 2.0 * PI_TRUNC / (double)m);
+    }
+    g.sp.V0 = 0.0;
+    g.sp.ndof = 2;
+    return PIMDK_OK;
+  }
+  if (s == "ccpol8sf") {  // mcmod_waterdimer_ccpol.f90:9-16 -> init_ccpol(3,1,1,0)
+    int rc = ensure_ccpol_tables();
+    if (rc) return rc;
+    const int iemon = np > 0 ? (int)pp[0] : 1;
+    if (iemon != 0 && iemon != 1) return fail(PIMDK_EINVAL, "wrong value of iemonomer");
+    const char* m = build_ccpol_dev(g.htab, iemon, &g.hdev);
+    if (m[0]) return fail(PIMDK_EDATA, "%s", m);
+    rc = upload_ccpol_dev();
+    if (rc) return rc;
+    g.pes = PES_CCPOL;
+    g.ndim = 3;
+    g.natom = 6;
+    return PIMDK_OK;
+  }
+  return fail(PIMDK_EINVAL, "unknown PES '%s' (1d, 2dtest, ccpol8sf)", s.c_str());
+}
+
+int pimdk_pes_info(pimdk_int* ndim, pimdk_int* natom) {
+  if (g.pes == PES_NONE) return fail(PIMDK_EINVAL, "no PES selected");
+  if (ndim) *ndim = g.ndim;
+  if (natom) *natom = g.natom;
+  return PIMDK_OK;
+}
+
+int pimdk_pes_set_v0(double v0) {
+  NEED_INIT();
+  if (g.pes == PES_CCPOL) {
+    g.hdev.V0 = v0;
+    return upload_ccpol_dev();
+  }
+  if (g.pes == PES_2DTEST) g.sp.V0 = v0;  // mcmod_1d's V ignores V0 (mcmod_1d.f90:20)
+  return PIMDK_OK;
+}
+
+static int check_dims(pimdk_int ndim, pimdk_int natom) {
+  if (g.pes == PES_NONE) return fail(PIMDK_EINVAL, "no PES selected (pimdk_pes_select)");
+  if (g.pes == PES_1D) {  // any shape: the 1D surface sums over all components (mcmod_1d.f90:20)
+    g.sp.ndof = (int)(ndim * natom);
+    g.ndim = (int)ndim;
+    g.natom = (int)natom;
+    return PIMDK_OK;
+  }
+  if (ndim != g.ndim || natom != g.natom)
+    return fail(PIMDK_EINVAL, "PES expects ndim=%d natom=%d, got %lld %lld", g.ndim, g.natom, (long long)ndim,
+                (long long)natom);
+  return PIMDK_OK;
+}
+
+int pimdk_pes_eval_dev(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, const double* x, double* v, double* grad) {
+  NEED_INIT();
+  int rc = check_dims(ndim, natom);
+  if (rc) return rc;
+  const long ndof = ndim * natom;
+  GeomLayout L{1, ndof, 0, 1};
+  rc = clear_flags();
+  if (rc) return rc;
+  double* xw = const_cast<double*>(x);
+  if (grad && g.pes == PES_CCPOL) {  // keep the caller's x untouched: FD perturbation works on a copy
+    CU(g.wX.ensure(sizeof(double) * nbatch * ndof));
+    CU(cudaMemcpyAsync(g.wX.p, x, sizeof(double) * nbatch * ndof, cudaMemcpyDeviceToDevice, g.stream));
+    xw = g.wX.as<double>();
+  }
+  rc = pes_eval_dev(L, xw, v, grad, nbatch, 0);
+  if (rc) return rc;
+  return check_flags(false);
+}
+
+static int pes_eval_host(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, double* x, double* v, double* grad,
+                         int inplace) {
+  NEED_INIT();
+  int rc = check_dims(ndim, natom);
+  if (rc) return rc;
+  if (nbatch <= 0) return PIMDK_OK;
+  const size_t nx = (size_t)nbatch * ndim * natom;
+  CU(g.wX.ensure(nx * sizeof(double)));
+  CU(g.wG.ensure(nx * sizeof(double)));
+  CU(g.wV.ensure((size_t)nbatch * sizeof(double)));
+  CU(cudaMemcpyAsync(g.wX.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  rc = clear_flags();
+  if (rc) return rc;
+  GeomLayout L{1, (long)(ndim * natom), 0, 1};
+  rc = pes_eval_dev(L, g.wX.as<double>(), v ? g.wV.as<double>() : nullptr, grad ? g.wG.as<double>() : nullptr, nbatch,
+                    inplace);
+  if (rc) return rc;
+  if (v) CU(cudaMemcpyAsync(v, g.wV.p, (size_t)nbatch * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  if (grad) CU(cudaMemcpyAsync(grad, g.wG.p, nx * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  if (inplace) CU(cudaMemcpyAsync(x, g.wX.p, nx * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  return check_flags(false);
+}
+
+int pimdk_pes_eval(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, const double* x, double* v, double* grad) {
+  return pes_eval_host(nbatch, ndim, natom, const_cast<double*>(x), v, grad, 0);
+}
+
+int pimdk_pes_vprime_inplace(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, double* x, double* grad) {
+  if (!grad) return fail(PIMDK_EINVAL, "grad must not be NULL");
+  return pes_eval_host(nbatch, ndim, natom, x, nullptr, grad, 1);
+}
+
+int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x, const double* a,
+                         const double* b, const double* mass, double betan, pimdk_int fixedends, double* f,
+                         double* gout) {
+  NEED_INIT();
+  int rc = check_dims(ndim, natom);
+  if (rc) return rc;
+  if (n < 2) return fail(PIMDK_EINVAL, "n must be >= 2");
+  if (fixedends && (!a || !b)) return fail(PIMDK_EINVAL, "fixedends needs a and b");
+  const long ndof = ndim * natom;
+  const size_t nx = (size_t)n * ndof;
+  CU(g.wX.ensure(nx * sizeof(double)));
+  CU(g.wG.ensure(nx * sizeof(double)));
+  CU(g.wGn.ensure(nx * sizeof(double)));
+  CU(g.wV.ensure((size_t)n * sizeof(double)));
+  CU(g.wMisc.ensure((size_t)(3 * ndof + natom + 2) * sizeof(double)));
+  double* dmisc = g.wMisc.as<double>();
+  double *da = dmisc, *db = dmisc + ndof, *dm = dmisc + 2 * ndof, *dum = dmisc + 2 * ndof + natom;
+  CU(cudaMemcpyAsync(g.wX.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  if (fixedends) {
+    CU(cudaMemcpyAsync(da, a, ndof * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(db, b, ndof * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  }
+  CU(cudaMemcpyAsync(dm, mass, natom * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  rc = clear_flags();
+  if (rc) return rc;
+  GeomLayout L{n, ndof * n, 1, n};
+  // x is intent(in) in UM*: the FD perturbation of ccpol works on the copy and its drift is dropped
+  double* xw = g.wX.as<double>();
+  if (gout && g.pes == PES_CCPOL) {
+    CU(g.wAux.ensure(nx * sizeof(double)));
+    CU(cudaMemcpyAsync(g.wAux.p, g.wX.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    xw = g.wAux.as<double>();
+  }
+  rc = pes_eval_dev(L, xw, f ? g.wV.as<double>() : nullptr, gout ? g.wG.as<double>() : nullptr, n, 0);
+  if (rc) return rc;
+  {
+    Scope s("um", (f ? 1 : 0) + (gout ? 1 : 0));
+    CU(launch_um((int)n, (int)ndim, (int)natom, g.wX.as<double>(), da, db, dm, betan, fixedends != 0,
+                 g.wV.as<double>(), g.wG.as<double>(), f ? dum : nullptr, gout ? g.wGn.as<double>() : nullptr, g.stream));
+  }
+  if (f) CU(cudaMemcpyAsync(f, dum, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  if (gout) CU(cudaMemcpyAsync(gout, g.wGn.p, nx * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  return check_flags(false);
+}
+
+int pimdk_nm_setup(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* mass, double betan, double tau) {
+  NEED_INIT();
+  if (n < 2 || ndim < 1 || natom < 1 || !mass || !(betan > 0.0)) return fail(PIMDK_EINVAL, "bad nm_setup arguments");
+  g.n = (int)n;
+  g.nm_ndim = (int)ndim;
+  g.nm_natom = (int)natom;
+  g.betan = betan;
+  g.tau = tau;
+  g.mass.assign(mass, mass + natom);
+  g.lam.assign(n, 0.0);
+  g.beadmass.assign((size_t)natom * n, 0.0);
+  g.T.assign((size_t)n * n, 0.0);
+  std::vector<double> sA(n), sB(n), lamb2(n);
+  // init_nm, verletmodule.f90:306-338
+  for (long i = 1; i <= n; ++i) {
+    g.lam[i - 1] = 2.0 * std::sin((double)i * PI_TRUNC / (double)(2 * n + 2)) / betan;
+    for (long j = 1; j <= natom; ++j)
+      g.beadmass[(size_t)(i - 1) * natom + (j - 1)] = mass[j - 1] * ((g.lam[i - 1] * tau) * (g.lam[i - 1] * tau));
+    for (long l = i; l <= n; ++l) {
+      const double t = std::sin((double)(i * l) * PI_TRUNC / (double)(n + 1)) * std::sqrt(2.0 / (double)(n + 1));
+      if (t != t) return fail(PIMDK_ENAN, "Nan!");
+      g.T[(size_t)(l - 1) * n + (i - 1)] = t;
+      g.T[(size_t)(i - 1) * n + (l - 1)] = t;
+    }
+    sA[i - 1] = std::sin((double)i * PI_TRUNC / (double)(n + 1));
+    sB[i - 1] = std::sin((double)(n * i) * PI_TRUNC / (double)(n + 1));
+    lamb2[i - 1] = (g.lam[i - 1] * betan) * (g.lam[i - 1] * betan);
+  }
+  CU(g.dT.ensure(g.T.size() * sizeof(double)));
+  CU(g.dsA.ensure(n * sizeof(double)));
+  CU(g.dsB.ensure(n * sizeof(double)));
+  CU(g.dlamb2.ensure(n * sizeof(double)));
+  CU(g.dmass.ensure(natom * sizeof(double)));
+  CU(cudaMemcpyAsync(g.dT.p, g.T.data(), g.T.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.dsA.p, sA.data(), n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.dsB.p, sB.data(), n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.dlamb2.p, lamb2.data(), n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.dmass.p, mass, natom * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  g.nm_ready = true;
+  return PIMDK_OK;
+}
+
+int pimdk_nm_get(double* T, double* lam, double* beadmass) {
+  if (!g.nm_ready) return fail(PIMDK_EINVAL, "pimdk_nm_setup has not been called");
+  if (T) std::memcpy(T, g.T.data(), g.T.size() * sizeof(double));
+  if (lam) std::memcpy(lam, g.lam.data(), g.lam.size() * sizeof(double));
+  if (beadmass) std::memcpy(beadmass, g.beadmass.data(), g.beadmass.size() * sizeof(double));
+  return PIMDK_OK;
+}
+
+int pimdk_nm_transform(pimdk_int forward, pimdk_int nvec, const double* vin, const double* beadvec, double* vout) {
+  NEED_INIT();
+  if (!g.nm_ready) return fail(PIMDK_EINVAL, "pimdk_nm_setup has not been called");
+  const size_t cnt = (size_t)nvec * g.n;
+  std::vector<double> tmp;
+  const double* src = vin;
+  if (!forward && beadvec) {  // nmtransform_backward: qprop + beadvec before the product (:274-278)
+    tmp.resize(cnt);
+    for (size_t i = 0; i < cnt; ++i) tmp[i] = vin[i] + beadvec[i];
+    src = tmp.data();
+  }
+  CU(g.wX.ensure(cnt * sizeof(double)));
+  CU(g.wG.ensure(cnt * sizeof(double)));
+  CU(cudaMemcpyAsync(g.wX.p, src, cnt * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  NmTables nm = nm_tables_base();
+  {
+    Scope s("gemm");
+    CU(launch_nm_gemm(nm, GEMM_PLAIN, g.wX.as<double>(), g.wG.as<double>(), nvec, nullptr, nullptr, g.stream));
+  }
+  CU(cudaMemcpyAsync(vout, g.wG.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  if (forward && beadvec)  // nmtransform_forward: qprop - beadvec after the product (:260-264)
+    for (size_t i = 0; i < cnt; ++i) vout[i] = vout[i] - beadvec[i];
+  return PIMDK_OK;
+}
+
+static int upload_gid(const pimdk_int* gid, pimdk_int ntraj, const int64_t** dgid) {
+  *dgid = nullptr;
+  if (!gid) return PIMDK_OK;
+  CU(g.wGid.ensure(sizeof(int64_t) * ntraj));
+  CU(cudaMemcpyAsync(g.wGid.p, gid, sizeof(int64_t) * ntraj, cudaMemcpyHostToDevice, g.stream));
+  *dgid = g.wGid.as<int64_t>();
+  return PIMDK_OK;
+}
+
+int pimdk_init_path(pimdk_int ntraj, pimdk_int npath, const double* lampath, const double* path,
+                    const double* splinepath, const double* xi, uint64_t seed, const pimdk_int* traj_gid, double* x,
+                    double* p) {
+  NEED_INIT();
+  if (!g.nm_ready) return fail(PIMDK_EINVAL, "pimdk_nm_setup has not been called");
+  if (ntraj <= 0) return PIMDK_OK;
+  if (npath < 2) return fail(PIMDK_EINVAL, "npath must be >= 2");
+  const int ndof = g.nm_ndim * g.nm_natom;
+  const size_t tot = (size_t)ntraj * ndof * g.n;
+  CU(g.wX.ensure(tot * sizeof(double)));
+  CU(g.wP.ensure(tot * sizeof(double)));
+  CU(g.wPp.ensure(tot * sizeof(double)));
+  const size_t np = (size_t)npath, npd = np * ndof;
+  CU(g.wMisc.ensure((np + 2 * npd + ntraj) * sizeof(double)));
+  double* d = g.wMisc.as<double>();
+  double *dl = d, *dpth = d + np, *dspl = d + np + npd, *dxi = d + np + 2 * npd;
+  CU(cudaMemcpyAsync(dl, lampath, np * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(dpth, path, npd * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(dspl, splinepath, npd * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(dxi, xi, ntraj * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  const int64_t* dgid;
+  int rc = upload_gid(traj_gid, ntraj, &dgid);
+  if (rc) return rc;
+  NmTables nm = nm_tables_base();
+  rc = build_step_tables(&nm, 0.0, 0.0, 0);
+  if (rc) return rc;
+  {
+    Scope s("init", 3);
+    long blocks = (long)((tot + 255) / 256);
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    init_path_kernel<<<(unsigned)blocks, 256, 0, g.stream>>>(g.n, ndof, (int)npath, dl, dpth, dspl, dxi, ntraj,
+                                                            g.wX.as<double>());
+    CU(cudaGetLastError());
+    CU(launch_sample_momenta(nm, g.wP.as<double>(), ntraj, seed, 0, 0, dgid, g.stream));
+    CU(launch_nm_gemm(nm, GEMM_PLAIN, g.wP.as<double>(), g.wPp.as<double>(), (long)ntraj * ndof, nullptr, nullptr,
+                      g.stream));
+  }
+  CU(cudaMemcpyAsync(x, g.wX.p, tot * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaMemcpyAsync(p, g.wPp.p, tot * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return PIMDK_OK;
+}
+
+int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p, const double* a, const double* b,
+                        const double* dbdl, double dt, double gamma, pimdk_int NMC, pimdk_int imin, pimdk_int Noutput,
+                        pimdk_int cayley, uint64_t seed, const pimdk_int* traj_gid, double* dHdr) {
+  NEED_INIT();
+  if (!g.nm_ready) return fail(PIMDK_EINVAL, "pimdk_nm_setup has not been called");
+  if (g.pes == PES_NONE) return fail(PIMDK_EINVAL, "no PES selected (pimdk_pes_select)");
+  if (thermostat != PIMDK_THERMOSTAT_ANDERSEN && thermostat != PIMDK_THERMOSTAT_PILE)
+    return fail(PIMDK_EINVAL, "Incorrect thermostat option.");
+  int rc = check_dims(g.nm_ndim, g.nm_natom);
+  if (rc) return rc;
+  if (ntraj <= 0) return PIMDK_OK;
+  if (NMC < 0 || imin < 0 || NMC - imin <= 0) return fail(PIMDK_EINVAL, "need NMC > imin >= 0");
+  const int n = g.n, ndof = g.nm_ndim * g.nm_natom;
+  const long rows = (long)ntraj * ndof;
+  const size_t tot = (size_t)rows * n;
+  CU(g.wP.ensure(tot * sizeof(double)));
+  CU(g.wQ.ensure(tot * sizeof(double)));
+  CU(g.wG.ensure(tot * sizeof(double)));
+  CU(g.wGn.ensure(tot * sizeof(double)));
+  if (thermostat == PIMDK_THERMOSTAT_ANDERSEN) {
+    CU(g.wCount.ensure(sizeof(int) * ntraj));
+    CU(g.wKick.ensure(sizeof(int) * ntraj));
+  }
+  NmTables nm = nm_tables_base();
+  rc = build_step_tables(&nm, dt, gamma, (int)cayley);
+  if (rc) return rc;
+  rc = clear_flags();
+  if (rc) return rc;
+  const int64_t* dgid = reinterpret_cast<const int64_t*>(traj_gid);
+  double *P = g.wP.as<double>(), *Q = g.wQ.as<double>(), *G = g.wG.as<double>(), *Gn = g.wGn.as<double>();
+  int* flags = g.wFlags.as<int>();
+  GeomLayout L{n, (long)ndof * n, 1, n};
+  CU(cudaMemsetAsync(dHdr, 0, sizeof(double) * ntraj, g.stream));  // restart < 2: dHdr = 0 (:199,387)
+  {
+    Scope s("gemm", 2);
+    CU(launch_nm_gemm(nm, GEMM_PLAIN, p, P, rows, a, b, g.stream));
+    CU(launch_nm_gemm(nm, GEMM_SUB_BEADVEC, x, Q, rows, a, b, g.stream));
+  }
+  if (thermostat == PIMDK_THERMOSTAT_PILE) {
+    for (pimdk_int ii = 1; ii <= NMC; ++ii) {
+      rc = pes_eval_dev(L, x, nullptr, G, (long)ntraj * n, 1);  // step_v's Vprime per bead
+      if (rc) return rc;
+      {
+        Scope s("gemm");
+        CU(launch_nm_gemm(nm, GEMM_PLAIN, G, Gn, rows, a, b, g.stream));
+      }
+      {
+        Scope s("update");
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 2, 1, seed, (uint64_t)ii, dgid, flags, g.stream));
+      }
+      {
+        Scope s("gemm");
+        CU(launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream));
+      }
+      if (ii > imin) {
+        Scope s("estimator");
+        CU(launch_estimator(nm, x, dbdl, dHdr, ntraj, g.stream));
+      }
+    }
+  } else {
+    int* count = g.wCount.as<int>();
+    int* rkick = g.wKick.as<int>();
+    {
+      Scope s("update");
+      CU(launch_andersen_init(ntraj, seed, (double)Noutput, dgid, count, rkick, g.stream));
+    }
+    for (pimdk_int ii = 1; ii <= NMC; ++ii) {
+      {
+        Scope s("update", 3);
+        CU(launch_andersen(nm, P, ntraj, seed, (uint64_t)ii, (double)Noutput, dgid, count, rkick, g.stream));
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)ii, dgid, flags, g.stream));
+      }
+      {
+        Scope s("gemm");
+        CU(launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream));
+      }
+      rc = pes_eval_dev(L, x, nullptr, G, (long)ntraj * n, 1);
+      if (rc) return rc;
+      {
+        Scope s("gemm");
+        CU(launch_nm_gemm(nm, GEMM_PLAIN, G, Gn, rows, a, b, g.stream));
+      }
+      {
+        Scope s("update");
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)ii, dgid, flags, g.stream));
+      }
+      {
+        Scope s("gemm");
+        CU(launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream));
+      }
+      if (ii > imin) {
+        Scope s("estimator");
+        CU(launch_estimator(nm, x, dbdl, dHdr, ntraj, g.stream));
+      }
+    }
+  }
+  {
+    Scope s("gemm");
+    CU(launch_nm_gemm(nm, GEMM_PLAIN, P, p, rows, a, b, g.stream));
+  }
+  {
+    Scope s("estimator");
+    CU(launch_scale(dHdr, (double)(NMC - imin), ntraj, g.stream));  // dHdr/dble(NMC+restartnmc-imin) (:247,413)
+  }
+  rc = check_flags(false);
+  if (rc == PIMDK_ENAN) {
+    long long first = (long long)ntraj;
+    long long* dfirst = nullptr;
+    if (cudaMalloc(&dfirst, sizeof(long long)) == cudaSuccess) {
+      cudaMemcpy(dfirst, &first, sizeof(long long), cudaMemcpyHostToDevice);
+      first_nan_kernel<<<148, 256, 0, g.stream>>>(P, (long)ndof * n, ntraj, dfirst);
+      cudaMemcpy(&first, dfirst, sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaFree(dfirst);
+    }
+    g.last_nan_traj = first < ntraj ? (long)first : -1;
+  } else {
+    g.last_nan_traj = -1;
+  }
+  if (g.profiling) resolve_spans();
+  return rc;
+}
+
+int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p, const double* a, const double* b,
+                    const double* dbdl, double dt, double gamma, pimdk_int NMC, pimdk_int imin, pimdk_int Noutput,
+                    pimdk_int cayley, uint64_t seed, const pimdk_int* traj_gid, double* dHdr) {
+  NEED_INIT();
+  if (!g.nm_ready) return fail(PIMDK_EINVAL, "pimdk_nm_setup has not been called");
+  if (ntraj <= 0) return PIMDK_OK;
+  const int ndof = g.nm_ndim * g.nm_natom;
+  const size_t tot = (size_t)ntraj * ndof * g.n, nb = (size_t)ntraj * ndof;
+  CU(g.wX.ensure(tot * sizeof(double)));
+  CU(g.wPp.ensure(tot * sizeof(double)));
+  CU(g.wA.ensure(ndof * sizeof(double)));
+  CU(g.wB.ensure(nb * sizeof(double)));
+  CU(g.wDbdl.ensure(nb * sizeof(double)));
+  CU(g.wDhdr.ensure(ntraj * sizeof(double)));
+  CU(cudaMemcpyAsync(g.wX.p, x, tot * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.wPp.p, p, tot * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.wA.p, a, ndof * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.wB.p, b, nb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.wDbdl.p, dbdl, nb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  const int64_t* dgid;
+  int rc = upload_gid(traj_gid, ntraj, &dgid);
+  if (rc) return rc;
+  rc = pimdk_propagate_dev(thermostat, ntraj, g.wX.as<double>(), g.wPp.as<double>(), g.wA.as<double>(),
+                           g.wB.as<double>(), g.wDbdl.as<double>(), dt, gamma, NMC, imin, Noutput, cayley, seed,
+                           reinterpret_cast<const pimdk_int*>(dgid), g.wDhdr.as<double>());
+  if (rc != PIMDK_OK && rc != PIMDK_ENAN) return rc;
+  std::string keep = g.err;
+  CU(cudaMemcpyAsync(x, g.wX.p, tot * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaMemcpyAsync(p, g.wPp.p, tot * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaMemcpyAsync(dHdr, g.wDhdr.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  g.err = keep;
+  return rc;
+}
+
+pimdk_int pimdk_last_nan_trajectory(void) { return g.last_nan_traj; }
+
+int pimdk_ti_partial_sums(pimdk_int ntraj, const double* dHdr, const pimdk_int* gid, pimdk_int nrep,
+                          pimdk_int nintegral, double betan, double* sums) {
+  if (nrep <= 0 || nintegral <= 0) return fail(PIMDK_EINVAL, "nrep and nintegral must be positive");
+  for (pimdk_int i = 0; i < 3 * nintegral; ++i) sums[i] = 0.0;
+  for (pimdk_int t = 0; t < ntraj; ++t) {
+    const pimdk_int id = gid ? gid[t] : t;
+    const pimdk_int il = id / nrep;  // global id = nrep*(ilambda-1) + irep (pimd_par.f90:249-253)
+    if (il < 0 || il >= nintegral) return fail(PIMDK_EINVAL, "trajectory id %lld outside nintegral*nrep", (long long)id);
+    const double I = dHdr[t] / (betan * betan);  // integrand(ii)=dHdr/(betan**2) (pimd_par.f90:379)
+    sums[3 * il + 0] += I;
+    sums[3 * il + 1] += I * I;
+    sums[3 * il + 2] += 1.0;
+  }
+  return PIMDK_OK;
+}
+
+int pimdk_ti_finish(pimdk_int nintegral, const double* sums, const double* weights, double betan, double* mean,
+                    double* var, double* deltaA, double* sigmaA, double* qq0) {
+  double answer = 0.0, sA = 0.0;
+  for (pimdk_int i = 0; i < nintegral; ++i) {  // pimd_par.f90:401-418
+    const double cnt = sums[3 * i + 2];
+    if (!(cnt > 0.0)) return fail(PIMDK_EINVAL, "lambda point %lld has no trajectories", (long long)i);
+    const double m = sums[3 * i] / cnt;
+    double s = sums[3 * i + 1] / cnt;
+    s = s - m * m;
+    if (mean) mean[i] = m;
+    if (var) var[i] = s;
+    if (m == m) answer = answer + weights[i] * m;
+    sA = sA + s * weights[i] * weights[i];
+  }
+  if (deltaA) *deltaA = answer;
+  if (sigmaA) *sigmaA = std::sqrt(sA);
+  if (qq0) *qq0 = std::exp(-answer * betan);
+  return PIMDK_OK;
+}
+
+int pimdk_gauleg(double x1, double x2, pimdk_int nintegral, double* x, double* w) {
+  if (nintegral < 1) return fail(PIMDK_EINVAL, "nintegral must be >= 1");
+  const double EPS = 3.e-14;
+  const pimdk_int m = (nintegral + 1) / 2;
+  const double xm = 0.5 * (x2 + x1), xl = 0.5 * (x2 - x1);
+  for (pimdk_int i = 1; i <= m; ++i) {
+    double z = std::cos(PI_TRUNC * (i - 0.25) / (nintegral + 0.5));
+    double z1, pp;
+    do {
+      double p1 = 1.0, p2 = 0.0;
+      for (pimdk_int j = 1; j <= nintegral; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j;
+      }
+      pp = nintegral * (z * p1 - p2) / (z * z - 1.0);
+      z1 = z;
+      z = z1 - p1 / pp;
+    } while (std::fabs(z - z1) > EPS);
+    x[i - 1] = xm - xl * z;
+    x[nintegral - i] = xm + xl * z;
+    w[i - 1] = 2.0 * xl / ((1.0 - z * z) * pp * pp);
+    w[nintegral - i] = w[i - 1];
+  }
+  return PIMDK_OK;
+}
+
+int pimdk_profile(pimdk_int enable) {
+  g.profiling = enable != 0;
+  return PIMDK_OK;
+}
+int pimdk_profile_reset(void) {
+  resolve_spans();
+  g.prof.clear();
+  g.launch_count = 0;
+  return PIMDK_OK;
+}
+int pimdk_profile_get(const char* family, double* ms, pimdk_int* launches) {
+  resolve_spans();
+  auto it = g.prof.find(family ? family : "");
+  if (ms) *ms = it == g.prof.end() ? 0.0 : it->second.ms;
+  if (launches) *launches = it == g.prof.end() ? 0 : it->second.launches;
+  return PIMDK_OK;
+}
+int pimdk_fp64_peak(double* tflops) {
+  NEED_INIT();
+  CU(fp64_peak_probe(g.num_sms, tflops, g.stream));
+  return PIMDK_OK;
+}
+pimdk_int pimdk_launch_count(void) { return g.launch_count; }
+
+}  // extern "C"

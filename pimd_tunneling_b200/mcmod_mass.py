@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference's PES plugin interface `module mcmod_mass`
+(current form: mcmod_waterdimer.f90:1-105; in-scope plugins mcmod_1d.f90, mcmod_2dtest.f90,
+mcmod_waterdimer_ccpol.f90).  Same names and argument meaning: V_init, V, Vprime, potforce; module
+variables n, ndim, natom, ndof, totdof, V0, eps2, potforcepresent.  Coordinates are (ndim, natom)
+arrays like the Fortran x(:,:); batched variants take (ndim, natom, nbatch).  All arithmetic runs in
+the CUDA library; nothing here computes a potential on the CPU."""
+import numpy as np
+
+from . import _lib
+from ._lib import check, f64, hptr, lib
+
+_SHAPES = {"1d": (1, 1), "2dtest": (2, 1), "ccpol8sf": (3, 6)}
+
+
+class McmodMass:
+    """One selected PES (= one linked mcmod_<PES>.o in the reference, makefile:105-290)."""
+
+    eps2 = 1.0e-5             # pgtol handed to L-BFGS-B (instantonmod.f90:746)
+    potforcepresent = True    # potforce is provided for every PES here
+    atom1, atom2, atom3 = 1, 2, 3
+
+    def __init__(self, name, params=None, n=0):
+        if name not in _SHAPES:
+            raise ValueError("unknown PES %r (1d, 2dtest, ccpol8sf)" % name)
+        self.name = name
+        self.params = None if params is None else np.asarray(params, dtype=np.float64)
+        self.ndim, self.natom = _SHAPES[name]
+        self.ndof = self.ndim * self.natom
+        self.n = n
+        self.totdof = n * self.ndof
+        self.V0 = 0.0
+        self.label = ["O", "H", "H", "O", "H", "H"] if name == "ccpol8sf" else ["X"] * self.natom
+        self.basename = ""
+        self._selected = False
+
+    # subroutine V_init(iproc)
+    def V_init(self, iproc=0):
+        _lib.ensure_init()
+        p = self.params
+        check(lib().pimdk_pes_select(self.name.encode(), hptr(p), 0 if p is None else p.size))
+        self.V0 = 0.0
+        self._selected = True
+        return self
+
+    def set_V0(self, v0):
+        """assignment to the module variable V0 (pimd_par.f90:166)"""
+        self._need()
+        check(lib().pimdk_pes_set_v0(float(v0)))
+        self.V0 = float(v0)
+
+    def _need(self):
+        if not self._selected:
+            raise RuntimeError("V_init has not been called")
+
+    # function V(x)
+    def V(self, x):
+        return float(self.V_batch(np.asarray(x, dtype=np.float64).reshape(self.ndim, self.natom, 1, order="F"))[0])
+
+    # subroutine Vprime(x, grad)
+    def Vprime(self, x, inplace=False):
+        """Returns grad(ndim,natom) = +dV/dx.  inplace=True reproduces the reference's in-place
+        finite-difference perturbation of x for ccpol8sf (mcmod_waterdimer_ccpol.f90:48-52)."""
+        self._need()
+        xb = f64(np.asarray(x, dtype=np.float64).reshape(self.ndim, self.natom, 1, order="F"))
+        g = np.empty_like(xb)
+        if inplace:
+            check(lib().pimdk_pes_vprime_inplace(1, self.ndim, self.natom, hptr(xb), hptr(g)))
+            np.asarray(x)[...] = xb[:, :, 0]
+        else:
+            check(lib().pimdk_pes_eval(1, self.ndim, self.natom, hptr(xb), None, hptr(g)))
+        return g[:, :, 0]
+
+    # subroutine potforce(x, grad, energy)
+    def potforce(self, x):
+        xb = np.asarray(x, dtype=np.float64).reshape(self.ndim, self.natom, 1, order="F")
+        v, g = self.eval_batch(xb, energy=True, gradient=True)
+        return g[:, :, 0], float(v[0])
+
+    # batched forms --------------------------------------------------------------------------
+    def eval_batch(self, x, energy=True, gradient=True):
+        self._need()
+        x = f64(x)
+        assert x.ndim == 3 and x.shape[:2] == (self.ndim, self.natom), x.shape
+        nb = x.shape[2]
+        v = np.empty(nb, dtype=np.float64) if energy else None
+        g = np.empty_like(x) if gradient else None
+        check(lib().pimdk_pes_eval(nb, self.ndim, self.natom, hptr(x), hptr(v), hptr(g)))
+        return v, g
+
+    def V_batch(self, x):
+        return self.eval_batch(x, energy=True, gradient=False)[0]
+
+    def Vprime_batch(self, x):
+        return self.eval_batch(x, energy=False, gradient=True)[1]
+
+    def Vprime_batch_inplace(self, x):
+        self._need()
+        assert x.dtype == np.float64 and x.flags["F_CONTIGUOUS"] and x.shape[:2] == (self.ndim, self.natom)
+        g = np.empty_like(x)
+        check(lib().pimdk_pes_vprime_inplace(x.shape[2], self.ndim, self.natom, hptr(x), hptr(g)))
+        return g

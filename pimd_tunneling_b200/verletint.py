@@ -1,0 +1,159 @@
+"""Host-side mirror of the reference's propagation module `module verletint` (verletmodule.f90),
+batched over independent ring polymers: the (lambda x repetition) task loop of pimd_par.f90:321-381
+becomes one call.  Array shapes follow the Fortran: x, p are (n, ndim, natom[, ntraj]); a is
+(ndim, natom); b, dbdl are (ndim, natom[, ntraj]).  Everything numerical runs in libpimdk.so."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, f64, hptr, lib
+
+ANDERSEN, PILE = 1, 2
+
+
+class VerletInt:
+    def __init__(self, pes, n, mass, beta, tau=1.0, gamma=1.0, dt=1e-3, NMC=0, imin=0, Noutput=100000,
+                 cayley=False, seed=0):
+        # defaults = pimd_par.f90:60-88
+        self.pes = pes
+        self.n = int(n)
+        self.ndim, self.natom, self.ndof = pes.ndim, pes.natom, pes.ndim * pes.natom
+        self.mass = f64(np.asarray(mass, dtype=np.float64).reshape(self.natom))
+        self.beta = float(beta)
+        self.betan = self.beta / (self.n + 1)  # pimd_par.f90:94
+        self.tau, self.gamma, self.dt = float(tau), float(gamma), float(dt)
+        self.NMC, self.imin, self.Noutput = int(NMC), int(imin), int(Noutput)
+        self.cayley = bool(cayley)
+        self.seed = int(seed)
+        self._ready = False
+
+    # alloc_nm (verletmodule.f90:350-368): the reference seeds MT19937 from the clock; here the
+    # seed is explicit (RNG contract)
+    def alloc_nm(self, iproc=0, seed=None):
+        if seed is not None:
+            self.seed = int(seed)
+        return self
+
+    # init_nm (verletmodule.f90:306-338), a,b-independent part; beadvec is formed in-kernel
+    def init_nm(self):
+        _lib.ensure_init()
+        check(lib().pimdk_nm_setup(self.n, self.ndim, self.natom, hptr(self.mass), self.betan, self.tau))
+        self._ready = True
+        return self
+
+    def _need(self):
+        if not self._ready:
+            self.init_nm()
+
+    @property
+    def transmatrix(self):
+        self._need()
+        T = np.empty((self.n, self.n), order="F")
+        check(lib().pimdk_nm_get(hptr(T), None, None))
+        return T
+
+    @property
+    def lam(self):
+        self._need()
+        v = np.empty(self.n)
+        check(lib().pimdk_nm_get(None, hptr(v), None))
+        return v
+
+    @property
+    def beadmass(self):
+        self._need()
+        v = np.empty((self.natom, self.n), order="F")
+        check(lib().pimdk_nm_get(None, None, hptr(v)))
+        return v
+
+    def beadvec(self, a, b):
+        """beadvec(n, ndof) of init_nm (verletmodule.f90:328-333) for one (a, b) pair (host-side helper)."""
+        n = self.n
+        pi = 3.14159265358979
+        a = np.asarray(a, dtype=np.float64).reshape(self.ndim, self.natom, order="F")
+        b = np.asarray(b, dtype=np.float64).reshape(self.ndim, self.natom, order="F")
+        lam = self.lam
+        i = np.arange(1, n + 1, dtype=np.float64)
+        out = np.empty((n, self.ndof), order="F")
+        for k in range(self.natom):
+            for j in range(self.ndim):
+                v = a[j, k] * np.sin(i * pi / (n + 1)) + b[j, k] * np.sin(n * i * pi / (n + 1))
+                v = v * np.sqrt(2.0 / (n + 1))
+                out[:, k * self.ndim + j] = v / (lam * self.betan) ** 2
+        return out
+
+    # nmtransform_forward / nmtransform_backward (verletmodule.f90:254-286) over vectors v(n, nvec)
+    def nmtransform_forward(self, v, beadvec=None):
+        return self._transform(1, v, beadvec)
+
+    def nmtransform_backward(self, q, beadvec=None):
+        return self._transform(0, q, beadvec)
+
+    def _transform(self, fwd, v, beadvec):
+        self._need()
+        v = f64(np.asarray(v, dtype=np.float64).reshape(self.n, -1, order="F"))
+        bv = None if beadvec is None else f64(np.asarray(beadvec, dtype=np.float64).reshape(self.n, -1, order="F"))
+        out = np.empty_like(v)
+        check(lib().pimdk_nm_transform(fwd, v.shape[1], hptr(v), hptr(bv), hptr(out)))
+        return out
+
+    # init_path (verletmodule.f90:32-119)
+    def init_path(self, xi, lampath, path, splinepath, traj_gid=None):
+        self._need()
+        xi = f64(np.atleast_1d(np.asarray(xi, dtype=np.float64)))
+        ntraj = xi.size
+        npath = len(lampath)
+        path = f64(path, (npath, self.ndim, self.natom))
+        spl = f64(splinepath, (npath, self.ndim, self.natom))
+        lam = f64(np.asarray(lampath, dtype=np.float64))
+        gid = None if traj_gid is None else np.ascontiguousarray(traj_gid, dtype=np.int64)
+        x = np.empty((self.n, self.ndim, self.natom, ntraj), order="F")
+        p = np.empty_like(x)
+        check(lib().pimdk_init_path(ntraj, npath, hptr(lam), hptr(path), hptr(spl), hptr(xi), self.seed, hptr(gid),
+                                    hptr(x), hptr(p)))
+        return x, p
+
+    def _propagate(self, thermostat, x, p, a, b, dbdl, traj_gid):
+        self._need()
+        x = np.asarray(x)
+        single = x.ndim == 3
+        shp4 = (self.n, self.ndim, self.natom, 1 if single else x.shape[3])
+        ntraj = shp4[3]
+        xw = f64(np.array(x, dtype=np.float64, order="F").reshape(shp4, order="F"))
+        pw = f64(np.array(p, dtype=np.float64, order="F").reshape(shp4, order="F"))
+        a = f64(np.asarray(a, dtype=np.float64).reshape(self.ndim, self.natom, order="F"))
+        b = f64(np.asarray(b, dtype=np.float64).reshape((self.ndim, self.natom, ntraj), order="F"))
+        dbdl = f64(np.asarray(dbdl, dtype=np.float64).reshape((self.ndim, self.natom, ntraj), order="F"))
+        gid = None if traj_gid is None else np.ascontiguousarray(traj_gid, dtype=np.int64)
+        dHdr = np.zeros(ntraj)
+        check(lib().pimdk_propagate(thermostat, ntraj, hptr(xw), hptr(pw), hptr(a), hptr(b), hptr(dbdl), self.dt,
+                                    self.gamma, self.NMC, self.imin, self.Noutput, 1 if self.cayley else 0, self.seed,
+                                    hptr(gid), hptr(dHdr)))
+        if single:
+            return xw[..., 0], pw[..., 0], float(dHdr[0])
+        return xw, pw, dHdr
+
+    # propagate_pimd_pile (verletmodule.f90:372-416): returns (x, p, dHdr)
+    def propagate_pimd_pile(self, x, p, a, b, dbdl, traj_gid=None):
+        return self._propagate(PILE, x, p, a, b, dbdl, traj_gid)
+
+    # propagate_pimd_nm (verletmodule.f90:190-250)
+    def propagate_pimd_nm(self, x, p, a, b, dbdl, traj_gid=None):
+        return self._propagate(ANDERSEN, x, p, a, b, dbdl, traj_gid)
+
+    def propagate_dev(self, thermostat, ntraj, x_ptr, p_ptr, a_ptr, b_ptr, dbdl_ptr, gid_ptr, dHdr_ptr, NMC=None):
+        """Device-resident form (pointers into HBM, e.g. torch tensors' data_ptr()); enqueues on the
+        library stream and returns after the NaN/convergence flag has been read back."""
+        self._need()
+        check(lib().pimdk_propagate_dev(thermostat, ntraj, x_ptr, p_ptr, a_ptr, b_ptr, dbdl_ptr, self.dt, self.gamma,
+                                        self.NMC if NMC is None else NMC, self.imin, self.Noutput,
+                                        1 if self.cayley else 0, self.seed, gid_ptr, dHdr_ptr))
+
+    # gauleg (verletmodule.f90:124-160)
+    @staticmethod
+    def gauleg(x1, x2, nintegral):
+        x = np.empty(nintegral)
+        w = np.empty(nintegral)
+        check(lib().pimdk_gauleg(float(x1), float(x2), nintegral, hptr(x), hptr(w)))
+        return x, w
