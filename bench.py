@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""bench.py — ring-polymer bead-steps/s of the hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c4|c5|c2|c1]
+    torchrun ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+A "step" is one thermostatted Verlet step (PES gradient on every bead + normal-mode transforms +
+thermostat + TI estimator) of ALL ring polymers resident on the GPU.  Default workload = BASELINE
+config C4: CCpol-8sf water dimer, 512 beads x 8192 trajectories (16 lambda x 512 rep), PILE thermostat,
+beta = 12000 a.u., dt = 1e-3; per-GPU work is fixed as N grows (weak scaling: trajectories are
+independent units; the only exchange is one all-reduce of 3*nintegral estimator sums per call).
+
+  value  : device-resident throughput (state in HBM before the timed region), CUDA events, max over ranks
+  e2e    : same metric through the host-buffer C ABI call pimdk_propagate (H2D + D2H inside the region)
+  roofline: dominant kernel = CCpol finite-difference gradient; achieved = algorithmic FP64 flop
+           (exact source-level census of the reference arithmetic) / measured kernel time;
+           peak = DFMA pipe measured live by pimdk_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline / --impl reference: the CPU oracle (C++ restatement of the reference's algorithm; the
+           Fortran reference cannot be compiled in this image) on all host cores, bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_O, M_H = 15.9949146221 * 1822.888486, 1.0078250321 * 1822.888486
+
+# exact source-level FP64 operation census of ONE `ccpol` energy at the known-answer geometry
+# (oracle/opcount.hpp, tests/test_oracle.py::test_opcount): add 25156, mul 33156, div 1760, sqrt 806,
+# exp 1129, pow 33, trig 28
+FLOP_PER_ENERGY = 25156 + 33156 + 1760 + 806 + 1129 + 33 + 28
+FLOP_PER_BEAD_GRAD = {"ccpol8sf": 36 * FLOP_PER_ENERGY + 36, "2dtest": 6 * (2 + 14) + 12, "1d": 8}
+
+CONFIGS = {
+    # name: pes, n, nintegral, nrep, thermostat, beta, Noutput
+    "c4": dict(pes="ccpol8sf", n=512, nintegral=16, nrep=512, thermostat=2, beta=12000.0, Noutput=100000,
+               label="C4: CCpol-8sf water dimer acceptor-switch TI, 512 beads x 8192 trajectories, 16 lambda, PILE"),
+    "c5": dict(pes="ccpol8sf", n=1024, nintegral=16, nrep=256, thermostat=2, beta=12000.0, Noutput=100000,
+               label="C5: CCpol-8sf water dimer, 1024 beads x 4096 trajectories, PILE"),
+    "c2": dict(pes="2dtest", n=256, nintegral=16, nrep=256, thermostat=1, beta=10.0, Noutput=100,
+               label="C2: 2D coupled double well TI, 256 beads x 4096 trajectories, Andersen"),
+    "c1": dict(pes="1d", n=64, nintegral=16, nrep=16, thermostat=2, beta=10.0, Noutput=100000,
+               label="C1: 1D double well TI, 64 beads x 256 trajectories, Langevin"),
+}
+
+
+def wells(pes):
+    if pes == "ccpol8sf":
+        with open(os.path.join(ROOT, "pimd_tunneling_b200", "data", "ccpol_wells.json")) as f:
+            w = json.load(f)
+        a = np.asfortranarray(np.array(w["well1"]).T)
+        b = np.asfortranarray(np.array(w["well2"]).T)
+        return a, b, np.array(w["masses_me"])
+    if pes == "2dtest":
+        a = np.array([[3.0], [0.0]])  # wells k=6 and k=1 of the C6 ring
+        b = np.array([[3.0 * np.cos(np.pi / 3)], [3.0 * np.sin(np.pi / 3)]])
+        return np.asfortranarray(a), np.asfortranarray(b), np.array([1.0])
+    return np.array([[-1.0]]), np.array([[1.0]]), np.array([1.0])
+
+
+def ti_path(pes, a, b):
+    """(lampath, path, splinepath) as read_path would leave them.  1D/2D: the straight line a->b (the
+    natural spline of a line is the line).  Water dimer: a synthetic acceptor-switch
+    path (rigid rotation of the acceptor's hydrogens about its bisector; a straight line would drive the
+    two hydrogens through each other at lambda = 1/2)."""
+    from pimd_tunneling_b200 import path as P
+
+    if pes == "ccpol8sf":
+        return P.build_path(P.acceptor_switch_path(a, b, 9))
+    pts = np.empty((2,) + a.shape, order="F")
+    pts[0], pts[1] = a, b
+    return P.build_path(pts)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([s.strip() for s in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 7 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 7 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """one host core: one ring polymer of the workload advanced `nsteps` steps by the oracle"""
+    pes, n, beta, thermostat, nsteps, seed, Noutput = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+
+    orc = Oracle().select(pes)
+    a, b, mass = wells(pes)
+    betan = beta / (n + 1)
+    orc.nm_setup(n, mass, betan, 1.0, 1.0, 1e-3, False, True)
+    orc.set_rng(seed, seed)
+    from pimd_tunneling_b200 import path as P
+
+    lam, path, spl = ti_path(pes, a, b)
+    xint, dbd = P.endpoints(lam, path, spl, [0.5])
+    orc.init_nm(a, xint[..., 0])
+    x, p = orc.init_path(0.5, lam, path, spl)
+    dbdl = np.asfortranarray(dbd[..., 0])
+    t0 = time.perf_counter()
+    orc.propagate(thermostat, x, p, dbdl, nsteps, 0, Noutput)
+    return time.perf_counter() - t0
+
+
+def cpu_throughput(cfg, nsteps, cores):
+    """bead-steps/s of the oracle with one independent trajectory per core (the reference's MPI model,
+    pimd_par.f90:109-110,321-381)"""
+    import multiprocessing as mp
+
+    jobs = [(cfg["pes"], cfg["n"], cfg["beta"], cfg["thermostat"], nsteps, 1000 + i, cfg["Noutput"]) for i in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        per = pool.map(_cpu_worker, jobs)
+    wall = max(per)
+    return cores * cfg["n"] * nsteps / wall, wall, time.perf_counter() - t0
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: one trajectory per core, n beads, a few steps
+    per_step = 4 if cfg["pes"] == "ccpol8sf" else 200
+    for _ in range(args.warmup if cfg["pes"] != "ccpol8sf" else 1):
+        cpu_throughput(cfg, per_step, cores)
+    t_tot, units = 0.0, 0
+    for _ in range(args.steps):
+        v, wall, _ = cpu_throughput(cfg, per_step, cores)
+        t_tot += wall
+        units += cores * cfg["n"] * per_step
+    value = units / t_tot
+    sample = "%d cores x 1 trajectory x %d beads x %d oracle step(s) per timed step" % (cores, cfg["n"], per_step)
+    line = {
+        "impl": "reference", "metric": "ring-polymer bead-steps/sec", "value": value, "unit": "bead-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["label"], "note": "CPU oracle (C++ restatement of the reference algorithm, g++ -O2, "
+                   "no MKL/ifort: the Fortran reference cannot be compiled in this image)"},
+        "cpu_baseline": {"value": value, "unit": "bead-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "bead-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import pimd_tunneling_b200 as pk
+    from pimd_tunneling_b200 import ti
+    from pimd_tunneling_b200._lib import check, lib
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pk.init(local_rank)
+    L = lib()
+    if args.mode == "fast":
+        check(L.pimdk_set_mode(1))
+    pes = pk.McmodMass(cfg["pes"]).V_init()
+    a, b, mass = wells(cfg["pes"])
+    n, nd, na = cfg["n"], pes.ndim, pes.natom
+    ndof = nd * na
+    nintegral, nrep = cfg["nintegral"], cfg["nrep"]
+    if args.ntraj:
+        nrep = max(1, args.ntraj // nintegral)
+    ntraj = nintegral * nrep                     # per GPU (weak scaling)
+    K, W = args.steps, args.warmup
+    vi = pk.VerletInt(pes, n, mass, cfg["beta"], dt=1e-3, gamma=1.0, NMC=1, imin=0, Noutput=cfg["Noutput"],
+                      seed=0x5EED0000).init_nm()
+    xi, wts = vi.gauleg(0.0, 1.0, nintegral)
+    # global ids: rank r owns ids [r*ntraj, (r+1)*ntraj) of a (world*nrep)-repetition job
+    gid = np.arange(ntraj, dtype=np.int64) + rank * ntraj
+    nrep_glob = nrep * world
+    il = (gid // nrep_glob) % nintegral
+    from pimd_tunneling_b200 import path as P
+
+    lam, path, spl = ti_path(cfg["pes"], a, b)
+    xint, dbdxi = P.endpoints(lam, path, spl, xi)       # pimd_par.f90:214-221
+    bt = np.asfortranarray(xint[:, :, il])              # endpoints(ii,:,:)
+    dbdl = np.asfortranarray(dbdxi[:, :, il])           # gradpoints(ii,:,:)
+    # init_path in chunks (host staging of the full state is 2 x ntraj*n*ndof*8 bytes)
+    x_h = torch.empty((ntraj, ndof, n), dtype=torch.float64).pin_memory()
+    p_h = torch.empty((ntraj, ndof, n), dtype=torch.float64).pin_memory()
+    chunk = max(1, min(ntraj, (1 << 27) // (n * ndof)))
+    for lo in range(0, ntraj, chunk):
+        hi = min(ntraj, lo + chunk)
+        xc, pc = vi.init_path(xi[il[lo:hi]], lam, path, spl, traj_gid=gid[lo:hi])
+        x_h[lo:hi] = torch.from_numpy(np.ascontiguousarray(xc.reshape(-1, order="F").reshape(hi - lo, ndof, n)))
+        p_h[lo:hi] = torch.from_numpy(np.ascontiguousarray(pc.reshape(-1, order="F").reshape(hi - lo, ndof, n)))
+    dev = torch.device("cuda", local_rank)
+    x_d, p_d = x_h.to(dev), p_h.to(dev)
+    a_d = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))).to(dev)
+    b_d = torch.from_numpy(np.ascontiguousarray(bt.reshape(-1, order="F"))).to(dev)
+    dbdl_d = torch.from_numpy(np.ascontiguousarray(dbdl.reshape(-1, order="F"))).to(dev)
+    gid_d = torch.from_numpy(gid).to(dev)
+    dH_d = torch.zeros(ntraj, dtype=torch.float64, device=dev)
+    sums_d = torch.zeros(3 * nintegral, dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_call(nsteps, seed_off=0):
+        vi.seed = 0x5EED0000 + seed_off
+        vi.propagate_dev(cfg["thermostat"], ntraj, x_d.data_ptr(), p_d.data_ptr(), a_d.data_ptr(), b_d.data_ptr(),
+                         dbdl_d.data_ptr(), gid_d.data_ptr(), dH_d.data_ptr(), NMC=nsteps)
+        if world > 1:   # the single collective of the path: estimator sums per lambda
+            I = dH_d / (vi.betan ** 2)
+            s = torch.stack([torch.zeros(nintegral, dtype=torch.float64, device=dev).index_add_(0, torch.from_numpy(il).to(dev), I),
+                             torch.zeros(nintegral, dtype=torch.float64, device=dev).index_add_(0, torch.from_numpy(il).to(dev), I * I),
+                             torch.bincount(torch.from_numpy(il).to(dev), minlength=nintegral).double()], dim=1).reshape(-1)
+            dist.all_reduce(s)
+            sums_d.copy_(s)
+
+    # ---- device-resident timing ("value") ----
+    one_call(W, 1)                                     # W untimed warm-up steps
+    barrier()
+    check(L.pimdk_profile(1))
+    check(L.pimdk_profile_reset())
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    one_call(K, 2)                                     # exactly K timed steps
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = int(L.pimdk_launch_count())
+    pes_ms, pes_n = ctypes.c_double(), ctypes.c_int64()
+    check(L.pimdk_profile_get(b"pes", ctypes.byref(pes_ms), ctypes.byref(pes_n)))
+    fam = {}
+    for f in ("gemm", "update", "estimator"):
+        m_, c_ = ctypes.c_double(), ctypes.c_int64()
+        check(L.pimdk_profile_get(f.encode(), ctypes.byref(m_), ctypes.byref(c_)))
+        fam[f] = {"ms": m_.value, "launches": int(c_.value)}
+    check(L.pimdk_profile(0))
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    units_total = world * ntraj * n * K
+    value = units_total / (ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C ABI ("e2e") ----
+    xw = x_h.numpy().reshape(-1).reshape((n, nd, na, ntraj), order="F")
+    pw = p_h.numpy().reshape(-1).reshape((n, nd, na, ntraj), order="F")
+    dH_h = np.zeros(ntraj)
+    Ke = K
+    from pimd_tunneling_b200._lib import hptr
+
+    def e2e_call(nsteps):
+        check(L.pimdk_propagate(cfg["thermostat"], ntraj, hptr(xw), hptr(pw), hptr(a), hptr(bt), hptr(dbdl), 1e-3, 1.0,
+                                nsteps, 0, cfg["Noutput"], 0, 0x5EED0003, hptr(gid), hptr(dH_h)))
+        sums = ti.partial_sums(dH_h, gid % (nintegral * nrep_glob), nrep_glob, nintegral, vi.betan)
+        return ti.allreduce_sums(sums)
+
+    barrier()
+    t0 = time.perf_counter()
+    sums = e2e_call(Ke)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * ntraj * n * Ke / float(te.item())
+    stats = ti.finish(sums, wts, vi.betan)
+    state_bytes = 2 * ntraj * n * ndof * 8
+    small = ndof * 8 + 2 * ntraj * ndof * 8 + ntraj * 8
+
+    if rank == 0:
+        peak = ctypes.c_double()
+        check(L.pimdk_fp64_peak(ctypes.byref(peak)))
+        flop_per_launch = FLOP_PER_BEAD_GRAD[cfg["pes"]] * ntraj * n
+        avg_pes_s = (pes_ms.value / max(1, pes_n.value)) * 1e-3
+        achieved = flop_per_launch / avg_pes_s / 1e12 if avg_pes_s > 0 else None
+        line = {
+            "metric": "ring-polymer bead-steps/sec", "value": value, "unit": "bead-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["label"], "pes": cfg["pes"], "beads": n, "trajectories_per_gpu": ntraj,
+                       "lambda_points": nintegral, "thermostat": "PILE" if cfg["thermostat"] == 2 else "Andersen",
+                       "beta": cfg["beta"], "dt": 1e-3, "mode": args.mode,
+                       "l2": "state per step (x,p,P,Q,G: %.2f GB) exceeds the 126 MB L2" % (5 * state_bytes / 2 / 1e9),
+                       "parallelism": "independent trajectories sharded by global id; 1 all-reduce of %d doubles" % (3 * nintegral)},
+            "e2e": {"value": e2e_value, "unit": "bead-steps/s", "h2d_bytes_per_step": (state_bytes + small) / Ke,
+                    "d2h_bytes_per_step": (state_bytes + ntraj * 8) / Ke, "steps_per_call": Ke,
+                    "deltaA": stats["deltaA"], "sigmaA": stats["sigmaA"]},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+                         "frac": (achieved / peak.value) if achieved else None, "traffic": None,
+                         "kernel": "ccpol_grad_kernel_" + args.mode if cfg["pes"] == "ccpol8sf" else "simple_pes_kernel",
+                         "kernel_ms": pes_ms.value / max(1, pes_n.value), "kernel_launches": int(pes_n.value),
+                         "kernel_share_of_step": pes_ms.value / ms,
+                         "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "flop_per_bead_gradient": FLOP_PER_BEAD_GRAD[cfg["pes"]], "other_kernels_ms": fam},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            per_step = 12 if cfg["pes"] == "ccpol8sf" else 400
+            v, wall, tot = cpu_throughput(cfg, per_step, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "bead-steps/s", "cores": cores, "kind": "port",
+                                    "sample": "%d cores x 1 trajectory x %d beads x %d steps (%.1f s)" % (cores, n, per_step, wall)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    pk.finalize()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--ntraj", type=int, default=0, help="override trajectories per GPU (testing)")
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,138 @@
+"""Host-side path set-up that feeds the hot path (row N1 of SURVEY §8f): natural cubic splines
+(`spline`/`tridag`/`splint`/`splin_grad`/`locate`, instantonmod.f90:397-596), the reaction-coordinate
+normalisation of read_path (instantonmod.f90:923-936) and the Gauss-Legendre end points / tangents
+of pimd_par.f90:212-221.  O(npath) work done once per run; plain numpy."""
+import numpy as np
+
+
+def spline(x, y, yp1=1.0e31, ypn=1.0e31):
+    """second derivatives y2 of the interpolating cubic (natural when yp > 0.99e30)"""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = x.size
+    a = np.zeros(n + 1)
+    b = np.zeros(n + 1)
+    c = np.zeros(n + 1)
+    r = np.zeros(n + 1)
+    c[1:n] = x[1:] - x[:-1]
+    r[1:n] = 6.0 * ((y[1:] - y[:-1]) / c[1:n])
+    r[2:n] = r[2:n] - r[1:n - 1]
+    a[2:n] = c[1:n - 1]
+    b[2:n] = 2.0 * (c[2:n] + a[2:n])
+    b[1] = b[n] = 1.0
+    if yp1 > 0.99e30:
+        r[1] = c[1] = 0.0
+    else:
+        r[1] = (3.0 / (x[1] - x[0])) * ((y[1] - y[0]) / (x[1] - x[0]) - yp1)
+        c[1] = 0.5
+    if ypn > 0.99e30:
+        r[n] = a[n] = 0.0
+    else:
+        r[n] = (-3.0 / (x[-1] - x[-2])) * ((y[-1] - y[-2]) / (x[-1] - x[-2]) - ypn)
+        a[n] = 0.5
+    u = np.zeros(n + 1)
+    gam = np.zeros(n + 2)
+    bet = b[1]
+    u[1] = r[1] / bet
+    for j in range(2, n + 1):
+        gam[j] = c[j - 1] / bet
+        bet = b[j] - a[j] * gam[j]
+        if bet == 0.0:
+            raise ZeroDivisionError("tridag_ser: Error at code stage 2")
+        u[j] = (r[j] - a[j] * u[j - 1]) / bet
+    for j in range(n - 1, 0, -1):
+        u[j] = u[j] - gam[j + 1] * u[j + 1]
+    return u[1:].copy()
+
+
+def locate(xx, x):
+    n = len(xx)
+    ascnd = xx[-1] >= xx[0]
+    jl, ju = 0, n + 1
+    while ju - jl > 1:
+        jm = (ju + jl) // 2
+        if ascnd == (x >= xx[jm - 1]):
+            jl = jm
+        else:
+            ju = jm
+    if x == xx[0]:
+        return 1
+    if x == xx[-1]:
+        return n - 1
+    return jl
+
+
+def _bracket(xa, x):
+    n = len(xa)
+    klo = max(min(locate(xa, x), n - 1), 1)
+    khi = klo + 1
+    h = xa[khi - 1] - xa[klo - 1]
+    if h == 0.0:
+        raise ZeroDivisionError("bad xa input in splint")
+    return klo, khi, h, (xa[khi - 1] - x) / h, (x - xa[klo - 1]) / h
+
+
+def splint(xa, ya, y2a, x):
+    klo, khi, h, a, b = _bracket(xa, x)
+    return a * ya[klo - 1] + b * ya[khi - 1] + ((a ** 3 - a) * y2a[klo - 1] + (b ** 3 - b) * y2a[khi - 1]) * (h ** 2) / 6.0
+
+
+def splin_grad(xa, ya, y2a, x):
+    klo, khi, h, a, b = _bracket(xa, x)
+    return ((ya[khi - 1] - ya[klo - 1]) / h) + ((1.0 - 3.0 * a ** 2) * y2a[klo - 1] + (3.0 * b ** 2 - 1.0) * y2a[khi - 1]) * h / 6.0
+
+
+def build_path(points):
+    """points(npath, ndim, natom) -> (lampath, path, splinepath) as read_path leaves them:
+    lampath = cumulative Euclidean distance normalised to [0,1]; natural splines per coordinate."""
+    path = np.asfortranarray(points, dtype=np.float64)
+    npath = path.shape[0]
+    lam = np.zeros(npath)
+    for i in range(1, npath):
+        lam[i] = lam[i - 1] + np.sqrt(np.sum((path[i] - path[i - 1]) ** 2))
+    lam = lam / lam[-1]
+    spl = np.zeros_like(path, order="F")
+    for i in range(path.shape[1]):
+        for j in range(path.shape[2]):
+            spl[:, i, j] = spline(lam, path[:, i, j])
+    return lam, path, spl
+
+
+def endpoints(lam, path, spl, xi):
+    """xint(k,:,:) and dbdxi(k,:,:) of pimd_par.f90:214-221 for the quadrature nodes xi"""
+    nd, na = path.shape[1], path.shape[2]
+    xint = np.empty((nd, na, len(xi)), order="F")
+    dbd = np.empty_like(xint)
+    for k, x in enumerate(xi):
+        for i in range(nd):
+            for j in range(na):
+                xint[i, j, k] = splint(lam, path[:, i, j], spl[:, i, j], x)
+                dbd[i, j, k] = splin_grad(lam, path[:, i, j], spl[:, i, j], x)
+    return xint, dbd
+
+
+def acceptor_switch_path(well1, well2, npath=9):
+    """Synthetic acceptor-switch path for the water dimer (atoms O,H,H | O,H,H as columns of (3,6)):
+    the acceptor's hydrogens (atoms 5,6) rotate by pi about the acceptor's bisector through O_b, with a
+    linear blend so that the last point is exactly well2.  (A straight line well1->well2 would drive the
+    two hydrogens through each other at lambda = 1/2.)"""
+    w1 = np.asarray(well1, dtype=np.float64)
+    w2 = np.asarray(well2, dtype=np.float64)
+    O, H1, H2 = w1[:, 3], w1[:, 4], w1[:, 5]
+    u = 0.5 * (H1 + H2) - O
+    u = u / np.linalg.norm(u)
+
+    def rot(v, th):
+        return v * np.cos(th) + np.cross(u, v) * np.sin(th) + u * np.dot(u, v) * (1.0 - np.cos(th))
+
+    end = w1.copy()
+    end[:, 4] = O + rot(H1 - O, np.pi)
+    end[:, 5] = O + rot(H2 - O, np.pi)
+    pts = np.empty((npath, 3, 6), order="F")
+    for k in range(npath):
+        s = k / (npath - 1)
+        g = w1.copy()
+        g[:, 4] = O + rot(H1 - O, s * np.pi)
+        g[:, 5] = O + rot(H2 - O, s * np.pi)
+        pts[k] = g + s * (w2 - end)
+    return pts

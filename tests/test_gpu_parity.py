@@ -1,0 +1,319 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C ABI (libpimdk.so) and is
+compared with the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star: deterministic paths to 1e-10 relative FP64):
+  * PES energy / gradient, strict mode: BIT-EXACT (the kernels evaluate the reference's operation order
+    with the shared math policy; the FD gradient, eps=1e-4, amplifies any last-bit difference by ~1e3-1e4,
+    so anything weaker than bit-exact cannot deliver 1e-10 on it — see DESIGN.md §Parity)
+  * PES fast mode (FMA contraction): energy 1e-10 relative, gradient 2e-8 of max|grad| (the measured
+    sensitivity of the reference's own FD gradient to contraction)
+  * normal-mode transform, NVE / thermostatted steps, init_path, UM*: 1e-10 relative (max-norm)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import GOLDEN_GEOM_ANG, Oracle, thermal_dimer_geometries
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+M_O, M_H = 15.9949146221 * 1822.888486, 1.0078250321 * 1822.888486
+DIMER_MASS = [M_O, M_H, M_H, M_O, M_H, M_H]
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import pimd_tunneling_b200 as pk
+
+    pk.init(0)
+    yield pk
+    pk.finalize()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+def relmax(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---------------------------------------------------------------- PES plugin (mcmod_mass) ---------
+def test_ccpol_known_answer(pk):
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    e = pes.V((GOLDEN_GEOM_ANG / 0.529177).reshape(6, 3).T) * 627.510
+    # main_CCpol-8sf.f:182-183: 25.15660 printed by a build without -r8; with -r8 (repo makefile) 25.15658
+    assert abs(e - 25.15660) < 3e-5
+    pes0 = pk.McmodMass("ccpol8sf", params=[0]).V_init()   # iemonomer = 0
+    e0 = pes0.V((GOLDEN_GEOM_ANG / 0.529177).reshape(6, 3).T) * 627.510
+    assert abs(e0 - (-1.34676)) < 5.1e-6
+
+
+@pytest.mark.parametrize("nbatch", [1, 7, 252, 1000])
+def test_ccpol_energy_gradient_bit_exact(pk, orc, nbatch):
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    orc.select("ccpol8sf")
+    x = thermal_dimer_geometries(nbatch, seed=nbatch)
+    v, g = pes.eval_batch(x)
+    vo, go, xo = orc.pes_eval(x)
+    assert np.array_equal(v, vo)
+    assert np.array_equal(g, go)
+    xi = x.copy(order="F")
+    gi = pes.Vprime_batch_inplace(xi)
+    assert np.array_equal(gi, go) and np.array_equal(xi, xo)   # in-place FD drift reproduced
+    assert np.abs(xi - x).max() > 0.0
+
+
+def test_ccpol_frozen_vectors_and_v0(pk):
+    G = json.load(open(os.path.join(HERE, "golden", "oracle_vectors.json")))
+    for name, shape in (("ccpol8sf", (3, 6)), ("2dtest", (2, 1)), ("1d", (1, 1))):
+        pes = pk.McmodMass(name).V_init()
+        d = G[name]
+        x = np.array([float.fromhex(h) for h in d["x"]]).reshape(shape + (d["nbatch"],), order="F")
+        v, g = pes.eval_batch(x)
+        assert [float(t).hex() for t in v] == d["v"]
+        assert [float(t).hex() for t in g.reshape(-1, order="F")] == d["grad"]
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    x = thermal_dimer_geometries(3, seed=1)
+    v = pes.V_batch(x)
+    pes.set_V0(v[0])
+    assert np.array_equal(pes.V_batch(x), v - v[0])
+    pes.set_V0(0.0)
+
+
+def test_ccpol_fast_mode_within_contraction_noise(pk, orc):
+    from pimd_tunneling_b200._lib import check, lib
+
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    orc.select("ccpol8sf")
+    x = thermal_dimer_geometries(200, seed=9)
+    vo, go, _ = orc.pes_eval(x)
+    check(lib().pimdk_set_mode(1))
+    try:
+        v, g = pes.eval_batch(x)
+    finally:
+        check(lib().pimdk_set_mode(0))
+    assert np.abs(v - vo).max() <= 1e-10 * np.abs(vo).max()
+    gscale = np.abs(go).max(axis=(0, 1))
+    assert (np.abs(g - go).max(axis=(0, 1)) / gscale).max() < 2e-8
+
+
+@pytest.mark.parametrize("name,scale", [("1d", 1.5), ("2dtest", 2.5)])
+def test_model_surfaces_bit_exact(pk, orc, name, scale):
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    x = np.asfortranarray(np.random.default_rng(3).normal(0, scale, size=(pes.ndim, pes.natom, 4097)))
+    v, g = pes.eval_batch(x)
+    vo, go, _ = orc.pes_eval(x)
+    assert np.array_equal(v, vo) and np.array_equal(g, go)
+    # scalar forms of the plugin interface
+    assert pes.V(x[:, :, 5]) == vo[5]
+    assert np.array_equal(pes.Vprime(x[:, :, 5]), go[:, :, 5])
+    gg, ee = pes.potforce(x[:, :, 6])
+    assert ee == vo[6] and np.array_equal(gg, go[:, :, 6])
+
+
+def test_edge_cases(pk):
+    pes = pk.McmodMass("2dtest").V_init()
+    v, g = pes.eval_batch(np.zeros((2, 1, 0), order="F"))     # empty batch
+    assert v.size == 0 and g.size == 0
+    with pytest.raises(pk.PimdkError):                        # wrong shape for the selected PES
+        from pimd_tunneling_b200._lib import check, hptr, lib
+        x = np.zeros((3, 6, 1), order="F")
+        check(lib().pimdk_pes_eval(1, 3, 6, hptr(x), None, hptr(x.copy(order="F"))))
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    x = thermal_dimer_geometries(2, seed=1)
+    x[:, 4, 1] = x[:, 5, 1]                                   # coincident hydrogens -> NaN trap
+    with pytest.raises(pk.PimdkError) as ei:
+        pes.eval_batch(x)
+    assert ei.value.code in (5, 6)
+
+
+# ---------------------------------------------------------------- module verletint ----------------
+def test_normal_mode_tables_and_transform(pk, orc):
+    pes = pk.McmodMass("1d").V_init()
+    orc.select("1d")
+    for n in (5, 64, 200):
+        betan = 10.0 / (n + 1)
+        vi = pk.VerletInt(pes, n, [1.3], 10.0, tau=0.7).init_nm()
+        orc.nm_setup(n, [1.3], betan, 0.7)
+        a, b = np.array([[-1.0]]), np.array([[0.8]])
+        orc.init_nm(a, b)
+        T, lam, bm, bv = orc.get_nm()
+        assert np.array_equal(vi.transmatrix, T) and np.array_equal(vi.lam, lam) and np.array_equal(vi.beadmass, bm)
+        assert relmax(vi.beadvec(a, b), bv) < 1e-14
+        v = np.asfortranarray(np.random.default_rng(n).normal(size=(n, 37)))
+        q = vi.nmtransform_forward(v)
+        assert relmax(q, T @ v) < RTOL
+        assert relmax(vi.nmtransform_backward(q), v) < RTOL          # T*T = I
+        bvn = np.asfortranarray(np.repeat(bv, 37, axis=1))
+        qf = vi.nmtransform_forward(v, bvn)
+        assert relmax(qf, T @ v - bvn) < RTOL
+        assert relmax(vi.nmtransform_backward(qf, bvn), v) < RTOL
+
+
+def _traj_inputs(pes, n, ntraj, a, b, sigma, mass, seed=5):
+    from pimd_tunneling_b200 import path as P
+
+    rng = np.random.default_rng(seed)
+    nd, na = pes.ndim, pes.natom
+    xi = 0.2 + 0.6 * np.arange(ntraj) / max(1, ntraj - 1)
+    if pes.name == "ccpol8sf":
+        lam, path, spl = P.build_path(P.acceptor_switch_path(a, b, 9))
+    else:
+        pts = np.empty((2, nd, na), order="F")
+        pts[0], pts[1] = a, b
+        lam, path, spl = P.build_path(pts)
+    bt, dbdl = P.endpoints(lam, path, spl, xi)
+    x = np.empty((n, nd, na, ntraj), order="F")
+    for t in range(ntraj):
+        for k in range(n):
+            x[k, :, :, t] = a + (bt[..., t] - a) * (k + 1) / (n + 1) + rng.normal(0, sigma, size=(nd, na))
+    p = np.asfortranarray(rng.normal(0, 1.0, size=x.shape) * np.sqrt(np.asarray(mass))[None, None, :, None] * 0.02)
+    return x, p, bt, dbdl, (lam, path, spl, xi)
+
+
+CASES = [
+    # name, n, ntraj, steps, thermostat, beta, mass, sigma, Noutput, cayley, gamma
+    ("1d", 16, 5, 50, 2, 10.0, [1.0], 0.05, 100000, False, 1.0),
+    ("1d", 16, 5, 50, 1, 10.0, [1.0], 0.05, 7, False, 1.0),
+    ("1d", 33, 3, 40, 2, 10.0, [1.0], 0.05, 100000, True, 1.0),
+    ("2dtest", 24, 4, 50, 2, 10.0, [1.0], 0.05, 100000, False, 1.0),
+    ("2dtest", 24, 4, 50, 1, 10.0, [1.0], 0.05, 5, False, 1.0),
+    ("2dtest", 24, 4, 100, 2, 10.0, [1.0], 0.05, 100000, False, 0.0),     # NVE (gamma=0)
+    ("2dtest", 24, 4, 100, 1, 10.0, [1.0], 0.05, 10 ** 9, False, 1.0),   # NVE (no Andersen collision)
+    ("ccpol8sf", 8, 3, 10, 2, 200.0, DIMER_MASS, 0.01, 100000, False, 1.0),
+    ("ccpol8sf", 8, 3, 10, 1, 200.0, DIMER_MASS, 0.01, 3, False, 1.0),
+    ("ccpol8sf", 8, 2, 20, 2, 200.0, DIMER_MASS, 0.01, 100000, False, 0.0),  # NVE
+]
+
+
+def _wells(name):
+    import sys
+    sys.path.insert(0, ROOT)
+    from bench import wells
+    return wells(name)[:2]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-n%d-th%d-%s%s" % (c[0], c[1], c[4], "cayley" if c[9] else "exact", "-nve" if c[10] == 0 or c[8] > 10 ** 8 else ""))
+def test_propagate_matches_oracle(pk, orc, case):
+    name, n, ntraj, steps, thermostat, beta, mass, sigma, Noutput, cayley, gamma = case
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    a, b = _wells(name)
+    vi = pk.VerletInt(pes, n, mass, beta, dt=1e-3, gamma=gamma, NMC=steps, Noutput=Noutput, cayley=cayley, seed=4242).init_nm()
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, sigma, mass)
+    gid = np.arange(ntraj, dtype=np.int64) * 3 + 11
+    fn = vi.propagate_pimd_pile if thermostat == 2 else vi.propagate_pimd_nm
+    xg, pg, dg = fn(x, p, a, bt, dbdl, traj_gid=gid)
+    for t in range(ntraj):
+        orc.nm_setup(n, mass, vi.betan, 1.0, gamma, 1e-3, cayley, True)
+        orc.init_nm(a, bt[..., t])
+        orc.set_rng(4242, int(gid[t]))
+        xo, po, do = orc.propagate(thermostat, x[..., t], p[..., t], dbdl[..., t], steps, 0, Noutput)
+        assert relmax(xg[..., t], xo) < RTOL
+        assert relmax(pg[..., t], po) < RTOL
+        assert abs(dg[t] - do) <= RTOL * abs(do)
+
+
+def test_partition_invariance_and_imin(pk):
+    """results depend on the global trajectory id only, not on how trajectories are batched/sharded"""
+    pes = pk.McmodMass("2dtest").V_init()
+    a, b = _wells("2dtest")
+    n, ntraj = 32, 12
+    vi = pk.VerletInt(pes, n, [1.0], 10.0, NMC=30, imin=10, Noutput=6, seed=99).init_nm()
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, 0.05, [1.0])
+    gid = np.arange(ntraj, dtype=np.int64)
+    for fn in (vi.propagate_pimd_pile, vi.propagate_pimd_nm):
+        xa, pa, da = fn(x, p, a, bt, dbdl, traj_gid=gid)
+        perm = np.random.default_rng(1).permutation(ntraj)
+        xb, pb, db = fn(x[..., perm], p[..., perm], a, bt[..., perm], dbdl[..., perm], traj_gid=gid[perm])
+        assert np.array_equal(xa[..., perm], xb) and np.array_equal(pa[..., perm], pb) and np.array_equal(da[perm], db)
+        lo = fn(x[..., :5], p[..., :5], a, bt[..., :5], dbdl[..., :5], traj_gid=gid[:5])
+        hi = fn(x[..., 5:], p[..., 5:], a, bt[..., 5:], dbdl[..., 5:], traj_gid=gid[5:])
+        assert np.array_equal(np.concatenate([lo[2], hi[2]]), da)
+    # imin: the estimator averages steps imin+1..NMC only (verletmodule.f90:397,413)
+    vi2 = pk.VerletInt(pes, n, [1.0], 10.0, NMC=30, imin=0, Noutput=6, seed=99).init_nm()
+    _, _, d0 = vi2.propagate_pimd_pile(x, p, a, bt, dbdl, traj_gid=gid)
+    assert not np.array_equal(d0, vi.propagate_pimd_pile(x, p, a, bt, dbdl, traj_gid=gid)[2])
+
+
+def test_init_path_matches_oracle(pk, orc):
+    for name, n, beta, mass in (("2dtest", 40, 10.0, [1.0]), ("ccpol8sf", 12, 300.0, DIMER_MASS)):
+        pes = pk.McmodMass(name).V_init()
+        orc.select(name)
+        a, b = _wells(name)
+        vi = pk.VerletInt(pes, n, mass, beta, seed=31337).init_nm()
+        _, _, bt, _, (lam, path, spl, xi) = _traj_inputs(pes, n, 4, a, b, 0.0, mass)
+        gid = np.array([0, 5, 6, 2 ** 31 + 7], dtype=np.int64)
+        xg, pg = vi.init_path(xi, lam, path, spl, traj_gid=gid)
+        for t in range(4):
+            orc.nm_setup(n, mass, vi.betan)
+            orc.init_nm(a, bt[..., t])
+            orc.set_rng(31337, int(gid[t]))
+            xo, po = orc.init_path(float(xi[t]), lam, path, spl)
+            assert np.array_equal(xg[..., t], xo)          # spline evaluation: same operation order
+            assert relmax(pg[..., t], po) < RTOL
+
+
+# ---------------------------------------------------------------- module instantonmod -------------
+@pytest.mark.parametrize("name,n,beta,mass,fixedends", [("2dtest", 1024, 30.0, [1.0], True), ("2dtest", 64, 30.0, [1.0], False),
+                                                        ("1d", 128, 10.0, [1.0], True), ("ccpol8sf", 16, 300.0, DIMER_MASS, True)])
+def test_um_forceenergy_matches_oracle(pk, orc, name, n, beta, mass, fixedends):
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    a, b = _wells(name)
+    im = pk.InstantonMod(pes, mass, beta, n, fixedends=fixedends, rpi=True)
+    orc.nm_setup(n, mass, im.betan, 1.0, 1.0, 1e-3, False, fixedends)
+    rng = np.random.default_rng(8)
+    x = np.empty((n, pes.ndim, pes.natom), order="F")
+    if name == "ccpol8sf":
+        from pimd_tunneling_b200 import path as P
+        lam, path, spl = P.build_path(P.acceptor_switch_path(a, b, 9))
+        xs, _ = P.endpoints(lam, path, spl, np.linspace(0, 1, n))
+        for k in range(n):
+            x[k] = xs[..., k] + rng.normal(0, 0.01, size=(3, 6))
+    else:
+        for k in range(n):   # rpi_ser.f90:157-163 linear interpolation start
+            x[k] = a + (b - a) * k / (n - 1) + rng.normal(0, 0.02, size=a.shape)
+    g, f = im.UMforceenergy(x, a, b)
+    go, fo = orc.UMforceenergy(x, a, b)
+    assert f == fo                                    # scalar accumulated in the reference's order
+    assert np.array_equal(g, go)
+    assert im.UM(x, a, b) == orc.UM(x, a, b)
+    assert np.array_equal(im.UMprime(x, a, b), orc.UMprime(x, a, b))
+
+
+def test_instanton_lbfgs_iterates_match(pk, orc):
+    """config C3 in miniature: scipy's L-BFGS-B (same algorithm as the vendored setulb: m=8, factr=1e6,
+    pgtol=1e-5, maxls=40) driven by GPU f/g and by oracle f/g produce the same iterate sequence."""
+    from scipy.optimize import fmin_l_bfgs_b
+
+    name, n, beta = "2dtest", 256, 30.0
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    a, b = _wells(name)
+    im = pk.InstantonMod(pes, [1.0], beta, n, fixedends=True, rpi=True)
+    orc.nm_setup(n, [1.0], im.betan)
+    x0 = np.empty((n, 2, 1), order="F")
+    for k in range(n):
+        x0[k] = a + (b - a) * k / (n - 1)
+
+    def run(fg):
+        its = []
+        def f(xf):
+            x = np.asfortranarray(xf.reshape((n, 2, 1), order="F"))
+            g, e = fg(x)
+            return e, g.reshape(-1, order="F").copy()
+        xf, fmin, info = fmin_l_bfgs_b(f, x0.reshape(-1, order="F"), m=8, factr=1e6, pgtol=1e-5, maxls=40, maxiter=60,
+                                       callback=lambda xk: its.append(xk.copy()))
+        return np.array(its), fmin
+
+    ig, fgpu = run(lambda x: im.UMforceenergy(x, a, b))
+    io, fcpu = run(lambda x: orc.UMforceenergy(x, a, b))
+    assert ig.shape == io.shape and relmax(ig, io) < RTOL and abs(fgpu - fcpu) <= RTOL * abs(fcpu)

@@ -1,0 +1,142 @@
+"""CPU tests of the host side: the C ABI library loads and exports every symbol include/pimdk.h
+declares, compute calls fail loudly without a GPU, the path/TI bookkeeping matches the reference's
+formulas, and the multi-rank reduction works over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    from pimd_tunneling_b200._lib import LIB_PATH, lib
+
+    hdr = open(os.path.join(ROOT, "include", "pimdk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pimdk_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), "libpimdk.so does not export %s" % name
+    out = subprocess.run(["nm", "-D", LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (pimdk_[a-z0-9_]+)", out))
+    assert declared <= exported
+
+
+def test_product_does_not_touch_the_oracle():
+    """the shipped path must not import, link or execute anything under oracle/"""
+    pkg = os.path.join(ROOT, "pimd_tunneling_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert not re.search(r'#include\s+"[^"]*oracle/', text), (dp, f)
+                assert "liboracle" not in text and "oracle_lib" not in text, (dp, f)
+    out = subprocess.run(["ldd", os.path.join(pkg, "libpimdk.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+@pytest.mark.skipif(_gpu(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    import pimd_tunneling_b200 as pk
+
+    with pytest.raises(pk.PimdkError) as ei:
+        pk.init()
+    assert ei.value.code == 2 and "no CPU path" in str(ei.value)
+    pes = pk.McmodMass("1d")
+    with pytest.raises(Exception):
+        pes.V_init()
+    with pytest.raises(RuntimeError):
+        pes.V(np.zeros((1, 1)))
+
+
+def test_gauleg_and_ti_statistics_match_reference_formulas():
+    from pimd_tunneling_b200 import VerletInt, ti
+
+    x, w = VerletInt.gauleg(0.0, 1.0, 16)
+    xr, wr = np.polynomial.legendre.leggauss(16)
+    assert np.abs(np.sort(x) - (xr + 1) / 2).max() < 1e-13 and abs(w.sum() - 1.0) < 1e-13
+    nint, nrep, betan = 16, 8, 0.31
+    rng = np.random.default_rng(0)
+    dH = rng.normal(1.0, 0.3, nint * nrep)
+    gid = ti.global_ids(nint, nrep)
+    sums = ti.partial_sums(dH, gid, nrep, nint, betan)
+    res = ti.finish(sums, w, betan)
+    # pimd_par.f90:401-424 restated
+    I = (dH / betan ** 2).reshape(nint, nrep)
+    mean = I.mean(axis=1)
+    var = (I ** 2).mean(axis=1) - mean ** 2
+    assert np.allclose(res["mean"], mean, rtol=1e-13) and np.allclose(res["var"], var, rtol=1e-9, atol=1e-12)
+    assert abs(res["deltaA"] - np.sum(w * mean)) < 1e-12 * abs(res["deltaA"])
+    assert abs(res["sigmaA"] - np.sqrt(np.sum(w ** 2 * var))) < 1e-10
+    assert abs(res["q_over_q0"] - np.exp(-res["deltaA"] * betan)) < 1e-15
+    # block partition of pimd_par.f90:109-110
+    assert [ti.shard(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert sum(hi - lo for lo, hi in (ti.shard(8192, r, 8) for r in range(8))) == 8192
+
+
+def test_path_module_matches_scipy():
+    from scipy.interpolate import CubicSpline
+
+    from pimd_tunneling_b200 import path as P
+
+    pts = np.zeros((7, 2, 1), order="F")
+    t = np.linspace(0, np.pi / 3, 7)
+    pts[:, 0, 0], pts[:, 1, 0] = 3 * np.cos(t), 3 * np.sin(t)
+    lam, path, spl = P.build_path(pts)
+    assert lam[0] == 0.0 and lam[-1] == 1.0 and np.all(np.diff(lam) > 0)
+    cs = CubicSpline(lam, path[:, 1, 0], bc_type="natural")
+    xint, dbd = P.endpoints(lam, path, spl, [0.0, 0.3, 0.77, 1.0])
+    for k, x in enumerate([0.0, 0.3, 0.77, 1.0]):
+        assert abs(xint[1, 0, k] - cs(x)) < 1e-13 and abs(dbd[1, 0, k] - cs(x, 1)) < 1e-12
+    # straight line: spline of a line is the line
+    lam, path, spl = P.build_path(np.array([[[-1.0]], [[1.0]]]))
+    xint, dbd = P.endpoints(lam, path, spl, [0.25])
+    assert xint[0, 0, 0] == -0.5 and dbd[0, 0, 0] == 2.0
+
+
+_GLOO_WORKER = r"""
+import os, sys, numpy as np
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+from pimd_tunneling_b200 import ti
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+nint, nrep, betan = 8, 6, 0.4
+rng = np.random.default_rng(5)
+dH = rng.normal(2.0, 0.5, nint * nrep)
+gid = ti.global_ids(nint, nrep)
+lo, hi = ti.shard(nint * nrep, dist.get_rank(), 2)
+sums = ti.allreduce_sums(ti.partial_sums(dH[lo:hi], gid[lo:hi], nrep, nint, betan))
+full = ti.partial_sums(dH, gid, nrep, nint, betan)
+assert np.allclose(sums, full, rtol=1e-14, atol=0), (sums, full)
+w = np.full(nint, 1.0 / nint)
+r = ti.finish(sums, w, betan)
+assert abs(r["deltaA"] - ti.finish(full, w, betan)["deltaA"]) < 1e-13
+dist.destroy_process_group()
+print("rank", sys.argv[1], "ok")
+"""
+
+
+def test_two_rank_estimator_allreduce_gloo(tmp_path):
+    """the N>1 path: shard trajectories by global id, ONE all-reduce of {sum, sum^2, count} per lambda"""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER % {"root": ROOT, "port": 29000 + os.getpid() % 2000})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)

@@ -1,0 +1,231 @@
+"""CPU tests of the oracle (oracle/): pinned against the reference's only golden vectors and against
+mathematical identities.  No GPU needed."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import (GOLDEN_GEOM_ANG, GOLDEN_VAL, GOLDEN_VALM, REF_DATA, SAPT_FOR_SURF, Oracle,
+                        thermal_dimer_geometries)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+# ---- the reference's own known-answer vectors: main_CCpol-8sf.f:180-189 (test_parameters) ----------
+@pytest.mark.parametrize("isurf", range(1, 11))
+def test_golden_interaction_energy(orc, isurf):
+    orc.load_ccpol(isurf, 0)
+    e = orc.ccpol_energy_ang(GOLDEN_GEOM_ANG)
+    assert abs(e - GOLDEN_VAL[isurf - 1]) < 5.1e-6  # printed f10.5
+
+
+@pytest.mark.parametrize("isurf", range(1, 11))
+def test_golden_energy_with_monomers(orc, isurf):
+    """valm(1:10) were produced by a build WITHOUT -r8 (PJT2's default-REAL literals in single
+    precision); with the repo makefile's -r8 the same code gives values 1.7e-5 kcal/mol lower."""
+    orc.load_ccpol(isurf, 1)
+    orc.L.orc_ccpol_set_pjt2_r8(0)
+    e = orc.ccpol_energy_ang(GOLDEN_GEOM_ANG)
+    assert abs(e - GOLDEN_VALM[isurf - 1]) < 5.1e-6
+    orc.L.orc_ccpol_set_pjt2_r8(1)
+    e8 = orc.ccpol_energy_ang(GOLDEN_GEOM_ANG)
+    assert abs(e8 - GOLDEN_VALM[isurf - 1]) < 3e-5 and abs(e8 - e) > 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference data files not present on this box")
+@pytest.mark.parametrize("isurf", [1, 3, 8, 10])
+def test_text_and_packed_loaders_agree(orc, isurf):
+    orc.load_ccpol(isurf, 1, text_dir=REF_DATA)
+    a = orc.tables_image()
+    orc.load_ccpol(isurf, 1)
+    assert a == orc.tables_image()
+
+
+def test_frozen_vectors(orc):
+    """oracle bits are frozen in tests/golden/oracle_vectors.json (tests/golden/make_golden.py)"""
+    G = json.load(open(os.path.join(HERE, "golden", "oracle_vectors.json")))
+    for name, shape in (("ccpol8sf", (3, 6)), ("2dtest", (2, 1)), ("1d", (1, 1))):
+        orc.select(name)
+        d = G[name]
+        nb = d["nbatch"]
+        x = np.array([float.fromhex(h) for h in d["x"]]).reshape(shape + (nb,), order="F")
+        v, g, xd = orc.pes_eval(x)
+        assert [float(t).hex() for t in v] == d["v"]
+        assert [float(t).hex() for t in g.reshape(-1, order="F")] == d["grad"]
+        if "x_after_vprime" in d:
+            assert [float(t).hex() for t in xd.reshape(-1, order="F")] == d["x_after_vprime"]
+    for r in G["normals"]:
+        assert float(orc.L.orc_normal(r["seed"], r["stream"], r["step"], r["gid"], r["idx"])).hex() == r["z"]
+
+
+def test_opcount(orc):
+    orc.load_ccpol(3, 1)
+    c, e = orc.ccpol_opcount(GOLDEN_GEOM_ANG)
+    assert abs(e - orc.ccpol_energy_ang(GOLDEN_GEOM_ANG)) == 0.0
+    # the census bench.py's roofline uses (FLOP_PER_ENERGY)
+    assert c == {"add": 25156, "mul": 33156, "div": 1760, "sqrt": 806, "exp": 1129, "pow": 33, "trig": 28}
+
+
+def test_fd_gradient_is_central_difference(orc):
+    orc.select("ccpol8sf")
+    x = thermal_dimer_geometries(2, seed=3)
+    _, g, xd = orc.pes_eval(x)
+    for b in range(2):
+        for i in range(3):
+            for j in range(6):
+                xp = x[:, :, b:b + 1].copy(order="F")
+                xm = xp.copy(order="F")
+                xp[i, j, 0] += 1e-4
+                xm[i, j, 0] -= 1e-4
+                vp = orc.pes_eval(xp, gradient=False)[0][0]
+                vm = orc.pes_eval(xm, gradient=False)[0][0]
+                assert abs((vp - vm) / 2e-4 - g[i, j, b]) < 2e-8 * np.abs(g[:, :, b]).max()
+    assert np.abs(xd - x).max() < 1e-15 * 10  # in-place perturbation drift is at the ulp level
+
+
+# ---- shared deterministic math policy vs mpmath ------------------------------------------------------
+def test_detmath_accuracy():
+    import ctypes
+    import subprocess
+    import tempfile
+
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    root = os.path.dirname(HERE)
+    src = os.path.join(tempfile.mkdtemp(), "dm.c")
+    with open(src, "w") as f:
+        f.write('#include "pimdk_detmath.h"\n'
+                "double dm_exp(double x){return pimdk_exp(x);} double dm_log(double x){return pimdk_log(x);}\n"
+                "double dm_pow(double x,double y){return pimdk_pow(x,y);} double dm_sin(double x){return pimdk_sin(x);}\n"
+                "double dm_cos(double x){return pimdk_cos(x);} double dm_acos(double x){return pimdk_acos(x);}\n"
+                "double dm_tanh(double x){return pimdk_tanh(x);}\n")
+    so = src[:-2] + ".so"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(root, "include"), "-o", so,
+                    src, "-lm"], check=True)
+    L = ctypes.CDLL(so)
+    for f in "exp log sin cos acos tanh".split():
+        getattr(L, "dm_" + f).restype = ctypes.c_double
+        getattr(L, "dm_" + f).argtypes = [ctypes.c_double]
+    L.dm_pow.restype = ctypes.c_double
+    L.dm_pow.argtypes = [ctypes.c_double] * 2
+    rng = np.random.default_rng(1)
+
+    def ulps(got, exact):
+        return float(abs(mp.mpf(got) - exact) / mp.mpf(np.spacing(abs(float(exact)))))
+
+    cases = [("exp", mp.exp, rng.uniform(-200, 50, 600), 1.0), ("log", mp.log, np.exp(rng.uniform(-30, 30, 600)), 2.0),
+             ("sin", mp.sin, rng.uniform(-7, 7, 600), 2.0), ("cos", mp.cos, rng.uniform(-7, 7, 600), 2.0),
+             ("acos", mp.acos, rng.uniform(-1, 1, 600), 2.0), ("tanh", mp.tanh, rng.uniform(-3, 3, 600), 4.0)]
+    for name, ref, xs, tol in cases:
+        worst = max(ulps(getattr(L, "dm_" + name)(float(x)), ref(mp.mpf(float(x)))) for x in xs)
+        assert worst < tol, (name, worst)
+    for y in (-1.5, -3.0, 0.66666666666666666):
+        worst = max(ulps(L.dm_pow(float(x), y), mp.power(mp.mpf(float(x)), mp.mpf(y))) for x in np.exp(rng.uniform(-8, 3, 400)))
+        assert worst < 6.0, (y, worst)
+
+
+def test_philox_known_answer(orc):
+    """Random123 known-answer vectors for philox4x32-10 (kat_vectors: zero and all-ones counter/key)."""
+    import ctypes
+
+    # reach the raw generator through the normal: reproduce Box-Muller from the published words
+    def normal_from_words(r):
+        u1 = (((r[0] << 32) | r[1]) >> 11) + 0.5
+        u2 = (((r[2] << 32) | r[3]) >> 11) + 0.5
+        u1 *= 2.0 ** -53
+        u2 *= 2.0 ** -53
+        return math.sqrt(-2.0 * math.log(u1)) * math.cos(6.283185307179586 * u2)
+
+    kat0 = [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]  # ctr=0 key=0
+    z = orc.L.orc_normal(0, 0, 0, 0, 0)
+    assert abs(z - normal_from_words(kat0)) < 1e-13
+    kat1 = [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]  # ctr=ff..f key=ff..f
+    seed = 0xffffffffffffffff
+    step = (0xffffff << 32) | 0xffffffff
+    z = orc.L.orc_normal(ctypes.c_ulonglong(seed), 0xff, ctypes.c_ulonglong(step), 0xffffffff, ctypes.c_ulonglong(0x1fffffffe))
+    assert abs(z - normal_from_words(kat1)) < 1e-13
+
+
+# ---- module verletint: identities (parity is UNPINNED by the reference) ------------------------------
+def test_transmatrix_identities(orc):
+    orc.select("1d")
+    n, betan = 33, 0.37
+    orc.nm_setup(n, [1.0], betan)
+    orc.init_nm(np.array([[-1.0]]), np.array([[1.0]]))
+    T, lam, bm, bv = orc.get_nm()
+    assert np.abs(T @ T - np.eye(n)).max() < 1e-13 and np.abs(T - T.T).max() == 0.0
+    # T diagonalises the open-chain spring matrix with eigenvalues (betan*lam_k)^2
+    K = 2 * np.eye(n) - np.eye(n, k=1) - np.eye(n, k=-1)
+    D = T @ K @ T
+    assert np.abs(D - np.diag((lam * betan) ** 2)).max() < 1e-12
+    # beadvec = T * (spring-force image of the fixed ends) / (lam betan)^2
+    e = np.zeros(n)
+    e[0], e[-1] = -1.0, 1.0
+    assert np.abs(bv[:, 0] - (T @ e) / (lam * betan) ** 2).max() < 1e-12
+
+
+def test_gauleg_and_splines(orc):
+    for n in (1, 2, 5, 16):
+        x, w = orc.gauleg(0.0, 1.0, n)
+        xr, wr = np.polynomial.legendre.leggauss(n)
+        assert np.abs(np.sort(x) - (xr + 1) / 2).max() < 1e-13 and np.abs(w[np.argsort(x)] - wr / 2).max() < 1e-13
+    from scipy.interpolate import CubicSpline
+
+    xs = np.cumsum(np.random.default_rng(0).uniform(0.1, 1.0, 12))
+    ys = np.sin(xs)
+    y2 = orc.spline(xs, ys)
+    cs = CubicSpline(xs, ys, bc_type="natural")
+    for t in np.linspace(xs[0], xs[-1], 37):
+        assert abs(orc.splint(xs, ys, y2, t) - cs(t)) < 1e-13
+        assert abs(orc.splin_grad(xs, ys, y2, t) - cs(t, 1)) < 1e-12
+
+
+def test_nve_energy_conservation_and_um_gradient(orc):
+    orc.select("2dtest")
+    n, beta = 16, 8.0
+    betan = beta / (n + 1)
+    a = np.array([[3.0], [0.0]])
+    b = np.array([[1.5], [2.598076211353316]])
+    orc.nm_setup(n, [1.0], betan, 1.0, 0.0, 1e-3)  # gamma = 0: PILE without noise or friction = NVE
+    orc.init_nm(a, b)
+    rng = np.random.default_rng(4)
+    x = np.empty((n, 2, 1), order="F")
+    for k in range(n):
+        x[k, :, 0] = (a + (b - a) * (k + 1) / (n + 1))[:, 0] + rng.normal(0, 0.05, 2)
+    T, lam, bm, bv = orc.get_nm()
+    p = np.asfortranarray(rng.normal(0, 0.02, size=(n, 2, 1)))
+
+    def energy(x, p):
+        # H = sum_k P_k^2/(2 beadmass_k) + UM(x): fictitious-mass kinetic energy + springs + V
+        P = np.stack([T @ p[:, d, 0] for d in range(2)], axis=1)
+        return np.sum(P ** 2 / (2.0 * bm[0][:, None])) + orc.UM(x, a, b)
+
+    e0 = energy(x, p)
+    # time_step_pile = V(dt).NM(dt/2).O.NM(dt/2) is a first-order (Lie-Trotter) splitting when gamma=0;
+    # time_step_nm = NM(dt/2).V(dt).NM(dt/2) is symmetric (second order).  Symplectic: bounded error, no drift.
+    for thermostat, order in ((2, 1), (1, 2)):
+        errs = []
+        for dt, steps in ((1e-3, 200), (5e-4, 400)):
+            orc.nm_setup(n, [1.0], betan, 1.0, 0.0, dt)
+            orc.init_nm(a, b)
+            x1, p1, _ = orc.propagate(thermostat, x, p, np.asfortranarray(b - a), steps, 0, 10 ** 9)
+            errs.append(abs(energy(x1, p1) - e0))
+        assert errs[0] < 1e-3 * abs(e0), errs
+        assert 0.8 * 2 ** order < errs[0] / errs[1] < 1.25 * 2 ** order, (thermostat, errs)
+    # UMprime is the gradient of UM
+    g = orc.UMprime(x, a, b)
+    g2, f = orc.UMforceenergy(x, a, b)
+    assert np.abs(g - g2).max() < 1e-13 and abs(f - orc.UM(x, a, b)) < 1e-12
+    for (k, d) in ((0, 0), (5, 1), (n - 1, 0)):
+        xp = x.copy(order="F")
+        xm = x.copy(order="F")
+        xp[k, d, 0] += 1e-5
+        xm[k, d, 0] -= 1e-5
+        assert abs((orc.UM(xp, a, b) - orc.UM(xm, a, b)) / 2e-5 - g[k, d, 0]) < 1e-6 * max(1.0, abs(g[k, d, 0]))
