@@ -49,6 +49,47 @@
 #define PIMDK_SQRT(a) sqrt((a))
 #endif
 
+
+/* Polynomial coefficient tables.  On the device they live in constant memory: the compiler then
+ * fetches them with wide uniform loads (LDCU.128, two coefficients per instruction, hoistable out of
+ * loops) instead of materialising every 64-bit literal with two UMOVs per use — measured 10% of all
+ * issued instructions in the CCpol kernel before this change (profiles/r1_ccpol_grad_v0.md). */
+#define PIMDK_EXP_COEFS {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, \
+  2.7557319223985893e-06, 2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, \
+  0.041666666666666664, 0.16666666666666666, 0.5, 1.0, 1.0}
+#define PIMDK_LOG_COEFS {0.08695652173913043, 0.09523809523809523, 0.10526315789473684, 0.11764705882352941, \
+  0.13333333333333333, 0.15384615384615385, 0.18181818181818182, 0.2222222222222222, 0.2857142857142857, 0.4, \
+  0.6666666666666666}
+#define PIMDK_SIN_COEFS {-8.22063524662433e-18, 2.8114572543455206e-15, -7.647163731819816e-13, 1.6059043836821613e-10, \
+  -2.505210838544172e-08, 2.7557319223985893e-06, -0.0001984126984126984, 0.008333333333333333, -0.16666666666666666}
+#define PIMDK_COS_COEFS {4.110317623312165e-19, -1.5619206968586225e-16, 4.779477332387385e-14, -1.1470745597729725e-11, \
+  2.08767569878681e-09, -2.755731922398589e-07, 2.48015873015873e-05, -0.001388888888888889, 0.041666666666666664, -0.5}
+#define PIMDK_ASIN_COEFS {0.0018622264064031275, 0.0019650336162772837, 0.0020776610325181676, 0.0022014739737101384, \
+  0.002338091892111975, 0.0024894486782468836, 0.00265787063820729, 0.002846178401108942, 0.0030578216492580306, \
+  0.003297059503473485, 0.0035692053938259347, 0.003880964558837669, 0.004240907093679363, 0.004660143486915096, \
+  0.005153309682319905, 0.005740037670841924, 0.006447210311889649, 0.0073125258735988454, 0.008390335809616815, \
+  0.009761609529194078, 0.011551800896139705, 0.01396484375, 0.017352764423076924, 0.022372159090909092, \
+  0.030381944444444444, 0.044642857142857144, 0.075, 0.16666666666666666}
+#if defined(__CUDACC__)
+static __constant__ double pimdk_dc_exp[14] = PIMDK_EXP_COEFS;
+static __constant__ double pimdk_dc_log[11] = PIMDK_LOG_COEFS;
+static __constant__ double pimdk_dc_sin[9] = PIMDK_SIN_COEFS;
+static __constant__ double pimdk_dc_cos[10] = PIMDK_COS_COEFS;
+static __constant__ double pimdk_dc_asin[28] = PIMDK_ASIN_COEFS;
+#endif
+static const double pimdk_hc_exp[14] = PIMDK_EXP_COEFS;
+static const double pimdk_hc_log[11] = PIMDK_LOG_COEFS;
+static const double pimdk_hc_sin[9] = PIMDK_SIN_COEFS;
+static const double pimdk_hc_cos[10] = PIMDK_COS_COEFS;
+static const double pimdk_hc_asin[28] = PIMDK_ASIN_COEFS;
+#if defined(__CUDA_ARCH__)
+#define PIMDK_TAB(n) pimdk_dc_##n
+#define PIMDK_UNROLL _Pragma("unroll")
+#else
+#define PIMDK_TAB(n) pimdk_hc_##n
+#define PIMDK_UNROLL
+#endif
+
 PIMDK_HD uint64_t pimdk_d2u(double x) {
 #if defined(__CUDA_ARCH__)
   return (uint64_t)__double_as_longlong(x);
@@ -69,31 +110,35 @@ PIMDK_HD double pimdk_u2d(uint64_t u) {
 }
 
 /* exp(x): x = k ln2 + r, |r| <= ln2/2 (Cody-Waite, two-part ln2), degree-13 Taylor in Horner/fma
- * form, scaled by 2^k through the exponent field.  Flushes to 0 below -708, +inf above 709. */
+ * form, scaled by 2^k through the exponent field.  Flushes to 0 below -708, +inf above 709.
+ * Device fast path (|x| < 700): one scaling by 2^k — the same bits as the general two-step scaling
+ * whenever neither overflows nor underflows, which |x| < 700 guarantees. */
+PIMDK_HD double pimdk_exp_poly(double r) {
+  double p = PIMDK_TAB(exp)[0];
+  PIMDK_UNROLL
+  for (int i = 1; i < 14; ++i) p = PIMDK_FMA(p, r, PIMDK_TAB(exp)[i]);
+  return p;
+}
 PIMDK_HD double pimdk_exp(double x) {
+  const double shifter = 6755399441055744.0; /* 1.5 * 2^52 */
+#if defined(__CUDA_ARCH__)
+  if (fabs(x) < 700.0) {
+    double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
+    int k = __double2loint(t);
+    double kd = PIMDK_SUB(t, shifter);
+    double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x);
+    r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);
+    return PIMDK_MUL(pimdk_exp_poly(r), __hiloint2double((k + 1023) << 20, 0));
+  }
+#endif
   if (!(x > -708.0)) return (x != x) ? x : 0.0;
   if (x > 709.0) return pimdk_u2d(0x7ff0000000000000ull);
-  const double shifter = 6755399441055744.0; /* 1.5 * 2^52 */
   double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
-  int64_t k = (int64_t)(pimdk_d2u(t) & 0xffffffffull);
-  k = (int64_t)(int32_t)k;
+  int64_t k = (int64_t)(int32_t)(pimdk_d2u(t) & 0xffffffffull);
   double kd = PIMDK_SUB(t, shifter);
   double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x); /* ln2 high part (fdlibm split) */
   r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);        /* ln2 low part */
-  double p = 1.6059043836821613e-10;                         /* 1/13! */
-  p = PIMDK_FMA(p, r, 2.08767569878681e-09);                 /* 1/12! */
-  p = PIMDK_FMA(p, r, 2.505210838544172e-08);                /* 1/11! */
-  p = PIMDK_FMA(p, r, 2.755731922398589e-07);                /* 1/10! */
-  p = PIMDK_FMA(p, r, 2.7557319223985893e-06);               /* 1/9!  */
-  p = PIMDK_FMA(p, r, 2.48015873015873e-05);                 /* 1/8!  */
-  p = PIMDK_FMA(p, r, 0.0001984126984126984);                /* 1/7!  */
-  p = PIMDK_FMA(p, r, 0.001388888888888889);                 /* 1/6!  */
-  p = PIMDK_FMA(p, r, 0.008333333333333333);                 /* 1/5!  */
-  p = PIMDK_FMA(p, r, 0.041666666666666664);                 /* 1/4!  */
-  p = PIMDK_FMA(p, r, 0.16666666666666666);                  /* 1/3!  */
-  p = PIMDK_FMA(p, r, 0.5);
-  p = PIMDK_FMA(p, r, 1.0);
-  p = PIMDK_FMA(p, r, 1.0);
+  double p = pimdk_exp_poly(r);
   /* 2^k in two halves so that k in [-1022-52, 1023] never overflows the exponent field */
   int64_t k1 = k / 2, k2 = k - k1;
   double s1 = pimdk_u2d((uint64_t)(k1 + 1023) << 52);
@@ -117,17 +162,9 @@ PIMDK_HD double pimdk_log(double x) {
   double f = PIMDK_SUB(m, 1.0);
   double s = PIMDK_DIV(f, PIMDK_ADD(m, 1.0));
   double z = PIMDK_MUL(s, s);
-  double q = 0.08695652173913043;           /* 2/23 */
-  q = PIMDK_FMA(q, z, 0.09523809523809523);  /* 2/21 */
-  q = PIMDK_FMA(q, z, 0.10526315789473684);  /* 2/19 */
-  q = PIMDK_FMA(q, z, 0.11764705882352941);  /* 2/17 */
-  q = PIMDK_FMA(q, z, 0.13333333333333333);  /* 2/15 */
-  q = PIMDK_FMA(q, z, 0.15384615384615385);  /* 2/13 */
-  q = PIMDK_FMA(q, z, 0.18181818181818182);  /* 2/11 */
-  q = PIMDK_FMA(q, z, 0.2222222222222222);   /* 2/9  */
-  q = PIMDK_FMA(q, z, 0.2857142857142857);   /* 2/7  */
-  q = PIMDK_FMA(q, z, 0.4);                  /* 2/5  */
-  q = PIMDK_FMA(q, z, 0.6666666666666666);   /* 2/3  */
+  double q = PIMDK_TAB(log)[0];
+  PIMDK_UNROLL
+  for (int i = 1; i < 11; ++i) q = PIMDK_FMA(q, z, PIMDK_TAB(log)[i]);
   /* log m = 2s + s*z*q ; 2s = f - s*f exactly-ish: use f - s*f to avoid the rounding of 2s */
   double sf = PIMDK_MUL(s, f);
   double lm = PIMDK_ADD(PIMDK_SUB(f, sf), PIMDK_MUL(PIMDK_MUL(s, z), q)); /* f - s f = 2s */
@@ -163,29 +200,16 @@ PIMDK_HD double pimdk_pow(double x, double y) {
 /* sin/cos kernels on |r| <= pi/4 */
 PIMDK_HD double pimdk_sin_k(double r) {
   double z = PIMDK_MUL(r, r);
-  double p = -8.22063524662433e-18;            /* -1/19! */
-  p = PIMDK_FMA(p, z, 2.8114572543455206e-15);  /*  1/17! */
-  p = PIMDK_FMA(p, z, -7.647163731819816e-13);  /* -1/15! */
-  p = PIMDK_FMA(p, z, 1.6059043836821613e-10);  /*  1/13! */
-  p = PIMDK_FMA(p, z, -2.505210838544172e-08);  /* -1/11! */
-  p = PIMDK_FMA(p, z, 2.7557319223985893e-06);  /*  1/9!  */
-  p = PIMDK_FMA(p, z, -0.0001984126984126984);  /* -1/7!  */
-  p = PIMDK_FMA(p, z, 0.008333333333333333);    /*  1/5!  */
-  p = PIMDK_FMA(p, z, -0.16666666666666666);    /* -1/3!  */
+  double p = PIMDK_TAB(sin)[0];
+  PIMDK_UNROLL
+  for (int i = 1; i < 9; ++i) p = PIMDK_FMA(p, z, PIMDK_TAB(sin)[i]);
   return PIMDK_FMA(PIMDK_MUL(r, z), p, r);
 }
 PIMDK_HD double pimdk_cos_k(double r) {
   double z = PIMDK_MUL(r, r);
-  double p = 4.110317623312165e-19;             /*  1/20! */
-  p = PIMDK_FMA(p, z, -1.5619206968586225e-16); /* -1/18! */
-  p = PIMDK_FMA(p, z, 4.779477332387385e-14);   /*  1/16! */
-  p = PIMDK_FMA(p, z, -1.1470745597729725e-11); /* -1/14! */
-  p = PIMDK_FMA(p, z, 2.08767569878681e-09);    /*  1/12! */
-  p = PIMDK_FMA(p, z, -2.755731922398589e-07);  /* -1/10! */
-  p = PIMDK_FMA(p, z, 2.48015873015873e-05);    /*  1/8!  */
-  p = PIMDK_FMA(p, z, -0.001388888888888889);   /* -1/6!  */
-  p = PIMDK_FMA(p, z, 0.041666666666666664);    /*  1/4!  */
-  p = PIMDK_FMA(p, z, -0.5);
+  double p = PIMDK_TAB(cos)[0];
+  PIMDK_UNROLL
+  for (int i = 1; i < 10; ++i) p = PIMDK_FMA(p, z, PIMDK_TAB(cos)[i]);
   return PIMDK_FMA(z, p, 1.0);
 }
 /* sin and cos together for |x| < ~1e5 (three-part pi/2 Cody-Waite reduction) */
@@ -212,34 +236,9 @@ PIMDK_HD double pimdk_cos(double x) { double s, c; pimdk_sincos(x, &s, &c); retu
 PIMDK_HD double pimdk_asin_k(double x) {
   double z = PIMDK_MUL(x, x);
   /* coefficients c_k = (2k)! / (4^k (k!)^2 (2k+1)), k = 28 .. 1 */
-  double p = 0.0018622264064031275;
-  p = PIMDK_FMA(p, z, 0.0019650336162772837);
-  p = PIMDK_FMA(p, z, 0.0020776610325181676);
-  p = PIMDK_FMA(p, z, 0.0022014739737101384);
-  p = PIMDK_FMA(p, z, 0.002338091892111975);
-  p = PIMDK_FMA(p, z, 0.0024894486782468836);
-  p = PIMDK_FMA(p, z, 0.00265787063820729);
-  p = PIMDK_FMA(p, z, 0.002846178401108942);
-  p = PIMDK_FMA(p, z, 0.0030578216492580306);
-  p = PIMDK_FMA(p, z, 0.003297059503473485);
-  p = PIMDK_FMA(p, z, 0.0035692053938259347);
-  p = PIMDK_FMA(p, z, 0.003880964558837669);
-  p = PIMDK_FMA(p, z, 0.004240907093679363);
-  p = PIMDK_FMA(p, z, 0.004660143486915096);
-  p = PIMDK_FMA(p, z, 0.005153309682319905);
-  p = PIMDK_FMA(p, z, 0.005740037670841924);
-  p = PIMDK_FMA(p, z, 0.006447210311889649);
-  p = PIMDK_FMA(p, z, 0.0073125258735988454);
-  p = PIMDK_FMA(p, z, 0.008390335809616815);
-  p = PIMDK_FMA(p, z, 0.009761609529194078);
-  p = PIMDK_FMA(p, z, 0.011551800896139705);
-  p = PIMDK_FMA(p, z, 0.01396484375);
-  p = PIMDK_FMA(p, z, 0.017352764423076924);
-  p = PIMDK_FMA(p, z, 0.022372159090909092);
-  p = PIMDK_FMA(p, z, 0.030381944444444444);
-  p = PIMDK_FMA(p, z, 0.044642857142857144);
-  p = PIMDK_FMA(p, z, 0.075);
-  p = PIMDK_FMA(p, z, 0.16666666666666666);
+  double p = PIMDK_TAB(asin)[0];
+  PIMDK_UNROLL
+  for (int i = 1; i < 28; ++i) p = PIMDK_FMA(p, z, PIMDK_TAB(asin)[i]);
   return PIMDK_FMA(PIMDK_MUL(x, z), p, x);
 }
 /* acos(x), |x| <= 1 */

@@ -285,6 +285,15 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
         next += 28;
       }
     }
+  for (int tb = 0; tb < kNType; ++tb)
+    for (int ta = 0; ta < kNType; ++ta) {
+      const double* pb = &h.parab[(tb * 6 + ta) * 84];
+      uint8_t f = 0;
+      if (pb[0] != 0.0 || pb[40] != 0.0 || pb[41] != 0.0 || pb[45] != 0.0 || pb[46] != 0.0) f |= 1;
+      if (pb[5] != 0.0) f |= 2;                                  // dmp1
+      if (pb[6] != 0.0 || pb[7] != 0.0 || pb[8] != 0.0) f |= 4;  // dmp6, dmp8, dmp10
+      o->pairflags[tb * kNType + ta] = f;
+    }
   if (next - 1 != h.numlin) {
     g_msg = "linear-coefficient index map does not cover the coefficient table";
     return g_msg.c_str();
@@ -312,6 +321,18 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
     for (int a = 0; a < 25; ++a) {
       if ((a >= 3 || b >= 3) && h.ind_d6[b * 25 + a] != 0) { g_msg = "ind_d6 outside 3x3"; return g_msg.c_str(); }
     }
+  // site classes of the rigid model: consecutive sites whose ind_beta rows AND columns coincide
+  o->ncls = 0;
+  for (int a = 0; a < 25; ++a) {
+    bool same = a > 0;
+    for (int b = 0; same && b < 25; ++b)
+      same = h.ind_beta[b * 25 + a] == h.ind_beta[b * 25 + a - 1] && h.ind_beta[a * 25 + b] == h.ind_beta[(a - 1) * 25 + b];
+    if (!same) o->cls_start[o->ncls++] = (uint8_t)a;
+  }
+  o->cls_start[o->ncls] = 25;
+  for (int b = 0; b < 25; ++b)
+    for (int a = 0; a < 25; ++a)
+      if (h.ind_beta[b * 25 + a] == 0) { g_msg = "ind_beta has empty entries; not supported"; return g_msg.c_str(); }
   o->iemonomer = iemonomer;
   o->V0 = 0.0;
   return "";

@@ -28,8 +28,16 @@ struct CcpolDev {
   uint8_t ind_charge[5];
   uint8_t ind_d1[25];                        // 5x5, [b*5+a]
   uint8_t ind_d6[9], ind_d8[9], ind_d10[9], ind_c6[9], ind_c8[9], ind_c10[9];  // 3x3, [b*3+a]
+  // static per type-pair facts (bit 0: carries exponential/linear terms, bit 1: damped electrostatics
+  // (dmp1 != 0), bit 2: damped dispersion (any of dmp6/8/10 != 0)).  A term whose damping parameter is
+  // exactly zero evaluates to +-0 in the reference (function d returns 0 for br == 0,
+  // proc_sapt5sf_new_ncd.f:1234-1237) and adding +-0 changes no bits, so the kernels skip it.
+  uint8_t pairflags[kNType * kNType];
+  // CCpol-8s site classes: runs of consecutive sites with identical ind_beta rows (8 classes of
+  // sizes 1,2,2,4,4,4,4,4 for data_ccdata); cls_start[c]..cls_start[c+1]-1 are the sites of class c
+  uint8_t cls_start[26];
+  int32_t ncls;
   int32_t iemonomer;
-  int32_t pad_;
 };
 
 // Host-side full tables (same content as the reference's COMMON block) and loaders.
