@@ -1,9 +1,17 @@
-// CCpol-8sf batched energy and finite-difference gradient kernels (sm_100a).
+// CCpol-8sf batched energy and finite-difference gradient (sm_100a): a four-stage kernel pipeline.
 // Compiled twice by the build: -fmad=false -DPIMDK_CCPOL_STRICT=1 (bit-faithful to the oracle's
 // operation order; default at run time) and -fmad=true -DPIMDK_CCPOL_STRICT=0 ("fast").
 //
 // Replaces mcmod_waterdimer_ccpol.f90:18-58 (V, Vprime) called once per bead by step_v
 // (verletmodule.f90:572-573) and by UM/UMprime (instantonmod.f90:26,79).
+//
+//   stage 0  setup    thread = energy   displaced geometry (Vprime's in-place +eps/-2eps/+eps walk), COM
+//                                       alignment, Radau embedding, PJT2 monomers   -> 36 coordinates + emon
+//   stage 1  sapt     thread = (energy, flexible|rigid geometry)   SAPT-5s'f site-site sum + dipole induction
+//   stage 2  rigid    thread = energy   CCpol-8s: iterated induction, 625-pair exponential sweep, elst, dispersion
+//   stage 3  combine  thread = (geometry, component)   V+ and V-  -> central difference, drift write-back
+// Staging buffers are structure-of-arrays [field][energy] so every stage reads and writes coalesced;
+// 320 B per energy against ~1e5 FP64 operations.  Each stage has its own register budget / occupancy.
 #if PIMDK_CCPOL_STRICT
 #define PIMDK_CCPOL_NS ccpol_strict_impl
 #else
@@ -22,129 +30,177 @@ namespace pimdk {
 
 namespace {
 
-constexpr int kBlock = PIMDK_CCPOL_BLOCK;
+constexpr int kSetupBlock = 128;
+constexpr int kSaptBlock = 128;
+constexpr int kRigidBlock = 128;
+constexpr int kFields = 40;  // 18 flexible + 18 rigid coordinates, emon, val, vall, erigid
+enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39 };
+constexpr size_t kTabBytes = (sizeof(CcpolDev) + 15) / 16 * 16;
 
-__device__ __forceinline__ void stage_tables(const CcpolDev* __restrict__ g, CcpolDev* s) {
+__device__ __forceinline__ const CcpolDev& stage_tables(const CcpolDev* __restrict__ g, unsigned char* smem) {
   const int4* src = reinterpret_cast<const int4*>(g);
-  int4* dst = reinterpret_cast<int4*>(s);
+  int4* dst = reinterpret_cast<int4*>(smem);
   for (int i = threadIdx.x; i < (int)(sizeof(CcpolDev) / sizeof(int4)); i += blockDim.x) dst[i] = src[i];
   __syncthreads();
+  return *reinterpret_cast<const CcpolDev*>(smem);
 }
 
-// energies: one thread per geometry
-__global__ void __launch_bounds__(kBlock, 1)
-KNAME(ccpol_energy_kernel)(const CcpolDev* __restrict__ tab, GeomLayout L, const double* __restrict__ x,
-                           double* __restrict__ v, long ngeom, int* __restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  CcpolDev* T = reinterpret_cast<CcpolDev*>(smem);
-  double* scr_base = reinterpret_cast<double*>(smem + sizeof(CcpolDev));
-  stage_tables(tab, T);
-  Scratch scr{scr_base + threadIdx.x};
-  for (long g = (long)blockIdx.x * kBlock + threadIdx.x; g < ngeom; g += (long)gridDim.x * kBlock) {
-    double xb[18];
-    const long base = L.base(g);
-#pragma unroll
-    for (int d = 0; d < 18; ++d) xb[d] = x[base + d * L.stride_dof];
-    int fl = 0;
-    v[g] = ccpol_V(*T, scr, xb, &fl);
-    if (fl) atomicOr(flags, PIMDK_FLAG_NOCONV);
-  }
-}
-
-// Vprime: 36 threads per geometry (component c in the reference's loop order i=dim outer, j=atom inner;
-// even thread = +eps, odd thread = -eps), 7 whole geometries (252 threads) per CTA pass so that a
-// geometry never straddles CTAs.  The in-place perturbation drift of the reference
-// (x+eps, -2eps, +eps; mcmod_waterdimer_ccpol.f90:48-52) is reproduced and optionally written back.
-constexpr int kGeomPerPass = kBlock / 36;
-
-__global__ void __launch_bounds__(kBlock, 1)
-KNAME(ccpol_grad_kernel)(const CcpolDev* __restrict__ tab, GeomLayout L, double* __restrict__ x,
-                         double* __restrict__ grad, long ngeom, int write_drift, int* __restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  CcpolDev* T = reinterpret_cast<CcpolDev*>(smem);
-  double* scr_base = reinterpret_cast<double*>(smem + sizeof(CcpolDev));
-  stage_tables(tab, T);
-  Scratch scr{scr_base + threadIdx.x};
+// ---- stage 0 ------------------------------------------------------------------------------------
+// grad = 1: energy e = 36*g + 2*c + s is the displaced geometry for component c (loop order i=dim outer,
+// j=atom inner: c = i*6 + j), s = 0 for +eps, 1 for -eps; components already visited by the reference's
+// loop carry its round-off drift x+eps-2eps+eps (mcmod_waterdimer_ccpol.f90:48-52).
+__global__ void __launch_bounds__(kSetupBlock)
+KNAME(ccpol_setup_kernel)(int iemonomer, GeomLayout L, const double* __restrict__ x, long geom0, long ne, int grad,
+                          double* __restrict__ buf) {
+  const long e = (long)blockIdx.x * kSetupBlock + threadIdx.x;
+  if (e >= ne) return;
   const double eps = 1e-4;
-  const int lg = threadIdx.x / 36;           // geometry slot within the pass
-  const int t = threadIdx.x - lg * 36;
-  const int c = t >> 1;                      // component in loop order: c = i*6 + j  (i = dim, j = atom)
-  const int minus = t & 1;
-  const int ci = c / 6, cj = c - ci * 6;
-  const int my_dof = cj * 3 + ci;            // position in x(3,6): atom-major
-  const long npass = (ngeom + kGeomPerPass - 1) / kGeomPerPass;
-  for (long pass = blockIdx.x; pass < npass; pass += gridDim.x) {
-    const long g = pass * kGeomPerPass + lg;
-    const bool active = lg < kGeomPerPass && g < ngeom;
-    double xb[18];
-    double vpm = 0.0;
-    double mydrift = 0.0;
-    const long base = active ? L.base(g) : 0;
-    if (active) {
+  const long g = geom0 + (grad ? e / 36 : e);
+  const int t = grad ? (int)(e % 36) : 0;
+  const int c = t >> 1, minus = t & 1;
+  const long base = L.base(g);
+  double xb[18];
 #pragma unroll
-      for (int d = 0; d < 18; ++d) {
-        double x0 = x[base + d * L.stride_dof];
-        const int di = d % 3, dj = d / 3;   // d = atom*3 + dim
-        const int cd = di * 6 + dj;         // its place in the loop order
-        double xp = x0 + eps;
-        double xm = xp - 2.0 * eps;
-        double xr = xm + eps;               // value left behind by the reference
-        double val = x0;
-        if (cd < c) val = xr;
-        if (cd == c) { val = minus ? xm : xp; mydrift = xr; }
-        xb[d] = val;
-      }
+  for (int d = 0; d < 18; ++d) {
+    const double x0 = x[base + d * L.stride_dof];
+    double val = x0;
+    if (grad) {
+      const int di = d % 3, dj = d / 3;  // d = atom*3 + dim
+      const int cd = di * 6 + dj;        // its place in the loop order
+      const double xp = x0 + eps;
+      const double xm = xp - 2.0 * eps;
+      const double xr = xm + eps;        // value left behind by the reference
+      if (cd < c) val = xr;
+      if (cd == c) val = minus ? xm : xp;
     }
-    __syncthreads();  // every read of x above precedes every drift write below
-    if (active) {
-      int fl = 0;
-      vpm = ccpol_V(*T, scr, xb, &fl);
-      if (fl) atomicOr(flags, PIMDK_FLAG_NOCONV);
+    xb[d] = val;
+  }
+  double A[3][3], B[3][3], rg[6][3], emon;
+  ccpol_setup(iemonomer, xb, A, B, rg, emon);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      buf[(F_FLEX + i * 3 + j) * ne + e] = A[i][j];
+      buf[(F_FLEX + 9 + i * 3 + j) * ne + e] = B[i][j];
     }
-    const double other = __shfl_xor_sync(0xffffffffu, vpm, 1);
-    if (active && !minus) {
-      const double gval = (vpm - other) / (2.0 * eps);
-      grad[base + my_dof * L.stride_dof] = gval;
-      if (gval != gval) atomicOr(flags, PIMDK_FLAG_NAN);
-      if (write_drift) x[base + my_dof * L.stride_dof] = mydrift;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) buf[(F_RIGID + i * 3 + j) * ne + e] = rg[i][j];
+  buf[F_EMON * ne + e] = emon;
+}
+
+// ---- stage 1 ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSaptBlock, 3)
+KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const CcpolDev& T = stage_tables(tab, smem);
+  double* scr_base = reinterpret_cast<double*>(smem + kTabBytes);
+  const long j = (long)blockIdx.x * kSaptBlock + threadIdx.x;
+  if (j >= 2 * ne) return;
+  const int which = j >= ne;  // 0: flexible geometry (val), 1: embedded rigid geometry (vall)
+  const long e = which ? j - ne : j;
+  const int f0 = which ? F_RIGID : F_FLEX;
+  double ca[3][3], cb[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ca[i][k] = buf[(f0 + i * 3 + k) * ne + e];
+      cb[i][k] = buf[(f0 + 9 + i * 3 + k) * ne + e];
     }
+  Scratch<kSaptBlock> scr{scr_base + threadIdx.x};
+  buf[(which ? F_VALL : F_VAL) * ne + e] = sapt5sf(T, scr, ca, cb);
+}
+
+// ---- stage 2 ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRigidBlock, 4)
+KNAME(ccpol_rigid_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf, int* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const CcpolDev& T = stage_tables(tab, smem);
+  double* scr_base = reinterpret_cast<double*>(smem + kTabBytes);
+  const long e = (long)blockIdx.x * kRigidBlock + threadIdx.x;
+  if (e >= ne) return;
+  double rg[6][3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rg[i][k] = buf[(F_RIGID + i * 3 + k) * ne + e];
+  Scratch<kRigidBlock> scr{scr_base + threadIdx.x};
+  int fl = 0;
+  buf[F_ERIG * ne + e] = ccpol8s_dimer(T, scr, rg, &fl);
+  if (fl) atomicOr(flags, PIMDK_FLAG_NOCONV);
+}
+
+// ---- stage 3 ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+KNAME(ccpol_combine_kernel)(int iemonomer, double V0, GeomLayout L, double* __restrict__ x, long geom0, long ne, int grad,
+                            const double* __restrict__ buf, double* __restrict__ v, double* __restrict__ gradout,
+                            int write_drift, int* __restrict__ flags) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double eps = 1e-4;
+  if (!grad) {
+    if (i >= ne) return;
+    v[geom0 + i] = ccpol_combine(iemonomer, V0, buf[F_ERIG * ne + i], buf[F_VAL * ne + i], buf[F_VALL * ne + i],
+                                 buf[F_EMON * ne + i]);
+    return;
+  }
+  if (i >= ne / 2) return;  // one thread per (geometry, component)
+  const long ep = 2 * i, em = ep + 1;
+  const double vp = ccpol_combine(iemonomer, V0, buf[F_ERIG * ne + ep], buf[F_VAL * ne + ep], buf[F_VALL * ne + ep],
+                                  buf[F_EMON * ne + ep]);
+  const double vm = ccpol_combine(iemonomer, V0, buf[F_ERIG * ne + em], buf[F_VAL * ne + em], buf[F_VALL * ne + em],
+                                  buf[F_EMON * ne + em]);
+  const long g = geom0 + i / 18;
+  const int c = (int)(i % 18);
+  const int ci = c / 6, cj = c - ci * 6;
+  const long addr = L.base(g) + (long)(cj * 3 + ci) * L.stride_dof;
+  const double gval = (vp - vm) / (2.0 * eps);
+  gradout[addr] = gval;
+  if (gval != gval) atomicOr(flags, PIMDK_FLAG_NAN);
+  if (write_drift) {
+    const double x0 = x[addr];
+    const double xp = x0 + eps;
+    const double xm = xp - 2.0 * eps;
+    x[addr] = xm + eps;
   }
 }
+
+size_t sapt_smem() { return kTabBytes + (size_t)kSaptSlots * kSaptBlock * sizeof(double); }
+size_t rigid_smem() { return kTabBytes + (size_t)kRigidSlots * kRigidBlock * sizeof(double); }
 
 }  // namespace
 
-size_t KNAME(ccpol_smem_bytes)() { return sizeof(CcpolDev) + (size_t)kScratchSlots * kBlock * sizeof(double); }
-
-cudaError_t KNAME(launch_ccpol_energy)(const CcpolDev* tab, GeomLayout L, const double* x, double* v, long ngeom,
-                                       int* flags, int num_sms, cudaStream_t st) {
-  static bool attr = false;
-  size_t sm = KNAME(ccpol_smem_bytes)();
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(KNAME(ccpol_energy_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  long blocks = (ngeom + kBlock - 1) / kBlock;
-  if (blocks > 8L * num_sms) blocks = 8L * num_sms;
-  if (blocks < 1) blocks = 1;
-  KNAME(ccpol_energy_kernel)<<<(unsigned)blocks, kBlock, sm, st>>>(tab, L, x, v, ngeom, flags);
-  return cudaGetLastError();
+size_t KNAME(ccpol_work_bytes)(long ngeom, int grad) {
+  const long cap = grad ? 32768 : 1048576;  // geometries per pass (grad: 1.18 M energies, 377 MB)
+  const long n = ngeom < cap ? ngeom : cap;
+  return (size_t)(n < 1 ? 1 : n) * kFields * 8 * (grad ? 36 : 1);
 }
 
-cudaError_t KNAME(launch_ccpol_grad)(const CcpolDev* tab, GeomLayout L, double* x, double* grad, long ngeom,
-                                     int write_drift, int* flags, int num_sms, cudaStream_t st) {
+cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, double V0, GeomLayout L, double* x, double* v,
+                                double* grad, long ngeom, int write_drift, int* flags, double* work, size_t work_bytes,
+                                cudaStream_t st) {
   static bool attr = false;
-  size_t sm = KNAME(ccpol_smem_bytes)();
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(KNAME(ccpol_grad_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaError_t e = cudaFuncSetAttribute(KNAME(ccpol_sapt_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sapt_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(KNAME(ccpol_rigid_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rigid_smem());
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  long blocks = (ngeom + kGeomPerPass - 1) / kGeomPerPass;
-  // persistent-style grid: one resident CTA per SM, each looping over passes of 7 geometries
-  if (blocks > 16L * num_sms) blocks = 16L * num_sms;
-  if (blocks < 1) blocks = 1;
-  KNAME(ccpol_grad_kernel)<<<(unsigned)blocks, kBlock, sm, st>>>(tab, L, x, grad, ngeom, write_drift, flags);
+  const int g = grad != nullptr;
+  const long chunk = (long)(work_bytes / ((size_t)kFields * 8 * (g ? 36 : 1)));
+  if (chunk < 1) return cudaErrorInvalidValue;
+  for (long g0 = 0; g0 < ngeom; g0 += chunk) {
+    const long ng = (ngeom - g0 < chunk) ? ngeom - g0 : chunk;
+    const long ne = ng * (g ? 36 : 1);
+    KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, L, x, g0, ne, g, work);
+    KNAME(ccpol_sapt_kernel)<<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
+    KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, rigid_smem(), st>>>(tab, ne, work, flags);
+    const long nt = g ? ne / 2 : ne;
+    KNAME(ccpol_combine_kernel)<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(iemonomer, V0, L, x, g0, ne, g, work, v, grad, write_drift, flags);
+  }
   return cudaGetLastError();
 }
 

@@ -33,12 +33,13 @@ struct SimplePesParams {  // mcmod_1d.f90:9-12, mcmod_2dtest.f90:16-24
 };
 
 // ---- CCpol (ccpol_kernels.cu, built twice) ----
-#define PIMDK_DECL_CCPOL(sfx)                                                                                        \
-  size_t ccpol_smem_bytes_##sfx();                                                                                   \
-  cudaError_t launch_ccpol_energy_##sfx(const CcpolDev* tab, GeomLayout L, const double* x, double* v, long ngeom,   \
-                                        int* flags, int num_sms, cudaStream_t st);                                   \
-  cudaError_t launch_ccpol_grad_##sfx(const CcpolDev* tab, GeomLayout L, double* x, double* grad, long ngeom,        \
-                                      int write_drift, int* flags, int num_sms, cudaStream_t st);
+// v != NULL: energies; grad != NULL: finite-difference gradients (write_drift: leave x where the
+// reference's in-place perturbation leaves it).  `work` is a staging buffer of ccpol_work_bytes().
+#define PIMDK_DECL_CCPOL(sfx)                                                                                       \
+  size_t ccpol_work_bytes_##sfx(long ngeom, int grad);                                                              \
+  cudaError_t launch_ccpol_##sfx(const CcpolDev* tab, int iemonomer, double V0, GeomLayout L, double* x, double* v, \
+                                 double* grad, long ngeom, int write_drift, int* flags, double* work,               \
+                                 size_t work_bytes, cudaStream_t st);
 PIMDK_DECL_CCPOL(strict)
 PIMDK_DECL_CCPOL(fast)
 #undef PIMDK_DECL_CCPOL

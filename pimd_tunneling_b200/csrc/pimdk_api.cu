@@ -69,7 +69,7 @@ struct Ctx {
   std::vector<double> mass, lam, beadmass, T;
   DevBuf dT, dsA, dsB, dlamb2, dmass, dtabs;  // dtabs: 8 per-call (natom,n) tables
   // workspaces
-  DevBuf wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc;
+  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc;
   // profiling
   bool profiling = false;
   std::map<std::string, Prof> prof;
@@ -174,16 +174,20 @@ int pes_eval_dev(GeomLayout L, double* x, double* v, double* grad, long ngeom, i
   int* flags = g.wFlags.as<int>();
   if (g.pes == PES_CCPOL) {
     const CcpolDev* tab = g.dtab.as<CcpolDev>();
-    if (v) {
-      Scope s("pes");
-      CU(g.mode == PIMDK_MODE_FAST ? launch_ccpol_energy_fast(tab, L, x, v, ngeom, flags, g.num_sms, g.stream)
-                                   : launch_ccpol_energy_strict(tab, L, x, v, ngeom, flags, g.num_sms, g.stream));
-    }
-    if (grad) {
-      Scope s("pes");
-      CU(g.mode == PIMDK_MODE_FAST
-             ? launch_ccpol_grad_fast(tab, L, x, grad, ngeom, write_drift, flags, g.num_sms, g.stream)
-             : launch_ccpol_grad_strict(tab, L, x, grad, ngeom, write_drift, flags, g.num_sms, g.stream));
+    const bool fast = g.mode == PIMDK_MODE_FAST;
+    for (int pass = 0; pass < 2; ++pass) {  // energies, then gradients (two pipeline runs, like V then Vprime)
+      double* vv = pass == 0 ? v : nullptr;
+      double* gg = pass == 1 ? grad : nullptr;
+      if (!vv && !gg) continue;
+      const size_t wb = fast ? ccpol_work_bytes_fast(ngeom, gg != nullptr) : ccpol_work_bytes_strict(ngeom, gg != nullptr);
+      CU(g.wCc.ensure(wb));
+      const long per = (long)(40 * 8 * (gg ? 36 : 1));
+      const long npass = (ngeom + (long)(g.wCc.cap / per) - 1) / (long)(g.wCc.cap / per);
+      Scope s("pes", (int)(4 * npass));
+      CU(fast ? launch_ccpol_fast(tab, g.hdev.iemonomer, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
+                                  g.wCc.as<double>(), g.wCc.cap, g.stream)
+              : launch_ccpol_strict(tab, g.hdev.iemonomer, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
+                                    g.wCc.as<double>(), g.wCc.cap, g.stream));
     }
   } else {
     Scope s("pes");
@@ -323,7 +327,7 @@ int pimdk_finalize(void) {
   if (!g.inited) return PIMDK_OK;
   cudaStreamSynchronize(g.stream);
   resolve_spans();
-  DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wP, &g.wQ, &g.wG, &g.wGn,
+  DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
                     &g.wDhdr, &g.wPp, &g.wMisc};
   for (DevBuf* b : bufs) b->release();
