@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpimdk.so")
+LIB_PATH = os.environ.get("PIMDK_LIB", os.path.join(_HERE, "libpimdk.so"))
 DATA_DIR = os.path.join(_HERE, "data")
 
 _i64 = ctypes.c_int64

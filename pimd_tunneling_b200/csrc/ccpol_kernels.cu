@@ -30,17 +30,26 @@ namespace pimdk {
 
 namespace {
 
+#ifndef PIMDK_SAPT_MINB
+#define PIMDK_SAPT_MINB 3
+#endif
+#ifndef PIMDK_RIGID_MINB
+#define PIMDK_RIGID_MINB 5
+#endif
 constexpr int kSetupBlock = 128;
 constexpr int kSaptBlock = 128;
 constexpr int kRigidBlock = 128;
 constexpr int kFields = 40;  // 18 flexible + 18 rigid coordinates, emon, val, vall, erigid
 enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39 };
-constexpr size_t kTabBytes = (sizeof(CcpolDev) + 15) / 16 * 16;
+constexpr int kTabBytes = (int)((sizeof(CcpolDev) + 15) / 16 * 16);
+static_assert(kRigidTableBytes >= (int)offsetof(CcpolDev, param) && kRigidTableBytes <= kTabBytes, "rigid block covers the leading members");
 
+template <int BYTES>
 __device__ __forceinline__ const CcpolDev& stage_tables(const CcpolDev* __restrict__ g, unsigned char* smem) {
+  static_assert(BYTES % 16 == 0, "16-byte granules");
   const int4* src = reinterpret_cast<const int4*>(g);
   int4* dst = reinterpret_cast<int4*>(smem);
-  for (int i = threadIdx.x; i < (int)(sizeof(CcpolDev) / sizeof(int4)); i += blockDim.x) dst[i] = src[i];
+  for (int i = threadIdx.x; i < BYTES / (int)sizeof(int4); i += blockDim.x) dst[i] = src[i];
   __syncthreads();
   return *reinterpret_cast<const CcpolDev*>(smem);
 }
@@ -92,10 +101,10 @@ KNAME(ccpol_setup_kernel)(int iemonomer, GeomLayout L, const double* __restrict_
 }
 
 // ---- stage 1 ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSaptBlock, 3)
+__global__ void __launch_bounds__(kSaptBlock, PIMDK_SAPT_MINB)
 KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const CcpolDev& T = stage_tables(tab, smem);
+  const CcpolDev& T = stage_tables<kTabBytes>(tab, smem);
   double* scr_base = reinterpret_cast<double*>(smem + kTabBytes);
   const long j = (long)blockIdx.x * kSaptBlock + threadIdx.x;
   if (j >= 2 * ne) return;
@@ -115,11 +124,11 @@ KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __re
 }
 
 // ---- stage 2 ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRigidBlock, 4)
+__global__ void __launch_bounds__(kRigidBlock, PIMDK_RIGID_MINB)
 KNAME(ccpol_rigid_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf, int* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const CcpolDev& T = stage_tables(tab, smem);
-  double* scr_base = reinterpret_cast<double*>(smem + kTabBytes);
+  const CcpolDev& T = stage_tables<kRigidTableBytes>(tab, smem);  // only the CCpol-8s members are valid here
+  double* scr_base = reinterpret_cast<double*>(smem + kRigidTableBytes);
   const long e = (long)blockIdx.x * kRigidBlock + threadIdx.x;
   if (e >= ne) return;
   double rg[6][3];
@@ -168,7 +177,7 @@ KNAME(ccpol_combine_kernel)(int iemonomer, double V0, GeomLayout L, double* __re
 }
 
 size_t sapt_smem() { return kTabBytes + (size_t)kSaptSlots * kSaptBlock * sizeof(double); }
-size_t rigid_smem() { return kTabBytes + (size_t)kRigidSlots * kRigidBlock * sizeof(double); }
+size_t rigid_smem() { return kRigidTableBytes + (size_t)kRigidSlots * kRigidBlock * sizeof(double); }
 
 }  // namespace
 

@@ -330,6 +330,10 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
     if (!same) o->cls_start[o->ncls++] = (uint8_t)a;
   }
   o->cls_start[o->ncls] = 25;
+  for (int c = 0; c < o->ncls; ++c) {
+    const int sz = o->cls_start[c + 1] - o->cls_start[c];
+    if (sz != 1 && sz != 2 && sz != 4) { g_msg = "CCpol-8s site classes must have 1, 2 or 4 sites"; return g_msg.c_str(); }
+  }
   for (int b = 0; b < 25; ++b)
     for (int a = 0; a < 25; ++a)
       if (h.ind_beta[b * 25 + a] == 0) { g_msg = "ind_beta has empty entries; not supported"; return g_msg.c_str(); }

@@ -11,34 +11,40 @@ constexpr int kNParab = 84;
 constexpr int kNParam = 18;
 
 struct CcpolDev {
-  double param[kNParam * kNType];            // param(k,t)         -> [(t-1)*18 + k-1]
-  double parab[kNParab * kNType * kNType];   // parab(k,ta,tb)     -> [((tb-1)*5+(ta-1))*84 + k-1]
-  double c[568];                             // SAPT-5s'f linear coefficients
+  // ---- CCpol-8s rigid model (the only part the rigid stage stages into shared memory) ----
   double cc[144];                            // CCpol-8s linear coefficients
   double params[134];                        // CCpol-8s nonlinear parameters (1-based in the file)
   double sites[75];                          // sites(3,25) body-frame coordinates
   double chrg[5];                            // induction charges of sites 1..5
   double V0;                                 // module variable V0 of mcmod_mass
+  uint8_t ind_beta[625];                     // ind_beta(nsA,nsB) -> [nsB*25 + nsA] (0-based)
+  uint8_t ind_charge[5];
+  uint8_t ind_d1[25];                        // 5x5, [b*5+a]
+  uint8_t ind_d6[9], ind_d8[9], ind_d10[9], ind_c6[9], ind_c8[9], ind_c10[9];  // 3x3, [b*3+a]
+  // CCpol-8s site classes: runs of consecutive sites with identical ind_beta rows (8 classes of
+  // sizes 1,2,2,4,4,4,4,4 for data_ccdata); cls_start[c]..cls_start[c+1]-1 are the sites of class c
+  uint8_t cls_start[26];
+  uint8_t pad0_[5];
+  int32_t ncls;
+  int32_t iemonomer;
+  // ---- SAPT-5s'f flexible model ----
+  double param[kNParam * kNType];            // param(k,t)         -> [(t-1)*18 + k-1]
+  double parab[kNParab * kNType * kNType];   // parab(k,ta,tb)     -> [((tb-1)*5+(ta-1))*84 + k-1]
+  double c[568];                             // SAPT-5s'f linear coefficients
   // static image of poten's first-encounter index map itypus (proc_sapt5sf_new_ncd.f:181-203):
   // first linear coefficient (1-based) of the symmetric / antisymmetric block of a type pair,
   // 0 when the pair type carries no exponential.
   int16_t itu_s[kNType * kNType];
   int16_t itu_a[kNType * kNType];
-  uint8_t ind_beta[625];                     // ind_beta(nsA,nsB) -> [nsB*25 + nsA] (0-based)
-  uint8_t ind_charge[5];
-  uint8_t ind_d1[25];                        // 5x5, [b*5+a]
-  uint8_t ind_d6[9], ind_d8[9], ind_d10[9], ind_c6[9], ind_c8[9], ind_c10[9];  // 3x3, [b*3+a]
   // static per type-pair facts (bit 0: carries exponential/linear terms, bit 1: damped electrostatics
   // (dmp1 != 0), bit 2: damped dispersion (any of dmp6/8/10 != 0)).  A term whose damping parameter is
   // exactly zero evaluates to +-0 in the reference (function d returns 0 for br == 0,
   // proc_sapt5sf_new_ncd.f:1234-1237) and adding +-0 changes no bits, so the kernels skip it.
   uint8_t pairflags[kNType * kNType];
-  // CCpol-8s site classes: runs of consecutive sites with identical ind_beta rows (8 classes of
-  // sizes 1,2,2,4,4,4,4,4 for data_ccdata); cls_start[c]..cls_start[c+1]-1 are the sites of class c
-  uint8_t cls_start[26];
-  int32_t ncls;
-  int32_t iemonomer;
+  uint8_t pad1_[3];
 };
+// bytes of the leading rigid-model block (multiple of 16)
+constexpr int kRigidTableBytes = 16 * ((144 + 134 + 75 + 5 + 1) * 8 / 16 + (625 + 5 + 25 + 54 + 26 + 5 + 8 + 15) / 16 + 1);
 
 // Host-side full tables (same content as the reference's COMMON block) and loaders.
 struct CcpolHost {
