@@ -139,6 +139,9 @@ int pimdk_profile_get(const char* family, double* ms, pimdk_int* launches);
 int pimdk_profile_reset(void);
 int pimdk_fp64_peak(double* tflops);
 pimdk_int pimdk_launch_count(void);
+/* GPU self-test: number of operands (of 9 x 2^28) for which the kernels' three-instruction division by a
+ * small integer constant differs from IEEE division in any bit (must be 0). */
+int pimdk_selftest_division(pimdk_int* mismatches);
 
 #ifdef __cplusplus
 }

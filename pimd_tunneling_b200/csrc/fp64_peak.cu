@@ -2,6 +2,8 @@
 // MEASURED_PEAKS.json carries no FP64 number, so bench.py measures the denominator of the PES
 // kernel's roofline here, on the same device and clocks as the timed run.
 #include "kernels.h"
+#define PIMDK_CCPOL_NS selftest_impl
+#include "ccpol_device.cuh"
 
 namespace pimdk {
 namespace {
@@ -19,7 +21,41 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
   out[(long)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// bit-equality of div_by_int<I>(t) with t / I over pseudo-random operands spanning the exponent range
+template <int I>
+__device__ unsigned long long div_mismatch(unsigned long long h, int reps) {
+  unsigned long long bad = 0;
+  for (int r = 0; r < reps; ++r) {
+    h = h * 6364136223846793005ull + 1442695040888963407ull;
+    const unsigned long long mant = h >> 12;
+    const unsigned long long ex = 1023ull - 300ull + (unsigned long long)((h >> 3) % 600ull);
+    const double t = __longlong_as_double((long long)((ex << 52) | mant | ((h & 1ull) << 63)));
+    const double a = div_by_int<I>(t), b = t / (double)I;
+    bad += (__double_as_longlong(a) != __double_as_longlong(b));
+  }
+  return bad;
+}
+__global__ void div_selftest_kernel(unsigned long long* out, int reps) {
+  const unsigned long long h = 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+  unsigned long long bad = div_mismatch<3>(h, reps) + div_mismatch<5>(h, reps) + div_mismatch<6>(h, reps) +
+                           div_mismatch<7>(h, reps) + div_mismatch<9>(h, reps) + div_mismatch<10>(h, reps) +
+                           div_mismatch<2>(h, reps) + div_mismatch<4>(h, reps) + div_mismatch<8>(h, reps);
+  if (bad) atomicAdd(out, bad);
+}
+
 }  // namespace
+
+cudaError_t div_selftest(unsigned long long* mismatches, cudaStream_t st) {
+  unsigned long long* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(*d));
+  if (e != cudaSuccess) return e;
+  cudaMemsetAsync(d, 0, sizeof(*d), st);
+  div_selftest_kernel<<<1024, 256, 0, st>>>(d, 1024);  // 2^28 operands per divisor
+  e = cudaMemcpyAsync(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  return e;
+}
 
 cudaError_t fp64_peak_probe(int num_sms, double* tflops, cudaStream_t st) {
   const int blocks = num_sms * 4, threads = 256, iters = 4096;

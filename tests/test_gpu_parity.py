@@ -134,6 +134,16 @@ def test_edge_cases(pk):
     assert ei.value.code in (5, 6)
 
 
+def test_division_by_small_integers(pk):
+    """the damping series divides by 1..10 with a 3-instruction correctly rounded sequence: 0 mismatches vs '/'"""
+    import ctypes
+    from pimd_tunneling_b200._lib import check, lib
+
+    bad = ctypes.c_int64(-1)
+    check(lib().pimdk_selftest_division(ctypes.byref(bad)))
+    assert bad.value == 0
+
+
 # ---------------------------------------------------------------- module verletint ----------------
 def test_normal_mode_tables_and_transform(pk, orc):
     pes = pk.McmodMass("1d").V_init()
