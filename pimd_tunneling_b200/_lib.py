@@ -50,6 +50,7 @@ _SIGS = {
     "pimdk_profile_reset": [],
     "pimdk_fp64_peak": [ctypes.POINTER(_dbl)],
     "pimdk_selftest_division": [ctypes.POINTER(_i64)],
+    "pimdk_selftest_fastmath": [ctypes.POINTER(_i64)],
 }
 
 _lib = None

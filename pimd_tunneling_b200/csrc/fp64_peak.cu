@@ -43,7 +43,36 @@ __global__ void div_selftest_kernel(unsigned long long* out, int reps) {
   if (bad) atomicAdd(out, bad);
 }
 
+// bit-equality of fast_div / fast_sqrt with the built-ins on operands in the kernels' range
+__global__ void fastmath_selftest_kernel(unsigned long long* out, int reps) {
+  unsigned long long h = 0xD1B54A32D192ED03ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+  unsigned long long bad = 0;
+  for (int r = 0; r < reps; ++r) {
+    h = h * 6364136223846793005ull + 1442695040888963407ull;
+    const unsigned long long h2 = h * 0x9E3779B97F4A7C15ull + 12345ull;
+    // exponents in [-100, 100], random mantissas and signs
+    const double a = __longlong_as_double((long long)(((1023ull - 100ull + (h >> 5) % 201ull) << 52) | (h2 >> 12) | ((h & 1ull) << 63)));
+    const double b = __longlong_as_double((long long)(((1023ull - 100ull + (h2 >> 7) % 201ull) << 52) | (h >> 12) | ((h2 & 1ull) << 63)));
+    bad += (__double_as_longlong(fast_div(a, b)) != __double_as_longlong(a / b));
+    const double x = fabs(a);
+    bad += (__double_as_longlong(fast_sqrt(x)) != __double_as_longlong(sqrt(x)));
+  }
+  if (bad) atomicAdd(out, bad);
+}
+
 }  // namespace
+
+cudaError_t fastmath_selftest(unsigned long long* mismatches, cudaStream_t st) {
+  unsigned long long* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(*d));
+  if (e != cudaSuccess) return e;
+  cudaMemsetAsync(d, 0, sizeof(*d), st);
+  fastmath_selftest_kernel<<<4096, 256, 0, st>>>(d, 1024);  // 2^30 operand pairs
+  e = cudaMemcpyAsync(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  return e;
+}
 
 cudaError_t div_selftest(unsigned long long* mismatches, cudaStream_t st) {
   unsigned long long* d = nullptr;

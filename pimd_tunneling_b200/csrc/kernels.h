@@ -107,5 +107,7 @@ cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double*
 cudaError_t fp64_peak_probe(int num_sms, double* tflops, cudaStream_t st);
 // bit-equality self-test of the three-instruction division by small integers used in the damping series
 cudaError_t div_selftest(unsigned long long* mismatches, cudaStream_t st);
+// bit-equality self-test of fast_div / fast_sqrt (ccpol_device.cuh) against the built-ins
+cudaError_t fastmath_selftest(unsigned long long* mismatches, cudaStream_t st);
 
 }  // namespace pimdk

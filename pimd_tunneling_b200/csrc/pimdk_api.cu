@@ -898,6 +898,13 @@ int pimdk_fp64_peak(double* tflops) {
   return PIMDK_OK;
 }
 pimdk_int pimdk_launch_count(void) { return g.launch_count; }
+int pimdk_selftest_fastmath(pimdk_int* mismatches) {
+  NEED_INIT();
+  unsigned long long bad = 0;
+  CU(fastmath_selftest(&bad, g.stream));
+  *mismatches = (pimdk_int)bad;
+  return PIMDK_OK;
+}
 int pimdk_selftest_division(pimdk_int* mismatches) {
   NEED_INIT();
   unsigned long long bad = 0;

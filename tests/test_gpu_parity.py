@@ -144,6 +144,16 @@ def test_division_by_small_integers(pk):
     assert bad.value == 0
 
 
+def test_fast_div_sqrt_bit_identical(pk):
+    """branch-free IEEE division / sqrt sequences used in the site-site sums == built-ins, bit for bit"""
+    import ctypes
+    from pimd_tunneling_b200._lib import check, lib
+
+    bad = ctypes.c_int64(-1)
+    check(lib().pimdk_selftest_fastmath(ctypes.byref(bad)))
+    assert bad.value == 0
+
+
 # ---------------------------------------------------------------- module verletint ----------------
 def test_normal_mode_tables_and_transform(pk, orc):
     pes = pk.McmodMass("1d").V_init()
