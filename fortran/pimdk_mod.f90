@@ -1,0 +1,163 @@
+! pimdk_mod.f90 -- ISO_C_BINDING layer between the (unchanged) Fortran drivers of pimd-tunneling and
+! libpimdk.so (include/pimdk.h).  SOURCE ONLY: this image has no Fortran compiler, so this file has not
+! been compiled; it is deliberately thin and mechanical.  Build of the reference: ifort -i8 -r8
+! (makefile:5), hence integer(c_int64_t) / real(c_double) everywhere.
+!
+!   module pimdk           raw interfaces, one per C entry point
+!   module mcmod_mass      drop-in replacement of mcmod_waterdimer_ccpol.f90 / mcmod_1d.f90 / mcmod_2dtest.f90
+!                          (same module name, same procedures; choose the PES with -DPIMDK_PES=...)
+!   subroutine pimdk_propagate_tasks   what the task loop of pimd_par.f90:321-381 collapses to
+module pimdk
+  use iso_c_binding
+  implicit none
+  interface
+     integer(c_int) function pimdk_init(device, data_dir) bind(C, name="pimdk_init")
+       import; integer(c_int64_t), value :: device; character(kind=c_char) :: data_dir(*)
+     end function
+     integer(c_int) function pimdk_finalize() bind(C, name="pimdk_finalize")
+       import
+     end function
+     type(c_ptr) function pimdk_last_error() bind(C, name="pimdk_last_error")
+       import
+     end function
+     integer(c_int) function pimdk_pes_select(name, params, nparams) bind(C, name="pimdk_pes_select")
+       import; character(kind=c_char) :: name(*); type(c_ptr), value :: params; integer(c_int64_t), value :: nparams
+     end function
+     integer(c_int) function pimdk_pes_set_v0(v0) bind(C, name="pimdk_pes_set_v0")
+       import; real(c_double), value :: v0
+     end function
+     integer(c_int) function pimdk_pes_eval(nbatch, ndim, natom, x, v, grad) bind(C, name="pimdk_pes_eval")
+       import; integer(c_int64_t), value :: nbatch, ndim, natom
+       real(c_double) :: x(*); type(c_ptr), value :: v, grad
+     end function
+     integer(c_int) function pimdk_pes_vprime_inplace(nbatch, ndim, natom, x, grad) bind(C, name="pimdk_pes_vprime_inplace")
+       import; integer(c_int64_t), value :: nbatch, ndim, natom; real(c_double) :: x(*), grad(*)
+     end function
+     integer(c_int) function pimdk_um_forceenergy(n, ndim, natom, x, a, b, mass, betan, fixedends, f, g) &
+          bind(C, name="pimdk_um_forceenergy")
+       import; integer(c_int64_t), value :: n, ndim, natom, fixedends; real(c_double), value :: betan
+       real(c_double) :: x(*), mass(*); type(c_ptr), value :: a, b, f, g
+     end function
+     integer(c_int) function pimdk_nm_setup(n, ndim, natom, mass, betan, tau) bind(C, name="pimdk_nm_setup")
+       import; integer(c_int64_t), value :: n, ndim, natom; real(c_double) :: mass(*); real(c_double), value :: betan, tau
+     end function
+     integer(c_int) function pimdk_nm_get(transmatrix, lam, beadmass) bind(C, name="pimdk_nm_get")
+       import; type(c_ptr), value :: transmatrix, lam, beadmass
+     end function
+     integer(c_int) function pimdk_init_path(ntraj, npath, lampath, path, splinepath, xi, seed, gid, x, p) &
+          bind(C, name="pimdk_init_path")
+       import; integer(c_int64_t), value :: ntraj, npath, seed; type(c_ptr), value :: gid
+       real(c_double) :: lampath(*), path(*), splinepath(*), xi(*), x(*), p(*)
+     end function
+     integer(c_int) function pimdk_propagate(thermostat, ntraj, x, p, a, b, dbdl, dt, gamma, NMC, imin, Noutput, &
+          cayley, seed, gid, dHdr) bind(C, name="pimdk_propagate")
+       import; integer(c_int64_t), value :: thermostat, ntraj, NMC, imin, Noutput, cayley, seed
+       real(c_double), value :: dt, gamma; type(c_ptr), value :: gid
+       real(c_double) :: x(*), p(*), a(*), b(*), dbdl(*), dHdr(*)
+     end function
+     integer(c_int64_t) function pimdk_last_nan_trajectory() bind(C, name="pimdk_last_nan_trajectory")
+       import
+     end function
+     integer(c_int) function pimdk_gauleg(x1, x2, n, x, w) bind(C, name="pimdk_gauleg")
+       import; real(c_double), value :: x1, x2; integer(c_int64_t), value :: n; real(c_double) :: x(*), w(*)
+     end function
+  end interface
+contains
+  ! the reference's error convention: write a message and stop (verletmodule.f90:533-536,577-580)
+  subroutine pimdk_check(rc)
+    integer(c_int), intent(in) :: rc
+    character(kind=c_char), pointer :: msg(:)
+    integer :: i
+    if (rc .eq. 0) return
+    call c_f_pointer(pimdk_last_error(), msg, (/512/))
+    i = 1
+    do while (i .lt. 512 .and. msg(i) .ne. c_null_char)
+       i = i + 1
+    end do
+    write(*,*) "pimdk: ", msg(1:i-1)
+    if (rc .eq. 5) write(*,*) "NaN in pot propagation, trajectory", pimdk_last_nan_trajectory() + 1
+    stop
+  end subroutine pimdk_check
+end module pimdk
+
+!---------------------------------------------------------------------------------------------------------
+! Replacement plugin: same module name and procedures as mcmod_waterdimer_ccpol.f90:1-80, in the CURRENT
+! plugin interface (mcmod_waterdimer.f90:1-105): V_init(iproc), V, Vprime, potforce, module variables.
+module mcmod_mass
+  use iso_c_binding
+  use pimdk
+  implicit none
+  double precision::               V0, eps2=1.0d-5
+  integer::                        atom1=1, atom2=2, atom3=3
+  integer::                        n, ndim, ndof, natom, xunit, totdof
+  logical::                        potforcepresent=.true.
+  character, allocatable::         label(:)
+  character(len=20)::              basename
+contains
+  subroutine V_init(iproc)
+    integer, intent(in) :: iproc
+    ! data files are opened from the CWD like the reference (main_CCpol-8sf.f:49,115)
+    call pimdk_check(pimdk_init(-1_c_int64_t, "."//c_null_char))
+    call pimdk_check(pimdk_pes_select("ccpol8sf"//c_null_char, c_null_ptr, 0_c_int64_t))
+    write(*,*) "Potential initializaton complete"
+    V0=0.0d0
+  end subroutine V_init
+
+  function V(x)
+    double precision :: V, x(:,:)
+    double precision, target :: xc(ndim,natom), vv(1)
+    xc(:,:) = x(:,:)                                   ! callers pass strided slices x(i,:,:)
+    call pimdk_check(pimdk_pes_set_v0(V0))
+    call pimdk_check(pimdk_pes_eval(1_c_int64_t, int(ndim,c_int64_t), int(natom,c_int64_t), xc, c_loc(vv), c_null_ptr))
+    V = vv(1)
+  end function V
+
+  subroutine Vprime(x, grad)
+    double precision :: x(:,:), grad(:,:)
+    double precision :: xc(ndim,natom), gc(ndim,natom)
+    xc(:,:) = x(:,:)
+    call pimdk_check(pimdk_pes_vprime_inplace(1_c_int64_t, int(ndim,c_int64_t), int(natom,c_int64_t), xc, gc))
+    x(:,:) = xc(:,:)                                    ! the reference leaves x+eps-2eps+eps behind (:48-52)
+    grad(:,:) = gc(:,:)
+  end subroutine Vprime
+
+  subroutine potforce(x, grad, energy)
+    double precision :: x(:,:), grad(:,:), energy
+    double precision, target :: xc(ndim,natom), gc(ndim,natom), vv(1)
+    xc(:,:) = x(:,:)
+    call pimdk_check(pimdk_pes_eval(1_c_int64_t, int(ndim,c_int64_t), int(natom,c_int64_t), xc, c_loc(vv), c_loc(gc)))
+    grad(:,:) = gc(:,:); energy = vv(1)
+  end subroutine potforce
+  ! Vdoubleprime: unchanged from mcmod_waterdimer_ccpol.f90:60-77 (finite difference of Vprime), not on the hot path
+end module mcmod_mass
+
+!---------------------------------------------------------------------------------------------------------
+! The task loop of pimd_par.f90:321-381 (init_nm / init_path / propagate_pimd_* per task) as ONE batched call.
+! endpoints, gradpoints: (ncalcs, ndim, natom) as in pimd_par.f90:243-257; integrand(ncalcs) out.
+subroutine pimdk_propagate_tasks(thermostat, ncalcs, first_gid, startpoint, endpoints, gradpoints, xipoints, &
+     lampath, path, splinepath, npath, mass, betan, tau, dt, gamma, NMC, imin, Noutput, cayley, seed, integrand)
+  use iso_c_binding
+  use pimdk
+  use mcmod_mass, only: n, ndim, natom
+  implicit none
+  integer :: thermostat, ncalcs, first_gid, npath, NMC, imin, Noutput, seed, ii
+  logical :: cayley
+  double precision :: startpoint(ndim,natom), endpoints(ncalcs,ndim,natom), gradpoints(ncalcs,ndim,natom)
+  double precision :: xipoints(ncalcs), lampath(npath), path(npath,ndim,natom), splinepath(npath,ndim,natom)
+  double precision :: mass(natom), betan, tau, dt, gamma, integrand(ncalcs)
+  double precision, allocatable :: x(:,:,:,:), p(:,:,:,:), b(:,:,:), dbdl(:,:,:), dHdr(:)
+  integer(c_int64_t), allocatable, target :: gid(:)
+  allocate(x(n,ndim,natom,ncalcs), p(n,ndim,natom,ncalcs), b(ndim,natom,ncalcs), dbdl(ndim,natom,ncalcs))
+  allocate(dHdr(ncalcs), gid(ncalcs))
+  do ii = 1, ncalcs
+     b(:,:,ii) = endpoints(ii,:,:); dbdl(:,:,ii) = gradpoints(ii,:,:); gid(ii) = first_gid + ii - 1
+  end do
+  call pimdk_check(pimdk_nm_setup(int(n,c_int64_t), int(ndim,c_int64_t), int(natom,c_int64_t), mass, betan, tau))
+  call pimdk_check(pimdk_init_path(int(ncalcs,c_int64_t), int(npath,c_int64_t), lampath, path, splinepath, xipoints, &
+       int(seed,c_int64_t), c_loc(gid), x, p))
+  call pimdk_check(pimdk_propagate(int(thermostat,c_int64_t), int(ncalcs,c_int64_t), x, p, startpoint, b, dbdl, dt, gamma, &
+       int(NMC,c_int64_t), int(imin,c_int64_t), int(Noutput,c_int64_t), merge(1_c_int64_t,0_c_int64_t,cayley), &
+       int(seed,c_int64_t), c_loc(gid), dHdr))
+  integrand(:) = dHdr(:)/(betan**2)                     ! pimd_par.f90:379
+  deallocate(x, p, b, dbdl, dHdr, gid)
+end subroutine pimdk_propagate_tasks
