@@ -8,7 +8,10 @@
 //   stage 0  setup    thread = energy   displaced geometry (Vprime's in-place +eps/-2eps/+eps walk), COM
 //                                       alignment, Radau embedding, PJT2 monomers   -> 36 coordinates + emon
 //   stage 1  sapt     thread = (energy, flexible|rigid geometry)   SAPT-5s'f site-site sum + dipole induction
-//   stage 2  rigid    thread = energy   CCpol-8s: iterated induction, 625-pair exponential sweep, elst, dispersion
+//   stage 2a rigid    thread = energy   CCpol-8s: iterated induction (indN_iter), damped electrostatics, dispersion
+//   stage 2b sweep    8 lanes = energy  CCpol-8s: U0's 625-pair exponential sweep; each lane owns whole bins of
+//                                       aj(144) and walks them in the reference's pair order (registers ->
+//                                       shared memory, no local memory); lane 0 then forms Erigid
 //   stage 3  combine  thread = (geometry, component)   V+ and V-  -> central difference, drift write-back
 // Staging buffers are structure-of-arrays [field][energy] so every stage reads and writes coalesced;
 // 320 B per energy against ~1e5 FP64 operations.  Each stage has its own register budget / occupancy.
@@ -36,13 +39,21 @@ namespace {
 #ifndef PIMDK_RIGID_MINB
 #define PIMDK_RIGID_MINB 5
 #endif
+#ifndef PIMDK_SWEEP_MINB
+#define PIMDK_SWEEP_MINB 5
+#endif
 constexpr int kSetupBlock = 128;
 constexpr int kSaptBlock = 128;
 constexpr int kRigidBlock = 128;
-constexpr int kFields = 40;  // 18 flexible + 18 rigid coordinates, emon, val, vall, erigid
-enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39 };
+constexpr int kSweepBlock = 128;                          // 16 energies x 8 lanes
+constexpr int kSweepEnergies = kSweepBlock / kSweepLanes;
+constexpr int kSweepDoubles = 75 + 75 + 148;              // sites of A, sites of B, 4 x (36 bins + 1 dummy), per energy
+constexpr int kFields = 42;  // 18 flexible + 18 rigid coordinates, emon, val, vall, erigid, eind, a0u
+enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39, F_EIND = 40, F_A0U = 41 };
 constexpr int kTabBytes = (int)((sizeof(CcpolDev) + 15) / 16 * 16);
-static_assert(kRigidTableBytes >= (int)offsetof(CcpolDev, param) && kRigidTableBytes <= kTabBytes, "rigid block covers the leading members");
+constexpr int kRigidTableBytes = (int)PIMDK_RIGID_TABLE_BYTES;
+constexpr int kSaptTableBytes = kTabBytes - kRigidTableBytes;
+static_assert(kRigidTableBytes % 16 == 0 && kSaptTableBytes % 16 == 0, "table blocks are staged in 16-byte granules");
 
 template <int BYTES>
 __device__ __forceinline__ const CcpolDev& stage_tables(const CcpolDev* __restrict__ g, unsigned char* smem) {
@@ -104,8 +115,15 @@ KNAME(ccpol_setup_kernel)(int iemonomer, GeomLayout L, const double* __restrict_
 __global__ void __launch_bounds__(kSaptBlock, PIMDK_SAPT_MINB)
 KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const CcpolDev& T = stage_tables<kTabBytes>(tab, smem);
-  double* scr_base = reinterpret_cast<double*>(smem + kTabBytes);
+  // stage only the SAPT-5s'f members (param .. pairflags); T is a view whose leading (rigid) members are not backed
+  {
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + kRigidTableBytes);
+    int4* dst = reinterpret_cast<int4*>(smem);
+    for (int i = threadIdx.x; i < kSaptTableBytes / (int)sizeof(int4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const CcpolDev& T = *reinterpret_cast<const CcpolDev*>(smem - kRigidTableBytes);
+  double* scr_base = reinterpret_cast<double*>(smem + kSaptTableBytes);
   const long j = (long)blockIdx.x * kSaptBlock + threadIdx.x;
   if (j >= 2 * ne) return;
   const int which = j >= ne;  // 0: flexible geometry (val), 1: embedded rigid geometry (vall)
@@ -123,12 +141,11 @@ KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __re
   buf[(which ? F_VALL : F_VAL) * ne + e] = sapt5sf(T, scr, ca, cb);
 }
 
-// ---- stage 2 ------------------------------------------------------------------------------------
+// ---- stage 2a -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRigidBlock, PIMDK_RIGID_MINB)
 KNAME(ccpol_rigid_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf, int* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem[];
   const CcpolDev& T = stage_tables<kRigidTableBytes>(tab, smem);  // only the CCpol-8s members are valid here
-  double* scr_base = reinterpret_cast<double*>(smem + kRigidTableBytes);
   const long e = (long)blockIdx.x * kRigidBlock + threadIdx.x;
   if (e >= ne) return;
   double rg[6][3];
@@ -136,10 +153,110 @@ KNAME(ccpol_rigid_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __r
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int k = 0; k < 3; ++k) rg[i][k] = buf[(F_RIGID + i * 3 + k) * ne + e];
-  Scratch<kRigidBlock> scr{scr_base + threadIdx.x};
+  Frame fa, fb;
+  rigid_frames(rg, fa, fb);
   int fl = 0;
-  buf[F_ERIG * ne + e] = ccpol8s_dimer(T, scr, rg, &fl);
+  buf[F_EIND * ne + e] = ind2_iter(T, fa, fb, &fl);
+  buf[F_A0U * ne + e] = u0_elst_disp(T, fa, fb);
   if (fl) atomicOr(flags, PIMDK_FLAG_NOCONV);
+}
+
+// ---- stage 2b -----------------------------------------------------------------------------------
+// U0 (proc_ccpol8s-dimer_xyz_ncd.f:118-233): the reference walks the 25x25 site pairs in (nsA, nsB) order and
+// adds e^{-beta R} R^p (p = 0..3) into one of 36x4 bins aj(ind) chosen by the pair of site classes.  The sums
+// of different bins are independent, so the 36 bins are dealt to 8 lanes (static longest-processing-time
+// schedule built on the host, ~79 pairs per lane); each lane walks its bins' pairs in the reference's order
+// with the four sums in registers, i.e. performs exactly the reference's additions per bin, and writes each
+// finished bin once to shared memory.  Lane 0 then forms E = Eind + sum_nl c(nl) aj(nl) + a0 in the
+// reference's order (:105-110).
+__global__ void __launch_bounds__(kSweepBlock, PIMDK_SWEEP_MINB)
+KNAME(ccpol_sweep_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const CcpolDev& T = stage_tables<kRigidTableBytes>(tab, smem);
+  double* es = reinterpret_cast<double*>(smem + kRigidTableBytes) + (threadIdx.x / kSweepLanes) * kSweepDoubles;
+  double* sA = es;          // sites of monomer A, 25 x 3
+  double* sB = es + 75;     // sites of monomer B
+  double* aj = es + 150;    // finished bins
+  const int lane = threadIdx.x % kSweepLanes;
+  const long e = (long)blockIdx.x * kSweepEnergies + threadIdx.x / kSweepLanes;
+  const bool active = e < ne;
+  const long ec = active ? e : ne - 1;   // lanes of a partial last group still take part in the warp syncs
+  {
+    double rg[6][3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) rg[i][k] = buf[(F_RIGID + i * 3 + k) * ne + ec];
+    Frame fa, fb;
+    rigid_frames(rg, fa, fb);
+    // fill_sites (:487-548): the group's 50 sites, dealt round-robin to its lanes
+#pragma unroll 1
+    for (int s = lane; s < 50; s += kSweepLanes) {
+      double r[3];
+      if (s < 25) {
+        frame_site(T, fa, s, r);
+        sA[s * 3 + 0] = r[0]; sA[s * 3 + 1] = r[1]; sA[s * 3 + 2] = r[2];
+      } else {
+        frame_site(T, fb, s - 25, r);
+        sB[(s - 25) * 3 + 0] = r[0]; sB[(s - 25) * 3 + 1] = r[1]; sB[(s - 25) * 3 + 2] = r[2];
+      }
+    }
+  }
+  __syncwarp();
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  const uint64_t* sched = T.sweep[lane];
+  const int nquads = T.sweep_quads;
+  // one quad (four site pairs of one bin) per iteration: the four distance / sqrt / exp chains are
+  // independent instruction streams, the sums are then added in the reference's order
+#pragma unroll 1
+  for (int i = 0; i < nquads; ++i) {
+    const uint64_t w = sched[i];
+    const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+    const int bin = (hi >> 24) & 0x3f;
+    const double beta = T.bin_beta[bin];
+    double R[4], e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t d = (uint32_t)(w >> (14 * q));
+      u0_pair(&sA[d & 0x7f], &sB[(d >> 7) & 0x7f], beta, R[q], e[q]);
+    }
+    (void)lo;
+    if (hi & (1u << 30)) { acc0 = 0.0; acc1 = 0.0; acc2 = 0.0; acc3 = 0.0; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc0 = acc0 + e[q];
+      acc1 = acc1 + e[q] * R[q];
+      acc2 = acc2 + e[q] * R[q] * R[q];
+      acc3 = acc3 + e[q] * R[q] * R[q] * R[q];
+    }
+    if (hi & (1u << 31)) {
+      aj[bin] = acc0; aj[bin + 37] = acc1; aj[bin + 74] = acc2; aj[bin + 111] = acc3;
+    }
+  }
+  if (lane == kSweepLanes - 1) {  // bins outside the quad schedule (the single O-O pair), pair by pair
+    for (int i = 0; i < T.sweep_ntail; ++i) {
+      const uint32_t d = T.sweep_tail[i];
+      const int bin = (d >> 14) & 0x3f;
+      double R, ee;
+      u0_pair(&sA[d & 0x7f], &sB[(d >> 7) & 0x7f], T.bin_beta[bin], R, ee);
+      if (d & (1u << 20)) { acc0 = 0.0; acc1 = 0.0; acc2 = 0.0; acc3 = 0.0; }
+      acc0 = acc0 + ee;
+      acc1 = acc1 + ee * R;
+      acc2 = acc2 + ee * R * R;
+      acc3 = acc3 + ee * R * R * R;
+      if (d & (1u << 21)) {
+        aj[bin] = acc0; aj[bin + 37] = acc1; aj[bin + 74] = acc2; aj[bin + 111] = acc3;
+      }
+    }
+  }
+  __syncwarp();
+  if (active && lane == 0) {
+    double E = buf[F_EIND * ne + e];
+#pragma unroll 4
+    for (int nl = 0; nl < 144; ++nl) E = E + T.cc[nl] * aj[nl + nl / 36];  // bins stored 37 apart (dummy bin 36)
+    E = E + buf[F_A0U * ne + e];
+    buf[F_ERIG * ne + e] = E * 627.510;
+  }
 }
 
 // ---- stage 3 ------------------------------------------------------------------------------------
@@ -176,8 +293,9 @@ KNAME(ccpol_combine_kernel)(int iemonomer, double V0, GeomLayout L, double* __re
   }
 }
 
-size_t sapt_smem() { return kTabBytes + (size_t)kSaptSlots * kSaptBlock * sizeof(double); }
-size_t rigid_smem() { return kRigidTableBytes + (size_t)kRigidSlots * kRigidBlock * sizeof(double); }
+size_t sapt_smem() { return kSaptTableBytes + (size_t)kSaptSlots * kSaptBlock * sizeof(double); }
+size_t rigid_smem() { return kRigidTableBytes; }
+size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepEnergies * kSweepDoubles * sizeof(double); }
 
 }  // namespace
 
@@ -196,6 +314,8 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, double V0, G
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(KNAME(ccpol_rigid_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rigid_smem());
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(KNAME(ccpol_sweep_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem());
+    if (e != cudaSuccess) return e;
     attr = true;
   }
   const int g = grad != nullptr;
@@ -207,6 +327,7 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, double V0, G
     KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, L, x, g0, ne, g, work);
     KNAME(ccpol_sapt_kernel)<<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
     KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, rigid_smem(), st>>>(tab, ne, work, flags);
+    KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + kSweepEnergies - 1) / kSweepEnergies), kSweepBlock, sweep_smem(), st>>>(tab, ne, work);
     const long nt = g ? ne / 2 : ne;
     KNAME(ccpol_combine_kernel)<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(iemonomer, V0, L, x, g0, ne, g, work, v, grad, write_drift, flags);
   }

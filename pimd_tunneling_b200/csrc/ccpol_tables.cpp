@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -337,6 +338,82 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
   for (int b = 0; b < 25; ++b)
     for (int a = 0; a < 25; ++a)
       if (h.ind_beta[b * 25 + a] == 0) { g_msg = "ind_beta has empty entries; not supported"; return g_msg.c_str(); }
+  // ---- U0 sweep schedule: bins -> lanes (LPT), pairs of a bin in the reference's order
+  {
+    struct Bin { int ca, cb, i0, npairs; };
+    std::vector<Bin> bins;
+    for (int ca = 0; ca < o->ncls; ++ca)
+      for (int cb = ca; cb < o->ncls; ++cb) {
+        const int a0 = o->cls_start[ca], na = o->cls_start[ca + 1] - a0;
+        const int b0 = o->cls_start[cb], nb = o->cls_start[cb + 1] - b0;
+        const int ib = h.ind_beta[b0 * 25 + a0];
+        int indlin = ib - 98;
+        if (indlin < 0) indlin += 65;
+        if (indlin < 1 || indlin > 36) { g_msg = "ind_beta maps outside the 36 bins"; return g_msg.c_str(); }
+        // every pair of the two blocks must carry the same ind_beta (same bin, same beta)
+        for (int i = 0; i < na; ++i)
+          for (int j = 0; j < nb; ++j)
+            if (h.ind_beta[(b0 + j) * 25 + a0 + i] != ib || h.ind_beta[(a0 + i) * 25 + b0 + j] != ib) {
+              g_msg = "ind_beta is not constant on site-class blocks";
+              return g_msg.c_str();
+            }
+        bins.push_back({ca, cb, indlin - 1, na * nb * (ca == cb ? 1 : 2)});
+        o->bin_beta[indlin - 1] = h.params[ib - 1];
+      }
+    if (bins.size() != 36) { g_msg = "expected 36 site-class pair bins"; return g_msg.c_str(); }
+    auto pairs_of = [&](const Bin& b) {
+      std::vector<std::pair<int, int>> v;
+      const int a0 = o->cls_start[b.ca], na = o->cls_start[b.ca + 1] - a0;
+      const int b0 = o->cls_start[b.cb], nb = o->cls_start[b.cb + 1] - b0;
+      for (int i = 0; i < na; ++i)        // block (A-class ca) x (B-class cb)
+        for (int j = 0; j < nb; ++j) v.emplace_back(a0 + i, b0 + j);
+      if (b.ca != b.cb)
+        for (int i = 0; i < nb; ++i)      // block (A-class cb) x (B-class ca): later in the reference's sweep
+          for (int j = 0; j < na; ++j) v.emplace_back(b0 + i, a0 + j);
+      return v;
+    };
+    std::vector<int> order;
+    o->sweep_ntail = 0;
+    for (size_t i = 0; i < bins.size(); ++i) {
+      if (bins[i].npairs % 4 == 0) { order.push_back((int)i); continue; }
+      auto v = pairs_of(bins[i]);
+      if (o->sweep_ntail + (int)v.size() > 8) { g_msg = "too many U0 pairs outside the quad schedule"; return g_msg.c_str(); }
+      for (size_t k = 0; k < v.size(); ++k)
+        o->sweep_tail[o->sweep_ntail++] = (uint32_t)(v[k].first * 3) | (uint32_t)(v[k].second * 3) << 7 |
+                                          (uint32_t)bins[i].i0 << 14 | (k == 0 ? 1u << 20 : 0u) |
+                                          (k + 1 == v.size() ? 1u << 21 : 0u);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bins[x].npairs > bins[y].npairs; });
+    int load[kSweepLanes] = {0};
+    std::vector<int> lane_bins[kSweepLanes];
+    for (int idx : order) {
+      int best = 0;
+      for (int l = 1; l < kSweepLanes; ++l)
+        if (load[l] < load[best]) best = l;
+      lane_bins[best].push_back(idx);
+      load[best] += bins[idx].npairs / 4;
+    }
+    o->sweep_quads = 0;
+    for (int l = 0; l < kSweepLanes; ++l) o->sweep_quads = load[l] > o->sweep_quads ? load[l] : o->sweep_quads;
+    if (o->sweep_quads > kSweepMaxQuads) { g_msg = "U0 sweep schedule longer than kSweepMaxQuads"; return g_msg.c_str(); }
+    for (int l = 0; l < kSweepLanes; ++l) {
+      int pos = 0;
+      for (int idx : lane_bins[l]) {
+        auto v = pairs_of(bins[idx]);
+        for (size_t k = 0; k < v.size(); k += 4) {
+          uint64_t w = 0;
+          for (int q = 0; q < 4; ++q)
+            w |= (uint64_t)((uint32_t)(v[k + q].first * 3) | (uint32_t)(v[k + q].second * 3) << 7) << (14 * q);
+          w |= (uint64_t)bins[idx].i0 << 56;
+          if (k == 0) w |= 1ull << 62;
+          if (k + 4 == v.size()) w |= 1ull << 63;
+          o->sweep[l][pos++] = w;
+        }
+      }
+      // padding quads: four copies of pair (0,0) summed into the dummy bin 36, first and last at once
+      for (; pos < kSweepMaxQuads; ++pos) o->sweep[l][pos] = 36ull << 56 | 1ull << 62 | 1ull << 63;
+    }
+  }
   o->iemonomer = iemonomer;
   o->V0 = 0.0;
   return "";

@@ -2,6 +2,7 @@
 // main_CCpol-8sf.f:6-11), trimmed to what the hot path reads and laid out for shared-memory
 // staging: every access in the kernels is warp-uniform, so a table read is one broadcast LDS.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 namespace pimdk {
@@ -9,6 +10,8 @@ namespace pimdk {
 constexpr int kNType = 5;      // SAPT-5s'f site types actually used (1..5; type 6 never occurs)
 constexpr int kNParab = 84;
 constexpr int kNParam = 18;
+constexpr int kSweepLanes = 8;     // lanes that share one energy in the CCpol-8s exponential sweep
+constexpr int kSweepMaxQuads = 24;  // 624 pairs / 8 lanes / 4 = 19.5 quads per lane; LPT packing needs <= 24
 
 struct CcpolDev {
   // ---- CCpol-8s rigid model (the only part the rigid stage stages into shared memory) ----
@@ -27,6 +30,20 @@ struct CcpolDev {
   uint8_t pad0_[5];
   int32_t ncls;
   int32_t iemonomer;
+  // U0 sweep schedule for kSweepLanes lanes per energy.  Each of the 36 bins aj(ind) is owned by one lane,
+  // which walks the bin's site pairs in the reference's (nsA, nsB) order (block (ca,cb), then block
+  // (cb,ca)), four pairs ("quad") per loop iteration.  A quad is one 64-bit word:
+  //   bits  0..55  four pairs, 14 bits each: 3*nsA | 3*nsB << 7
+  //   bits 56..61  bin (36 = dummy bin used by padding quads), bit 62 first quad of the bin, bit 63 last
+  // Bins are dealt to lanes by a longest-processing-time rule.  Bins whose pair count is not a multiple
+  // of four (only O-O, one pair, for data_ccdata) are walked pair by pair from `sweep_tail`
+  // (3*nsA | 3*nsB << 7 | bin << 14 | first << 20 | last << 21) by the last lane.
+  alignas(8) uint64_t sweep[kSweepLanes][kSweepMaxQuads];
+  double bin_beta[37];                       // beta of each bin (params(ind_beta) of its site pairs); [36] dummy
+  uint32_t sweep_tail[8];
+  int32_t sweep_quads;                       // quads per lane
+  int32_t sweep_ntail;
+  int32_t pad2_[2];                          // keeps `param` 16-byte aligned (staging granule)
   // ---- SAPT-5s'f flexible model ----
   double param[kNParam * kNType];            // param(k,t)         -> [(t-1)*18 + k-1]
   double parab[kNParab * kNType * kNType];   // parab(k,ta,tb)     -> [((tb-1)*5+(ta-1))*84 + k-1]
@@ -43,8 +60,8 @@ struct CcpolDev {
   uint8_t pairflags[kNType * kNType];
   uint8_t pad1_[3];
 };
-// bytes of the leading rigid-model block (multiple of 16)
-constexpr int kRigidTableBytes = 16 * ((144 + 134 + 75 + 5 + 1) * 8 / 16 + (625 + 5 + 25 + 54 + 26 + 5 + 8 + 15) / 16 + 1);
+// bytes of the leading rigid-model block = offset of the first SAPT member (a multiple of 16)
+#define PIMDK_RIGID_TABLE_BYTES (offsetof(::pimdk::CcpolDev, param))
 
 // Host-side full tables (same content as the reference's COMMON block) and loaders.
 struct CcpolHost {

@@ -181,9 +181,9 @@ int pes_eval_dev(GeomLayout L, double* x, double* v, double* grad, long ngeom, i
       if (!vv && !gg) continue;
       const size_t wb = fast ? ccpol_work_bytes_fast(ngeom, gg != nullptr) : ccpol_work_bytes_strict(ngeom, gg != nullptr);
       CU(g.wCc.ensure(wb));
-      const long per = (long)(40 * 8 * (gg ? 36 : 1));
+      const long per = (long)(42 * 8 * (gg ? 36 : 1));
       const long npass = (ngeom + (long)(g.wCc.cap / per) - 1) / (long)(g.wCc.cap / per);
-      Scope s("pes", (int)(4 * npass));
+      Scope s("pes", (int)(5 * npass));
       CU(fast ? launch_ccpol_fast(tab, g.hdev.iemonomer, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
                                   g.wCc.as<double>(), g.wCc.cap, g.stream)
               : launch_ccpol_strict(tab, g.hdev.iemonomer, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
