@@ -39,6 +39,9 @@ M_O, M_H = 15.9949146221 * 1822.888486, 1.0078250321 * 1822.888486
 # exp 1129, pow 33, trig 28
 FLOP_PER_ENERGY = 25156 + 33156 + 1760 + 806 + 1129 + 33 + 28
 FLOP_PER_BEAD_GRAD = {"ccpol8sf": 36 * FLOP_PER_ENERGY + 36, "2dtest": 6 * (2 + 14) + 12, "1d": 8}
+# DRAM bytes per bead-gradient of the CCpol pipeline, dram__bytes_read.sum + dram__bytes_write.sum summed over
+# its five kernels in one `ncu --set full` capture of a 32 768-bead pass (profiles/r1_ccpol_pipeline_final.md)
+CCPOL_DRAM_BYTES_PER_BEAD = None
 
 CONFIGS = {
     # name: pes, n, nintegral, nrep, thermostat, beta, Noutput
@@ -251,10 +254,10 @@ def run_ours(args, cfg, rank, world, local_rank):
             dist.all_reduce(s)
             sums_d.copy_(s)
 
-    # ---- device-resident timing ("value") ----
+    # ---- device-resident timing ("value"): CUDA events on the launching stream, no per-kernel profiling ----
     one_call(W, 1)                                     # W untimed warm-up steps
     barrier()
-    check(L.pimdk_profile(1))
+    check(L.pimdk_profile(0))
     check(L.pimdk_profile_reset())
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -267,6 +270,15 @@ def run_ours(args, cfg, rank, world, local_rank):
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
     launches = int(L.pimdk_launch_count())
+    # ---- a second pass of K steps with per-kernel-family CUDA events (roofline of the dominant kernels) ----
+    check(L.pimdk_profile(1))
+    check(L.pimdk_profile_reset())
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    one_call(K, 3)
+    p1.record()
+    torch.cuda.synchronize()
+    ms_prof = p0.elapsed_time(p1)
     pes_ms, pes_n = ctypes.c_double(), ctypes.c_int64()
     check(L.pimdk_profile_get(b"pes", ctypes.byref(pes_ms), ctypes.byref(pes_n)))
     fam = {}
@@ -328,11 +340,14 @@ def run_ours(args, cfg, rank, world, local_rank):
                     "deltaA": stats["deltaA"], "sigmaA": stats["sigmaA"]},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                         "frac": (achieved / peak.value) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak.value) if achieved else None,
+                         "traffic": (CCPOL_DRAM_BYTES_PER_BEAD * ntraj * n / 1e9) if (CCPOL_DRAM_BYTES_PER_BEAD and cfg["pes"] == "ccpol8sf") else None,
+                         "traffic_unit": "GB per step (all beads), from ncu dram__bytes_read+write per bead",
+                         "algorithmic_bytes": 32 * ndof * ntraj * n / 1e9,
                          "kernel": ("ccpol_{setup,sapt,rigid,combine}_kernel_" + args.mode + " (one PES-gradient pipeline)")
                          if cfg["pes"] == "ccpol8sf" else "simple_pes_kernel",
                          "kernel_ms_per_step": pes_ms.value / K, "kernel_launches": int(pes_n.value),
-                         "kernel_share_of_step": pes_ms.value / ms,
+                         "kernel_share_of_step": pes_ms.value / ms_prof,
                          "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "flop_per_bead_gradient": FLOP_PER_BEAD_GRAD[cfg["pes"]], "other_kernels_ms": fam},
             "clocks": sampler.summary(),

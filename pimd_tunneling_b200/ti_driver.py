@@ -1,0 +1,115 @@
+"""Native front end for a thermodynamic-integration run (row N1 of SURVEY §8f): what `program pimd`
+(pimd_par.f90) does around the hot path — namelist MCDATA with the reference's defaults (:60-88), wells and
+masses files (:119-165), V0 = V(well1) (:166), spline path (read_path), Gauss-Legendre nodes and end points
+(:212-221), the (lambda x repetition) task layout (:243-257, 281-295), ONE batched propagate call instead of
+the task loop (:321-381), and the statistics (:397-424) with one all-reduce instead of MPI_Gather (:389).
+Alignment of the wells (get_align/align_atoms) is the identity here (out of scope).  All
+numerical work is done by libpimdk.so."""
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import path as P
+from . import ti
+from .mcmod_mass import McmodMass
+from .verletint import ANDERSEN, PILE, VerletInt
+
+
+@dataclass
+class MCData:
+    """namelist /MCDATA/ with the defaults of pimd_par.f90:60-88 (only the members the hot path reads)"""
+    n: int = 100
+    beta: float = 100.0
+    NMC: int = 5000000
+    Noutput: int = 100000
+    dt: float = 1e-3
+    nintegral: int = 5
+    nrep: int = 1
+    thermostat: int = 1
+    ndim: int = 3
+    natom: int = 1
+    xunit: int = 1
+    imin: int = 0
+    tau: float = 1.0
+    gamma: float = 1.0
+    cayley: bool = False
+    fixedends: bool = True
+    dHdrlimit: float = -1.0
+    seed: int = 0
+    extra: dict = field(default_factory=dict)
+
+
+def read_namelist(text):
+    """&MCDATA key=value, ... /   (Fortran logicals .true./.false., d-exponents)"""
+    body = re.search(r"&\s*MCDATA(.*?)(/|&end)", text, flags=re.S | re.I)
+    if not body:
+        raise ValueError("no &MCDATA namelist found")
+    mc = MCData()
+    for key, val in re.findall(r"(\w+)\s*=\s*([^,\n/]+)", body.group(1)):
+        v = val.strip().strip("'\"")
+        lk = {f.lower(): f for f in mc.__dataclass_fields__}
+        if key.lower() not in lk:
+            mc.extra[key] = v
+            continue
+        name = lk[key.lower()]
+        cur = getattr(mc, name)
+        if isinstance(cur, bool):
+            setattr(mc, name, v.lower().startswith((".t", "t")))
+        elif isinstance(cur, int):
+            setattr(mc, name, int(float(v.lower().replace("d", "e"))))
+        else:
+            setattr(mc, name, float(v.lower().replace("d", "e")))
+    return mc
+
+
+def read_wells(path1, path2, masses_path, ndim, natom, xunit=1):
+    """well1.dat / well2.dat: natom lines of ndim numbers; masses.dat: label mass (pimd_par.f90:123-165)"""
+    w1 = np.loadtxt(path1, ndmin=2)[:natom, :ndim].T.copy()
+    w2 = np.loadtxt(path2, ndmin=2)[:natom, :ndim].T.copy()
+    if xunit == 2:
+        w1, w2 = w1 / 0.529177, w2 / 0.529177
+    labels, mass = [], []
+    with open(masses_path) as f:
+        for line in f:
+            t = line.split()
+            if len(t) >= 2:
+                labels.append(t[0])
+                mass.append(float(t[1].lower().replace("d", "e")))
+    return np.asfortranarray(w1), np.asfortranarray(w2), np.array(mass[:natom]), labels[:natom]
+
+
+def run_ti(pes_name, mc, well1, well2, mass, path_points=None, rank=0, world=1, max_traj_per_call=None):
+    """One TI run.  Returns the statistics of pimd_par.f90:397-424 plus the per-trajectory integrands of this
+    rank.  With world > 1 (torch.distributed initialised) the estimator sums are all-reduced."""
+    pes = McmodMass(pes_name).V_init()
+    well1 = np.asfortranarray(well1, dtype=np.float64)
+    well2 = np.asfortranarray(well2, dtype=np.float64)
+    pes.set_V0(0.0)
+    pes.set_V0(pes.V(well1))                                   # V0 = V(well1), pimd_par.f90:166
+    if path_points is None:
+        path_points = np.stack([well1, well2], axis=0)
+    lam, path, spl = P.build_path(path_points)
+    vi = VerletInt(pes, mc.n, mass, mc.beta, tau=mc.tau, gamma=mc.gamma, dt=mc.dt, NMC=mc.NMC, imin=mc.imin,
+                   Noutput=mc.Noutput, cayley=mc.cayley, seed=mc.seed).init_nm()
+    xi, weights = vi.gauleg(0.0, 1.0, mc.nintegral)
+    xint, dbdxi = P.endpoints(lam, path, spl, xi)
+    ids = ti.global_ids(mc.nintegral, mc.nrep)
+    lo, hi = ti.shard(ids.size, rank, world)
+    gid = ids[lo:hi]
+    il = gid // mc.nrep
+    startpoint = np.asfortranarray(path[0])                    # startpoint(:,:) = path(1,:,:), :251
+    dH = np.empty(gid.size)
+    step = max_traj_per_call or gid.size or 1
+    for s in range(0, gid.size, step):
+        sl = slice(s, min(gid.size, s + step))
+        x, p = vi.init_path(xi[il[sl]], lam, path, spl, traj_gid=gid[sl])
+        b = np.asfortranarray(xint[:, :, il[sl]])
+        dbdl = np.asfortranarray(dbdxi[:, :, il[sl]])
+        fn = vi.propagate_pimd_pile if mc.thermostat == PILE else vi.propagate_pimd_nm
+        _, _, dH[sl] = fn(x, p, startpoint, b, dbdl, traj_gid=gid[sl])
+    sums = ti.allreduce_sums(ti.partial_sums(dH, gid, mc.nrep, mc.nintegral, vi.betan))
+    out = ti.finish(sums, weights, vi.betan)
+    out.update({"xi": xi, "weights": weights, "integrand": dH / vi.betan ** 2, "traj_gid": gid, "betan": vi.betan,
+                "V0": pes.V0})
+    return out

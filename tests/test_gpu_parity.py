@@ -337,3 +337,39 @@ def test_instanton_lbfgs_iterates_match(pk, orc):
     ig, fgpu = run(lambda x: im.UMforceenergy(x, a, b))
     io, fcpu = run(lambda x: orc.UMforceenergy(x, a, b))
     assert ig.shape == io.shape and relmax(ig, io) < RTOL and abs(fgpu - fcpu) <= RTOL * abs(fcpu)
+
+
+# ---------------------------------------------------------------- stochastic agreement ------------
+def test_ti_averages_agree_with_oracle_within_error_bars(pk, orc):
+    """north_star: stochastic TI averages must agree with the reference within combined statistical error bars.
+    1D double well, PILE: the GPU run and the CPU oracle use DIFFERENT seeds (independent samples); the per-lambda
+    means of dH/dlambda must agree within 4 combined standard errors, and so must Delta A."""
+    from pimd_tunneling_b200 import path as P
+    from pimd_tunneling_b200.ti_driver import MCData, run_ti
+
+    mc = MCData(n=16, beta=6.0, NMC=1500, imin=300, dt=5e-3, nintegral=4, nrep=48, thermostat=2, ndim=1, natom=1, seed=2024)
+    a, b = np.array([[-1.0]]), np.array([[1.0]])
+    res = run_ti("1d", mc, a, b, [1.0])
+    nrep_o = 24
+    orc.select("1d")
+    betan = mc.beta / (mc.n + 1)
+    lam, path, spl = P.build_path(np.stack([a, b], axis=0))
+    xint, dbd = P.endpoints(lam, path, spl, res["xi"])
+    I = np.empty((mc.nintegral, nrep_o))
+    for k in range(mc.nintegral):
+        for r in range(nrep_o):
+            orc.nm_setup(mc.n, [1.0], betan, 1.0, 1.0, mc.dt)
+            orc.init_nm(a, xint[..., k])
+            orc.set_rng(777, 100000 + k * nrep_o + r)
+            x0, p0 = orc.init_path(float(res["xi"][k]), lam, path, spl)
+            _, _, d = orc.propagate(2, x0, p0, dbd[..., k], mc.NMC, mc.imin)
+            I[k, r] = d / betan ** 2
+    mo, so = I.mean(axis=1), I.std(axis=1, ddof=1) / np.sqrt(nrep_o)
+    mg, sg = res["mean"], np.sqrt(np.maximum(res["var"], 0) / (mc.nrep - 1))
+    z = np.abs(mg - mo) / np.sqrt(so ** 2 + sg ** 2)
+    assert np.all(z < 4.0), (z, mg, mo)
+    dA_o = np.sum(res["weights"] * mo)
+    s_dA = np.sqrt(np.sum(res["weights"] ** 2 * (so ** 2 + sg ** 2)))
+    assert abs(res["deltaA"] - dA_o) < 4.0 * s_dA
+    # symmetric double well: the integrand is antisymmetric about lambda = 1/2, so Delta A ~ 0 within noise
+    assert abs(res["deltaA"]) < 5.0 * np.sqrt(np.sum(res["weights"] ** 2 * sg ** 2)) + 1e-12

@@ -140,3 +140,13 @@ def test_two_rank_estimator_allreduce_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_namelist_reader_defaults_and_overrides():
+    from pimd_tunneling_b200.ti_driver import MCData, read_namelist
+
+    d = MCData()
+    assert (d.n, d.beta, d.NMC, d.Noutput, d.dt, d.nintegral, d.nrep, d.thermostat) == (100, 100.0, 5000000, 100000, 1e-3, 5, 1, 1)
+    mc = read_namelist("&MCDATA\n n=64, beta=10.0d0, NMC=2000, thermostat=2,\n nintegral=8, nrep=4, cayley=.true., basename='x'\n/\n")
+    assert (mc.n, mc.beta, mc.NMC, mc.thermostat, mc.nintegral, mc.nrep, mc.cayley) == (64, 10.0, 2000, 2, 8, 4, True)
+    assert mc.extra == {"basename": "x"} and mc.tau == 1.0 and mc.gamma == 1.0
