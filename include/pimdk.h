@@ -53,6 +53,9 @@ int pimdk_set_stream(void* cuda_stream);
 /* PIMDK_MODE_STRICT (default): CCpol arithmetic in the reference's operation order without FMA
  * contraction; PIMDK_MODE_FAST: same kernels with contraction. */
 int pimdk_set_mode(pimdk_int mode);
+/* Small systems (1D/2D surfaces, n <= 128 beads) are propagated by one persistent warp-per-ring-polymer
+ * kernel (default on); 0 forces the streamed multi-kernel path.  Both give bit-identical results. */
+int pimdk_set_fused(pimdk_int enable);
 
 /* ---- PES plugin: module mcmod_mass -------------------------------------------------------
  * pimdk_pes_select  = V_init  (mcmod_1d.f90:8, mcmod_2dtest.f90:11, mcmod_waterdimer_ccpol.f90:9

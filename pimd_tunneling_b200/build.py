@@ -23,6 +23,7 @@ UNITS = [
     ("ccpol_kernels.cu", "ccpol_fast.o", ["-fmad=true", "-DPIMDK_CCPOL_STRICT=0"]),
     ("pes_simple.cu", "pes_simple.o", ["-fmad=false"]),
     ("nm_kernels.cu", "nm_kernels.o", ["-fmad=false"]),
+    ("fused_small.cu", "fused_small.o", ["-fmad=false"]),
     ("um_kernels.cu", "um_kernels.o", ["-fmad=false"]),
     ("fp64_peak.cu", "fp64_peak.o", ["-fmad=false"]),
     ("pimdk_api.cu", "pimdk_api.o", ["-fmad=false"]),

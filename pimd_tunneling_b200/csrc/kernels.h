@@ -97,6 +97,13 @@ cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* 
                              cudaStream_t st);
 cudaError_t launch_scale(double* v, double s, long n, cudaStream_t st);
 
+// ---- fused warp-per-ring-polymer propagation for small systems (fused_small.cu) ----
+bool fused_small_supported(PesKind kind, int n, int ndim, int natom);
+cudaError_t launch_fused_small(const NmTables& nm, PesKind kind, const SimplePesParams& pp, int thermostat, long ntraj,
+                               double* x, double* p, const double* a, const double* b, const double* dbdl, double dt,
+                               long NMC, long imin, double lambda, uint64_t seed, const int64_t* gid, double* dHdr,
+                               int* flags, cudaStream_t st);
+
 // ---- ring-polymer potential (um_kernels.cu): instantonmod.f90:17-151 ----
 cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double* a, const double* b,
                       const double* mass, double betan, int fixedends, const double* vbead /*n or NULL*/,

@@ -54,6 +54,7 @@ struct Ctx {
   std::string data_dir = ".";
   std::string err;
   int mode = PIMDK_MODE_STRICT;
+  bool fused = true;  // small systems: one persistent warp-per-ring-polymer kernel
   // PES
   PesKind pes = PES_NONE;
   int ndim = 0, natom = 0;
@@ -341,6 +342,11 @@ int pimdk_finalize(void) {
 
 int pimdk_set_stream(void* s) {
   g.stream = reinterpret_cast<cudaStream_t>(s);
+  return PIMDK_OK;
+}
+
+int pimdk_set_fused(pimdk_int enable) {
+  g.fused = enable != 0;
   return PIMDK_OK;
 }
 
@@ -682,6 +688,17 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   rc = clear_flags();
   if (rc) return rc;
   const int64_t* dgid = reinterpret_cast<const int64_t*>(traj_gid);
+  if (g.fused && fused_small_supported(g.pes, n, g.nm_ndim, g.nm_natom)) {
+    {
+      Scope s("fused");
+      CU(launch_fused_small(nm, g.pes, g.sp, (int)thermostat, ntraj, x, p, a, b, dbdl, dt, NMC, imin, (double)Noutput, seed,
+                            dgid, dHdr, g.wFlags.as<int>(), g.stream));
+    }
+    rc = check_flags(false);
+    g.last_nan_traj = -1;
+    if (g.profiling) resolve_spans();
+    return rc;
+  }
   double *P = g.wP.as<double>(), *Q = g.wQ.as<double>(), *G = g.wG.as<double>(), *Gn = g.wGn.as<double>();
   int* flags = g.wFlags.as<int>();
   GeomLayout L{n, (long)ndof * n, 1, n};

@@ -241,6 +241,27 @@ def test_propagate_matches_oracle(pk, orc, case):
         assert abs(dg[t] - do) <= RTOL * abs(do)
 
 
+@pytest.mark.parametrize("name,n,mass", [("1d", 64, [1.0]), ("1d", 37, [1.3]), ("2dtest", 48, [1.0]), ("2dtest", 128, [1.0])])
+@pytest.mark.parametrize("thermostat", [1, 2])
+def test_fused_small_system_kernel_equals_streamed_path(pk, name, n, mass, thermostat):
+    """the persistent warp-per-ring-polymer kernel and the streamed GEMM path give the same bits"""
+    from pimd_tunneling_b200._lib import check, lib
+
+    pes = pk.McmodMass(name).V_init()
+    a, b = _wells(name)
+    vi = pk.VerletInt(pes, n, mass, 10.0, NMC=40, imin=5, Noutput=6, seed=5).init_nm()
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, 9, a, b, 0.05, mass)
+    gid = np.arange(9, dtype=np.int64) + 100
+    fn = vi.propagate_pimd_pile if thermostat == 2 else vi.propagate_pimd_nm
+    out = []
+    for fused in (1, 0):
+        check(lib().pimdk_set_fused(fused))
+        out.append(fn(x, p, a, bt, dbdl, traj_gid=gid))
+    check(lib().pimdk_set_fused(1))
+    for u, v in zip(out[0], out[1]):
+        assert np.array_equal(u, v)
+
+
 def test_partition_invariance_and_imin(pk):
     """results depend on the global trajectory id only, not on how trajectories are batched/sharded"""
     pes = pk.McmodMass("2dtest").V_init()
