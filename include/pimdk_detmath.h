@@ -119,18 +119,14 @@ PIMDK_HD double pimdk_exp_poly(double r) {
   for (int i = 1; i < 14; ++i) p = PIMDK_FMA(p, r, PIMDK_TAB(exp)[i]);
   return p;
 }
-PIMDK_HD double pimdk_exp(double x) {
-  const double shifter = 6755399441055744.0; /* 1.5 * 2^52 */
-#if defined(__CUDA_ARCH__)
-  if (fabs(x) < 700.0) {
-    double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
-    int k = __double2loint(t);
-    double kd = PIMDK_SUB(t, shifter);
-    double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x);
-    r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);
-    return PIMDK_MUL(pimdk_exp_poly(r), __hiloint2double((k + 1023) << 20, 0));
-  }
+/* general path: any x (the device keeps it out of line so that each inlined copy of pimdk_exp is only
+ * the ~22-instruction fast path; the hot kernels' code must stay inside the 32 KB instruction cache) */
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__ double pimdk_exp_general(double x) {
+#else
+static inline double pimdk_exp_general(double x) {
 #endif
+  const double shifter = 6755399441055744.0; /* 1.5 * 2^52 */
   if (!(x > -708.0)) return (x != x) ? x : 0.0;
   if (x > 709.0) return pimdk_u2d(0x7ff0000000000000ull);
   double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
@@ -144,6 +140,20 @@ PIMDK_HD double pimdk_exp(double x) {
   double s1 = pimdk_u2d((uint64_t)(k1 + 1023) << 52);
   double s2 = pimdk_u2d((uint64_t)(k2 + 1023) << 52);
   return PIMDK_MUL(PIMDK_MUL(p, s1), s2);
+}
+PIMDK_HD double pimdk_exp(double x) {
+#if defined(__CUDA_ARCH__)
+  if (fabs(x) < 700.0) {
+    const double shifter = 6755399441055744.0;
+    double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
+    int k = __double2loint(t);
+    double kd = PIMDK_SUB(t, shifter);
+    double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x);
+    r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);
+    return PIMDK_MUL(pimdk_exp_poly(r), __hiloint2double((k + 1023) << 20, 0));
+  }
+#endif
+  return pimdk_exp_general(x);
 }
 
 /* log(x), x > 0 finite normal: x = 2^e m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s),

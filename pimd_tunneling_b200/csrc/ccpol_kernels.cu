@@ -34,7 +34,7 @@ namespace pimdk {
 namespace {
 
 #ifndef PIMDK_SAPT_MINB
-#define PIMDK_SAPT_MINB 3
+#define PIMDK_SAPT_MINB 1
 #endif
 #ifndef PIMDK_RIGID_MINB
 #define PIMDK_RIGID_MINB 5
@@ -43,13 +43,20 @@ namespace {
 #define PIMDK_SWEEP_MINB 5
 #endif
 constexpr int kSetupBlock = 128;
-constexpr int kSaptBlock = 128;
+#ifndef PIMDK_SAPT_BLOCK
+#define PIMDK_SAPT_BLOCK 512
+#endif
+constexpr int kSaptBlock = PIMDK_SAPT_BLOCK;
+
 constexpr int kRigidBlock = 128;
 constexpr int kSweepBlock = 128;                          // 16 energies x 8 lanes
 constexpr int kSweepEnergies = kSweepBlock / kSweepLanes;
 constexpr int kSweepDoubles = 75 + 75 + 148;              // sites of A, sites of B, 4 x (36 bins + 1 dummy), per energy
-constexpr int kFields = 42;  // 18 flexible + 18 rigid coordinates, emon, val, vall, erigid, eind, a0u
-enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39, F_EIND = 40, F_A0U = 41 };
+// staging fields per energy: 18 flexible + 18 rigid coordinates, emon, val, vall, erigid, eind, a0u, then the
+// SAPT-5s'f sites: 4 blocks (flexible A, flexible B, rigid A, rigid B) of 24 site coordinates + 3 symmetry coordinates
+constexpr int kSiteFields = 27;
+constexpr int kFields = 44 + 4 * kSiteFields;
+enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39, F_EIND = 40, F_A0U = 41, F_FCIND = 42, F_SITES = 44 };
 constexpr int kTabBytes = (int)((sizeof(CcpolDev) + 15) / 16 * 16);
 constexpr int kRigidTableBytes = (int)PIMDK_RIGID_TABLE_BYTES;
 constexpr int kSaptTableBytes = kTabBytes - kRigidTableBytes;
@@ -111,11 +118,50 @@ KNAME(ccpol_setup_kernel)(int iemonomer, GeomLayout L, const double* __restrict_
   buf[F_EMON * ne + e] = emon;
 }
 
-// ---- stage 1 ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSaptBlock, PIMDK_SAPT_MINB)
-KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
+// ---- stage 1a -----------------------------------------------------------------------------------
+// set_sites (proc_sapt5sf_new_ncd.f:1574-1758) for the four monomer geometries of an energy (flexible A, B and
+// embedded-rigid A, B): thread = (energy, geometry block).  8 sites (Angstrom) + symmetry coordinates s1..s3.
+struct GlobalSlots {  // set_sites' output sink: slot k of this thread's block lives at p[k * stride]
+  double* p;
+  long stride;
+  __device__ __forceinline__ double& operator[](int k) const { return p[k * stride]; }
+};
+__global__ void __launch_bounds__(128)
+KNAME(ccpol_sites_kernel)(long ne, double* __restrict__ buf) {
+  const long i = (long)blockIdx.x * 128 + threadIdx.x;
+  if (i >= 4 * ne) return;
+  const int blk = (int)(i / ne);             // 0 flexible A, 1 flexible B, 2 rigid A, 3 rigid B
+  const long e = i - blk * ne;
+  const int f0 = blk * 9;                    // F_FLEX + {0, 9}, F_RIGID + {0, 9}
+  const double a0 = 0.529177249;
+  double c[3][3], s[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[a][k] = fast_div(buf[(f0 + a * 3 + k) * ne + e], a0);
+  GlobalSlots out{buf + (long)(F_SITES + blk * kSiteFields) * ne + e, ne};
+  set_sites(c, out, 0, s);
+  out[24] = s[0];
+  out[25] = s[1];
+  out[26] = s[2];
+}
+
+// ---- stage 1b -----------------------------------------------------------------------------------
+// dipind (proc_sapt5sf_new_ncd.f:1363-1533): thread = item (an energy's flexible or embedded-rigid geometry).
+// Kept apart from the site-pair kernel: it runs once per item but is 27 KB of code (cbrt, pow, damping), and
+// the pair kernel's loop has to stay inside the 32 KB instruction cache.
+struct GlobalSites {  // slot k of the item in the staging buffer: sites of A, s of A, sites of B, s of B
+  const double* p;
+  long stride;
+  // k: 0..23 sites of A, 24..47 sites of B, 48..50 s of A, 51..53 s of B
+  __device__ __forceinline__ double operator[](int k) const {
+    const int f = k < 24 ? k : (k < 48 ? k + 3 : (k < 51 ? k - 24 : k));
+    return __ldg(p + (long)f * stride);
+  }
+};
+__global__ void __launch_bounds__(128)
+KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
-  // stage only the SAPT-5s'f members (param .. pairflags); T is a view whose leading (rigid) members are not backed
   {
     const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + kRigidTableBytes);
     int4* dst = reinterpret_cast<int4*>(smem);
@@ -123,22 +169,44 @@ KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __re
     __syncthreads();
   }
   const CcpolDev& T = *reinterpret_cast<const CcpolDev*>(smem - kRigidTableBytes);
-  double* scr_base = reinterpret_cast<double*>(smem + kSaptTableBytes);
+  const long j = (long)blockIdx.x * 128 + threadIdx.x;
+  if (j >= 2 * ne) return;
+  const int which = j >= ne;
+  const long e = which ? j - ne : j;
+  GlobalSites S{buf + (long)(F_SITES + which * 2 * kSiteFields) * ne + e, ne};
+  const double sa[3] = {__ldg(S.p + 24 * ne), __ldg(S.p + 25 * ne), __ldg(S.p + 26 * ne)};
+  const double sb[3] = {__ldg(S.p + 51 * ne), __ldg(S.p + 52 * ne), __ldg(S.p + 53 * ne)};
+  buf[(F_FCIND + which) * ne + e] = dipind(T, S, sa, sb);
+}
+
+// ---- stage 1c -----------------------------------------------------------------------------------
+// poten's 8 x 8 site-pair sum (proc_sapt5sf_new_ncd.f:130-213) + dipind: thread = item.  Sites and symmetry
+// coordinates come from stage 1a through the staging buffer ([slot][item]: coalesced, L1-resident for the
+// CTA's lifetime), so the kernel needs no per-thread shared-memory scratch; parameter tables in shared memory
+// (every read warp-uniform -> broadcast).  One 512-thread CTA per SM: the pair loop is ~45 KB of straight-line
+// FP64 code, more than the instruction cache, and every thread follows the same path through it; warps that
+// start together stay close enough in the code that one warp's instruction fetch serves the others (measured:
+// 128-thread CTAs at equal or higher occupancy are 11% slower and stall on instruction fetch).
+__global__ void __launch_bounds__(kSaptBlock, PIMDK_SAPT_MINB)
+KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  // stage only the SAPT-5s'f members (param .. sapt_ntask); T is a view whose leading (rigid) members are not backed
+  {
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + kRigidTableBytes);
+    int4* dst = reinterpret_cast<int4*>(smem);
+    for (int i = threadIdx.x; i < kSaptTableBytes / (int)sizeof(int4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const CcpolDev& T = *reinterpret_cast<const CcpolDev*>(smem - kRigidTableBytes);
   const long j = (long)blockIdx.x * kSaptBlock + threadIdx.x;
   if (j >= 2 * ne) return;
-  const int which = j >= ne;  // 0: flexible geometry (val), 1: embedded rigid geometry (vall)
+  const int which = j >= ne;    // 0: flexible geometry (val), 1: embedded rigid geometry (vall)
   const long e = which ? j - ne : j;
-  const int f0 = which ? F_RIGID : F_FLEX;
-  double ca[3][3], cb[3][3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      ca[i][k] = buf[(f0 + i * 3 + k) * ne + e];
-      cb[i][k] = buf[(f0 + 9 + i * 3 + k) * ne + e];
-    }
-  Scratch<kSaptBlock> scr{scr_base + threadIdx.x};
-  buf[(which ? F_VALL : F_VAL) * ne + e] = sapt5sf(T, scr, ca, cb);
+  GlobalSites S{buf + (long)(F_SITES + which * 2 * kSiteFields) * ne + e, ne};
+  const double sa[3] = {S[48], S[49], S[50]};
+  const double sb[3] = {S[51], S[52], S[53]};
+  const double val = sapt_pair_sum(T, S, sa, sb);
+  buf[(which ? F_VALL : F_VAL) * ne + e] = val + buf[(F_FCIND + which) * ne + e];
 }
 
 // ---- stage 2a -----------------------------------------------------------------------------------
@@ -293,7 +361,8 @@ KNAME(ccpol_combine_kernel)(int iemonomer, double V0, GeomLayout L, double* __re
   }
 }
 
-size_t sapt_smem() { return kSaptTableBytes + (size_t)kSaptSlots * kSaptBlock * sizeof(double); }
+size_t sapt_smem() { return kSaptTableBytes; }
+size_t dipind_smem() { return kSaptTableBytes; }
 size_t rigid_smem() { return kRigidTableBytes; }
 size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepEnergies * kSweepDoubles * sizeof(double); }
 
@@ -325,6 +394,8 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, double V0, G
     const long ng = (ngeom - g0 < chunk) ? ngeom - g0 : chunk;
     const long ne = ng * (g ? 36 : 1);
     KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, L, x, g0, ne, g, work);
+    KNAME(ccpol_sites_kernel)<<<(unsigned)((4 * ne + 127) / 128), 128, 0, st>>>(ne, work);
+    KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, dipind_smem(), st>>>(tab, ne, work);
     KNAME(ccpol_sapt_kernel)<<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
     KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, rigid_smem(), st>>>(tab, ne, work, flags);
     KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + kSweepEnergies - 1) / kSweepEnergies), kSweepBlock, sweep_smem(), st>>>(tab, ne, work);

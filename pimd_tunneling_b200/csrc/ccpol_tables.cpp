@@ -295,6 +295,29 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
       if (pb[6] != 0.0 || pb[7] != 0.0 || pb[8] != 0.0) f |= 4;  // dmp6, dmp8, dmp10
       o->pairflags[tb * kNType + ta] = f;
     }
+  {  // SAPT stage task order (cost model in FP64 instruction slots, from the pair-type flags)
+    int cost[65];
+    for (int ia = 0; ia < 8; ++ia)
+      for (int ib = 0; ib < 8; ++ib) {
+        const int ta = types[ia] - 1, tb = types[ib] - 1;
+        const uint8_t f = o->pairflags[tb * kNType + ta];
+        int cst = 0;
+        if (f) cst += 60;
+        if (f & 1) cst += 200 + (ta != tb ? 90 : 0);
+        if (f & 2) cst += 50;
+        if (f & 4) cst += 300;
+        cost[ia * 8 + ib] = cst;
+      }
+    cost[64] = 700;  // dipind
+    int idx[65];
+    for (int i = 0; i < 65; ++i) idx[i] = i;
+    std::stable_sort(idx, idx + 65, [&](int a, int b) { return cost[a] > cost[b]; });
+    o->sapt_ntask = 0;
+    for (int i = 0; i < 65; ++i) {
+      o->sapt_order[i] = (uint8_t)idx[i];
+      if (cost[idx[i]] > 0) o->sapt_ntask = i + 1;
+    }
+  }
   if (next - 1 != h.numlin) {
     g_msg = "linear-coefficient index map does not cover the coefficient table";
     return g_msg.c_str();

@@ -59,6 +59,12 @@ struct CcpolDev {
   // proc_sapt5sf_new_ncd.f:1234-1237) and adding +-0 changes no bits, so the kernels skip it.
   uint8_t pairflags[kNType * kNType];
   uint8_t pad1_[3];
+  // task order of the pair-parallel SAPT stage: the 64 site pairs (ia*8+ib) and the dipole-induction
+  // task (64), most expensive first, so that the warps of a CTA that pull tasks from a shared counter
+  // finish together.  Pairs whose type contributes exactly +0 come last (sapt_ntask counts the others).
+  uint8_t sapt_order[65];
+  uint8_t pad3_[3];
+  int32_t sapt_ntask;
 };
 // bytes of the leading rigid-model block = offset of the first SAPT member (a multiple of 16)
 #define PIMDK_RIGID_TABLE_BYTES (offsetof(::pimdk::CcpolDev, param))
