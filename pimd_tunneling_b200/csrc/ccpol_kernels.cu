@@ -40,7 +40,7 @@ namespace {
 #define PIMDK_RIGID_MINB 5
 #endif
 #ifndef PIMDK_SWEEP_MINB
-#define PIMDK_SWEEP_MINB 5
+#define PIMDK_SWEEP_MINB 2
 #endif
 constexpr int kSetupBlock = 128;
 #ifndef PIMDK_SAPT_BLOCK
@@ -49,14 +49,16 @@ constexpr int kSetupBlock = 128;
 constexpr int kSaptBlock = PIMDK_SAPT_BLOCK;
 
 constexpr int kRigidBlock = 128;
-constexpr int kSweepBlock = 128;                          // 16 energies x 8 lanes
-constexpr int kSweepEnergies = kSweepBlock / kSweepLanes;
-constexpr int kSweepDoubles = 75 + 75 + 148;              // sites of A, sites of B, 4 x (36 bins + 1 dummy), per energy
+#ifndef PIMDK_SWEEP_BLOCK
+#define PIMDK_SWEEP_BLOCK 384
+#endif
+constexpr int kSweepBlock = PIMDK_SWEEP_BLOCK;            // warps that share 32 energies in the U0 sweep
 // staging fields per energy: 18 flexible + 18 rigid coordinates, emon, val, vall, erigid, eind, a0u, then the
 // SAPT-5s'f sites: 4 blocks (flexible A, flexible B, rigid A, rigid B) of 24 site coordinates + 3 symmetry coordinates
 constexpr int kSiteFields = 27;
-constexpr int kFields = 44 + 4 * kSiteFields;
-enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39, F_EIND = 40, F_A0U = 41, F_FCIND = 42, F_SITES = 44 };
+constexpr int kFrameFields = 24;                 // body frames of the two rigid monomers (ex, ey, ez, com) x 2
+constexpr int kFields = 44 + 4 * kSiteFields + kFrameFields;
+enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39, F_EIND = 40, F_A0U = 41, F_FCIND = 42, F_SITES = 44, F_FRAME = 44 + 4 * kSiteFields };
 constexpr int kTabBytes = (int)((sizeof(CcpolDev) + 15) / 16 * 16);
 constexpr int kRigidTableBytes = (int)PIMDK_RIGID_TABLE_BYTES;
 constexpr int kSaptTableBytes = kTabBytes - kRigidTableBytes;
@@ -223,6 +225,17 @@ KNAME(ccpol_rigid_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __r
     for (int k = 0; k < 3; ++k) rg[i][k] = buf[(F_RIGID + i * 3 + k) * ne + e];
   Frame fa, fb;
   rigid_frames(rg, fa, fb);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {   // the sweep stage (2b) builds the 50 sites from these frames
+    buf[(F_FRAME + 0 + k) * ne + e] = fa.ex[k];
+    buf[(F_FRAME + 3 + k) * ne + e] = fa.ey[k];
+    buf[(F_FRAME + 6 + k) * ne + e] = fa.ez[k];
+    buf[(F_FRAME + 9 + k) * ne + e] = fa.com[k];
+    buf[(F_FRAME + 12 + k) * ne + e] = fb.ex[k];
+    buf[(F_FRAME + 15 + k) * ne + e] = fb.ey[k];
+    buf[(F_FRAME + 18 + k) * ne + e] = fb.ez[k];
+    buf[(F_FRAME + 21 + k) * ne + e] = fb.com[k];
+  }
   int fl = 0;
   buf[F_EIND * ne + e] = ind2_iter(T, fa, fb, &fl);
   buf[F_A0U * ne + e] = u0_elst_disp(T, fa, fb);
@@ -232,96 +245,138 @@ KNAME(ccpol_rigid_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __r
 // ---- stage 2b -----------------------------------------------------------------------------------
 // U0 (proc_ccpol8s-dimer_xyz_ncd.f:118-233): the reference walks the 25x25 site pairs in (nsA, nsB) order and
 // adds e^{-beta R} R^p (p = 0..3) into one of 36x4 bins aj(ind) chosen by the pair of site classes.  The sums
-// of different bins are independent, so the 36 bins are dealt to 8 lanes (static longest-processing-time
-// schedule built on the host, ~79 pairs per lane); each lane walks its bins' pairs in the reference's order
-// with the four sums in registers, i.e. performs exactly the reference's additions per bin, and writes each
-// finished bin once to shared memory.  Lane 0 then forms E = Eind + sum_nl c(nl) aj(nl) + a0 in the
-// reference's order (:105-110).
+// of different bins are independent.  A CTA owns 32 energies; lane = energy, so a warp-level task is uniform in
+// control flow and addresses: the warps first build the 50 sites (fill_sites :487-548) from the frames of stage
+// 2a into shared memory (slot-major [slot][energy], conflict-free), then pull bins from a shared counter,
+// largest first, and walk each bin's site pairs in the reference's order (block (ca,cb), then block (cb,ca))
+// with the four sums in registers — exactly the reference's additions per bin; four consecutive pairs are
+// evaluated as independent instruction streams before their terms are added in order.  A finished bin leaves
+// c(nl)*aj(nl) in shared memory; warp 0 then forms E = Eind + sum_nl c(nl) aj(nl) + a0 in the reference's order
+// (:105-110).
+constexpr int kSweepWarps = kSweepBlock / 32;
+constexpr int kSweepSlots = 150 + 144;      // sites of A (75), sites of B (75), c(nl)*aj(nl)
+
+// four (or fewer) consecutive pairs of a block: pair k -> (A site a0 + k / nb, B site b0 + k % nb)
+template <int N>
+__device__ __forceinline__ void sweep_chunk(const double* sA, const double* sB, int a0, int b0, int nb, int k0, double beta,
+                                            double& acc0, double& acc1, double& acc2, double& acc3) {
+  double R[N], e[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const int k = k0 + q, i = k / nb, j = k - i * nb;
+    const double* ra = sA + (a0 + i) * 96;     // 3 slots x 32 energies per site
+    const double* rb = sB + (b0 + j) * 96;
+    double r12 = ra[0] - rb[0];
+    double d = r12 * r12;                      // the reference's 0 + r12*r12: a square is never -0
+    r12 = ra[32] - rb[32];
+    d = d + r12 * r12;
+    r12 = ra[64] - rb[64];
+    d = d + r12 * r12;
+    R[q] = fast_sqrt(d);
+    e[q] = pimdk_exp(-beta * R[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    acc0 = acc0 + e[q];
+    acc1 = acc1 + e[q] * R[q];
+    acc2 = acc2 + e[q] * R[q] * R[q];
+    acc3 = acc3 + e[q] * R[q] * R[q] * R[q];
+  }
+}
+// one A site against the four B sites of a class (the common block shape): the A site is read once
+__device__ __forceinline__ void sweep_row4(const double* ra, const double* sB, int b0, double beta, double& acc0,
+                                           double& acc1, double& acc2, double& acc3) {
+  const double ax = ra[0], ay = ra[32], az = ra[64];
+  double R[4], e[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double* rb = sB + (b0 + q) * 96;
+    double r12 = ax - rb[0];
+    double d = r12 * r12;
+    r12 = ay - rb[32];
+    d = d + r12 * r12;
+    r12 = az - rb[64];
+    d = d + r12 * r12;
+    R[q] = fast_sqrt(d);
+    e[q] = pimdk_exp(-beta * R[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    acc0 = acc0 + e[q];
+    acc1 = acc1 + e[q] * R[q];
+    acc2 = acc2 + e[q] * R[q] * R[q];
+    acc3 = acc3 + e[q] * R[q] * R[q] * R[q];
+  }
+}
+__device__ __forceinline__ void sweep_block(const double* sA, const double* sB, int a0, int na, int b0, int nb, double beta,
+                                            double& acc0, double& acc1, double& acc2, double& acc3) {
+  if (nb == 4) {
+#pragma unroll 1
+    for (int i = 0; i < na; ++i) sweep_row4(sA + (a0 + i) * 96, sB, b0, beta, acc0, acc1, acc2, acc3);
+    return;
+  }
+  const int np = na * nb;
+  if (np >= 4) {
+#pragma unroll 1
+    for (int k0 = 0; k0 < np; k0 += 4) sweep_chunk<4>(sA, sB, a0, b0, nb, k0, beta, acc0, acc1, acc2, acc3);
+  } else if (np == 2) {
+    sweep_chunk<2>(sA, sB, a0, b0, nb, 0, beta, acc0, acc1, acc2, acc3);
+  } else {
+    sweep_chunk<1>(sA, sB, a0, b0, nb, 0, beta, acc0, acc1, acc2, acc3);
+  }
+}
+
 __global__ void __launch_bounds__(kSweepBlock, PIMDK_SWEEP_MINB)
 KNAME(ccpol_sweep_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
   const CcpolDev& T = stage_tables<kRigidTableBytes>(tab, smem);
-  double* es = reinterpret_cast<double*>(smem + kRigidTableBytes) + (threadIdx.x / kSweepLanes) * kSweepDoubles;
-  double* sA = es;          // sites of monomer A, 25 x 3
-  double* sB = es + 75;     // sites of monomer B
-  double* aj = es + 150;    // finished bins
-  const int lane = threadIdx.x % kSweepLanes;
-  const long e = (long)blockIdx.x * kSweepEnergies + threadIdx.x / kSweepLanes;
+  double* slots = reinterpret_cast<double*>(smem + kRigidTableBytes);
+  int* queue = reinterpret_cast<int*>(slots + kSweepSlots * 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sA = slots + lane;            // site s, coordinate c of A at sA[(s*3 + c) * 32]
+  double* sB = slots + 75 * 32 + lane;
+  double* cw = slots + 150 * 32 + lane; // c(nl)*aj(nl) at cw[nl * 32]; the frames live here until the sites are built
+  const long e = (long)blockIdx.x * 32 + lane;
   const bool active = e < ne;
-  const long ec = active ? e : ne - 1;   // lanes of a partial last group still take part in the warp syncs
-  {
-    double rg[6][3];
+  const long ec = active ? e : ne - 1;  // idle lanes of the last CTA recompute its last energy
+  if (threadIdx.x == 0) *queue = 0;
+  for (int k = warp; k < kFrameFields; k += kSweepWarps) cw[k * 32] = buf[(long)(F_FRAME + k) * ne + ec];
+  __syncthreads();
+  // fill_sites (:487-548): the 50 sites of the 32 energies, dealt to the warps
+  for (int s = warp; s < 50; s += kSweepWarps) {
+    const int m = s >= 25, k = s - 25 * m;
+    const double* f = cw + (12 * m) * 32;
+    const double s1 = T.sites[k * 3 + 0], s2 = T.sites[k * 3 + 1], s3 = T.sites[k * 3 + 2];
+    double* out = (m ? sB : sA) + k * 96;
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) rg[i][k] = buf[(F_RIGID + i * 3 + k) * ne + ec];
-    Frame fa, fb;
-    rigid_frames(rg, fa, fb);
-    // fill_sites (:487-548): the group's 50 sites, dealt round-robin to its lanes
-#pragma unroll 1
-    for (int s = lane; s < 50; s += kSweepLanes) {
-      double r[3];
-      if (s < 25) {
-        frame_site(T, fa, s, r);
-        sA[s * 3 + 0] = r[0]; sA[s * 3 + 1] = r[1]; sA[s * 3 + 2] = r[2];
-      } else {
-        frame_site(T, fb, s - 25, r);
-        sB[(s - 25) * 3 + 0] = r[0]; sB[(s - 25) * 3 + 1] = r[1]; sB[(s - 25) * 3 + 2] = r[2];
-      }
+    for (int j = 0; j < 3; ++j) {   // frame_site: (ex s1 + ey s2 + ez s3) + com
+      const double t = f[j * 32] * s1 + f[(3 + j) * 32] * s2 + f[(6 + j) * 32] * s3;
+      out[j * 32] = t + f[(9 + j) * 32];
     }
   }
-  __syncwarp();
-  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-  const uint64_t* sched = T.sweep[lane];
-  const int nquads = T.sweep_quads;
-  // one quad (four site pairs of one bin) per iteration: the four distance / sqrt / exp chains are
-  // independent instruction streams, the sums are then added in the reference's order
+  __syncthreads();
 #pragma unroll 1
-  for (int i = 0; i < nquads; ++i) {
-    const uint64_t w = sched[i];
-    const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-    const int bin = (hi >> 24) & 0x3f;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(queue, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= 36) break;
+    const uint32_t w = T.tbins[t];
+    const int a0 = w & 31, na = (w >> 5) & 7, b0 = (w >> 8) & 31, nb = (w >> 13) & 7, bin = (w >> 16) & 63;
     const double beta = T.bin_beta[bin];
-    double R[4], e[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t d = (uint32_t)(w >> (14 * q));
-      u0_pair(&sA[d & 0x7f], &sB[(d >> 7) & 0x7f], beta, R[q], e[q]);
-    }
-    (void)lo;
-    if (hi & (1u << 30)) { acc0 = 0.0; acc1 = 0.0; acc2 = 0.0; acc3 = 0.0; }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      acc0 = acc0 + e[q];
-      acc1 = acc1 + e[q] * R[q];
-      acc2 = acc2 + e[q] * R[q] * R[q];
-      acc3 = acc3 + e[q] * R[q] * R[q] * R[q];
-    }
-    if (hi & (1u << 31)) {
-      aj[bin] = acc0; aj[bin + 37] = acc1; aj[bin + 74] = acc2; aj[bin + 111] = acc3;
-    }
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    sweep_block(sA, sB, a0, na, b0, nb, beta, acc0, acc1, acc2, acc3);
+    if (a0 != b0) sweep_block(sA, sB, b0, nb, a0, na, beta, acc0, acc1, acc2, acc3);
+    cw[bin * 32] = T.cc[bin] * acc0;
+    cw[(bin + 36) * 32] = T.cc[bin + 36] * acc1;
+    cw[(bin + 72) * 32] = T.cc[bin + 72] * acc2;
+    cw[(bin + 108) * 32] = T.cc[bin + 108] * acc3;
   }
-  if (lane == kSweepLanes - 1) {  // bins outside the quad schedule (the single O-O pair), pair by pair
-    for (int i = 0; i < T.sweep_ntail; ++i) {
-      const uint32_t d = T.sweep_tail[i];
-      const int bin = (d >> 14) & 0x3f;
-      double R, ee;
-      u0_pair(&sA[d & 0x7f], &sB[(d >> 7) & 0x7f], T.bin_beta[bin], R, ee);
-      if (d & (1u << 20)) { acc0 = 0.0; acc1 = 0.0; acc2 = 0.0; acc3 = 0.0; }
-      acc0 = acc0 + ee;
-      acc1 = acc1 + ee * R;
-      acc2 = acc2 + ee * R * R;
-      acc3 = acc3 + ee * R * R * R;
-      if (d & (1u << 21)) {
-        aj[bin] = acc0; aj[bin + 37] = acc1; aj[bin + 74] = acc2; aj[bin + 111] = acc3;
-      }
-    }
-  }
-  __syncwarp();
-  if (active && lane == 0) {
+  __syncthreads();
+  if (warp == 0 && active) {
     double E = buf[F_EIND * ne + e];
-#pragma unroll 4
-    for (int nl = 0; nl < 144; ++nl) E = E + T.cc[nl] * aj[nl + nl / 36];  // bins stored 37 apart (dummy bin 36)
+#pragma unroll 8
+    for (int nl = 0; nl < 144; ++nl) E = E + cw[nl * 32];
     E = E + buf[F_A0U * ne + e];
     buf[F_ERIG * ne + e] = E * 627.510;
   }
@@ -364,7 +419,7 @@ KNAME(ccpol_combine_kernel)(int iemonomer, double V0, GeomLayout L, double* __re
 size_t sapt_smem() { return kSaptTableBytes; }
 size_t dipind_smem() { return kSaptTableBytes; }
 size_t rigid_smem() { return kRigidTableBytes; }
-size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepEnergies * kSweepDoubles * sizeof(double); }
+size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepSlots * 32 * sizeof(double) + 16; }
 
 }  // namespace
 
@@ -398,7 +453,7 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, double V0, G
     KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, dipind_smem(), st>>>(tab, ne, work);
     KNAME(ccpol_sapt_kernel)<<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
     KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, rigid_smem(), st>>>(tab, ne, work, flags);
-    KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + kSweepEnergies - 1) / kSweepEnergies), kSweepBlock, sweep_smem(), st>>>(tab, ne, work);
+    KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + 31) / 32), kSweepBlock, sweep_smem(), st>>>(tab, ne, work);
     const long nt = g ? ne / 2 : ne;
     KNAME(ccpol_combine_kernel)<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(iemonomer, V0, L, x, g0, ne, g, work, v, grad, write_drift, flags);
   }

@@ -395,6 +395,17 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
           for (int j = 0; j < na; ++j) v.emplace_back(b0 + i, a0 + j);
       return v;
     };
+    {
+      std::vector<int> big(bins.size());
+      for (size_t i = 0; i < bins.size(); ++i) big[i] = (int)i;
+      std::stable_sort(big.begin(), big.end(), [&](int x, int y) { return bins[x].npairs > bins[y].npairs; });
+      for (size_t k = 0; k < big.size(); ++k) {
+        const Bin& b = bins[big[k]];
+        const int a0 = o->cls_start[b.ca], na = o->cls_start[b.ca + 1] - a0;
+        const int b0 = o->cls_start[b.cb], nb = o->cls_start[b.cb + 1] - b0;
+        o->tbins[k] = (uint32_t)a0 | (uint32_t)na << 5 | (uint32_t)b0 << 8 | (uint32_t)nb << 13 | (uint32_t)b.i0 << 16;
+      }
+    }
     std::vector<int> order;
     o->sweep_ntail = 0;
     for (size_t i = 0; i < bins.size(); ++i) {

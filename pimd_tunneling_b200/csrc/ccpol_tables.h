@@ -44,6 +44,9 @@ struct CcpolDev {
   int32_t sweep_quads;                       // quads per lane
   int32_t sweep_ntail;
   int32_t pad2_[2];                          // keeps `param` 16-byte aligned (staging granule)
+  // The 36 bins as tasks of the item-per-lane sweep (a warp walks one bin for 32 energies), largest first:
+  //   bits 0..4 first site of class ca, 5..7 its size, 8..12 first site of class cb, 13..15 its size, 16..21 bin
+  uint32_t tbins[36];
   // ---- SAPT-5s'f flexible model ----
   double param[kNParam * kNType];            // param(k,t)         -> [(t-1)*18 + k-1]
   double parab[kNParab * kNType * kNType];   // parab(k,ta,tb)     -> [((tb-1)*5+(ta-1))*84 + k-1]
