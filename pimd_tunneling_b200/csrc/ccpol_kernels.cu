@@ -205,9 +205,13 @@ KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __re
   const int which = j >= ne;    // 0: flexible geometry (val), 1: embedded rigid geometry (vall)
   const long e = which ? j - ne : j;
   GlobalSites S{buf + (long)(F_SITES + which * 2 * kSiteFields) * ne + e, ne};
+  // the 8 sites of B are read once per site of A: keep them in shared memory, slot-major (conflict-free)
+  Scratch<kSaptBlock> sitesB{reinterpret_cast<double*>(smem + kSaptTableBytes) + threadIdx.x};
+#pragma unroll
+  for (int k = 0; k < 24; ++k) sitesB[k] = S[24 + k];
   const double sa[3] = {S[48], S[49], S[50]};
   const double sb[3] = {S[51], S[52], S[53]};
-  const double val = sapt_pair_sum(T, S, sa, sb);
+  const double val = sapt_pair_sum(T, S, sitesB, sa, sb);
   buf[(which ? F_VALL : F_VAL) * ne + e] = val + buf[(F_FCIND + which) * ne + e];
 }
 
@@ -416,7 +420,7 @@ KNAME(ccpol_combine_kernel)(int iemonomer, double V0, GeomLayout L, double* __re
   }
 }
 
-size_t sapt_smem() { return kSaptTableBytes; }
+size_t sapt_smem() { return kSaptTableBytes + (size_t)24 * kSaptBlock * sizeof(double); }
 size_t dipind_smem() { return kSaptTableBytes; }
 size_t rigid_smem() { return kRigidTableBytes; }
 size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepSlots * 32 * sizeof(double) + 16; }
