@@ -40,8 +40,12 @@ M_O, M_H = 15.9949146221 * 1822.888486, 1.0078250321 * 1822.888486
 FLOP_PER_ENERGY = 25156 + 33156 + 1760 + 806 + 1129 + 33 + 28
 FLOP_PER_BEAD_GRAD = {"ccpol8sf": 36 * FLOP_PER_ENERGY + 36, "2dtest": 6 * (2 + 14) + 12, "1d": 8}
 # DRAM bytes per bead-gradient of the CCpol pipeline, dram__bytes_read.sum + dram__bytes_write.sum summed over
-# its five kernels in one `ncu --set full` capture of a 32 768-bead pass (profiles/r1_ccpol_pipeline_final.md)
-CCPOL_DRAM_BYTES_PER_BEAD = None
+# its seven kernels in one `ncu --set full` capture of a 32 768-bead pass (profiles/r1_ccpol_pipeline_v9.md)
+CCPOL_DRAM_BYTES_PER_BEAD = 134723
+# SASS-level FP64 flop per bead-gradient (2*DFMA + DMUL + DADD thread instructions of the seven kernels, same
+# capture): what the FP64 pipe actually executes for the 2 234 484 source-level operations, because exp, division
+# and square root expand to ~20, ~10 and ~10 pipe instructions and strict mode issues no contracted FMAs
+CCPOL_SASS_FLOP_PER_BEAD = 3400128
 
 CONFIGS = {
     # name: pes, n, nintegral, nrep, thermostat, beta, Noutput
@@ -344,12 +348,15 @@ def run_ours(args, cfg, rank, world, local_rank):
                          "traffic": (CCPOL_DRAM_BYTES_PER_BEAD * ntraj * n / 1e9) if (CCPOL_DRAM_BYTES_PER_BEAD and cfg["pes"] == "ccpol8sf") else None,
                          "traffic_unit": "GB per step (all beads), from ncu dram__bytes_read+write per bead",
                          "algorithmic_bytes": 32 * ndof * ntraj * n / 1e9,
-                         "kernel": ("ccpol_{setup,sapt,rigid,combine}_kernel_" + args.mode + " (one PES-gradient pipeline)")
+                         "kernel": ("ccpol_{setup,sites,dipind,sapt,rigid,sweep,combine}_kernel_" + args.mode + " (one PES-gradient pipeline)")
                          if cfg["pes"] == "ccpol8sf" else "simple_pes_kernel",
                          "kernel_ms_per_step": pes_ms.value / K, "kernel_launches": int(pes_n.value),
                          "kernel_share_of_step": pes_ms.value / ms_prof,
                          "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "flop_per_bead_gradient": FLOP_PER_BEAD_GRAD[cfg["pes"]], "other_kernels_ms": fam},
+                         "flop_per_bead_gradient": FLOP_PER_BEAD_GRAD[cfg["pes"]], "other_kernels_ms": fam,
+                         "achieved_sass": (CCPOL_SASS_FLOP_PER_BEAD * ntraj * n * K / (pes_ms.value * 1e-3) / 1e12)
+                         if (cfg["pes"] == "ccpol8sf" and args.mode == "strict" and pes_ms.value > 0) else None,
+                         "achieved_sass_note": "2*DFMA+DMUL+DADD executed per bead-gradient (ncu, profiles/) / kernel time"},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu and world == 1:
