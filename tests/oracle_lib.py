@@ -34,8 +34,31 @@ def _p(a):
 
 
 def build():
+    """make the oracle library (no-op when up to date); serialised across processes by a file lock because
+    bench.py's CPU legs start one worker per core and each of them lands here"""
+    import fcntl
+
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    with open(os.path.join(ORACLE_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            # -march=native: a library built on another host (it travels with the repo snapshot) is rebuilt when
+            # this host's CPU feature flags differ (oracle/.cpu_stamp is a prerequisite in the Makefile)
+            import hashlib
+
+            flags = ""
+            try:
+                with open("/proc/cpuinfo") as f:
+                    flags = next((ln for ln in f if ln.startswith("flags")), "")
+            except OSError:
+                pass
+            stamp, h = os.path.join(ORACLE_DIR, ".cpu_stamp"), hashlib.sha1(flags.encode()).hexdigest()
+            if not os.path.exists(stamp) or open(stamp).read().strip() != h:
+                with open(stamp, "w") as f:
+                    f.write(h + "\n")
+            subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return so
 
 
