@@ -55,6 +55,13 @@ module pimdk
        real(c_double), value :: dt, gamma; type(c_ptr), value :: gid
        real(c_double) :: x(*), p(*), a(*), b(*), dbdl(*), dHdr(*)
      end function
+     ! module variables restart / restartnmc (verletmodule.f90:10) and the running sums write_restart stores (:171)
+     integer(c_int) function pimdk_set_restart(restart, restartnmc) bind(C, name="pimdk_set_restart")
+       import; integer(c_int64_t), value :: restart, restartnmc
+     end function
+     integer(c_int) function pimdk_get_dhdr_sums(ntraj, sums) bind(C, name="pimdk_get_dhdr_sums")
+       import; integer(c_int64_t), value :: ntraj; real(c_double) :: sums(*)
+     end function
      integer(c_int64_t) function pimdk_last_nan_trajectory() bind(C, name="pimdk_last_nan_trajectory")
        import
      end function

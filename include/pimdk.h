@@ -119,6 +119,16 @@ int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p,
 int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p, const double* a, const double* b,
                         const double* dbdl, double dt, double gamma, pimdk_int NMC, pimdk_int imin, pimdk_int Noutput,
                         pimdk_int cayley, uint64_t seed, const pimdk_int* traj_gid, double* dHdr);
+/* Restart state of module verletint: `restart`, `restartnmc` (verletmodule.f90:10; namelist pimd_par.f90:45,75).
+ *   restart = 0/1  dHdr starts from zero (verletmodule.f90:200,388)
+ *   restart = 2    the dHdr array handed to pimdk_propagate holds the running sums read from the restart
+ *                  files (pimd_par.f90:356-370) and is continued; the mean divides by NMC + restartnmc - imin
+ *                  (:247,413).  The RNG step counters continue at restartnmc + 1, so a run of N steps followed
+ *                  by a restarted run of M steps draws the random numbers of one run of N + M steps.
+ * pimdk_get_dhdr_sums returns the running (un-normalised) sums of the last propagate call: the dHdr that
+ * write_restart stores (verletmodule.f90:162-185, called at :206, 246, 394, 412). */
+int pimdk_set_restart(pimdk_int restart, pimdk_int restartnmc);
+int pimdk_get_dhdr_sums(pimdk_int ntraj, double* sums);
 /* index (0-based, into the last call's batch) of the first trajectory that tripped the NaN trap, or -1 */
 pimdk_int pimdk_last_nan_trajectory(void);
 

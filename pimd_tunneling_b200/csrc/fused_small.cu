@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat, long ntraj, double* __restrict__ xg,
                    double* __restrict__ pg, const double* __restrict__ a, const double* __restrict__ b,
                    const double* __restrict__ dbdl, double dt, long NMC, long imin, double lambda, uint64_t seed,
-                   const int64_t* __restrict__ gid, double* __restrict__ dHdr, int* __restrict__ flags) {
+                   const int64_t* __restrict__ gid, double* __restrict__ dHdr, int* __restrict__ flags, long step0,
+                   int keep_sum, double* __restrict__ dHsum) {
   extern __shared__ __align__(16) double sm[];
   const int n = nm.n;
   double* Ts = sm;                                   // transmatrix, n x n
@@ -138,7 +139,7 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
   };
   // estimator (verletmodule.f90:397-403): the lane that owns the last bead
   const int last_lane = (n - 1) & 31, last_s = (n - 1) >> 5;
-  double acc = 0.0;
+  double acc = keep_sum ? dHdr[traj] : 0.0;   // restart = 2 continues the running sum (verletmodule.f90:200,388)
   auto estimator = [&]() {
     if (lane != last_lane) return;
     double contr = 0.0;
@@ -158,13 +159,13 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
 
   if (thermostat == 2) {  // time_step_pile (:423-435)
     for (long ii = 1; ii <= NMC; ++ii) {
-      kick_and_rotate(true, 2, (uint64_t)ii);
+      kick_and_rotate(true, 2, (uint64_t)(ii + step0));
       to_beads();
       if (ii > imin) estimator();
     }
   } else {                // propagate_pimd_nm (:190-250) / time_step_nm (:291-302)
     int count = 0;
-    int rkick = poisson_norm(seed, 0, g, lambda);
+    int rkick = poisson_norm(seed, (uint64_t)step0, g, lambda);
     for (long ii = 1; ii <= NMC; ++ii) {
       count = count + 1;
       if (count >= rkick) {
@@ -175,11 +176,11 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
           for (int s = 0; s < S; ++s) {
             const int k = lane + 32 * s;
             if (k < n) {
-              const double z = normal_at(seed, STREAM_ANDERSEN, (uint64_t)ii, g, (uint64_t)d * n + k);
+              const double z = normal_at(seed, STREAM_ANDERSEN, (uint64_t)(ii + step0), g, (uint64_t)d * n + k);
               r.P[d][s] = (0.0 + nm.stdev * z) * nm.sigp[(d / ndim) * n + k];
             }
           }
-        rkick = poisson_norm(seed, (uint64_t)ii, g, lambda);
+        rkick = poisson_norm(seed, (uint64_t)(ii + step0), g, lambda);
       }
 #pragma unroll
       for (int d = 0; d < NDOF; ++d)
@@ -189,7 +190,7 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
           if (k < n) rotate(nm, (d / ndim) * n + k, r.P[d][s], r.Q[d][s]);
         }
       to_beads();
-      kick_and_rotate(false, 1, (uint64_t)ii);
+      kick_and_rotate(false, 1, (uint64_t)(ii + step0));
       to_beads();
       if (ii > imin) estimator();
     }
@@ -215,19 +216,24 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
       }
     }
   }
-  if (lane == last_lane) dHdr[traj] = acc / (double)(NMC - imin);
+  if (lane == last_lane) {   // running sum (what write_restart stores, :171) and mean (:247,413)
+    dHsum[traj] = acc;
+    dHdr[traj] = acc / (double)(NMC + step0 - imin);
+  }
 }
 
 template <int NDOF, int S>
 cudaError_t launch_t(const NmTables& nm, int kind, const SimplePesParams& pp, int thermostat, long ntraj, double* x,
                      double* p, const double* a, const double* b, const double* dbdl, double dt, long NMC, long imin,
-                     double lambda, uint64_t seed, const int64_t* gid, double* dHdr, int* flags, cudaStream_t st) {
+                     double lambda, uint64_t seed, const int64_t* gid, double* dHdr, int* flags, long step0, int keep_sum,
+                     double* dHsum, cudaStream_t st) {
   const size_t smem = ((size_t)nm.n * nm.n + (size_t)kWarpsPerBlock * nm.n) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(fused_small_kernel<NDOF, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned blocks = (unsigned)((ntraj + kWarpsPerBlock - 1) / kWarpsPerBlock);
   fused_small_kernel<NDOF, S><<<blocks, kWarpsPerBlock * 32, smem, st>>>(nm, kind, pp, thermostat, ntraj, x, p, a, b, dbdl,
-                                                                        dt, NMC, imin, lambda, seed, gid, dHdr, flags);
+                                                                        dt, NMC, imin, lambda, seed, gid, dHdr, flags, step0,
+                                                                        keep_sum, dHsum);
   return cudaGetLastError();
 }
 
@@ -243,12 +249,12 @@ bool fused_small_supported(PesKind kind, int n, int ndim, int natom) {
 cudaError_t launch_fused_small(const NmTables& nm, PesKind kind, const SimplePesParams& pp, int thermostat, long ntraj,
                                double* x, double* p, const double* a, const double* b, const double* dbdl, double dt,
                                long NMC, long imin, double lambda, uint64_t seed, const int64_t* gid, double* dHdr,
-                               int* flags, cudaStream_t st) {
+                               int* flags, long step0, int keep_sum, double* dHsum, cudaStream_t st) {
   const int S = (nm.n + 31) / 32;
 #define PIMDK_FUSED_CASE(ND, SS)                                                                                        \
   if (nm.ndof == ND && S == SS)                                                                                         \
     return launch_t<ND, SS>(nm, (int)kind, pp, thermostat, ntraj, x, p, a, b, dbdl, dt, NMC, imin, lambda, seed, gid, \
-                            dHdr, flags, st);
+                            dHdr, flags, step0, keep_sum, dHsum, st);
   PIMDK_FUSED_CASE(1, 1) PIMDK_FUSED_CASE(1, 2) PIMDK_FUSED_CASE(1, 3) PIMDK_FUSED_CASE(1, 4)
   PIMDK_FUSED_CASE(2, 1) PIMDK_FUSED_CASE(2, 2) PIMDK_FUSED_CASE(2, 3) PIMDK_FUSED_CASE(2, 4)
 #undef PIMDK_FUSED_CASE

@@ -87,7 +87,7 @@ cudaError_t launch_nm_update(const NmTables& nm, double* P, double* Q, const dou
 // Andersen: P <- N(0, sqrt(1/betan))*sqrt(beadmass) for trajectories whose counter fired; updates counters.
 cudaError_t launch_andersen(const NmTables& nm, double* P, long ntraj, uint64_t seed, uint64_t step, double lambda,
                             const int64_t* gid, int* count, int* rkick, cudaStream_t st);
-cudaError_t launch_andersen_init(long ntraj, uint64_t seed, double lambda, const int64_t* gid, int* count, int* rkick,
+cudaError_t launch_andersen_init(long ntraj, uint64_t seed, uint64_t step0, double lambda, const int64_t* gid, int* count, int* rkick,
                                  cudaStream_t st);
 // init_path momenta directly in normal-mode space (stream 0)
 cudaError_t launch_sample_momenta(const NmTables& nm, double* P, long ntraj, uint64_t seed, int stream, uint64_t step,
@@ -102,7 +102,7 @@ bool fused_small_supported(PesKind kind, int n, int ndim, int natom);
 cudaError_t launch_fused_small(const NmTables& nm, PesKind kind, const SimplePesParams& pp, int thermostat, long ntraj,
                                double* x, double* p, const double* a, const double* b, const double* dbdl, double dt,
                                long NMC, long imin, double lambda, uint64_t seed, const int64_t* gid, double* dHdr,
-                               int* flags, cudaStream_t st);
+                               int* flags, long step0, int keep_sum, double* dHsum, cudaStream_t st);
 
 // ---- ring-polymer potential (um_kernels.cu): instantonmod.f90:17-151 ----
 cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double* a, const double* b,

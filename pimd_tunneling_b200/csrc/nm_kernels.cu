@@ -177,7 +177,7 @@ __global__ void andersen_clock_kernel(long ntraj, uint64_t seed, uint64_t step, 
   const uint32_t g = gid ? (uint32_t)gid[t] : (uint32_t)t;
   if (init) {
     count[t] = 0;
-    rkick[t] = poisson_norm(seed, 0, g, lambda);
+    rkick[t] = poisson_norm(seed, step, g, lambda);
     return;
   }
   int c = count[t] + 1;  // count=count+1 ; if (count .ge. rkick) ...  (verletmodule.f90:204,208)
@@ -251,9 +251,9 @@ cudaError_t launch_andersen(const NmTables& nm, double* P, long ntraj, uint64_t 
   return cudaGetLastError();
 }
 
-cudaError_t launch_andersen_init(long ntraj, uint64_t seed, double lambda, const int64_t* gid, int* count, int* rkick,
-                                 cudaStream_t st) {
-  andersen_clock_kernel<<<(unsigned)((ntraj + 127) / 128), 128, 0, st>>>(ntraj, seed, 0, lambda, gid, count, rkick, 1);
+cudaError_t launch_andersen_init(long ntraj, uint64_t seed, uint64_t step0, double lambda, const int64_t* gid, int* count,
+                                 int* rkick, cudaStream_t st) {
+  andersen_clock_kernel<<<(unsigned)((ntraj + 127) / 128), 128, 0, st>>>(ntraj, seed, step0, lambda, gid, count, rkick, 1);
   return cudaGetLastError();
 }
 

@@ -55,6 +55,8 @@ struct Ctx {
   std::string err;
   int mode = PIMDK_MODE_STRICT;
   bool fused = true;  // small systems: one persistent warp-per-ring-polymer kernel
+  long restart = 0, restartnmc = 0;  // module verletint's restart / restartnmc (verletmodule.f90:10)
+  long sums_n = 0;                   // trajectories in wDhSum (running sums of the last propagate call)
   // PES
   PesKind pes = PES_NONE;
   int ndim = 0, natom = 0;
@@ -70,7 +72,7 @@ struct Ctx {
   std::vector<double> mass, lam, beadmass, T;
   DevBuf dT, dsA, dsB, dlamb2, dmass, dtabs;  // dtabs: 8 per-call (natom,n) tables
   // workspaces
-  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc;
+  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum;
   // profiling
   bool profiling = false;
   std::map<std::string, Prof> prof;
@@ -330,7 +332,7 @@ int pimdk_finalize(void) {
   resolve_spans();
   DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
-                    &g.wDhdr, &g.wPp, &g.wMisc};
+                    &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum};
   for (DevBuf* b : bufs) b->release();
   g.inited = false;
   g.nm_ready = false;
@@ -671,6 +673,10 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   if (rc) return rc;
   if (ntraj <= 0) return PIMDK_OK;
   if (NMC < 0 || imin < 0 || NMC - imin <= 0) return fail(PIMDK_EINVAL, "need NMC > imin >= 0");
+  const int keep_sum = g.restart == 2;                 // restart = 2: dHdr arrives holding the running sums
+  const long step0 = keep_sum ? g.restartnmc : 0;      // steps already done; also offsets the RNG step counter
+  CU(g.wDhSum.ensure(sizeof(double) * ntraj));
+  g.sums_n = ntraj;
   const int n = g.n, ndof = g.nm_ndim * g.nm_natom;
   const long rows = (long)ntraj * ndof;
   const size_t tot = (size_t)rows * n;
@@ -692,7 +698,7 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
     {
       Scope s("fused");
       CU(launch_fused_small(nm, g.pes, g.sp, (int)thermostat, ntraj, x, p, a, b, dbdl, dt, NMC, imin, (double)Noutput, seed,
-                            dgid, dHdr, g.wFlags.as<int>(), g.stream));
+                            dgid, dHdr, g.wFlags.as<int>(), step0, keep_sum, g.wDhSum.as<double>(), g.stream));
     }
     rc = check_flags(false);
     g.last_nan_traj = -1;
@@ -702,7 +708,7 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   double *P = g.wP.as<double>(), *Q = g.wQ.as<double>(), *G = g.wG.as<double>(), *Gn = g.wGn.as<double>();
   int* flags = g.wFlags.as<int>();
   GeomLayout L{n, (long)ndof * n, 1, n};
-  CU(cudaMemsetAsync(dHdr, 0, sizeof(double) * ntraj, g.stream));  // restart < 2: dHdr = 0 (:199,387)
+  if (!keep_sum) CU(cudaMemsetAsync(dHdr, 0, sizeof(double) * ntraj, g.stream));  // restart < 2: dHdr = 0 (:200,388)
   {
     Scope s("gemm", 2);
     CU(launch_nm_gemm(nm, GEMM_PLAIN, p, P, rows, a, b, g.stream));
@@ -718,7 +724,7 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       }
       {
         Scope s("update");
-        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 2, 1, seed, (uint64_t)ii, dgid, flags, g.stream));
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 2, 1, seed, (uint64_t)(ii + step0), dgid, flags, g.stream));
       }
       {
         Scope s("gemm");
@@ -734,13 +740,13 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
     int* rkick = g.wKick.as<int>();
     {
       Scope s("update");
-      CU(launch_andersen_init(ntraj, seed, (double)Noutput, dgid, count, rkick, g.stream));
+      CU(launch_andersen_init(ntraj, seed, (uint64_t)step0, (double)Noutput, dgid, count, rkick, g.stream));
     }
     for (pimdk_int ii = 1; ii <= NMC; ++ii) {
       {
         Scope s("update", 3);
-        CU(launch_andersen(nm, P, ntraj, seed, (uint64_t)ii, (double)Noutput, dgid, count, rkick, g.stream));
-        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)ii, dgid, flags, g.stream));
+        CU(launch_andersen(nm, P, ntraj, seed, (uint64_t)(ii + step0), (double)Noutput, dgid, count, rkick, g.stream));
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream));
       }
       {
         Scope s("gemm");
@@ -754,7 +760,7 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       }
       {
         Scope s("update");
-        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)ii, dgid, flags, g.stream));
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream));
       }
       {
         Scope s("gemm");
@@ -772,7 +778,9 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   }
   {
     Scope s("estimator");
-    CU(launch_scale(dHdr, (double)(NMC - imin), ntraj, g.stream));  // dHdr/dble(NMC+restartnmc-imin) (:247,413)
+    // the running sum is what write_restart stores (:171, 246, 412); then dHdr/dble(NMC+restartnmc-imin) (:247,413)
+    CU(cudaMemcpyAsync(g.wDhSum.p, dHdr, sizeof(double) * ntraj, cudaMemcpyDeviceToDevice, g.stream));
+    CU(launch_scale(dHdr, (double)(NMC + step0 - imin), ntraj, g.stream));
   }
   rc = check_flags(false);
   if (rc == PIMDK_ENAN) {
@@ -811,6 +819,7 @@ int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p,
   CU(cudaMemcpyAsync(g.wA.p, a, ndof * sizeof(double), cudaMemcpyHostToDevice, g.stream));
   CU(cudaMemcpyAsync(g.wB.p, b, nb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
   CU(cudaMemcpyAsync(g.wDbdl.p, dbdl, nb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  if (g.restart == 2) CU(cudaMemcpyAsync(g.wDhdr.p, dHdr, ntraj * sizeof(double), cudaMemcpyHostToDevice, g.stream));
   const int64_t* dgid;
   int rc = upload_gid(traj_gid, ntraj, &dgid);
   if (rc) return rc;
@@ -828,6 +837,21 @@ int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p,
 }
 
 pimdk_int pimdk_last_nan_trajectory(void) { return g.last_nan_traj; }
+
+int pimdk_set_restart(pimdk_int restart, pimdk_int restartnmc) {
+  if (restart < 0 || restart > 2 || restartnmc < 0) return fail(PIMDK_EINVAL, "restart must be 0, 1 or 2 and restartnmc >= 0");
+  g.restart = (long)restart;
+  g.restartnmc = (long)restartnmc;
+  return PIMDK_OK;
+}
+
+int pimdk_get_dhdr_sums(pimdk_int ntraj, double* sums) {
+  NEED_INIT();
+  if (ntraj <= 0 || ntraj > g.sums_n || !sums) return fail(PIMDK_EINVAL, "no running sums for that many trajectories");
+  CU(cudaMemcpyAsync(sums, g.wDhSum.p, sizeof(double) * ntraj, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return PIMDK_OK;
+}
 
 int pimdk_ti_partial_sums(pimdk_int ntraj, const double* dHdr, const pimdk_int* gid, pimdk_int nrep,
                           pimdk_int nintegral, double betan, double* sums) {

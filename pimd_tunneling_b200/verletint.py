@@ -26,6 +26,10 @@ class VerletInt:
         self.NMC, self.imin, self.Noutput = int(NMC), int(imin), int(Noutput)
         self.cayley = bool(cayley)
         self.seed = int(seed)
+        # module variables restart / restartnmc (verletmodule.f90:10; namelist pimd_par.f90:45, default 0 :75):
+        # 0 no restart files, 1 write them, 2 continue from them
+        self.restart, self.restartnmc = 0, 0
+        self.last_sums = None   # running (un-normalised) dHdr sums of the last propagate call
         self._ready = False
 
     # alloc_nm (verletmodule.f90:350-368): the reference seeds MT19937 from the clock; here the
@@ -114,7 +118,7 @@ class VerletInt:
                                     hptr(x), hptr(p)))
         return x, p
 
-    def _propagate(self, thermostat, x, p, a, b, dbdl, traj_gid):
+    def _propagate(self, thermostat, x, p, a, b, dbdl, traj_gid, dHdr0=None):
         self._need()
         x = np.asarray(x)
         single = x.ndim == 3
@@ -126,21 +130,114 @@ class VerletInt:
         b = f64(np.asarray(b, dtype=np.float64).reshape((self.ndim, self.natom, ntraj), order="F"))
         dbdl = f64(np.asarray(dbdl, dtype=np.float64).reshape((self.ndim, self.natom, ntraj), order="F"))
         gid = None if traj_gid is None else np.ascontiguousarray(traj_gid, dtype=np.int64)
-        dHdr = np.zeros(ntraj)
+        check(lib().pimdk_set_restart(self.restart, self.restartnmc if self.restart == 2 else 0))
+        if self.restart == 2:    # dHdr as read from the restart files is continued (verletmodule.f90:200,388)
+            if dHdr0 is None:
+                raise ValueError("restart = 2 needs the running sums dHdr0 read from the restart files")
+            dHdr = f64(np.array(np.atleast_1d(dHdr0), dtype=np.float64).reshape(ntraj))
+        else:
+            dHdr = np.zeros(ntraj)
         check(lib().pimdk_propagate(thermostat, ntraj, hptr(xw), hptr(pw), hptr(a), hptr(b), hptr(dbdl), self.dt,
                                     self.gamma, self.NMC, self.imin, self.Noutput, 1 if self.cayley else 0, self.seed,
                                     hptr(gid), hptr(dHdr)))
+        sums = np.empty(ntraj)
+        check(lib().pimdk_get_dhdr_sums(ntraj, hptr(sums)))
+        self.last_sums = sums
         if single:
             return xw[..., 0], pw[..., 0], float(dHdr[0])
         return xw, pw, dHdr
 
     # propagate_pimd_pile (verletmodule.f90:372-416): returns (x, p, dHdr)
-    def propagate_pimd_pile(self, x, p, a, b, dbdl, traj_gid=None):
-        return self._propagate(PILE, x, p, a, b, dbdl, traj_gid)
+    def propagate_pimd_pile(self, x, p, a, b, dbdl, traj_gid=None, dHdr0=None):
+        return self._propagate(PILE, x, p, a, b, dbdl, traj_gid, dHdr0)
 
     # propagate_pimd_nm (verletmodule.f90:190-250)
-    def propagate_pimd_nm(self, x, p, a, b, dbdl, traj_gid=None):
-        return self._propagate(ANDERSEN, x, p, a, b, dbdl, traj_gid)
+    def propagate_pimd_nm(self, x, p, a, b, dbdl, traj_gid=None, dHdr0=None):
+        return self._propagate(ANDERSEN, x, p, a, b, dbdl, traj_gid, dHdr0)
+
+    # ---- restart files (verletmodule.f90:162-185 write_restart; read side pimd_par.f90:332-370) -------------
+    @staticmethod
+    def restart_filename(iproc, ii):
+        """"restart_proc<iproc>_<ii>.xyz" (pimd_par.f90:336-354; ii = 1-based task index of the rank)"""
+        return "restart_proc%d_%d.xyz" % (iproc, ii)
+
+    def write_restart(self, path, xprop, pprop, ii, dHdr):
+        """One trajectory's snapshot in the reference's layout: for every bead `natom`, `dHdr` (the running sum),
+        then `label x y z` per atom; then for every bead `natom`, `ii` (steps done), `label px py pz`.  The
+        reference writes list-directed records; 17 significant digits are written here so that the file
+        round-trips every bit.  (The reference hard-codes three coordinates per atom; surfaces with ndim < 3
+        write the coordinates they have.)"""
+        x = np.asarray(xprop).reshape(self.n, self.ndim, self.natom, order="F")
+        p = np.asarray(pprop).reshape(self.n, self.ndim, self.natom, order="F")
+        lab = list(self.pes.label)
+        with open(path, "w") as f:
+            for arr, second in ((x, "%.17e" % float(dHdr)), (p, "%d" % int(ii))):
+                for i in range(self.n):
+                    f.write(" %d\n %s\n" % (self.natom, second))
+                    for j in range(self.natom):
+                        f.write(" %s %s\n" % (lab[j], " ".join("%.17e" % arr[i, d, j] for d in range(self.ndim))))
+
+    def read_restart(self, path):
+        """-> x(n,ndim,natom), p(n,ndim,natom), dHdr (running sum), restartnmc   (pimd_par.f90:356-370)"""
+        x = np.empty((self.n, self.ndim, self.natom), order="F")
+        p = np.empty_like(x)
+        with open(path) as f:
+            tok = f.read().replace("D", "E").replace("d", "e").split()
+        pos, second = 0, [None, None]
+        for which, arr in enumerate((x, p)):
+            for i in range(self.n):
+                pos += 1                      # dummyint
+                second[which] = tok[pos]      # dHdr / restartnmc
+                pos += 1
+                for j in range(self.natom):
+                    pos += 1                  # dummychar
+                    for d in range(self.ndim):
+                        arr[i, d, j] = float(tok[pos])
+                        pos += 1
+        return x, p, float(second[0]), int(float(second[1]))
+
+    def propagate_restartable(self, thermostat, x, p, a, b, dbdl, traj_gid=None, iproc=0, directory="."):
+        """The reference's restart protocol around one batched propagate call (verletmodule.f90:199-206, 246,
+        387-394, 412; pimd_par.f90:328-370).  restart = 1: start fresh, write every trajectory's file every
+        Noutput steps and at the end; restart = 2: read the files first and continue.  Trajectory t of the batch
+        is the rank's task ii = t + 1.  Returns (x, p, dHdr)."""
+        import os
+
+        x = np.array(x, dtype=np.float64, order="F")
+        p = np.array(p, dtype=np.float64, order="F")
+        ntraj = x.shape[3]
+        files = [os.path.join(directory, self.restart_filename(iproc, t + 1)) for t in range(ntraj)]
+        sums = np.zeros(ntraj)
+        done = 0
+        if self.restart == 2:
+            for t in range(ntraj):
+                x[..., t], p[..., t], sums[t], done_t = self.read_restart(files[t])
+                done = done_t
+        NMC, imin, restart0 = self.NMC, self.imin, self.restart
+        seg = max(1, int(self.Noutput)) if restart0 > 0 else NMC
+        left, local = NMC, 0
+        try:
+            dH = None
+            while left > 0:
+                k = min(seg, left)
+                # one segment = a restarted run of k steps whose first `imin - local` steps are not sampled
+                self.NMC, self.imin = k, min(k - 1, max(0, imin - local)) if imin - local < k else k - 1
+                self.restart, self.restartnmc = (2, done + local) if (restart0 == 2 or local > 0) else (restart0, 0)
+                if imin - local >= k:   # the whole segment lies before imin: propagate without sampling
+                    keep = sums.copy()
+                    x, p, _ = self._propagate(thermostat, x, p, a, b, dbdl, traj_gid, sums if self.restart == 2 else None)
+                    sums = keep
+                else:
+                    x, p, dH = self._propagate(thermostat, x, p, a, b, dbdl, traj_gid, sums if self.restart == 2 else None)
+                    sums = self.last_sums.copy()
+                local += k
+                left -= k
+                if restart0 > 0:
+                    for t in range(ntraj):
+                        self.write_restart(files[t], x[..., t], p[..., t], done + local, sums[t])
+        finally:
+            self.NMC, self.imin, self.restart, self.restartnmc = NMC, imin, restart0, 0
+        return x, p, sums / float(NMC + done - imin)
 
     def propagate_dev(self, thermostat, ntraj, x_ptr, p_ptr, a_ptr, b_ptr, dbdl_ptr, gid_ptr, dHdr_ptr, NMC=None):
         """Device-resident form (pointers into HBM, e.g. torch tensors' data_ptr()); enqueues on the

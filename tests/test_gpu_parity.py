@@ -284,6 +284,62 @@ def test_partition_invariance_and_imin(pk):
     assert not np.array_equal(d0, vi.propagate_pimd_pile(x, p, a, bt, dbdl, traj_gid=gid)[2])
 
 
+@pytest.mark.parametrize("name,n,mass,beta,sigma", [("2dtest", 32, [1.0], 10.0, 0.05), ("2dtest", 160, [1.0], 10.0, 0.05),
+                                                   ("ccpol8sf", 8, DIMER_MASS, 200.0, 0.01)])
+@pytest.mark.parametrize("thermostat", [1, 2])
+def test_restart_protocol(pk, tmp_path, name, n, mass, beta, sigma, thermostat):
+    """write_restart / restart = 1, 2 (verletmodule.f90:162-185, 199-206, 246-247, 387-394, 412-413;
+    pimd_par.f90:328-370): (i) the file round-trips every bit; (ii) a run segmented every Noutput steps with
+    restart files equals the unsegmented run; (iii) 12 steps, then restart = 2 for 8 more, equals 20 steps
+    (same Philox counters; the only difference is the extra p <-> P transform at each segment boundary)."""
+    pes = pk.McmodMass(name).V_init()
+    a, b = _wells(name)
+    ntraj, steps = 3, 20 if name != "ccpol8sf" else 10
+    first = steps * 3 // 5
+    # PILE has no other use for Noutput, so it can serve as the restart cadence; the Andersen collision clock
+    # restarts with every call (verletmodule.f90:202), so there the comparison is made without collisions
+    nout = 8 if thermostat == 2 else 10 ** 9
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, sigma, mass)
+    gid = np.arange(ntraj, dtype=np.int64) + 7
+
+    def make(NMC, imin=0, Noutput=nout):
+        return pk.VerletInt(pes, n, mass, beta, dt=1e-3, NMC=NMC, imin=imin, Noutput=Noutput, seed=31).init_nm()
+
+    vi = make(steps, imin=2)
+    fn = vi.propagate_pimd_pile if thermostat == 2 else vi.propagate_pimd_nm
+    x_ref, p_ref, d_ref = fn(x, p, a, bt, dbdl, traj_gid=gid)
+    # (i)
+    f = str(tmp_path / vi.restart_filename(3, 12))
+    assert f.endswith("restart_proc3_12.xyz")
+    vi.write_restart(f, x_ref[..., 1], p_ref[..., 1], 1234, vi.last_sums[1])
+    xr, pr, dr, nr = vi.read_restart(f)
+    assert np.array_equal(xr, x_ref[..., 1]) and np.array_equal(pr, p_ref[..., 1]) and dr == vi.last_sums[1] and nr == 1234
+    assert open(f).read().split()[0] == str(pes.natom)
+    # (ii) restart = 1, segments of 8 steps (PILE) / one segment (Andersen)
+    d1 = tmp_path / "seg"
+    d1.mkdir()
+    vs = make(steps, imin=2, Noutput=8 if thermostat == 2 else nout)
+    vs.restart = 1
+    xs, ps, ds = vs.propagate_restartable(thermostat, x, p, a, bt, dbdl, traj_gid=gid, iproc=0, directory=str(d1))
+    assert relmax(xs, x_ref) < RTOL and relmax(ps, p_ref) < RTOL and np.abs(ds - d_ref).max() <= RTOL * np.abs(d_ref).max()
+    _, _, _, done = vs.read_restart(str(d1 / vs.restart_filename(0, 1)))
+    assert done == steps
+    # (iii) `first` steps with restart = 1, then restart = 2 for the rest, against one run of `steps` (imin = 0)
+    v0 = make(steps)
+    fn0 = v0.propagate_pimd_pile if thermostat == 2 else v0.propagate_pimd_nm
+    x0, p0, d0 = fn0(x, p, a, bt, dbdl, traj_gid=gid)
+    d2 = tmp_path / "cont"
+    d2.mkdir()
+    va = make(first, Noutput=nout if thermostat == 1 else 10 ** 6)
+    va.restart = 1
+    va.propagate_restartable(thermostat, x, p, a, bt, dbdl, traj_gid=gid, iproc=2, directory=str(d2))
+    vb = make(steps - first, Noutput=nout if thermostat == 1 else 10 ** 6)
+    vb.restart = 2
+    xb, pb, db = vb.propagate_restartable(thermostat, np.zeros_like(x), np.zeros_like(p), a, bt, dbdl, traj_gid=gid, iproc=2,
+                                          directory=str(d2))
+    assert relmax(xb, x0) < RTOL and relmax(pb, p0) < RTOL and np.abs(db - d0).max() <= RTOL * np.abs(d0).max()
+
+
 def test_init_path_matches_oracle(pk, orc):
     for name, n, beta, mass in (("2dtest", 40, 10.0, [1.0]), ("ccpol8sf", 12, 300.0, DIMER_MASS)):
         pes = pk.McmodMass(name).V_init()
