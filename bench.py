@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — ring-polymer bead-steps/s of the hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c4|c5|c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c4|c5|c3|c2|c1]
     torchrun ... bench.py --gpus N ...      (one rank per GPU, NCCL)
 
 A "step" is one thermostatted Verlet step (PES gradient on every bead + normal-mode transforms +
@@ -55,6 +55,9 @@ CONFIGS = {
                label="C5: CCpol-8sf water dimer, 1024 beads x 4096 trajectories, PILE"),
     "c2": dict(pes="2dtest", n=256, nintegral=16, nrep=256, thermostat=1, beta=10.0, Noutput=100,
                label="C2: 2D coupled double well TI, 256 beads x 4096 trajectories, Andersen"),
+    # C3: the GPU action gradient handed to L-BFGS-B on task 'FG' (instantonmod.f90:748-765); a single ring polymer
+    "c3": dict(pes="2dtest", n=1024, beta=30.0, instanton=True,
+               label="C3: 2D test PES ring-polymer instanton, 1024 beads, UMforceenergy f/g evaluations (L-BFGS-B on the host)"),
     "c1": dict(pes="1d", n=64, nintegral=16, nrep=16, thermostat=2, beta=10.0, Noutput=100000,
                label="C1: 1D double well TI, 64 beads x 256 trajectories, Langevin"),
 }
@@ -274,6 +277,19 @@ def run_ours(args, cfg, rank, world, local_rank):
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
     launches = int(L.pimdk_launch_count())
+    if args.quick:   # batch-scaling sweeps (C5): device-resident value only
+        tq = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"metric": "ring-polymer bead-steps/sec", "value": world * ntraj * n * K / (float(tq.item()) * 1e-3),
+                              "unit": "bead-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": float(tq.item()) / K,
+                              "config": {"workload": cfg["label"], "beads": n, "trajectories_per_gpu": ntraj, "mode": args.mode},
+                              "gpu_launches": launches, "clocks": sampler.summary(), "quick": True}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        pk.finalize()
+        return
     # ---- a second pass of K steps with per-kernel-family CUDA events (roofline of the dominant kernels) ----
     check(L.pimdk_profile(1))
     check(L.pimdk_profile_reset())
@@ -371,6 +387,96 @@ def run_ours(args, cfg, rank, world, local_rank):
     pk.finalize()
 
 
+def run_instanton(args, cfg, rank):
+    """C3: f/g evaluations per second of the ring-polymer action (UMforceenergy) through the host-buffer C ABI —
+    what `instanton` calls once per L-BFGS-B iteration — and the same through the CPU oracle; plus one full
+    optimisation with scipy's L-BFGS-B (same algorithm and settings as the vendored lbfgsb.f: m = 8, factr = 1e6,
+    pgtol = eps2 = 1e-5, maxls = 40) driven by the GPU gradient.  A single polymer does not shard: replicas only."""
+    if rank != 0:
+        return
+    import pimd_tunneling_b200 as pk
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    from scipy.optimize import fmin_l_bfgs_b
+
+    n, beta = cfg["n"], cfg["beta"]
+    a, b, mass = wells(cfg["pes"])
+    K, W = max(args.steps, 200), max(args.warmup, 20)
+    line = {"metric": "instanton action f/g evaluations/sec", "unit": "evaluations/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["label"], "beads": n, "beta": beta, "betan": "beta/n (rpi_ser.f90:45)"}}
+    # linear-interpolation start (rpi_ser.f90:157-163)
+    x0 = np.empty((n, a.shape[0], a.shape[1]), order="F")
+    for i in range(n):
+        x0[i] = a + (b - a) * i / (n - 1)
+    orc = Oracle().select(cfg["pes"])
+    orc.nm_setup(n, mass, beta / n, 1.0, 1.0, 1e-3, False, True)
+    if args.impl == "reference":
+        for _ in range(W):
+            orc.UMforceenergy(x0, a, b)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            orc.UMforceenergy(x0, a, b)
+        dt = time.perf_counter() - t0
+        line.update({"impl": "reference", "value": K / dt, "ms_per_step": 1e3 * dt / K, "gpu_launches": 0,
+                     "cpu_baseline": {"value": K / dt, "unit": "evaluations/s", "cores": 1, "kind": "port",
+                                      "sample": "%d evaluations of one 1024-bead polymer, 1 core (a single polymer is serial "
+                                                "in the reference too; parallelmod's MPI bead sharding is out of scope)" % K},
+                     "e2e": {"value": K / dt, "unit": "evaluations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(line), flush=True)
+        return
+    import torch
+    from pimd_tunneling_b200._lib import lib
+
+    pk.init(0)
+    pes = pk.McmodMass(cfg["pes"]).V_init()
+    im = pk.InstantonMod(pes, mass, beta, n, fixedends=True, rpi=True)
+    for _ in range(W):
+        im.UMforceenergy(x0, a, b)
+    torch.cuda.synchronize()
+    l0 = int(lib().pimdk_launch_count())
+    t0 = time.perf_counter()
+    for _ in range(K):
+        g, f = im.UMforceenergy(x0, a, b)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = int(lib().pimdk_launch_count()) - l0
+    nbytes = x0.nbytes
+    # one complete optimisation driven by the GPU gradient, iterate count and final action against the oracle's
+    def fg_gpu(v):
+        g_, f_ = im.UMforceenergy(v.reshape(x0.shape, order="F"), a, b)
+        return f_, g_.reshape(-1, order="F")
+
+    def fg_cpu(v):
+        g_, f_ = orc.UMforceenergy(v.reshape(x0.shape, order="F"), a, b)
+        return f_, g_.reshape(-1, order="F")
+
+    t1 = time.perf_counter()
+    xg, fgpu, ig = fmin_l_bfgs_b(fg_gpu, x0.reshape(-1, order="F"), m=8, factr=1e6, pgtol=1e-5, maxls=40, maxiter=15000)
+    t_opt = time.perf_counter() - t1
+    xc, fcpu, ic = fmin_l_bfgs_b(fg_cpu, x0.reshape(-1, order="F"), m=8, factr=1e6, pgtol=1e-5, maxls=40, maxiter=15000)
+    t0c = time.perf_counter()
+    for _ in range(K):
+        orc.UMforceenergy(x0, a, b)
+    dtc = time.perf_counter() - t0c
+    line.update({"value": K / dt, "ms_per_step": 1e3 * dt / K, "gpu_launches": launches,
+                 "e2e": {"value": K / dt, "unit": "evaluations/s", "h2d_bytes_per_step": nbytes + 2 * a.nbytes + mass.nbytes,
+                         "d2h_bytes_per_step": nbytes + 8,
+                         "note": "host-buffer C ABI call per evaluation, as L-BFGS-B on the host needs it; value == e2e"},
+                 "optimisation": {"iterations": int(ig["nit"]), "funcalls": int(ig["funcalls"]), "seconds": t_opt,
+                                  "action_betan_UM": float(fgpu) * beta / n, "oracle_iterations": int(ic["nit"]),
+                                  "oracle_funcalls": int(ic["funcalls"]), "rel_diff_action": abs(fgpu - fcpu) / abs(fcpu),
+                                  "max_abs_diff_path": float(np.abs(xg - xc).max())},
+                 "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                              "note": "1024 beads x 2 dof: ~1e5 flop and 50 KB per evaluation; the call is bound by launch and "
+                                      "PCIe round-trip latency, not by any throughput roofline"},
+                 "cpu_baseline": {"value": K / dtc, "unit": "evaluations/s", "cores": 1, "kind": "port",
+                                  "sample": "%d evaluations, 1 core" % K}})
+    print(json.dumps(line), flush=True)
+    pk.finalize()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -381,11 +487,15 @@ def main():
     ap.add_argument("--ntraj", type=int, default=0, help="override trajectories per GPU (testing)")
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="device-resident value only (no profiling, e2e or CPU legs)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if cfg.get("instanton"):
+        run_instanton(args, cfg, rank)
+        return
     if args.impl == "reference":
         run_reference(args, cfg, rank)
         return

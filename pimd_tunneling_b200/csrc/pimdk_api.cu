@@ -42,6 +42,27 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct PinBuf {  // page-locked host staging: asynchronous copies in both directions with one synchronisation
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct Prof {
   double ms = 0.0;
   long launches = 0;
@@ -72,7 +93,8 @@ struct Ctx {
   std::vector<double> mass, lam, beadmass, T;
   DevBuf dT, dsA, dsB, dlamb2, dmass, dtabs;  // dtabs: 8 per-call (natom,n) tables
   // workspaces
-  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum;
+  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wUmIn, wUmOut;
+  PinBuf hUm;
   // profiling
   bool profiling = false;
   std::map<std::string, Prof> prof;
@@ -332,8 +354,9 @@ int pimdk_finalize(void) {
   resolve_spans();
   DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
-                    &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum};
+                    &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wUmIn, &g.wUmOut};
   for (DevBuf* b : bufs) b->release();
+  g.hUm.release();
   g.inited = false;
   g.nm_ready = false;
   g.pes = PES_NONE;
@@ -495,41 +518,57 @@ int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const dou
   if (rc) return rc;
   if (n < 2) return fail(PIMDK_EINVAL, "n must be >= 2");
   if (fixedends && (!a || !b)) return fail(PIMDK_EINVAL, "fixedends needs a and b");
+  // This call sits inside L-BFGS-B's reverse-communication loop (instantonmod.f90:741-767): one small problem per
+  // call, so its cost is latency.  Inputs are packed into one page-locked block (one H2D copy), outputs and the
+  // flag word come back through it as well, and there is a single stream synchronisation.
   const long ndof = ndim * natom;
   const size_t nx = (size_t)n * ndof;
-  CU(g.wX.ensure(nx * sizeof(double)));
+  const size_t nin = nx + 2 * ndof + natom, nout = nx + 2;   // [x | a | b | mass]  /  [g | UM | flags]
+  CU(g.wUmIn.ensure(nin * sizeof(double)));
+  CU(g.wUmOut.ensure(nout * sizeof(double)));
   CU(g.wG.ensure(nx * sizeof(double)));
-  CU(g.wGn.ensure(nx * sizeof(double)));
   CU(g.wV.ensure((size_t)n * sizeof(double)));
-  CU(g.wMisc.ensure((size_t)(3 * ndof + natom + 2) * sizeof(double)));
-  double* dmisc = g.wMisc.as<double>();
-  double *da = dmisc, *db = dmisc + ndof, *dm = dmisc + 2 * ndof, *dum = dmisc + 2 * ndof + natom;
-  CU(cudaMemcpyAsync(g.wX.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(g.hUm.ensure((nin + nout) * sizeof(double)));
+  double* hin = g.hUm.as<double>();
+  double* hout = hin + nin;
+  std::memcpy(hin, x, nx * sizeof(double));
   if (fixedends) {
-    CU(cudaMemcpyAsync(da, a, ndof * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-    CU(cudaMemcpyAsync(db, b, ndof * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    std::memcpy(hin + nx, a, ndof * sizeof(double));
+    std::memcpy(hin + nx + ndof, b, ndof * sizeof(double));
   }
-  CU(cudaMemcpyAsync(dm, mass, natom * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  std::memcpy(hin + nx + 2 * ndof, mass, natom * sizeof(double));
+  double* dx = g.wUmIn.as<double>();
+  double *da = dx + nx, *db = da + ndof, *dm = db + ndof;
+  double* dg = g.wUmOut.as<double>();
+  double* dum = dg + nx;
+  CU(cudaMemcpyAsync(dx, hin, nin * sizeof(double), cudaMemcpyHostToDevice, g.stream));
   rc = clear_flags();
   if (rc) return rc;
   GeomLayout L{n, ndof * n, 1, n};
-  // x is intent(in) in UM*: the FD perturbation of ccpol works on the copy and its drift is dropped
-  double* xw = g.wX.as<double>();
+  // x is intent(in) in UM*: the FD perturbation of ccpol works on a copy and its drift is dropped
+  double* xw = dx;
   if (gout && g.pes == PES_CCPOL) {
     CU(g.wAux.ensure(nx * sizeof(double)));
-    CU(cudaMemcpyAsync(g.wAux.p, g.wX.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    CU(cudaMemcpyAsync(g.wAux.p, dx, nx * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
     xw = g.wAux.as<double>();
   }
   rc = pes_eval_dev(L, xw, f ? g.wV.as<double>() : nullptr, gout ? g.wG.as<double>() : nullptr, n, 0);
   if (rc) return rc;
   {
     Scope s("um", (f ? 1 : 0) + (gout ? 1 : 0));
-    CU(launch_um((int)n, (int)ndim, (int)natom, g.wX.as<double>(), da, db, dm, betan, fixedends != 0,
-                 g.wV.as<double>(), g.wG.as<double>(), f ? dum : nullptr, gout ? g.wGn.as<double>() : nullptr, g.stream));
+    CU(launch_um((int)n, (int)ndim, (int)natom, dx, da, db, dm, betan, fixedends != 0, g.wV.as<double>(),
+                 g.wG.as<double>(), f ? dum : nullptr, gout ? dg : nullptr, g.stream));
   }
-  if (f) CU(cudaMemcpyAsync(f, dum, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  if (gout) CU(cudaMemcpyAsync(gout, g.wGn.p, nx * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  return check_flags(false);
+  CU(cudaMemcpyAsync(hout, dg, (nx + 1) * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaMemcpyAsync(hout + nx + 1, g.wFlags.p, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  if (f) *f = hout[nx];
+  if (gout) std::memcpy(gout, hout, nx * sizeof(double));
+  int fl = 0;
+  std::memcpy(&fl, hout + nx + 1, sizeof(int));
+  if (fl & PIMDK_FLAG_NOCONV) return fail(PIMDK_ENOCONV, "No convergence in indN_iter");
+  if (fl & PIMDK_FLAG_NAN) return fail(PIMDK_ENAN, "NaN in pot propagation");
+  return PIMDK_OK;
 }
 
 int pimdk_nm_setup(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* mass, double betan, double tau) {

@@ -2,7 +2,8 @@
 // (instantonmod.f90:17-151).  The per-bead PES values/gradients come from the PES kernels; here the
 // spring terms are added.  The scalar UM is accumulated by ONE thread in exactly the reference's
 // order (bead energy, then that bead's springs, ..., then the fixed-end springs) so that the value
-// handed to L-BFGS-B is reproducible to the last bit; the gradient is elementwise.
+// handed to L-BFGS-B is reproducible to the last bit (its terms are formed in parallel first); the
+// gradient is elementwise.
 #include "kernels.h"
 
 namespace pimdk {
@@ -31,23 +32,55 @@ um_grad_kernel(int n, int ndim, int natom, const double* __restrict__ x, const d
   }
 }
 
-__global__ void um_energy_kernel(int n, int ndim, int natom, const double* __restrict__ x,
-                                 const double* __restrict__ a, const double* __restrict__ b,
-                                 const double* __restrict__ mass, double betan, int fixedends,
-                                 const double* __restrict__ vbead, double* __restrict__ um_out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  double um = 0.0;
+// One CTA.  The terms of UM (bead energy, that bead's ndof spring terms) are independent products: the CTA forms
+// them for a tile of beads in parallel into shared memory, then ONE thread adds them in the reference's order
+// (instantonmod.f90:24-33) — the additions are a serial dependency chain either way (8 cycles per DADD), but this
+// way no global-memory latency sits inside it.
+constexpr int kUmTile = 128;
+__global__ void __launch_bounds__(256)
+um_energy_kernel(int n, int ndim, int natom, const double* __restrict__ x, const double* __restrict__ a,
+                 const double* __restrict__ b, const double* __restrict__ mass, double betan, int fixedends,
+                 const double* __restrict__ vbead, double* __restrict__ um_out) {
+  extern __shared__ double terms[];   // [kUmTile][1 + ndof]
+  const int ndof = ndim * natom, w = 1 + ndof;
   const double bn2 = betan * betan;
-  for (int i = 0; i < n; ++i) {
-    um = um + vbead[i];
-    if (i < n - 1)
-      for (int j = 0; j < ndim; ++j)
-        for (int k = 0; k < natom; ++k) {
-          const long e = (long)(k * ndim + j) * n + i;
-          const double d = x[e + 1] - x[e];
-          um = um + (0.5 * mass[k] / bn2) * (d * d);
-        }
+  double um = 0.0;
+  for (int i0 = 0; i0 < n; i0 += kUmTile) {
+    const int nb = min(kUmTile, n - i0);
+    for (int t = threadIdx.x; t < nb * w; t += blockDim.x) {
+      const int ii = t / w, c = t - ii * w, i = i0 + ii;
+      double v;
+      if (c == 0) {
+        v = vbead[i];
+      } else if (i < n - 1) {
+        // reference loop order: j = dim outer, k = atom inner (:27-31); c - 1 = j * natom + k
+        const int j = (c - 1) / natom, k = (c - 1) - j * natom;
+        const long e = (long)(k * ndim + j) * n + i;
+        const double d = x[e + 1] - x[e];
+        v = (0.5 * mass[k] / bn2) * (d * d);
+      } else {
+        v = 0.0;   // the last bead has no spring to a successor; its slots are not added
+      }
+      terms[t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // terms[] is already in summation order (bead energy, its springs, next bead ...); the last bead of the
+      // polymer has no spring slots to add.  Eight loads are issued ahead of the eight dependent additions.
+      const int cnt = nb * w - ((i0 + nb == n) ? ndof : 0);
+      int t = 0;
+      for (; t + 8 <= cnt; t += 8) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = terms[t + q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) um = um + v[q];
+      }
+      for (; t < cnt; ++t) um = um + terms[t];
+    }
+    __syncthreads();
   }
+  if (threadIdx.x != 0) return;
   if (fixedends)
     for (int j = 0; j < ndim; ++j)
       for (int k = 0; k < natom; ++k) {
@@ -71,7 +104,9 @@ cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double*
     if (blocks > 148L * 8) blocks = 148L * 8;
     um_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(n, ndim, natom, x, a, b, mass, betan, fixedends, gbead, grad_out);
   }
-  if (um_out) um_energy_kernel<<<1, 32, 0, st>>>(n, ndim, natom, x, a, b, mass, betan, fixedends, vbead, um_out);
+  if (um_out)
+    um_energy_kernel<<<1, 256, (size_t)kUmTile * (1 + ndim * natom) * sizeof(double), st>>>(n, ndim, natom, x, a, b, mass, betan,
+                                                                                          fixedends, vbead, um_out);
   return cudaGetLastError();
 }
 
