@@ -431,6 +431,9 @@ def run_instanton(args, cfg, rank):
 
     pk.init(0)
     pes = pk.McmodMass(cfg["pes"]).V_init()
+    v0 = pes.V(a)                 # V0 = V(well1) (rpi_ser.f90:95)
+    pes.set_V0(v0)
+    orc.set_V0(v0)
     im = pk.InstantonMod(pes, mass, beta, n, fixedends=True, rpi=True)
     for _ in range(W):
         im.UMforceenergy(x0, a, b)
@@ -460,7 +463,11 @@ def run_instanton(args, cfg, rank):
     for _ in range(K):
         orc.UMforceenergy(x0, a, b)
     dtc = time.perf_counter() - t0c
-    line.update({"value": K / dt, "ms_per_step": 1e3 * dt / K, "gpu_launches": launches,
+    # close the calculation like `program rpi` does: V0 so that the wells sit at zero, fluctuation factor, splitting
+    t2 = time.perf_counter()
+    rpi = im.rpi_splitting(xg.reshape(x0.shape, order="F"), a, b)
+    rpi["seconds"] = time.perf_counter() - t2
+    line.update({"value": K / dt, "ms_per_step": 1e3 * dt / K, "gpu_launches": launches, "rpi": rpi,
                  "e2e": {"value": K / dt, "unit": "evaluations/s", "h2d_bytes_per_step": nbytes + 2 * a.nbytes + mass.nbytes,
                          "d2h_bytes_per_step": nbytes + 8,
                          "note": "host-buffer C ABI call per evaluation, as L-BFGS-B on the host needs it; value == e2e"},

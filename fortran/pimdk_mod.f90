@@ -55,6 +55,18 @@ module pimdk
        real(c_double), value :: dt, gamma; type(c_ptr), value :: gid
        real(c_double) :: x(*), p(*), a(*), b(*), dbdl(*), dHdr(*)
      end function
+     ! Vdoubleprime / UMhessian / detJ (mcmod_*.f90 Vdoubleprime; instantonmod.f90:155-217, 782-827)
+     integer(c_int) function pimdk_pes_hessian(nbatch, ndim, natom, x, hess) bind(C, name="pimdk_pes_hessian")
+       import; integer(c_int64_t), value :: nbatch, ndim, natom; real(c_double) :: x(*), hess(*)
+     end function
+     integer(c_int) function pimdk_um_hessian(n, ndim, natom, x, mass, betan, singlewell, band) bind(C, name="pimdk_um_hessian")
+       import; integer(c_int64_t), value :: n, ndim, natom, singlewell; real(c_double), value :: betan
+       real(c_double) :: x(*), mass(*), band(*)
+     end function
+     integer(c_int) function pimdk_detj(n, ndim, natom, x, mass, betan, singlewell, etasquared, eigvecs) bind(C, name="pimdk_detj")
+       import; integer(c_int64_t), value :: n, ndim, natom, singlewell; real(c_double), value :: betan
+       real(c_double) :: x(*), mass(*), etasquared(*); type(c_ptr), value :: eigvecs
+     end function
      ! module variables restart / restartnmc (verletmodule.f90:10) and the running sums write_restart stores (:171)
      integer(c_int) function pimdk_set_restart(restart, restartnmc) bind(C, name="pimdk_set_restart")
        import; integer(c_int64_t), value :: restart, restartnmc

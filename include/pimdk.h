@@ -81,6 +81,25 @@ int pimdk_pes_eval_dev(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, const 
 int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x, const double* a,
                          const double* b, const double* mass, double betan, pimdk_int fixedends, double* f, double* g);
 
+/* ---- second derivatives and the fluctuation factor -------------------------------
+ * pimdk_pes_hessian = Vdoubleprime(x, hess) of the selected plugin over a batch (mcmod_1d.f90:37-57: central
+ *   difference, eps = 1e-4, of the analytic gradient; mcmod_2dtest.f90:63-86: the reference's closed form, restated
+ *   literally — its four elements are assigned inside the loop over the wells, so only the last well contributes;
+ *   mcmod_waterdimer_ccpol.f90:59-76: central difference, eps = 1e-5, of the finite-difference Vprime).
+ *   x(ndim,natom,nbatch) is in/out: it is perturbed in place and keeps the reference's round-off drift.
+ *   hess(ndim,natom,ndim,natom,nbatch): hess(i,j,:,:) = d grad(:,:) / d x(i,j).
+ * pimdk_um_hessian  = UMhessian(x, singlewell, answer) (instantonmod.f90:155-217, no inithess):
+ *   band(ndof+1, totdof), LAPACK lower band storage of the mass-weighted ring-polymer Hessian exactly as the
+ *   reference fills it (spring coupling written for beads 2..n at row ndof+1; 2/betan**2 on every diagonal).
+ * pimdk_detj        = detJ(x, etasquared, singlewell[, eigvecs]) (instantonmod.f90:782-827): all eigenvalues of
+ *   that matrix in ascending order (the reference calls DSBEVD; here a dense FP64 eigensolver on the device),
+ *   eigvecs(totdof,totdof) optional (NULL = jobz 'N'). */
+int pimdk_pes_hessian(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, double* x, double* hess);
+int pimdk_um_hessian(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+                     pimdk_int singlewell, double* band);
+int pimdk_detj(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+               pimdk_int singlewell, double* etasquared, double* eigvecs);
+
 /* ---- module verletint -----------------------------------------------------------------------
  * pimdk_nm_setup = alloc_nm + the a,b-independent part of init_nm (verletmodule.f90:306-338):
  *   lam, beadmass, transmatrix.  beadvec (which depends on a and each trajectory's b) is formed

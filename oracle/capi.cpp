@@ -104,6 +104,7 @@ void orc_pes_set_dims(int ndim, int natom) { g_pes.ndim = ndim; g_pes.natom = na
 void orc_pes_set_V0(double v0) { g_pes.V0 = v0; }
 double orc_V(const double* x) { return g_pes.V(x); }
 void orc_Vprime(double* x, double* grad) { g_pes.Vprime(x, grad); }
+void orc_Vdoubleprime(double* x, double* hess) { g_pes.Vdoubleprime(x, hess); }
 // batch: x(ndim,natom,nbatch); v/grad may be NULL; x is updated in place when grad is requested
 // (the FD drift of mcmod_waterdimer_ccpol.f90:48-52 is kept, as step_v sees it)
 int orc_pes_eval(long nbatch, double* x, double* v, double* grad) {
@@ -162,6 +163,7 @@ double orc_normal(unsigned long long seed, int stream, unsigned long long step, 
   return normal_at(seed, stream, step, gid, idx);
 }
 double orc_UM(const double* x, const double* a, const double* b) { return g_v.UM(x, a, b); }
+void orc_UMhessian(double* x, int singlewell, double* answer) { g_v.UMhessian(x, singlewell != 0, answer); }
 void orc_UMprime(const double* x, double* g, const double* a, const double* b) { g_v.UMprime(x, g, a, b); }
 double orc_UMforceenergy(const double* x, double* g, const double* a, const double* b) {
   return g_v.UMforceenergy(x, g, a, b);

@@ -5,6 +5,7 @@
 #pragma once
 #include <cmath>
 #include <stdexcept>
+#include <vector>
 
 #include "ccpol_impl.hpp"
 #include "tables.hpp"
@@ -126,6 +127,47 @@ struct Pes {
         return;
       }
     }
+  }
+
+  // subroutine Vdoubleprime(x, hess): hess(ndim,natom,ndim,natom) column-major,
+  // index(i,j,i2,j2) = i + ndim*(j + natom*(i2 + ndim*j2)) (0-based); hess(i,j,:,:) = d grad(:,:) / d x(i,j).
+  //   1D    mcmod_1d.f90:37-57    central difference of the analytic gradient, eps = 1e-4, x perturbed in place
+  //   2D    mcmod_2dtest.f90:63-86  "analytic", but the four elements are ASSIGNED inside the loop over the wells,
+  //         so only the last well (k = m) survives, and the cross/diagonal terms reuse dudy/dudx as written.
+  //         Restated literally: this is what the reference's detJ sees.
+  //   CCpol mcmod_waterdimer_ccpol.f90:59-76  central difference, eps = 1e-5, of the finite-difference Vprime, whose
+  //         own in-place perturbation drift of x carries through the whole double loop
+  void Vdoubleprime(double* x, double* hess) {
+    const int nd = ndim * natom;
+    auto H = [&](int i, int j, int i2, int j2) -> double& { return hess[i + ndim * (j + natom * (i2 + ndim * j2))]; };
+    if (kind == PES_2DTEST) {
+      for (int q = 0; q < nd * nd; ++q) hess[q] = 0.0;
+      for (int k = 0; k < m; ++k) {
+        double u = (x[0] - wx[k]) * (x[0] - wx[k]) + (x[1] - wy[k]) * (x[1] - wy[k]);
+        double dvdu = a0 * pimdk_exp(-a0 * u) + b0 * pimdk_exp(-b0 * u);
+        double d2vdu2 = -(a0 * a0) * pimdk_exp(-a0 * u) - (b0 * b0) * pimdk_exp(-b0 * u);
+        double dudx = x[0] - wx[k];
+        double dudy = x[1] - wy[k];
+        H(0, 0, 0, 0) = (d2vdu2 * dudx + dvdu) * dudx;
+        H(1, 0, 0, 0) = (d2vdu2 * dudy + dvdu) * dudx;
+        H(0, 0, 1, 0) = (d2vdu2 * dudy + dvdu) * dudx;
+        H(1, 0, 1, 0) = (d2vdu2 * dudy + dvdu) * dudy;
+      }
+      return;
+    }
+    const double eps = (kind == PES_CCPOL) ? 1e-5 : 1e-4;
+    std::vector<double> gp(nd), gm(nd);
+    for (int i = 0; i < ndim; ++i)
+      for (int j = 0; j < natom; ++j) {
+        double& xij = x[j * ndim + i];
+        xij = xij + eps;
+        Vprime(x, gp.data());
+        xij = xij - 2.0 * eps;
+        Vprime(x, gm.data());
+        xij = xij + eps;
+        for (int j2 = 0; j2 < natom; ++j2)
+          for (int i2 = 0; i2 < ndim; ++i2) H(i, j, i2, j2) = (gp[j2 * ndim + i2] - gm[j2 * ndim + i2]) / (2.0 * eps);
+      }
   }
 };
 

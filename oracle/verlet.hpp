@@ -398,6 +398,44 @@ struct Verlet {
     return um;
   }
 
+  // UMhessian, instantonmod.f90:155-217 (no inithess): answer(ndof+1, totdof) column-major, LAPACK lower band
+  // storage as handed to DSBEVD('L', totdof, kd = ndof).  Literal restatement, including: the spring coupling
+  // -1/betan**2 is written at answer(ndof+1, fulldof1) for beads i > 1 (so the bead 1 - bead 2 coupling is
+  // absent and the last bead's entry lies outside the matrix), and every diagonal carries 2/betan**2.
+  // x (n,ndim,natom) is perturbed in place by the PES's Vdoubleprime exactly like the reference's x(i,:,:).
+  void UMhessian(double* x, bool singlewell, double* answer) {
+    const int totdof = n * ndof, ld = ndof + 1;
+    for (long q = 0; q < (long)ld * totdof; ++q) answer[q] = 0.0;
+    std::vector<double> hess((size_t)ndof * ndof, 0.0), xb(ndof);
+    auto Hs = [&](int j1, int k1, int j2, int k2) { return hess[(j1 - 1) + ndim * ((k1 - 1) + natom * ((j2 - 1) + ndim * (k2 - 1)))]; };
+    for (int i = 1; i <= n; ++i) {
+      if ((i == 1 && singlewell) || !singlewell) {
+        for (int j = 1; j <= ndim; ++j)
+          for (int k = 1; k <= natom; ++k) xb[(k - 1) * ndim + (j - 1)] = x[IX(i, j, k)];
+        pes->Vdoubleprime(xb.data(), hess.data());
+        for (int j = 1; j <= ndim; ++j)
+          for (int k = 1; k <= natom; ++k) x[IX(i, j, k)] = xb[(k - 1) * ndim + (j - 1)];
+      }
+      for (int j1 = 1; j1 <= ndim; ++j1)
+        for (int k1 = 1; k1 <= natom; ++k1)
+          for (int j2 = 1; j2 <= ndim; ++j2)
+            for (int k2 = 1; k2 <= natom; ++k2) {
+              const int idof1 = (k1 - 1) * ndim + j1, idof2 = (k2 - 1) * ndim + j2;
+              const int fulldof1 = ndof * (i - 1) + idof1, fulldof2 = ndof * (i - 1) + idof2;
+              if (fulldof2 < fulldof1) continue;
+              auto A = [&](int r, int c) -> double& { return answer[(r - 1) + (long)ld * (c - 1)]; };
+              if (idof1 == idof2) {
+                A(1, fulldof1) = 2.0 / (betan * betan) + Hs(j2, k2, j1, k1) / std::sqrt(mass[k1 - 1] * mass[k2 - 1]);
+                if (i > 1) A(ndof + 1, fulldof1) = -1.0 / (betan * betan);
+              } else {
+                const int index = 1 + fulldof2 - fulldof1;
+                if (index < 0) continue;
+                A(index, fulldof1) = Hs(j2, k2, j1, k1) / std::sqrt(mass[k1 - 1] * mass[k2 - 1]);
+              }
+            }
+    }
+  }
+
   // spring part of the gradient shared by UMprime :59-77 and UMforceenergy :117-134
   double spring_grad(const double* x, const double* a, const double* b, int i, int j, int k) const {
     double m = mass[k - 1], bn2 = betan * betan;

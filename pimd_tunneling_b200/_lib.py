@@ -37,6 +37,9 @@ _SIGS = {
     "pimdk_pes_vprime_inplace": [_i64, _i64, _i64, _pd, _pd],
     "pimdk_pes_eval_dev": [_i64, _i64, _i64, _pd, _pd, _pd],
     "pimdk_um_forceenergy": [_i64, _i64, _i64, _pd, _pd, _pd, _pd, _dbl, _i64, _pd, _pd],
+    "pimdk_pes_hessian": [_i64, _i64, _i64, _pd, _pd],
+    "pimdk_um_hessian": [_i64, _i64, _i64, _pd, _pd, _dbl, _i64, _pd],
+    "pimdk_detj": [_i64, _i64, _i64, _pd, _pd, _dbl, _i64, _pd, _pd],
     "pimdk_nm_setup": [_i64, _i64, _i64, _pd, _dbl, _dbl],
     "pimdk_nm_get": [_pd, _pd, _pd],
     "pimdk_nm_transform": [_i64, _i64, _pd, _pd, _pd],

@@ -25,6 +25,7 @@ UNITS = [
     ("nm_kernels.cu", "nm_kernels.o", ["-fmad=false"]),
     ("fused_small.cu", "fused_small.o", ["-fmad=false"]),
     ("um_kernels.cu", "um_kernels.o", ["-fmad=false"]),
+    ("hess_kernels.cu", "hess_kernels.o", ["-fmad=false"]),
     ("fp64_peak.cu", "fp64_peak.o", ["-fmad=false"]),
     ("pimdk_api.cu", "pimdk_api.o", ["-fmad=false"]),
     ("ccpol_tables.cpp", "ccpol_tables.o", []),
@@ -61,7 +62,7 @@ def build(verbose=False, force=False):
                 print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)
     if force or _newer(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart=shared"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart=shared", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

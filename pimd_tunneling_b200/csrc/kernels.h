@@ -104,6 +104,16 @@ cudaError_t launch_fused_small(const NmTables& nm, PesKind kind, const SimplePes
                                long NMC, long imin, double lambda, uint64_t seed, const int64_t* gid, double* dHdr,
                                int* flags, long step0, int keep_sum, double* dHsum, cudaStream_t st);
 
+// ---- second derivatives (hess_kernels.cu): Vdoubleprime, UMhessian (instantonmod.f90:155-217) ----
+cudaError_t launch_simple_hessian(PesKind kind, const SimplePesParams& P, int ndim, int natom, GeomLayout L, double* x,
+                                  double* hess, long ngeom, cudaStream_t st);
+cudaError_t launch_perturb(GeomLayout L, double* x, long ngeom, int dof, double delta, cudaStream_t st);
+cudaError_t launch_hess_column(GeomLayout L, const double* gp, const double* gm, long ngeom, int nd, int dof1, double eps,
+                               double* hess, cudaStream_t st);
+cudaError_t launch_um_band(int n, int ndim, int natom, const double* hess, const double* mass, double betan, int singlewell,
+                           double* band, cudaStream_t st);
+cudaError_t launch_band_to_dense(long N, int kd, const double* band, double* A, cudaStream_t st);
+
 // ---- ring-polymer potential (um_kernels.cu): instantonmod.f90:17-151 ----
 cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double* a, const double* b,
                       const double* mass, double betan, int fixedends, const double* vbead /*n or NULL*/,

@@ -3,6 +3,7 @@
 // ring-polymer rotation, PILE coefficients) uses the reference's own expressions
 // (verletmodule.f90:306-338, 381-386, 515-531) evaluated once per call in FP64 on the host.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -93,7 +94,7 @@ struct Ctx {
   std::vector<double> mass, lam, beadmass, T;
   DevBuf dT, dsA, dsB, dlamb2, dmass, dtabs;  // dtabs: 8 per-call (natom,n) tables
   // workspaces
-  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wUmIn, wUmOut;
+  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wUmIn, wUmOut, wHgp, wHgm, wHess, wBand, wDense, wEig, wWork;
   PinBuf hUm;
   // profiling
   bool profiling = false;
@@ -354,7 +355,8 @@ int pimdk_finalize(void) {
   resolve_spans();
   DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
-                    &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wUmIn, &g.wUmOut};
+                    &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wUmIn, &g.wUmOut, &g.wHgp, &g.wHgm, &g.wHess, &g.wBand,
+                    &g.wDense, &g.wEig, &g.wWork};
   for (DevBuf* b : bufs) b->release();
   g.hUm.release();
   g.inited = false;
@@ -568,6 +570,173 @@ int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const dou
   std::memcpy(&fl, hout + nx + 1, sizeof(int));
   if (fl & PIMDK_FLAG_NOCONV) return fail(PIMDK_ENOCONV, "No convergence in indN_iter");
   if (fl & PIMDK_FLAG_NAN) return fail(PIMDK_ENAN, "NaN in pot propagation");
+  return PIMDK_OK;
+}
+
+// ---- second derivatives: Vdoubleprime, UMhessian, detJ ------------------------------------------
+// Hessians of `ngeom` geometries laid out per L (device pointers); x is perturbed in place like the reference's.
+static int pes_hessian_dev(GeomLayout L, double* x, double* hess, long ngeom, int ndim, int natom) {
+  if (g.pes == PES_NONE) return fail(PIMDK_EINVAL, "no PES selected (pimdk_pes_select)");
+  if (ngeom <= 0) return PIMDK_OK;
+  const int nd = ndim * natom;
+  if (g.pes != PES_CCPOL) {
+    if (nd > 4) return fail(PIMDK_EINVAL, "Vdoubleprime of the model surfaces supports ndim*natom <= 4");
+    Scope s("hess");
+    CU(launch_simple_hessian(g.pes, g.sp, ndim, natom, L, x, hess, ngeom, g.stream));
+    return PIMDK_OK;
+  }
+  // mcmod_waterdimer_ccpol.f90:59-76: central difference (eps = 1e-5) of the finite-difference Vprime.  Every
+  // Vprime call perturbs all 18 coordinates in place and leaves its drift behind, so the 36 gradient passes are
+  // sequential in x by construction; each pass runs the whole batch through the gradient pipeline.
+  const double eps = 1e-5;
+  // extent of the coordinate array addressed by L (gradient buffers share its layout)
+  const long ext = L.base(ngeom - 1) + (long)(nd - 1) * L.stride_dof + 1;
+  CU(g.wHgp.ensure(sizeof(double) * ext));
+  CU(g.wHgm.ensure(sizeof(double) * ext));
+  double *gp = g.wHgp.as<double>(), *gm = g.wHgm.as<double>();
+  for (int i = 0; i < ndim; ++i)
+    for (int j = 0; j < natom; ++j) {
+      const int d1 = j * ndim + i;
+      CU(launch_perturb(L, x, ngeom, d1, eps, g.stream));
+      int rc = pes_eval_dev(L, x, nullptr, gp, ngeom, 1);
+      if (rc) return rc;
+      CU(launch_perturb(L, x, ngeom, d1, -2.0 * eps, g.stream));
+      rc = pes_eval_dev(L, x, nullptr, gm, ngeom, 1);
+      if (rc) return rc;
+      CU(launch_perturb(L, x, ngeom, d1, eps, g.stream));
+      CU(launch_hess_column(L, gp, gm, ngeom, nd, d1, eps, hess, g.stream));
+    }
+  return PIMDK_OK;
+}
+
+int pimdk_pes_hessian(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, double* x, double* hess) {
+  NEED_INIT();
+  int rc = check_dims(ndim, natom);
+  if (rc) return rc;
+  if (nbatch <= 0) return PIMDK_OK;
+  if (!x || !hess) return fail(PIMDK_EINVAL, "x and hess must not be NULL");
+  const long nd = ndim * natom;
+  CU(g.wX.ensure(sizeof(double) * nbatch * nd));
+  CU(g.wHess.ensure(sizeof(double) * nbatch * nd * nd));
+  CU(cudaMemcpyAsync(g.wX.p, x, sizeof(double) * nbatch * nd, cudaMemcpyHostToDevice, g.stream));
+  rc = clear_flags();
+  if (rc) return rc;
+  GeomLayout L{1, nd, 0, 1};
+  rc = pes_hessian_dev(L, g.wX.as<double>(), g.wHess.as<double>(), nbatch, (int)ndim, (int)natom);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(x, g.wX.p, sizeof(double) * nbatch * nd, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaMemcpyAsync(hess, g.wHess.p, sizeof(double) * nbatch * nd * nd, cudaMemcpyDeviceToHost, g.stream));
+  return check_flags(false);
+}
+
+// UMhessian into g.wBand (device); x (n,ndim,natom) on the host is updated with the perturbation drift
+static int um_hessian_dev(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+                          pimdk_int singlewell) {
+  int rc = check_dims(ndim, natom);
+  if (rc) return rc;
+  if (n < 1 || !x || !mass || !(betan > 0.0)) return fail(PIMDK_EINVAL, "bad UMhessian arguments");
+  const long nd = ndim * natom, nx = n * nd;
+  const long ngeom = singlewell ? 1 : n;   // singlewell: Vdoubleprime is called for bead 1 only (instantonmod.f90:183)
+  CU(g.wX.ensure(sizeof(double) * nx));
+  CU(g.wHess.ensure(sizeof(double) * ngeom * nd * nd));
+  CU(g.wBand.ensure(sizeof(double) * (nd + 1) * nx));
+  CU(g.wMisc.ensure(sizeof(double) * natom));
+  CU(cudaMemcpyAsync(g.wX.p, x, sizeof(double) * nx, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.wMisc.p, mass, sizeof(double) * natom, cudaMemcpyHostToDevice, g.stream));
+  rc = clear_flags();
+  if (rc) return rc;
+  GeomLayout L{n, nd * n, 1, n};   // x(n,ndim,natom): bead index fastest
+  rc = pes_hessian_dev(L, g.wX.as<double>(), g.wHess.as<double>(), ngeom, (int)ndim, (int)natom);
+  if (rc) return rc;
+  {
+    Scope s("hess");
+    CU(launch_um_band((int)n, (int)ndim, (int)natom, g.wHess.as<double>(), g.wMisc.as<double>(), betan, singlewell != 0,
+                      g.wBand.as<double>(), g.stream));
+  }
+  CU(cudaMemcpyAsync(x, g.wX.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, g.stream));
+  return check_flags(false);
+}
+
+int pimdk_um_hessian(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+                     pimdk_int singlewell, double* band) {
+  NEED_INIT();
+  if (!band) return fail(PIMDK_EINVAL, "band must not be NULL");
+  int rc = um_hessian_dev(n, ndim, natom, x, mass, betan, singlewell);
+  if (rc) return rc;
+  const long nd = ndim * natom;
+  CU(cudaMemcpyAsync(band, g.wBand.p, sizeof(double) * (nd + 1) * n * nd, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return PIMDK_OK;
+}
+
+// cuSOLVER (dense symmetric eigensolver) is bound at run time so that libpimdk.so itself only needs the CUDA runtime
+namespace {
+struct Cusolver {
+  void* lib = nullptr;
+  void* handle = nullptr;
+  int (*create)(void**) = nullptr;
+  int (*destroy)(void*) = nullptr;
+  int (*set_stream)(void*, cudaStream_t) = nullptr;
+  int (*bufsize)(void*, int, int, int, const double*, int, const double*, int*) = nullptr;
+  int (*syevd)(void*, int, int, int, double*, int, double*, double*, int, int*) = nullptr;
+} cs;
+int cusolver_load() {
+  if (cs.handle) return PIMDK_OK;
+  const char* names[] = {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so.11",
+                         "/usr/local/cuda/lib64/libcusolver.so"};
+  for (const char* nm : names) {
+    cs.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (cs.lib) break;
+  }
+  if (!cs.lib) return fail(PIMDK_ECUDA, "detJ needs cuSOLVER (libcusolver.so.11 not found: %s)", dlerror());
+  cs.create = (int (*)(void**))dlsym(cs.lib, "cusolverDnCreate");
+  cs.destroy = (int (*)(void*))dlsym(cs.lib, "cusolverDnDestroy");
+  cs.set_stream = (int (*)(void*, cudaStream_t))dlsym(cs.lib, "cusolverDnSetStream");
+  cs.bufsize = (int (*)(void*, int, int, int, const double*, int, const double*, int*))dlsym(cs.lib, "cusolverDnDsyevd_bufferSize");
+  cs.syevd = (int (*)(void*, int, int, int, double*, int, double*, double*, int, int*))dlsym(cs.lib, "cusolverDnDsyevd");
+  if (!cs.create || !cs.destroy || !cs.set_stream || !cs.bufsize || !cs.syevd) return fail(PIMDK_ECUDA, "cuSOLVER symbols missing");
+  if (cs.create(&cs.handle) != 0) {
+    cs.handle = nullptr;
+    return fail(PIMDK_ECUDA, "cusolverDnCreate failed");
+  }
+  return PIMDK_OK;
+}
+}  // namespace
+
+int pimdk_detj(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+               pimdk_int singlewell, double* etasquared, double* eigvecs) {
+  NEED_INIT();
+  if (!etasquared) return fail(PIMDK_EINVAL, "etasquared must not be NULL");
+  int rc = um_hessian_dev(n, ndim, natom, x, mass, betan, singlewell);   // "Hessian is cooked."
+  if (rc) return rc;
+  rc = cusolver_load();
+  if (rc) return rc;
+  const long nd = ndim * natom, N = n * nd;
+  if (N > 46000) return fail(PIMDK_EINVAL, "totdof too large for the dense eigensolver");
+  CU(g.wDense.ensure(sizeof(double) * N * N));
+  CU(g.wEig.ensure(sizeof(double) * N + sizeof(int)));
+  {
+    Scope s("hess");
+    CU(launch_band_to_dense(N, (int)nd, g.wBand.as<double>(), g.wDense.as<double>(), g.stream));
+  }
+  // DSBEVD(jobz, 'L', totdof, ndof, H, ndof+1, etasquared, ...) (instantonmod.f90:819-823): all eigenvalues, ascending
+  const int jobz = eigvecs ? 1 : 0;   // CUSOLVER_EIG_MODE_VECTOR / NOVECTOR
+  const int uplo = 0;                 // CUBLAS_FILL_MODE_LOWER
+  int lwork = 0;
+  if (cs.set_stream(cs.handle, g.stream) != 0) return fail(PIMDK_ECUDA, "cusolverDnSetStream failed");
+  if (cs.bufsize(cs.handle, jobz, uplo, (int)N, g.wDense.as<double>(), (int)N, g.wEig.as<double>(), &lwork) != 0)
+    return fail(PIMDK_ECUDA, "cusolverDnDsyevd_bufferSize failed");
+  CU(g.wWork.ensure(sizeof(double) * (size_t)lwork));
+  int* dinfo = reinterpret_cast<int*>(g.wEig.as<double>() + N);
+  const int st = cs.syevd(cs.handle, jobz, uplo, (int)N, g.wDense.as<double>(), (int)N, g.wEig.as<double>(),
+                          g.wWork.as<double>(), lwork, dinfo);
+  if (st != 0) return fail(PIMDK_ECUDA, "cusolverDnDsyevd failed (status %d)", st);
+  int info = 0;
+  CU(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaMemcpyAsync(etasquared, g.wEig.p, sizeof(double) * N, cudaMemcpyDeviceToHost, g.stream));
+  if (eigvecs) CU(cudaMemcpyAsync(eigvecs, g.wDense.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  if (info != 0) return fail(PIMDK_ECUDA, "eigensolver did not converge (info = %d)", info);
   return PIMDK_OK;
 }
 

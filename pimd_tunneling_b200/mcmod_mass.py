@@ -76,6 +76,26 @@ class McmodMass:
         v, g = self.eval_batch(xb, energy=True, gradient=True)
         return g[:, :, 0], float(v[0])
 
+    # subroutine Vdoubleprime(x, hess)
+    def Vdoubleprime(self, x, inplace=False):
+        """hess(ndim,natom,ndim,natom) with hess[i,j,:,:] = d grad / d x(i,j) (mcmod_1d.f90:37-57,
+        mcmod_2dtest.f90:63-86, mcmod_waterdimer_ccpol.f90:59-76).  inplace=True leaves the reference's
+        finite-difference drift in x."""
+        xb = np.array(np.asarray(x, dtype=np.float64).reshape(self.ndim, self.natom, 1, order="F"), order="F")
+        h = self.Vdoubleprime_batch(xb)
+        if inplace:
+            np.asarray(x)[...] = xb[:, :, 0]
+        return h[..., 0]
+
+    def Vdoubleprime_batch(self, x):
+        """x(ndim,natom,nbatch), F-contiguous float64, updated in place; returns hess(ndim,natom,ndim,natom,nbatch)"""
+        self._need()
+        assert x.dtype == np.float64 and x.flags["F_CONTIGUOUS"] and x.shape[:2] == (self.ndim, self.natom)
+        nb = x.shape[2]
+        h = np.empty((self.ndim, self.natom, self.ndim, self.natom, nb), order="F")
+        check(lib().pimdk_pes_hessian(nb, self.ndim, self.natom, hptr(x), hptr(h)))
+        return h
+
     # batched forms --------------------------------------------------------------------------
     def eval_batch(self, x, energy=True, gradient=True):
         self._need()

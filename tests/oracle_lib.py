@@ -222,6 +222,22 @@ class Oracle:
         f = self.L.orc_UMforceenergy(_p(x), _p(g), _p(a), _p(b))
         return g, f
 
+    def Vdoubleprime(self, x):
+        """-> hess(ndim,natom,ndim,natom), x after the in-place perturbation"""
+        x = np.array(x, dtype=np.float64, order="F")
+        h = np.empty((self.ndim, self.natom, self.ndim, self.natom), order="F")
+        self.L.orc_Vdoubleprime(_p(x), _p(h))
+        return h, x
+
+    def UMhessian(self, x, singlewell=False):
+        """-> answer(ndof+1, totdof) (needs nm_setup for n, mass, betan)"""
+        x = np.array(x, dtype=np.float64, order="F")
+        n = x.shape[0]
+        ndof = self.ndim * self.natom
+        band = np.empty((ndof + 1, n * ndof), order="F")
+        self.L.orc_UMhessian(_p(x), int(singlewell), _p(band))
+        return band
+
     def gauleg(self, x1, x2, n):
         x = np.empty(n)
         w = np.empty(n)

@@ -450,3 +450,117 @@ def test_ti_averages_agree_with_oracle_within_error_bars(pk, orc):
     assert abs(res["deltaA"] - dA_o) < 4.0 * s_dA
     # symmetric double well: the integrand is antisymmetric about lambda = 1/2, so Delta A ~ 0 within noise
     assert abs(res["deltaA"]) < 5.0 * np.sqrt(np.sum(res["weights"] ** 2 * sg ** 2)) + 1e-12
+
+
+# ---------------------------------------------------------------- second derivatives (row N2) -----
+def test_vdoubleprime_bit_exact(pk, orc):
+    """Vdoubleprime of the three plugins against the oracle's literal restatement, including the in-place drift"""
+    rng = np.random.default_rng(21)
+    for name, scale in (("1d", 1.5), ("2dtest", 2.5)):
+        pes = pk.McmodMass(name).V_init()
+        orc.select(name)
+        x = np.asfortranarray(rng.uniform(-scale, scale, size=(pes.ndim, pes.natom, 50)))
+        xg = x.copy(order="F")
+        h = pes.Vdoubleprime_batch(xg)
+        for t in range(50):
+            ho, xo = orc.Vdoubleprime(x[..., t])
+            assert np.array_equal(h[..., t], ho) and np.array_equal(xg[..., t], xo)
+    # 2D: symmetric by construction of the reference's formula; 1D: close to the analytic second derivative
+    pes = pk.McmodMass("1d").V_init()
+    h1 = pes.Vdoubleprime(np.array([[0.7]]))
+    assert abs(h1[0, 0, 0, 0] - (12 * 0.7 ** 2 - 4)) < 1e-6
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    orc.select("ccpol8sf")
+    x = thermal_dimer_geometries(3, seed=5)
+    xg = x.copy(order="F")
+    h = pes.Vdoubleprime_batch(xg)
+    for t in range(3):
+        ho, xo = orc.Vdoubleprime(x[..., t])
+        assert np.array_equal(xg[..., t], xo)
+        assert np.array_equal(h[..., t], ho)
+    hm = h[..., 0].reshape(18, 18, order="F")
+    assert np.abs(hm - hm.T).max() < 2e-3 * np.abs(hm).max()   # FD-of-FD noise level, eps 1e-5 / 1e-4
+
+
+@pytest.mark.parametrize("name,n,beta,mass,singlewell", [("2dtest", 64, 30.0, [1.0], False), ("2dtest", 1024, 30.0, [1.0], False),
+                                                         ("1d", 48, 10.0, [1.3], True), ("ccpol8sf", 6, 300.0, DIMER_MASS, False)])
+def test_umhessian_and_detj(pk, orc, name, n, beta, mass, singlewell):
+    """UMhessian band matrix bit-exact against the oracle; detJ eigenvalues against LAPACK's banded solver
+    (scipy.linalg.eigvals_banded = DSBEVX/DSBEVD family, the routine the reference calls) on the oracle's matrix"""
+    from scipy.linalg import eigvals_banded
+
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    a, b = _wells(name)
+    im = pk.InstantonMod(pes, mass, beta, n, fixedends=True, rpi=True)
+    orc.nm_setup(n, mass, im.betan, 1.0, 1.0, 1e-3, False, True)
+    rng = np.random.default_rng(3)
+    x = np.empty((n, pes.ndim, pes.natom), order="F")
+    if name == "ccpol8sf":
+        from pimd_tunneling_b200 import path as P
+        lam, path, spl = P.build_path(P.acceptor_switch_path(a, b, 9))
+        xs, _ = P.endpoints(lam, path, spl, np.linspace(0, 1, n))
+        for k in range(n):
+            x[k] = xs[..., k]
+    else:
+        for k in range(n):
+            x[k] = a + (b - a) * k / (n - 1) + rng.normal(0, 0.02, size=a.shape)
+    band = im.UMhessian(x, singlewell)
+    bo = orc.UMhessian(x, singlewell)
+    assert np.array_equal(band, bo)
+    eta = im.detJ(x, singlewell)
+    ref = eigvals_banded(bo, lower=True)
+    assert np.all(np.diff(eta) >= 0)
+    assert np.abs(eta - ref).max() <= 1e-10 * np.abs(ref).max()
+    if n <= 64:
+        eta2, z = im.detJ(x, singlewell, eigvecs=True)
+        assert np.abs(eta2 - ref).max() <= 1e-10 * np.abs(ref).max()
+        N = n * pes.ndof
+        dense = np.zeros((N, N))
+        for c in range(N):
+            for r in range(c, min(N, c + pes.ndof + 1)):
+                dense[r, c] = dense[c, r] = bo[r - c, c]
+        assert np.abs(dense @ z - z * eta2[None, :]).max() <= 1e-9 * np.abs(ref).max()
+        assert np.abs(z.T @ z - np.eye(N)).max() < 1e-10
+
+
+def test_rpi_splitting_closes_the_instanton_calculation(pk, orc):
+    """rpi_ser.f90:221-236, 350-381 through the GPU path (instanton by L-BFGS-B on the GPU gradient, two detJ calls,
+    kink action) against the same formulas on the oracle's UM / UMhessian with LAPACK eigenvalues."""
+    from scipy.linalg import eigvals_banded
+    from scipy.optimize import fmin_l_bfgs_b
+
+    name, n, beta, mass = "2dtest", 128, 30.0, [1.0]
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    a, b = _wells(name)
+    v0 = pes.V(a)                 # V0 = V(well1) (rpi_ser.f90:95): the wells sit at zero
+    pes.set_V0(v0)
+    orc.set_V0(v0)
+    im = pk.InstantonMod(pes, mass, beta, n, fixedends=True, rpi=True)
+    orc.nm_setup(n, mass, im.betan, 1.0, 1.0, 1e-3, False, True)
+    x0 = np.empty((n, 2, 1), order="F")
+    for i in range(n):
+        x0[i] = a + (b - a) * i / (n - 1)
+
+    def fg(v):
+        g_, f_ = im.UMforceenergy(v.reshape(x0.shape, order="F"), a, b)
+        return f_, g_.reshape(-1, order="F")
+
+    xs, _, info = fmin_l_bfgs_b(fg, x0.reshape(-1, order="F"), m=8, factr=1e6, pgtol=1e-5, maxls=40, maxiter=5000)
+    xt = np.asfortranarray(xs.reshape(x0.shape, order="F"))
+    r = im.rpi_splitting(xt, a, b)
+    xh = np.empty_like(xt)
+    xh[:] = a.reshape(1, 2, 1)
+    e0 = eigvals_banded(orc.UMhessian(xh, True), lower=True)
+    e1 = eigvals_banded(orc.UMhessian(xt, False), lower=True)[1:]
+    l0, l1 = np.sum(np.log(e0[e0 > 0])), np.sum(np.log(e1[e1 > 0]))
+    phi = np.exp(0.5 * (l1 - l0))
+    sk = im.betan * orc.UM(xt, a, b)
+    theta = im.betan * np.exp(-sk) * np.sqrt(sk / (2.0 * 3.14159265358979)) / phi
+    assert abs(r["lndetj0"] - l0) <= 1e-10 * abs(l0) and abs(r["lndetj"] - l1) <= 1e-10 * abs(l1)
+    assert abs(r["s_kink"] - sk) <= 1e-12 * abs(sk)
+    assert abs(r["delta"] - 2.0 * theta / im.betan) <= 1e-8 * abs(2.0 * theta / im.betan)
+    assert np.isfinite(r["delta"]) and r["delta"] > 0.0 and r["s_kink"] > 0.0
+    pes.set_V0(0.0)
+    orc.set_V0(0.0)
