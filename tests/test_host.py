@@ -150,3 +150,23 @@ def test_namelist_reader_defaults_and_overrides():
     mc = read_namelist("&MCDATA\n n=64, beta=10.0d0, NMC=2000, thermostat=2,\n nintegral=8, nrep=4, cayley=.true., basename='x'\n/\n")
     assert (mc.n, mc.beta, mc.NMC, mc.thermostat, mc.nintegral, mc.nrep, mc.cayley) == (64, 10.0, 2000, 2, 8, 4, True)
     assert mc.extra == {"basename": "x"} and mc.tau == 1.0 and mc.gamma == 1.0
+
+
+def test_multiwell_waterdimer_postprocessing():
+    """row N4: the two-temperature projection of python_utils/multiwell_waterdimer.py on its own input numbers"""
+    import numpy as np
+    from pimd_tunneling_b200 import multiwell as mw
+
+    rho1 = mw.class_weights(2.0 * 0.111478983128910, 0.0, 1.071538742584852e-3, 5.632020635958411e-3, 0.0)
+    rho2 = mw.class_weights(2.0 * 0.230546268494811, 0.0, 3.118506023220292e-3, 1.049548502801190e-2, 0.0)
+    out = mw.waterdimer_levels(rho1, rho2, 12000.0, 20000.0)
+    assert list(out) == ["A1+", "E+", "B1+", "A2-", "E-", "B2-"]
+    assert out["A1+"]["level_cm"] == 0.0 and out["A1+"]["I1"] == 0.0        # totally symmetric state is the origin
+    # independent evaluation of one level: E- with characters (1,-1,1,0,0,0,0,-1)
+    c = np.array([1, -1, 1, 0, 0, 0, 0, -1.0])
+    i1 = ((1 - c) * rho1).sum() / ((1 + c) * rho1).sum()
+    i2 = ((1 - c) * rho2).sum() / ((1 + c) * rho2).sum()
+    ref = 219475.0 * 2.0 * (np.arctanh(i2) - np.arctanh(i1)) / 8000.0
+    assert abs(out["E-"]["level_cm"] - ref) <= 1e-12 * abs(ref)
+    lv = [out[k]["level_cm"] for k in out]
+    assert all(np.isfinite(lv)) and lv[3] > lv[0] and lv[4] > 0      # acceptor-tunnelling partners lie above A1+
