@@ -178,6 +178,11 @@ int pimdk_selftest_division(pimdk_int* mismatches);
  * sequences and the compiler's built-in expansions (must be 0). */
 int pimdk_selftest_fastmath(pimdk_int* mismatches);
 
+/* GPU self-test: the shared math policy (pimdk_detmath.h) evaluated on the device for n host-supplied arguments;
+ * kind 0 exp, 1 log, 2 sin, 3 cos, 4 acos, 5 tanh, 6 pow(x,-1.5), 7 pow(x,-3), 8 pow(x,0.66666666666666666).
+ * tests/ compares the bits with the host form of the same header. */
+int pimdk_selftest_math(pimdk_int kind, pimdk_int n, const double* x, double* y);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ _SIGS = {
     "pimdk_profile_get": [ctypes.c_char_p, ctypes.POINTER(_dbl), ctypes.POINTER(_i64)],
     "pimdk_profile_reset": [],
     "pimdk_fp64_peak": [ctypes.POINTER(_dbl)],
+    "pimdk_selftest_math": [_i64, _i64, _pd, _pd],
     "pimdk_selftest_division": [ctypes.POINTER(_i64)],
     "pimdk_selftest_fastmath": [ctypes.POINTER(_i64)],
 }

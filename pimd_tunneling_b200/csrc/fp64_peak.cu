@@ -60,7 +60,44 @@ __global__ void fastmath_selftest_kernel(unsigned long long* out, int reps) {
   if (bad) atomicAdd(out, bad);
 }
 
+// the math policy evaluated on the device for host-supplied arguments (parity of include/pimdk_detmath.h between
+// its host and device forms is what makes oracle and kernels agree bit for bit)
+__global__ void math_eval_kernel(int kind, long n, const double* __restrict__ x, double* __restrict__ y) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r;
+  switch (kind) {
+    case 0: r = pimdk_exp(v); break;
+    case 1: r = pimdk_log(v); break;
+    case 2: r = pimdk_sin(v); break;
+    case 3: r = pimdk_cos(v); break;
+    case 4: r = pimdk_acos(v); break;
+    case 5: r = pimdk_tanh(v); break;
+    case 6: r = pimdk_pow(v, -1.5); break;
+    case 7: r = pimdk_pow(v, -3.0); break;
+    case 8: r = pimdk_pow(v, 0.66666666666666666); break;
+    default: r = v;
+  }
+  y[i] = r;
+}
+
 }  // namespace
+
+cudaError_t math_eval(int kind, long n, const double* hx, double* hy, cudaStream_t st) {
+  double *dx = nullptr, *dy = nullptr;
+  cudaError_t e = cudaMalloc(&dx, sizeof(double) * n);
+  if (e != cudaSuccess) return e;
+  e = cudaMalloc(&dy, sizeof(double) * n);
+  if (e != cudaSuccess) { cudaFree(dx); return e; }
+  cudaMemcpyAsync(dx, hx, sizeof(double) * n, cudaMemcpyHostToDevice, st);
+  math_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kind, n, dx, dy);
+  e = cudaMemcpyAsync(hy, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(dx);
+  cudaFree(dy);
+  return e;
+}
 
 cudaError_t fastmath_selftest(unsigned long long* mismatches, cudaStream_t st) {
   unsigned long long* d = nullptr;

@@ -125,6 +125,7 @@ cudaError_t fp64_peak_probe(int num_sms, double* tflops, cudaStream_t st);
 // bit-equality self-test of the three-instruction division by small integers used in the damping series
 cudaError_t div_selftest(unsigned long long* mismatches, cudaStream_t st);
 // bit-equality self-test of fast_div / fast_sqrt (ccpol_device.cuh) against the built-ins
+cudaError_t math_eval(int kind, long n, const double* hx, double* hy, cudaStream_t st);
 cudaError_t fastmath_selftest(unsigned long long* mismatches, cudaStream_t st);
 
 }  // namespace pimdk

@@ -1154,6 +1154,12 @@ int pimdk_selftest_fastmath(pimdk_int* mismatches) {
   *mismatches = (pimdk_int)bad;
   return PIMDK_OK;
 }
+int pimdk_selftest_math(pimdk_int kind, pimdk_int n, const double* x, double* y) {
+  NEED_INIT();
+  if (kind < 0 || kind > 8 || n <= 0 || !x || !y) return fail(PIMDK_EINVAL, "bad selftest_math arguments");
+  CU(math_eval((int)kind, (long)n, x, y, g.stream));
+  return PIMDK_OK;
+}
 int pimdk_selftest_division(pimdk_int* mismatches) {
   NEED_INIT();
   unsigned long long bad = 0;

@@ -144,6 +144,43 @@ def test_division_by_small_integers(pk):
     assert bad.value == 0
 
 
+def test_math_policy_host_equals_device(pk):
+    """include/pimdk_detmath.h: the device form (branch-free exp, __fma_rn ...) gives the bits of the host form (what
+    the oracle is built from) on the hot path's ranges AND at the edges (overflow, underflow, NaN, signed zero)."""
+    import ctypes
+    import subprocess
+    import tempfile
+
+    from pimd_tunneling_b200._lib import check, hptr, lib
+
+    src = os.path.join(tempfile.mkdtemp(), "dm.c")
+    with open(src, "w") as f:
+        f.write('#include "pimdk_detmath.h"\n'
+                "void dm(int kind, long n, const double* x, double* y){ for(long i=0;i<n;++i){ double v=x[i], r=v; switch(kind){\n"
+                "case 0: r=pimdk_exp(v);break; case 1: r=pimdk_log(v);break; case 2: r=pimdk_sin(v);break; case 3: r=pimdk_cos(v);break;\n"
+                "case 4: r=pimdk_acos(v);break; case 5: r=pimdk_tanh(v);break; case 6: r=pimdk_pow(v,-1.5);break;\n"
+                "case 7: r=pimdk_pow(v,-3.0);break; case 8: r=pimdk_pow(v,0.66666666666666666);break;} y[i]=r; } }\n")
+    so = src[:-2] + ".so"
+    subprocess.run(["gcc", "-O2", "-march=native", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                    "-o", so, src, "-lm"], check=True)
+    H = ctypes.CDLL(so)
+    rng = np.random.default_rng(12)
+    edges = np.array([0.0, -0.0, 1.0, -1.0, 700.0, -700.0, 707.999, -707.999, 708.0, -708.0, -708.0000000001, 708.5, 709.0,
+                      709.0000000001, 709.7, 709.9, 720.0, -720.0, -745.0, -746.0, 1e300, -1e300, np.inf, -np.inf, np.nan,
+                      5e-324, -5e-324, 1e-310])
+    args = {0: np.concatenate([edges, rng.uniform(-750, 720, 200000), rng.uniform(-60, 30, 200000)]),
+            1: np.exp(rng.uniform(-40, 40, 100000)), 2: rng.uniform(-50, 50, 100000), 3: rng.uniform(-50, 50, 100000),
+            4: np.concatenate([[1.0, -1.0, 0.5, -0.5, 0.0], rng.uniform(-1, 1, 100000)]), 5: rng.uniform(-25, 25, 100000),
+            6: np.exp(rng.uniform(-10, 10, 100000)), 7: np.exp(rng.uniform(-10, 10, 100000)), 8: np.exp(rng.uniform(-10, 10, 100000))}
+    for kind, x in args.items():
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        yd, yh = np.empty_like(x), np.empty_like(x)
+        check(lib().pimdk_selftest_math(kind, x.size, hptr(x), hptr(yd)))
+        H.dm(kind, ctypes.c_long(x.size), x.ctypes.data_as(ctypes.c_void_p), yh.ctypes.data_as(ctypes.c_void_p))
+        same = (yd.view(np.uint64) == yh.view(np.uint64)) | (np.isnan(yd) & np.isnan(yh))
+        assert same.all(), (kind, x[~same][:5], yd[~same][:5], yh[~same][:5])
+
+
 def test_fast_div_sqrt_bit_identical(pk):
     """branch-free IEEE division / sqrt sequences used in the site-site sums == built-ins, bit for bit"""
     import ctypes
