@@ -144,7 +144,7 @@ static inline double pimdk_exp_general(double x) {
 /* Device: branch-free.  On (-708, 709] the general path's two-step scaling (p*2^k1)*2^k2 is exact in both
  * steps (the result is a normal number: k + 1023 lies in [2, 2046]), so it equals the single scaling p*2^k
  * bit for bit; outside that interval the general path returns 0, x (NaN) or +inf without arithmetic, which
- * two selects reproduce.  No branch means no convergence barrier around every exp: independent exps of
+ * two selects (and NaN propagation through the arithmetic) reproduce.  No branch means no convergence barrier around every exp: independent exps of
  * neighbouring site pairs interleave in the FP64 pipe instead of running one after the other. */
 PIMDK_HD double pimdk_exp(double x) {
 #if defined(__CUDA_ARCH__)
@@ -155,9 +155,28 @@ PIMDK_HD double pimdk_exp(double x) {
   double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x);
   r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);
   double res = PIMDK_MUL(pimdk_exp_poly(r), __hiloint2double((k + 1023) << 20, 0));
+  /* +inf above 709, 0 at or below -708; a NaN argument fails both tests and leaves the NaN the arithmetic produced
+   * (the host form returns x itself: the same value up to the NaN payload) */
   res = (x > 709.0) ? __longlong_as_double(0x7ff0000000000000ll) : res;
-  res = (x > -708.0) ? res : ((x != x) ? x : 0.0);
+  res = (x <= -708.0) ? 0.0 : res;
   return res;
+#else
+  return pimdk_exp_general(x);
+#endif
+}
+
+/* exp(x) for callers that guarantee x <= 0 (or NaN): e^{-beta R} with beta, R >= 0.  Same bits as pimdk_exp there;
+ * the device form drops the overflow test (one FP64-pipe compare and a 64-bit select per call). */
+PIMDK_HD double pimdk_exp_nonpos(double x) {
+#if defined(__CUDA_ARCH__)
+  const double shifter = 6755399441055744.0;
+  double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
+  int k = __double2loint(t);
+  double kd = PIMDK_SUB(t, shifter);
+  double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x);
+  r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);
+  double res = PIMDK_MUL(pimdk_exp_poly(r), __hiloint2double((k + 1023) << 20, 0));
+  return (x <= -708.0) ? 0.0 : res;
 #else
   return pimdk_exp_general(x);
 #endif

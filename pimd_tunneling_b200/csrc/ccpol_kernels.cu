@@ -277,7 +277,7 @@ __device__ __forceinline__ void sweep_chunk(const double* sA, const double* sB, 
     r12 = ra[64] - rb[64];
     d = d + r12 * r12;
     R[q] = fast_sqrt(d);
-    e[q] = pimdk_exp(-beta * R[q]);
+    e[q] = pimdk_exp_nonpos(-beta * R[q]);   // beta >= 0 (checked when the tables are built), R >= 0
   }
 #pragma unroll
   for (int q = 0; q < N; ++q) {
@@ -302,7 +302,7 @@ __device__ __forceinline__ void sweep_row4(const double* ra, const double* sB, i
     r12 = az - rb[64];
     d = d + r12 * r12;
     R[q] = fast_sqrt(d);
-    e[q] = pimdk_exp(-beta * R[q]);
+    e[q] = pimdk_exp_nonpos(-beta * R[q]);   // beta >= 0 (checked when the tables are built), R >= 0
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {

@@ -382,6 +382,7 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
             }
         bins.push_back({ca, cb, indlin - 1, na * nb * (ca == cb ? 1 : 2)});
         o->bin_beta[indlin - 1] = h.params[ib - 1];
+        if (!(h.params[ib - 1] >= 0.0)) { g_msg = "negative exponent parameter in the CCpol-8s sweep (kernels assume beta >= 0)"; return g_msg.c_str(); }
       }
     if (bins.size() != 36) { g_msg = "expected 36 site-class pair bins"; return g_msg.c_str(); }
     auto pairs_of = [&](const Bin& b) {
