@@ -211,7 +211,8 @@ KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __re
   for (int k = 0; k < 24; ++k) sitesB[k] = S[24 + k];
   const double sa[3] = {S[48], S[49], S[50]};
   const double sb[3] = {S[51], S[52], S[53]};
-  const double val = sapt_pair_sum(T, S, sitesB, sa, sb);
+  Scratch<kSaptBlock> qb{reinterpret_cast<double*>(smem + kSaptTableBytes) + 24 * kSaptBlock + threadIdx.x};
+  const double val = sapt_pair_sum(T, S, sitesB, qb, sa, sb);
   buf[(which ? F_VALL : F_VAL) * ne + e] = val + buf[(F_FCIND + which) * ne + e];
 }
 
@@ -420,7 +421,7 @@ KNAME(ccpol_combine_kernel)(int iemonomer, double V0, GeomLayout L, double* __re
   }
 }
 
-size_t sapt_smem() { return kSaptTableBytes + (size_t)24 * kSaptBlock * sizeof(double); }
+size_t sapt_smem() { return kSaptTableBytes + (size_t)(24 + 8) * kSaptBlock * sizeof(double); }
 size_t dipind_smem() { return kSaptTableBytes; }
 size_t rigid_smem() { return kRigidTableBytes; }
 size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepSlots * 32 * sizeof(double) + 16; }
