@@ -174,7 +174,7 @@ pimdk_int pimdk_launch_count(void);
 /* GPU self-test: number of operands (of 9 x 2^28) for which the kernels' three-instruction division by a
  * small integer constant differs from IEEE division in any bit (must be 0). */
 int pimdk_selftest_division(pimdk_int* mismatches);
-/* GPU self-test: mismatches (of 2 x 2^30) between the kernels' branch-free IEEE division / square root
+/* GPU self-test: mismatches (of 4 x 2^30: two operand ranges for the division) between the kernels' branch-free IEEE division / square root
  * sequences and the compiler's built-in expansions (must be 0). */
 int pimdk_selftest_fastmath(pimdk_int* mismatches);
 

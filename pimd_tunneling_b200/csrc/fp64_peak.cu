@@ -56,6 +56,12 @@ __global__ void fastmath_selftest_kernel(unsigned long long* out, int reps) {
     bad += (__double_as_longlong(fast_div(a, b)) != __double_as_longlong(a / b));
     const double x = fabs(a);
     bad += (__double_as_longlong(fast_sqrt(x)) != __double_as_longlong(sqrt(x)));
+    // second range (the damping series tail): tiny numerators and denominators, exponents in [-260, -10]
+    const double c = __longlong_as_double((long long)(((1023ull - 260ull + (h2 >> 9) % 251ull) << 52) | (h2 >> 12) | ((h & 2ull) << 62)));
+    const double d = __longlong_as_double((long long)(((1023ull - 260ull + (h >> 11) % 251ull) << 52) | (h >> 12)));
+    bad += (__double_as_longlong(fast_div(c, d)) != __double_as_longlong(c / d));
+    const double di = (double)(1 + (int)((h >> 20) % 1000ull));
+    bad += (__double_as_longlong(fast_div(c, di)) != __double_as_longlong(c / di));
   }
   if (bad) atomicAdd(out, bad);
 }
