@@ -179,7 +179,7 @@ def run_reference(args, cfg, rank):
         "impl": "reference", "metric": "ring-polymer bead-steps/sec", "value": value, "unit": "bead-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["label"], "note": "CPU oracle (C++ restatement of the reference algorithm, g++ -O2, "
+        "config": {"workload": cfg["label"], "note": "CPU oracle (C++ restatement of the reference algorithm, g++ -O3 -march=native, "
                    "no MKL/ifort: the Fortran reference cannot be compiled in this image)"},
         "cpu_baseline": {"value": value, "unit": "bead-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "bead-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

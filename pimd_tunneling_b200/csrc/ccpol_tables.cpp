@@ -318,6 +318,11 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
       if (cost[idx[i]] > 0) o->sapt_ntask = i + 1;
     }
   }
+  for (int e = 0; e < kNType * kNType; ++e)   // the kernels read coefficient groups with 16-byte loads
+    if ((o->itu_s[e] && (o->itu_s[e] - 1) % 4) || (o->itu_a[e] && (o->itu_a[e] - 1) % 4)) {
+      g_msg = "linear-coefficient blocks are not 4-aligned";
+      return g_msg.c_str();
+    }
   if (next - 1 != h.numlin) {
     g_msg = "linear-coefficient index map does not cover the coefficient table";
     return g_msg.c_str();

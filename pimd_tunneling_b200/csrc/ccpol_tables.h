@@ -50,7 +50,7 @@ struct CcpolDev {
   // ---- SAPT-5s'f flexible model ----
   double param[kNParam * kNType];            // param(k,t)         -> [(t-1)*18 + k-1]
   double parab[kNParab * kNType * kNType];   // parab(k,ta,tb)     -> [((tb-1)*5+(ta-1))*84 + k-1]
-  double c[568];                             // SAPT-5s'f linear coefficients
+  alignas(16) double c[568];                 // SAPT-5s'f linear coefficients (read as 16-byte pairs)
   // static image of poten's first-encounter index map itypus (proc_sapt5sf_new_ncd.f:181-203):
   // first linear coefficient (1-based) of the symmetric / antisymmetric block of a type pair,
   // 0 when the pair type carries no exponential.
