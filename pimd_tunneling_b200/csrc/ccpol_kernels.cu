@@ -266,9 +266,10 @@ template <int N>
 __device__ __forceinline__ void sweep_chunk(const double* sA, const double* sB, int a0, int b0, int nb, int k0, double beta,
                                             double& acc0, double& acc1, double& acc2, double& acc3) {
   double R[N], e[N];
+  const int sh = nb >> 1;   // log2(nb) for nb = 1, 2, 4
 #pragma unroll
   for (int q = 0; q < N; ++q) {
-    const int k = k0 + q, i = k / nb, j = k - i * nb;
+    const int k = k0 + q, i = k >> sh, j = k & (nb - 1);   // class sizes are 1, 2 or 4 (checked with the tables)
     const double* ra = sA + (a0 + i) * 96;     // 3 slots x 32 energies per site
     const double* rb = sB + (b0 + j) * 96;
     double r12 = ra[0] - rb[0];
@@ -345,6 +346,8 @@ KNAME(ccpol_sweep_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __r
   const bool active = e < ne;
   const long ec = active ? e : ne - 1;  // idle lanes of the last CTA recompute its last energy
   if (threadIdx.x == 0) *queue = 0;
+  // the two scalars of the final sum are fetched now so that their latency is not part of the CTA's serial tail
+  const double eind = buf[F_EIND * ne + ec], a0u = buf[F_A0U * ne + ec];
   for (int k = warp; k < kFrameFields; k += kSweepWarps) cw[k * 32] = buf[(long)(F_FRAME + k) * ne + ec];
   __syncthreads();
   // fill_sites (:487-548): the 50 sites of the 32 energies, dealt to the warps
@@ -379,10 +382,10 @@ KNAME(ccpol_sweep_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __r
   }
   __syncthreads();
   if (warp == 0 && active) {
-    double E = buf[F_EIND * ne + e];
-#pragma unroll 8
+    double E = eind;
+#pragma unroll 16
     for (int nl = 0; nl < 144; ++nl) E = E + cw[nl * 32];
-    E = E + buf[F_A0U * ne + e];
+    E = E + a0u;
     buf[F_ERIG * ne + e] = E * 627.510;
   }
 }
