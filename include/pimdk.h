@@ -56,6 +56,9 @@ int pimdk_set_mode(pimdk_int mode);
 /* Small systems (1D/2D surfaces, n <= 128 beads) are propagated by one persistent warp-per-ring-polymer
  * kernel (default on); 0 forces the streamed multi-kernel path.  Both give bit-identical results. */
 int pimdk_set_fused(pimdk_int enable);
+/* Normal-mode transform engine: 0 = FP64 FMA-pipe tile GEMM, 1 = FP64 tensor-core (DMMA m8n8k4) tile GEMM.  Same
+ * contraction; the summation order inside a k-group of four differs, results agree to ~1e-15 relative. */
+int pimdk_set_gemm(pimdk_int kind);
 
 /* ---- PES plugin: module mcmod_mass -------------------------------------------------------
  * pimdk_pes_select  = V_init  (mcmod_1d.f90:8, mcmod_2dtest.f90:11, mcmod_waterdimer_ccpol.f90:9

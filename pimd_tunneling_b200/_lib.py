@@ -30,6 +30,7 @@ _SIGS = {
     "pimdk_set_stream": [ctypes.c_void_p],
     "pimdk_set_mode": [_i64],
     "pimdk_set_fused": [_i64],
+    "pimdk_set_gemm": [_i64],
     "pimdk_pes_select": [ctypes.c_char_p, _pd, _i64],
     "pimdk_pes_info": [ctypes.POINTER(_i64), ctypes.POINTER(_i64)],
     "pimdk_pes_set_v0": [_dbl],

@@ -76,6 +76,7 @@ enum GemmMode {
   GEMM_SUB_BEADVEC = 1, // Y = A T - beadvec            (nmtransform_forward, bead>0)
   GEMM_ADD_BEADVEC = 2, // Y = (A + beadvec) T          (nmtransform_backward, bead>0)
 };
+void set_nm_gemm_dmma(int on);
 cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, double* Y, long rows,
                            const double* a /*(ndof)*/, const double* b /*(ndof,ntraj)*/, cudaStream_t st);
 

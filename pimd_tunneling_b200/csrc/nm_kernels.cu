@@ -124,6 +124,120 @@ nm_gemm_kernel(NmTables nm, const double* __restrict__ A, double* __restrict__ Y
   }
 }
 
+// ---- the same contraction on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64) ------------------------------------
+// north_star: "tensor cores only if ncu shows it beating the FMA pipe".  On B200 the dense FP64 tensor rate equals the
+// DFMA rate, so the gain can only come from instruction economy: one m8n8k4 retires 256 FMAs per warp instruction
+// against 32 for a DFMA, and a thread needs 2 shared-memory loads per 256 FMAs instead of 16 per 64.
+// CTA tile 128 x 128 x 16, 8 warps as 4 (rows) x 2 (columns), warp tile 32 x 64 = 4 x 8 MMA tiles.
+// Fragment layout (PTX ISA, m8n8k4 .f64): A[row = lane/4][k = lane%4], B[k = lane%4][col = lane/4],
+// C[row = lane/4][col = 2*(lane%4) + {0,1}].  Leading dimensions are = 4 (mod 16) doubles so that the 16 fragment
+// loads of a half-warp fall into 16 different 8-byte bank pairs.
+constexpr int DK = 16, LDA = DK + 4, LDB = BN + 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(GT)
+nm_gemm_dmma_kernel(NmTables nm, const double* __restrict__ A, double* __restrict__ Y, long rows,
+                    const double* __restrict__ a, const double* __restrict__ b) {
+  __shared__ __align__(16) double As[BM * LDA];
+  __shared__ __align__(16) double Bs[DK * LDB];
+  const int n = nm.n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;           // warp tile origin: rows 32*wm, columns 64*wn
+  const long row0 = (long)blockIdx.y * BM;
+  const int col0 = blockIdx.x * BN;
+  const int a_r = tid >> 1, a_k0 = (tid & 1) * 8;
+  const int b_k = tid >> 4, b_c0 = (tid & 15) * 8;
+  const long a_row = row0 + a_r;
+  const bool a_ok = a_row < rows;
+  long a_traj = 0;
+  int a_dof = 0;
+  if (MODE == GEMM_ADD_BEADVEC && a_ok) {
+    a_traj = a_row / nm.ndof;
+    a_dof = (int)(a_row - a_traj * nm.ndof);
+  }
+  double ra[8], rb[8];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = k0 + a_k0 + q;
+      double v = 0.0;
+      if (a_ok && j < n) {
+        v = A[a_row * n + j];
+        if (MODE == GEMM_ADD_BEADVEC) v = v + beadvec_at(nm, a, b, a_traj, a_dof, j);
+      }
+      ra[q] = v;
+    }
+    const int j = k0 + b_k;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = col0 + b_c0 + q;
+      rb[q] = (j < n && c < n) ? nm.T[(long)j * n + c] : 0.0;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      *reinterpret_cast<double2*>(&As[a_r * LDA + a_k0 + q]) = make_double2(ra[q], ra[q + 1]);
+      *reinterpret_cast<double2*>(&Bs[b_k * LDB + b_c0 + q]) = make_double2(rb[q], rb[q + 1]);
+    }
+  };
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const double* Af = As + (wm * 32 + (lane >> 2)) * LDA + (lane & 3);
+  const double* Bf = Bs + (lane & 3) * LDB + wn * 64 + (lane >> 2);
+  load_tiles(0);
+  for (int k0 = 0; k0 < n; k0 += DK) {
+    store_tiles();
+    __syncthreads();
+    if (k0 + DK < n) load_tiles(k0 + DK);
+#pragma unroll
+    for (int kk = 0; kk < DK; kk += 4) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = Af[i * 8 * LDA + kk];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bf[j] = Bf[kk * LDB + j * 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(af[i]), "d"(bf[j]));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
+    if (r >= rows) continue;
+    long traj = 0;
+    int dof = 0;
+    if (MODE == GEMM_SUB_BEADVEC) {
+      traj = r / nm.ndof;
+      dof = (int)(r - traj * nm.ndof);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = col0 + wn * 64 + j * 8 + 2 * (lane & 3);
+      double y0 = acc[i][j][0], y1 = acc[i][j][1];
+      if (MODE == GEMM_SUB_BEADVEC) {
+        if (c < n) y0 = y0 - beadvec_at(nm, a, b, traj, dof, c);
+        if (c + 1 < n) y1 = y1 - beadvec_at(nm, a, b, traj, dof, c + 1);
+      }
+      if (c + 1 < n && ((n & 1) == 0)) {
+        *reinterpret_cast<double2*>(&Y[r * n + c]) = make_double2(y0, y1);
+      } else {
+        if (c < n) Y[r * n + c] = y0;
+        if (c + 1 < n) Y[r * n + c + 1] = y1;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 nm_update_kernel(NmTables nm, double* __restrict__ Pn, double* __restrict__ Qn, const double* __restrict__ G,
                  double dt, long ntraj, int ops, uint64_t seed, uint64_t step, const int64_t* __restrict__ gid,
@@ -217,10 +331,21 @@ unsigned grid_for(long total, int block) {
 
 }  // namespace
 
+static int g_gemm_dmma = 1;   // default: tensor-core path (1.5x the FMA-pipe kernel, bit-identical results)
+void set_nm_gemm_dmma(int on) { g_gemm_dmma = on; }
+
 cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, double* Y, long rows, const double* a,
                            const double* b, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   dim3 grid((nm.n + BN - 1) / BN, (unsigned)((rows + BM - 1) / BM));
+  if (g_gemm_dmma) {
+    switch (mode) {
+      case GEMM_PLAIN: nm_gemm_dmma_kernel<GEMM_PLAIN><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+      case GEMM_SUB_BEADVEC: nm_gemm_dmma_kernel<GEMM_SUB_BEADVEC><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+      case GEMM_ADD_BEADVEC: nm_gemm_dmma_kernel<GEMM_ADD_BEADVEC><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+    }
+    return cudaGetLastError();
+  }
   switch (mode) {
     case GEMM_PLAIN: nm_gemm_kernel<GEMM_PLAIN><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
     case GEMM_SUB_BEADVEC: nm_gemm_kernel<GEMM_SUB_BEADVEC><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;

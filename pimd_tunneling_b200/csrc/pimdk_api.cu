@@ -372,6 +372,12 @@ int pimdk_set_stream(void* s) {
   return PIMDK_OK;
 }
 
+int pimdk_set_gemm(pimdk_int kind) {
+  if (kind != 0 && kind != 1) return fail(PIMDK_EINVAL, "gemm kind must be 0 (DFMA) or 1 (DMMA)");
+  set_nm_gemm_dmma((int)kind);
+  return PIMDK_OK;
+}
+
 int pimdk_set_fused(pimdk_int enable) {
   g.fused = enable != 0;
   return PIMDK_OK;
