@@ -56,8 +56,9 @@ int pimdk_set_mode(pimdk_int mode);
 /* Small systems (1D/2D surfaces, n <= 128 beads) are propagated by one persistent warp-per-ring-polymer
  * kernel (default on); 0 forces the streamed multi-kernel path.  Both give bit-identical results. */
 int pimdk_set_fused(pimdk_int enable);
-/* Normal-mode transform engine: 0 = FP64 FMA-pipe tile GEMM, 1 = FP64 tensor-core (DMMA m8n8k4) tile GEMM.  Same
- * contraction; the summation order inside a k-group of four differs, results agree to ~1e-15 relative. */
+/* Normal-mode transform engine: 0 = FP64 FMA-pipe tile GEMM; 1 (default) = FP64 tensor-core (DMMA m8n8k4) tile GEMM with
+ * 128 x 64 CTA tiles, 2 = the same, 3 = DMMA with 128 x 128 CTA tiles.  All engines accumulate in k order with fused
+ * multiply-adds and give identical bits. */
 int pimdk_set_gemm(pimdk_int kind);
 
 /* ---- PES plugin: module mcmod_mass -------------------------------------------------------

@@ -132,21 +132,25 @@ nm_gemm_kernel(NmTables nm, const double* __restrict__ A, double* __restrict__ Y
 // Fragment layout (PTX ISA, m8n8k4 .f64): A[row = lane/4][k = lane%4], B[k = lane%4][col = lane/4],
 // C[row = lane/4][col = 2*(lane%4) + {0,1}].  Leading dimensions are = 4 (mod 16) doubles so that the 16 fragment
 // loads of a half-warp fall into 16 different 8-byte bank pairs.
-constexpr int DK = 16, LDA = DK + 4, LDB = BN + 4;
+constexpr int DK = 16, LDA = DK + 4;
 
-template <int MODE>
-__global__ void __launch_bounds__(GT)
+// NT = n8 tiles per warp: 8 -> CTA tile 128 x 128 (one CTA per SM, 208 registers); 4 -> CTA tile 128 x 64 (two CTAs per SM)
+template <int MODE, int NT>
+__global__ void __launch_bounds__(GT, NT == 4 ? 2 : 1)
 nm_gemm_dmma_kernel(NmTables nm, const double* __restrict__ A, double* __restrict__ Y, long rows,
                     const double* __restrict__ a, const double* __restrict__ b) {
+  constexpr int TN = 16 * NT;            // CTA tile columns
+  constexpr int LDB = TN + 4;
+  constexpr int BQ = TN / 16;            // T-tile doubles staged per thread (16 threads per k row)
   __shared__ __align__(16) double As[BM * LDA];
   __shared__ __align__(16) double Bs[DK * LDB];
   const int n = nm.n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;           // warp tile origin: rows 32*wm, columns 64*wn
+  const int wm = warp >> 1, wn = warp & 1;           // warp tile origin: rows 32*wm, columns 8*NT*wn
   const long row0 = (long)blockIdx.y * BM;
-  const int col0 = blockIdx.x * BN;
+  const int col0 = blockIdx.x * TN;
   const int a_r = tid >> 1, a_k0 = (tid & 1) * 8;
-  const int b_k = tid >> 4, b_c0 = (tid & 15) * 8;
+  const int b_k = tid >> 4, b_c0 = (tid & 15) * BQ;
   const long a_row = row0 + a_r;
   const bool a_ok = a_row < rows;
   long a_traj = 0;
@@ -155,7 +159,7 @@ nm_gemm_dmma_kernel(NmTables nm, const double* __restrict__ A, double* __restric
     a_traj = a_row / nm.ndof;
     a_dof = (int)(a_row - a_traj * nm.ndof);
   }
-  double ra[8], rb[8];
+  double ra[8], rb[BQ];
   auto load_tiles = [&](int k0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -169,25 +173,24 @@ nm_gemm_dmma_kernel(NmTables nm, const double* __restrict__ A, double* __restric
     }
     const int j = k0 + b_k;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < BQ; ++q) {
       const int c = col0 + b_c0 + q;
       rb[q] = (j < n && c < n) ? nm.T[(long)j * n + c] : 0.0;
     }
   };
   auto store_tiles = [&]() {
 #pragma unroll
-    for (int q = 0; q < 8; q += 2) {
-      *reinterpret_cast<double2*>(&As[a_r * LDA + a_k0 + q]) = make_double2(ra[q], ra[q + 1]);
-      *reinterpret_cast<double2*>(&Bs[b_k * LDB + b_c0 + q]) = make_double2(rb[q], rb[q + 1]);
-    }
+    for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2*>(&As[a_r * LDA + a_k0 + q]) = make_double2(ra[q], ra[q + 1]);
+#pragma unroll
+    for (int q = 0; q < BQ; q += 2) *reinterpret_cast<double2*>(&Bs[b_k * LDB + b_c0 + q]) = make_double2(rb[q], rb[q + 1]);
   };
-  double acc[4][8][2];
+  double acc[4][NT][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const double* Af = As + (wm * 32 + (lane >> 2)) * LDA + (lane & 3);
-  const double* Bf = Bs + (lane & 3) * LDB + wn * 64 + (lane >> 2);
+  const double* Bf = Bs + (lane & 3) * LDB + wn * 8 * NT + (lane >> 2);
   load_tiles(0);
   for (int k0 = 0; k0 < n; k0 += DK) {
     store_tiles();
@@ -195,15 +198,15 @@ nm_gemm_dmma_kernel(NmTables nm, const double* __restrict__ A, double* __restric
     if (k0 + DK < n) load_tiles(k0 + DK);
 #pragma unroll
     for (int kk = 0; kk < DK; kk += 4) {
-      double af[4], bf[8];
+      double af[4], bf[NT];
 #pragma unroll
       for (int i = 0; i < 4; ++i) af[i] = Af[i * 8 * LDA + kk];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bf[j] = Bf[kk * LDB + j * 8];
+      for (int j = 0; j < NT; ++j) bf[j] = Bf[kk * LDB + j * 8];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < NT; ++j)
           asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                        : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
                        : "d"(af[i]), "d"(bf[j]));
@@ -221,8 +224,8 @@ nm_gemm_dmma_kernel(NmTables nm, const double* __restrict__ A, double* __restric
       dof = (int)(r - traj * nm.ndof);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = col0 + wn * 64 + j * 8 + 2 * (lane & 3);
+    for (int j = 0; j < NT; ++j) {
+      const int c = col0 + wn * 8 * NT + j * 8 + 2 * (lane & 3);
       double y0 = acc[i][j][0], y1 = acc[i][j][1];
       if (MODE == GEMM_SUB_BEADVEC) {
         if (c < n) y0 = y0 - beadvec_at(nm, a, b, traj, dof, c);
@@ -339,10 +342,20 @@ cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, d
   if (rows <= 0) return cudaSuccess;
   dim3 grid((nm.n + BN - 1) / BN, (unsigned)((rows + BM - 1) / BM));
   if (g_gemm_dmma) {
-    switch (mode) {
-      case GEMM_PLAIN: nm_gemm_dmma_kernel<GEMM_PLAIN><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
-      case GEMM_SUB_BEADVEC: nm_gemm_dmma_kernel<GEMM_SUB_BEADVEC><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
-      case GEMM_ADD_BEADVEC: nm_gemm_dmma_kernel<GEMM_ADD_BEADVEC><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+    const int nt = g_gemm_dmma == 3 ? 8 : 4;   // 128 x 64 CTA tiles (two CTAs per SM) measured faster on every shape
+    if (nt == 4) {
+      dim3 g4((nm.n + 63) / 64, (unsigned)((rows + BM - 1) / BM));
+      switch (mode) {
+        case GEMM_PLAIN: nm_gemm_dmma_kernel<GEMM_PLAIN, 4><<<g4, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+        case GEMM_SUB_BEADVEC: nm_gemm_dmma_kernel<GEMM_SUB_BEADVEC, 4><<<g4, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+        case GEMM_ADD_BEADVEC: nm_gemm_dmma_kernel<GEMM_ADD_BEADVEC, 4><<<g4, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+      }
+    } else {
+      switch (mode) {
+        case GEMM_PLAIN: nm_gemm_dmma_kernel<GEMM_PLAIN, 8><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+        case GEMM_SUB_BEADVEC: nm_gemm_dmma_kernel<GEMM_SUB_BEADVEC, 8><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+        case GEMM_ADD_BEADVEC: nm_gemm_dmma_kernel<GEMM_ADD_BEADVEC, 8><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
+      }
     }
     return cudaGetLastError();
   }

@@ -373,7 +373,7 @@ int pimdk_set_stream(void* s) {
 }
 
 int pimdk_set_gemm(pimdk_int kind) {
-  if (kind != 0 && kind != 1) return fail(PIMDK_EINVAL, "gemm kind must be 0 (DFMA) or 1 (DMMA)");
+  if (kind < 0 || kind > 3) return fail(PIMDK_EINVAL, "gemm kind must be 0 (DFMA), 1 (DMMA, tile chosen by size), 2 (DMMA 128x64) or 3 (DMMA 128x128)");
   set_nm_gemm_dmma((int)kind);
   return PIMDK_OK;
 }
