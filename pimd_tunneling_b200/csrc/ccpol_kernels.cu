@@ -192,7 +192,7 @@ KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __
 __global__ void __launch_bounds__(kSaptBlock, PIMDK_SAPT_MINB)
 KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
-  // stage only the SAPT-5s'f members (param .. sapt_ntask); T is a view whose leading (rigid) members are not backed
+  // stage only the SAPT-5s'f members (param .. pairflags); T is a view whose leading (rigid) members are not backed
   {
     const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + kRigidTableBytes);
     int4* dst = reinterpret_cast<int4*>(smem);

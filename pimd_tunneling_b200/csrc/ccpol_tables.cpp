@@ -295,29 +295,6 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
       if (pb[6] != 0.0 || pb[7] != 0.0 || pb[8] != 0.0) f |= 4;  // dmp6, dmp8, dmp10
       o->pairflags[tb * kNType + ta] = f;
     }
-  {  // SAPT stage task order (cost model in FP64 instruction slots, from the pair-type flags)
-    int cost[65];
-    for (int ia = 0; ia < 8; ++ia)
-      for (int ib = 0; ib < 8; ++ib) {
-        const int ta = types[ia] - 1, tb = types[ib] - 1;
-        const uint8_t f = o->pairflags[tb * kNType + ta];
-        int cst = 0;
-        if (f) cst += 60;
-        if (f & 1) cst += 200 + (ta != tb ? 90 : 0);
-        if (f & 2) cst += 50;
-        if (f & 4) cst += 300;
-        cost[ia * 8 + ib] = cst;
-      }
-    cost[64] = 700;  // dipind
-    int idx[65];
-    for (int i = 0; i < 65; ++i) idx[i] = i;
-    std::stable_sort(idx, idx + 65, [&](int a, int b) { return cost[a] > cost[b]; });
-    o->sapt_ntask = 0;
-    for (int i = 0; i < 65; ++i) {
-      o->sapt_order[i] = (uint8_t)idx[i];
-      if (cost[idx[i]] > 0) o->sapt_ntask = i + 1;
-    }
-  }
   for (int e = 0; e < kNType * kNType; ++e)   // the kernels read coefficient groups with 16-byte loads
     if ((o->itu_s[e] && (o->itu_s[e] - 1) % 4) || (o->itu_a[e] && (o->itu_a[e] - 1) % 4)) {
       g_msg = "linear-coefficient blocks are not 4-aligned";
@@ -366,7 +343,8 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
   for (int b = 0; b < 25; ++b)
     for (int a = 0; a < 25; ++a)
       if (h.ind_beta[b * 25 + a] == 0) { g_msg = "ind_beta has empty entries; not supported"; return g_msg.c_str(); }
-  // ---- U0 sweep schedule: bins -> lanes (LPT), pairs of a bin in the reference's order
+  // ---- U0 sweep: the 36 bins (site-class pairs) as warp tasks, largest first; a bin's pairs are walked in the
+  // reference's order: block (A-class ca) x (B-class cb), then block (A-class cb) x (B-class ca)
   {
     struct Bin { int ca, cb, i0, npairs; };
     std::vector<Bin> bins;
@@ -390,17 +368,6 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
         if (!(h.params[ib - 1] >= 0.0)) { g_msg = "negative exponent parameter in the CCpol-8s sweep (kernels assume beta >= 0)"; return g_msg.c_str(); }
       }
     if (bins.size() != 36) { g_msg = "expected 36 site-class pair bins"; return g_msg.c_str(); }
-    auto pairs_of = [&](const Bin& b) {
-      std::vector<std::pair<int, int>> v;
-      const int a0 = o->cls_start[b.ca], na = o->cls_start[b.ca + 1] - a0;
-      const int b0 = o->cls_start[b.cb], nb = o->cls_start[b.cb + 1] - b0;
-      for (int i = 0; i < na; ++i)        // block (A-class ca) x (B-class cb)
-        for (int j = 0; j < nb; ++j) v.emplace_back(a0 + i, b0 + j);
-      if (b.ca != b.cb)
-        for (int i = 0; i < nb; ++i)      // block (A-class cb) x (B-class ca): later in the reference's sweep
-          for (int j = 0; j < na; ++j) v.emplace_back(b0 + i, a0 + j);
-      return v;
-    };
     {
       std::vector<int> big(bins.size());
       for (size_t i = 0; i < bins.size(); ++i) big[i] = (int)i;
@@ -411,47 +378,6 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
         const int b0 = o->cls_start[b.cb], nb = o->cls_start[b.cb + 1] - b0;
         o->tbins[k] = (uint32_t)a0 | (uint32_t)na << 5 | (uint32_t)b0 << 8 | (uint32_t)nb << 13 | (uint32_t)b.i0 << 16;
       }
-    }
-    std::vector<int> order;
-    o->sweep_ntail = 0;
-    for (size_t i = 0; i < bins.size(); ++i) {
-      if (bins[i].npairs % 4 == 0) { order.push_back((int)i); continue; }
-      auto v = pairs_of(bins[i]);
-      if (o->sweep_ntail + (int)v.size() > 8) { g_msg = "too many U0 pairs outside the quad schedule"; return g_msg.c_str(); }
-      for (size_t k = 0; k < v.size(); ++k)
-        o->sweep_tail[o->sweep_ntail++] = (uint32_t)(v[k].first * 3) | (uint32_t)(v[k].second * 3) << 7 |
-                                          (uint32_t)bins[i].i0 << 14 | (k == 0 ? 1u << 20 : 0u) |
-                                          (k + 1 == v.size() ? 1u << 21 : 0u);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bins[x].npairs > bins[y].npairs; });
-    int load[kSweepLanes] = {0};
-    std::vector<int> lane_bins[kSweepLanes];
-    for (int idx : order) {
-      int best = 0;
-      for (int l = 1; l < kSweepLanes; ++l)
-        if (load[l] < load[best]) best = l;
-      lane_bins[best].push_back(idx);
-      load[best] += bins[idx].npairs / 4;
-    }
-    o->sweep_quads = 0;
-    for (int l = 0; l < kSweepLanes; ++l) o->sweep_quads = load[l] > o->sweep_quads ? load[l] : o->sweep_quads;
-    if (o->sweep_quads > kSweepMaxQuads) { g_msg = "U0 sweep schedule longer than kSweepMaxQuads"; return g_msg.c_str(); }
-    for (int l = 0; l < kSweepLanes; ++l) {
-      int pos = 0;
-      for (int idx : lane_bins[l]) {
-        auto v = pairs_of(bins[idx]);
-        for (size_t k = 0; k < v.size(); k += 4) {
-          uint64_t w = 0;
-          for (int q = 0; q < 4; ++q)
-            w |= (uint64_t)((uint32_t)(v[k + q].first * 3) | (uint32_t)(v[k + q].second * 3) << 7) << (14 * q);
-          w |= (uint64_t)bins[idx].i0 << 56;
-          if (k == 0) w |= 1ull << 62;
-          if (k + 4 == v.size()) w |= 1ull << 63;
-          o->sweep[l][pos++] = w;
-        }
-      }
-      // padding quads: four copies of pair (0,0) summed into the dummy bin 36, first and last at once
-      for (; pos < kSweepMaxQuads; ++pos) o->sweep[l][pos] = 36ull << 56 | 1ull << 62 | 1ull << 63;
     }
   }
   o->iemonomer = iemonomer;

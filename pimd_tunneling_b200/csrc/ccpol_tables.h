@@ -10,8 +10,6 @@ namespace pimdk {
 constexpr int kNType = 5;      // SAPT-5s'f site types actually used (1..5; type 6 never occurs)
 constexpr int kNParab = 84;
 constexpr int kNParam = 18;
-constexpr int kSweepLanes = 8;     // lanes that share one energy in the CCpol-8s exponential sweep
-constexpr int kSweepMaxQuads = 24;  // 624 pairs / 8 lanes / 4 = 19.5 quads per lane; LPT packing needs <= 24
 
 struct CcpolDev {
   // ---- CCpol-8s rigid model (the only part the rigid stage stages into shared memory) ----
@@ -30,25 +28,12 @@ struct CcpolDev {
   uint8_t pad0_[5];
   int32_t ncls;
   int32_t iemonomer;
-  // U0 sweep schedule for kSweepLanes lanes per energy.  Each of the 36 bins aj(ind) is owned by one lane,
-  // which walks the bin's site pairs in the reference's (nsA, nsB) order (block (ca,cb), then block
-  // (cb,ca)), four pairs ("quad") per loop iteration.  A quad is one 64-bit word:
-  //   bits  0..55  four pairs, 14 bits each: 3*nsA | 3*nsB << 7
-  //   bits 56..61  bin (36 = dummy bin used by padding quads), bit 62 first quad of the bin, bit 63 last
-  // Bins are dealt to lanes by a longest-processing-time rule.  Bins whose pair count is not a multiple
-  // of four (only O-O, one pair, for data_ccdata) are walked pair by pair from `sweep_tail`
-  // (3*nsA | 3*nsB << 7 | bin << 14 | first << 20 | last << 21) by the last lane.
-  alignas(8) uint64_t sweep[kSweepLanes][kSweepMaxQuads];
-  double bin_beta[37];                       // beta of each bin (params(ind_beta) of its site pairs); [36] dummy
-  uint32_t sweep_tail[8];
-  int32_t sweep_quads;                       // quads per lane
-  int32_t sweep_ntail;
-  int32_t pad2_[2];                          // keeps `param` 16-byte aligned (staging granule)
+  double bin_beta[37];                       // beta of each bin (params(ind_beta) of its site pairs); [36] unused
   // The 36 bins as tasks of the item-per-lane sweep (a warp walks one bin for 32 energies), largest first:
   //   bits 0..4 first site of class ca, 5..7 its size, 8..12 first site of class cb, 13..15 its size, 16..21 bin
   uint32_t tbins[36];
   // ---- SAPT-5s'f flexible model ----
-  double param[kNParam * kNType];            // param(k,t)         -> [(t-1)*18 + k-1]
+  alignas(16) double param[kNParam * kNType];  // param(k,t) -> [(t-1)*18 + k-1]; 16-byte aligned: staging granule
   double parab[kNParab * kNType * kNType];   // parab(k,ta,tb)     -> [((tb-1)*5+(ta-1))*84 + k-1]
   alignas(16) double c[568];                 // SAPT-5s'f linear coefficients (read as 16-byte pairs)
   // static image of poten's first-encounter index map itypus (proc_sapt5sf_new_ncd.f:181-203):
@@ -62,12 +47,6 @@ struct CcpolDev {
   // proc_sapt5sf_new_ncd.f:1234-1237) and adding +-0 changes no bits, so the kernels skip it.
   uint8_t pairflags[kNType * kNType];
   uint8_t pad1_[3];
-  // task order of the pair-parallel SAPT stage: the 64 site pairs (ia*8+ib) and the dipole-induction
-  // task (64), most expensive first, so that the warps of a CTA that pull tasks from a shared counter
-  // finish together.  Pairs whose type contributes exactly +0 come last (sapt_ntask counts the others).
-  uint8_t sapt_order[65];
-  uint8_t pad3_[3];
-  int32_t sapt_ntask;
 };
 // bytes of the leading rigid-model block = offset of the first SAPT member (a multiple of 16)
 #define PIMDK_RIGID_TABLE_BYTES (offsetof(::pimdk::CcpolDev, param))

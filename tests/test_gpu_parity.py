@@ -214,6 +214,27 @@ def test_normal_mode_tables_and_transform(pk, orc):
         assert relmax(vi.nmtransform_backward(qf, bvn), v) < RTOL
 
 
+def test_transform_engines_give_identical_bits(pk):
+    """FMA-pipe tile GEMM, DMMA with 128 x 64 and with 128 x 128 CTA tiles: same k-ordered fused multiply-add chain
+    per output element, so the three engines must agree bit for bit (ragged sizes included)"""
+    from pimd_tunneling_b200._lib import check, hptr, lib
+
+    rng = np.random.default_rng(17)
+    for n, nvec in ((64, 5), (129, 300), (512, 1000), (250, 131)):
+        pes = pk.McmodMass("1d").V_init()
+        vi = pk.VerletInt(pes, n, [1.0], 10.0).init_nm()
+        v = np.asfortranarray(rng.normal(size=(n, nvec)))
+        bv = np.asfortranarray(rng.normal(size=(n, nvec)))
+        outs = []
+        for kind in (0, 1, 3):
+            check(lib().pimdk_set_gemm(kind))
+            outs.append((vi.nmtransform_forward(v, bv), vi.nmtransform_backward(v, bv)))
+        check(lib().pimdk_set_gemm(1))
+        for o in outs[1:]:
+            assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        assert relmax(vi.nmtransform_backward(outs[0][0], bv), v) < RTOL
+
+
 def _traj_inputs(pes, n, ntraj, a, b, sigma, mass, seed=5):
     from pimd_tunneling_b200 import path as P
 

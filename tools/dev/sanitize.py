@@ -1,0 +1,31 @@
+import sys, os, numpy as np
+R=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, R); sys.path.insert(0, R+"/tests")
+import pimd_tunneling_b200 as pk
+from bench import ti_path, wells
+from pimd_tunneling_b200 import path as P
+from oracle_lib import thermal_dimer_geometries
+pk.init(0)
+pes = pk.McmodMass("ccpol8sf").V_init()
+x = thermal_dimer_geometries(37, seed=11)          # ragged: 37*36 energies, not a multiple of 32
+v, g = pes.eval_batch(x)
+h = pes.Vdoubleprime_batch(np.asfortranarray(x[..., :2].copy()))
+a, b, mass = wells("ccpol8sf")
+for n, th in ((7, 2), (5, 1)):
+    vi = pk.VerletInt(pes, n, mass, 160.0, dt=1e-3, NMC=2, Noutput=1, seed=7).init_nm()
+    lam, path, spl = ti_path("ccpol8sf", a, b)
+    xi = np.linspace(0.2, 0.8, 3)
+    x0, p0 = vi.init_path(xi, lam, path, spl)
+    bt, dbdl = P.endpoints(lam, path, spl, xi)
+    (vi.propagate_pimd_pile if th == 2 else vi.propagate_pimd_nm)(x0, p0, a, bt, dbdl)
+    im = pk.InstantonMod(pes, mass, 160.0, n)
+    im.UMforceenergy(x0[..., 0], a, bt[..., 0]); im.detJ(x0[..., 0])
+pes2 = pk.McmodMass("2dtest").V_init()
+a2, b2, m2 = wells("2dtest")
+for n in (33, 200):
+    vi = pk.VerletInt(pes2, n, m2, 10.0, NMC=3, Noutput=2, seed=3).init_nm()
+    lam, path, spl = ti_path("2dtest", a2, b2)
+    xi = np.linspace(0.1, 0.9, 5)
+    x0, p0 = vi.init_path(xi, lam, path, spl)
+    bt, dbdl = P.endpoints(lam, path, spl, xi)
+    vi.propagate_pimd_pile(x0, p0, a2, bt, dbdl); vi.propagate_pimd_nm(x0, p0, a2, bt, dbdl)
+pk.finalize(); print("sanitize workload done")
