@@ -229,3 +229,50 @@ def test_nve_energy_conservation_and_um_gradient(orc):
         xp[k, d, 0] += 1e-5
         xm[k, d, 0] -= 1e-5
         assert abs((orc.UM(xp, a, b) - orc.UM(xm, a, b)) / 2e-5 - g[k, d, 0]) < 1e-6 * max(1.0, abs(g[k, d, 0]))
+
+
+def test_second_derivatives_restatement(orc):
+    """Pins the oracle's Vdoubleprime / UMhessian (unpinned by the reference: no tests, no fixtures) by identities, and
+    documents the two reference quirks that are restated literally."""
+    # 1D: central difference of the analytic gradient -> analytic second derivative 12 x^2 - 4 (Vheight = x0 = 1)
+    orc.select("1d")
+    for xv in (-1.2, 0.3, 0.9):
+        h, x = orc.Vdoubleprime(np.array([[xv]]))
+        assert abs(h[0, 0, 0, 0] - (12 * xv * xv - 4)) < 1e-6
+        assert abs(x[0, 0] - xv) < 1e-15            # in-place x + eps - 2 eps + eps: restored up to round-off
+    # 2D: the reference assigns inside its loop over the wells (mcmod_2dtest.f90:69-82): only well k = m survives
+    orc.select("2dtest")
+    xy = np.array([[2.7], [0.4]])
+    h, _ = orc.Vdoubleprime(xy)
+    a0, b0, rho0, m, pi = 2.0, 0.2, 3.0, 6, 3.14159265358979
+    wx, wy = rho0 * np.cos(m * 2.0 * pi / m), rho0 * np.sin(m * 2.0 * pi / m)
+    dx, dy = xy[0, 0] - wx, xy[1, 0] - wy
+    u = dx * dx + dy * dy
+    dv = a0 * np.exp(-a0 * u) + b0 * np.exp(-b0 * u)
+    d2 = -a0 ** 2 * np.exp(-a0 * u) - b0 ** 2 * np.exp(-b0 * u)
+    expect = np.array([[(d2 * dx + dv) * dx, (d2 * dy + dv) * dx], [(d2 * dy + dv) * dx, (d2 * dy + dv) * dy]])
+    assert np.abs(h.reshape(2, 2, order="F") - expect).max() < 1e-13
+    # UMhessian: equals the mass-weighted numerical Hessian of UM (central differences of the oracle's own UMprime) in
+    # every entry except the bead 1 - bead 2 spring coupling, which the reference never writes (instantonmod.f90:203)
+    orc.select("1d")
+    n, mass, betan = 7, [1.7], 0.35
+    orc.nm_setup(n, mass, betan, 1.0, 1.0, 1e-3, False, True)
+    rng = np.random.default_rng(4)
+    x = np.asfortranarray(rng.uniform(-1.2, 1.2, size=(n, 1, 1)))
+    a, b = np.array([[-1.0]]), np.array([[1.0]])
+    band = orc.UMhessian(x, False)
+    dense = np.zeros((n, n))
+    for c in range(n):
+        for r in range(c, min(n, c + 2)):
+            dense[r, c] = dense[c, r] = band[r - c, c]
+    num = np.zeros((n, n))
+    eps = 1e-5
+    for j in range(n):
+        xp, xm = x.copy(order="F"), x.copy(order="F")
+        xp[j] += eps
+        xm[j] -= eps
+        num[:, j] = (orc.UMprime(xp, a, b) - orc.UMprime(xm, a, b)).reshape(n) / (2 * eps) / mass[0]
+    mask = np.ones((n, n), bool)
+    mask[0, 1] = mask[1, 0] = False
+    assert np.abs(dense - num)[mask].max() < 1e-5 * np.abs(num).max()
+    assert dense[1, 0] == 0.0 and abs(num[1, 0] + 1.0 / betan ** 2) < 1e-5 / betan ** 2
