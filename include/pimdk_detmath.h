@@ -54,9 +54,41 @@
  * fetches them with wide uniform loads (LDCU.128, two coefficients per instruction, hoistable out of
  * loops) instead of materialising every 64-bit literal with two UMOVs per use — measured 10% of all
  * issued instructions in the CCpol kernel before this change (profiles/r1_ccpol_grad_v0.md). */
-#define PIMDK_EXP_COEFS {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, \
-  2.7557319223985893e-06, 2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, \
-  0.041666666666666664, 0.16666666666666666, 0.5, 1.0, 1.0}
+/* exp: 2^(j/128), j = 0..127, correctly rounded (mpmath), and the Taylor coefficients 1/120, 1/24, 1/6, 1/2 */
+#define PIMDK_EXP2_TAB { \
+  1, 1.0054299011128027, 1.0108892860517005, 1.0163783149109531, \
+  1.0218971486541166, 1.0274459491187637, 1.0330248790212284, 1.0386341019613787, \
+  1.0442737824274138, 1.0499440858006872, 1.0556451783605572, 1.0613772272892621, \
+  1.0671404006768237, 1.0729348675259756, 1.0787607977571199, 1.0846183622133092, \
+  1.0905077326652577, 1.0964290818163769, 1.1023825833078409, 1.1083684117236787, \
+  1.1143867425958924, 1.1204377524096067, 1.1265216186082418, 1.1326385195987192, \
+  1.1387886347566916, 1.1449721444318042, 1.1511892299529827, 1.1574400736337511, \
+  1.1637248587775775, 1.1700437696832502, 1.1763969916502812, 1.182784710984341, \
+  1.189207115002721, 1.1956643920398273, 1.2021567314527031, 1.2086843236265816, \
+  1.215247359980469, 1.2218460329727576, 1.22848053610687, 1.2351510639369334, \
+  1.241857812073484, 1.2486009771892048, 1.2553807570246911, 1.2621973503942507, \
+  1.2690509571917332, 1.275941778396392, 1.2828700160787783, 1.2898358734066657, \
+  1.2968395546510096, 1.3038812651919358, 1.3109612115247644, 1.318079601266064, \
+  1.3252366431597413, 1.3324325470831615, 1.3396675240533029, 1.3469417862329458, \
+  1.3542555469368927, 1.3616090206382248, 1.3690024229745905, 1.3764359707545302, \
+  1.383909881963832, 1.3914243757719262, 1.3989796725383112, 1.4065759938190154, \
+  1.4142135623730951, 1.4218926021691656, 1.42961333839197, 1.4373759974489824, \
+  1.4451808069770467, 1.4530279958490526, 1.460917794180647, 1.4688504333369818, \
+  1.4768261459394993, 1.4848451658727524, 1.4929077282912648, 1.5010140696264256, \
+  1.5091644275934228, 1.5173590411982147, 1.5255981507445384, 1.5338819978409559, \
+  1.5422108254079407, 1.550584877685, 1.5590044002378369, 1.567469639965553, \
+  1.5759808451078865, 1.5845382652524937, 1.593142151342267, 1.6017927556826934, \
+  1.6104903319492543, 1.6192351351948637, 1.6280274218573478, 1.6368674497669644, \
+  1.6457554781539649, 1.6546917676561943, 1.6636765803267364, 1.6727101796415966, \
+  1.681792830507429, 1.6909247992693053, 1.7001063537185235, 1.7093377631004629, \
+  1.7186192981224779, 1.7279512309618377, 1.7373338352737062, 1.746767386199169, \
+  1.7562521603732995, 1.7657884359332727, 1.7753764925265212, 1.785016611318935, \
+  1.7947090750031072, 1.8044541678066239, 1.8142521755003989, 1.8241033854070534, \
+  1.8340080864093424, 1.843966568958626, 1.8539791250833855, 1.864046048397789, \
+  1.8741676341103, 1.8843441790323345, 1.8945759815869656, 1.9048633418176741, \
+  1.9152065613971474, 1.925605943636125, 1.9360617934922943, 1.9465744175792332, \
+  1.9571441241754002, 1.9677712232331759, 1.9784560263879509, 1.9891988469672663}
+#define PIMDK_EXP_COEFS {0.008333333333333333, 0.041666666666666664, 0.16666666666666666, 0.5}
 #define PIMDK_LOG_COEFS {0.08695652173913043, 0.09523809523809523, 0.10526315789473684, 0.11764705882352941, \
   0.13333333333333333, 0.15384615384615385, 0.18181818181818182, 0.2222222222222222, 0.2857142857142857, 0.4, \
   0.6666666666666666}
@@ -71,13 +103,16 @@
   0.009761609529194078, 0.011551800896139705, 0.01396484375, 0.017352764423076924, 0.022372159090909092, \
   0.030381944444444444, 0.044642857142857144, 0.075, 0.16666666666666666}
 #if defined(__CUDACC__)
-static __constant__ double pimdk_dc_exp[14] = PIMDK_EXP_COEFS;
+static __constant__ double pimdk_dc_exp[4] = PIMDK_EXP_COEFS;
+/* the 2^(j/128) table is indexed per lane: global memory through the read-only path (L1-resident, 1 KB) */
+static __device__ const double pimdk_dg_exp2[128] = PIMDK_EXP2_TAB;
 static __constant__ double pimdk_dc_log[11] = PIMDK_LOG_COEFS;
 static __constant__ double pimdk_dc_sin[9] = PIMDK_SIN_COEFS;
 static __constant__ double pimdk_dc_cos[10] = PIMDK_COS_COEFS;
 static __constant__ double pimdk_dc_asin[28] = PIMDK_ASIN_COEFS;
 #endif
-static const double pimdk_hc_exp[14] = PIMDK_EXP_COEFS;
+static const double pimdk_hc_exp[4] = PIMDK_EXP_COEFS;
+static const double pimdk_hc_exp2[128] = PIMDK_EXP2_TAB;
 static const double pimdk_hc_log[11] = PIMDK_LOG_COEFS;
 static const double pimdk_hc_sin[9] = PIMDK_SIN_COEFS;
 static const double pimdk_hc_cos[10] = PIMDK_COS_COEFS;
@@ -109,59 +144,51 @@ PIMDK_HD double pimdk_u2d(uint64_t u) {
 #endif
 }
 
-/* exp(x): x = k ln2 + r, |r| <= ln2/2 (Cody-Waite, two-part ln2), degree-13 Taylor in Horner/fma
- * form, scaled by 2^k through the exponent field.  Flushes to 0 below -708, +inf above 709.
- * Device fast path (|x| < 700): one scaling by 2^k — the same bits as the general two-step scaling
- * whenever neither overflows nor underflows, which |x| < 700 guarantees. */
-PIMDK_HD double pimdk_exp_poly(double r) {
-  double p = PIMDK_TAB(exp)[0];
-  PIMDK_UNROLL
-  for (int i = 1; i < 14; ++i) p = PIMDK_FMA(p, r, PIMDK_TAB(exp)[i]);
-  return p;
-}
-/* general path: any x (the device keeps it out of line so that each inlined copy of pimdk_exp is only
- * the ~22-instruction fast path; the hot kernels' code must stay inside the 32 KB instruction cache) */
-#if defined(__CUDACC__)
-static __host__ __device__ __noinline__ double pimdk_exp_general(double x) {
-#else
-static inline double pimdk_exp_general(double x) {
-#endif
-  const double shifter = 6755399441055744.0; /* 1.5 * 2^52 */
-  if (!(x > -708.0)) return (x != x) ? x : 0.0;
-  if (x > 709.0) return pimdk_u2d(0x7ff0000000000000ull);
-  double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
-  int64_t k = (int64_t)(int32_t)(pimdk_d2u(t) & 0xffffffffull);
-  double kd = PIMDK_SUB(t, shifter);
-  double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x); /* ln2 high part (fdlibm split) */
-  r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);        /* ln2 low part */
-  double p = pimdk_exp_poly(r);
-  /* 2^k in two halves so that k in [-1022-52, 1023] never overflows the exponent field */
-  int64_t k1 = k / 2, k2 = k - k1;
-  double s1 = pimdk_u2d((uint64_t)(k1 + 1023) << 52);
-  double s2 = pimdk_u2d((uint64_t)(k2 + 1023) << 52);
-  return PIMDK_MUL(PIMDK_MUL(p, s1), s2);
-}
-/* Device: branch-free.  On (-708, 709] the general path's two-step scaling (p*2^k1)*2^k2 is exact in both
- * steps (the result is a normal number: k + 1023 lies in [2, 2046]), so it equals the single scaling p*2^k
- * bit for bit; outside that interval the general path returns 0, x (NaN) or +inf without arithmetic, which
- * two selects (and NaN propagation through the arithmetic) reproduce.  No branch means no convergence barrier around every exp: independent exps of
- * neighbouring site pairs interleave in the FP64 pipe instead of running one after the other. */
-PIMDK_HD double pimdk_exp(double x) {
+/* exp(x) = 2^k 2^(j/128) e^r:  ki = rint(x 128/ln2) = 128 k + j,  r = x - ki ln2/128 (Cody-Waite, two-part ln2;
+ * the first step is exact), |r| <= ln2/256, so e^r - 1 = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120) to 6e-19.
+ * The table value is scaled by 2^k through its exponent field BEFORE the last fma, T' (1 + q) = fma(T', q, T'):
+ * ten FP64 operations in all (the degree-13 Taylor form this replaces took nineteen), < 1 ulp (table 0.5 + final
+ * rounding 0.5).  Returns 0 at or below -708 and +inf above 709; on (-708, 709] every intermediate is a normal
+ * number, so the scaling is exact.  NaN propagates through the arithmetic (fma(T', NaN, T')). */
+#define PIMDK_EXP_CORE(x, res)                                                        \
+  do {                                                                                \
+    const double pimdk_t = PIMDK_FMA((x), 184.66496523378731, 6755399441055744.0);    \
+    const int32_t pimdk_ki = (int32_t)(uint32_t)(pimdk_d2u(pimdk_t) & 0xffffffffull); \
+    const double pimdk_kd = PIMDK_SUB(pimdk_t, 6755399441055744.0);                   \
+    double pimdk_r = PIMDK_FMA(pimdk_kd, -5.41521234663377981633e-03, (x)); /* ln2 high part / 128 (fdlibm split) */ \
+    pimdk_r = PIMDK_FMA(pimdk_kd, -1.49079291349264664064e-12, pimdk_r);    /* ln2 low part / 128 */ \
+    const double pimdk_T = pimdk_exp2_scaled(pimdk_ki);                               \
+    const double pimdk_r2 = PIMDK_MUL(pimdk_r, pimdk_r);                              \
+    double pimdk_p = PIMDK_FMA(PIMDK_TAB(exp)[0], pimdk_r, PIMDK_TAB(exp)[1]);        \
+    pimdk_p = PIMDK_FMA(pimdk_p, pimdk_r, PIMDK_TAB(exp)[2]);                         \
+    pimdk_p = PIMDK_FMA(pimdk_p, pimdk_r, PIMDK_TAB(exp)[3]);                         \
+    const double pimdk_q = PIMDK_FMA(pimdk_r2, pimdk_p, pimdk_r);                     \
+    (res) = PIMDK_FMA(pimdk_T, pimdk_q, pimdk_T);                                     \
+  } while (0)
+/* 2^(ki >> 7) * 2^((ki & 127)/128): the table entry with ki >> 7 added to its exponent field (integer pipe).  For
+ * arguments outside (-708, 709] the result is garbage that the callers' range tests discard. */
+PIMDK_HD double pimdk_exp2_scaled(int32_t ki) {
 #if defined(__CUDA_ARCH__)
-  const double shifter = 6755399441055744.0;
-  double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
-  int k = __double2loint(t);
-  double kd = PIMDK_SUB(t, shifter);
-  double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x);
-  r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);
-  double res = PIMDK_MUL(pimdk_exp_poly(r), __hiloint2double((k + 1023) << 20, 0));
-  /* +inf above 709, 0 at or below -708; a NaN argument fails both tests and leaves the NaN the arithmetic produced
-   * (the host form returns x itself: the same value up to the NaN payload) */
+  const double T = __ldg(&pimdk_dg_exp2[ki & 127]);
+  return __hiloint2double(__double2hiint(T) + (int)((uint32_t)(ki >> 7) << 20), __double2loint(T));
+#else
+  return pimdk_u2d(pimdk_d2u(pimdk_hc_exp2[ki & 127]) + ((uint64_t)((uint32_t)(ki >> 7) << 20) << 32));
+#endif
+}
+PIMDK_HD double pimdk_exp(double x) {
+  double res;
+#if defined(__CUDA_ARCH__)
+  /* branch-free: no convergence barrier around every exp, so the independent exps of neighbouring site pairs
+   * interleave in the FP64 pipe instead of running one after the other */
+  PIMDK_EXP_CORE(x, res);
   res = (x > 709.0) ? __longlong_as_double(0x7ff0000000000000ll) : res;
   res = (x <= -708.0) ? 0.0 : res;
   return res;
 #else
-  return pimdk_exp_general(x);
+  if (!(x > -708.0)) return (x != x) ? x : 0.0;
+  if (x > 709.0) return pimdk_u2d(0x7ff0000000000000ull);
+  PIMDK_EXP_CORE(x, res);
+  return res;
 #endif
 }
 
@@ -169,16 +196,11 @@ PIMDK_HD double pimdk_exp(double x) {
  * the device form drops the overflow test (one FP64-pipe compare and a 64-bit select per call). */
 PIMDK_HD double pimdk_exp_nonpos(double x) {
 #if defined(__CUDA_ARCH__)
-  const double shifter = 6755399441055744.0;
-  double t = PIMDK_FMA(x, 1.4426950408889634, shifter);
-  int k = __double2loint(t);
-  double kd = PIMDK_SUB(t, shifter);
-  double r = PIMDK_FMA(kd, -6.93147180369123816490e-01, x);
-  r = PIMDK_FMA(kd, -1.90821492927058770002e-10, r);
-  double res = PIMDK_MUL(pimdk_exp_poly(r), __hiloint2double((k + 1023) << 20, 0));
+  double res;
+  PIMDK_EXP_CORE(x, res);
   return (x <= -708.0) ? 0.0 : res;
 #else
-  return pimdk_exp_general(x);
+  return pimdk_exp(x);
 #endif
 }
 
