@@ -54,40 +54,41 @@
  * fetches them with wide uniform loads (LDCU.128, two coefficients per instruction, hoistable out of
  * loops) instead of materialising every 64-bit literal with two UMOVs per use — measured 10% of all
  * issued instructions in the CCpol kernel before this change (profiles/r1_ccpol_grad_v0.md). */
-/* exp: 2^(j/128), j = 0..127, correctly rounded (mpmath), and the Taylor coefficients 1/120, 1/24, 1/6, 1/2 */
+/* exp: bit patterns of 2^(j/128), j = 0..127, correctly rounded (mpmath), each with j << 45 subtracted so that adding
+ * ki << 45 (ki = 128 k + j) lands k in the exponent field; and the Taylor coefficients 1/120, 1/24, 1/6, 1/2 */
 #define PIMDK_EXP2_TAB { \
-  1, 1.0054299011128027, 1.0108892860517005, 1.0163783149109531, \
-  1.0218971486541166, 1.0274459491187637, 1.0330248790212284, 1.0386341019613787, \
-  1.0442737824274138, 1.0499440858006872, 1.0556451783605572, 1.0613772272892621, \
-  1.0671404006768237, 1.0729348675259756, 1.0787607977571199, 1.0846183622133092, \
-  1.0905077326652577, 1.0964290818163769, 1.1023825833078409, 1.1083684117236787, \
-  1.1143867425958924, 1.1204377524096067, 1.1265216186082418, 1.1326385195987192, \
-  1.1387886347566916, 1.1449721444318042, 1.1511892299529827, 1.1574400736337511, \
-  1.1637248587775775, 1.1700437696832502, 1.1763969916502812, 1.182784710984341, \
-  1.189207115002721, 1.1956643920398273, 1.2021567314527031, 1.2086843236265816, \
-  1.215247359980469, 1.2218460329727576, 1.22848053610687, 1.2351510639369334, \
-  1.241857812073484, 1.2486009771892048, 1.2553807570246911, 1.2621973503942507, \
-  1.2690509571917332, 1.275941778396392, 1.2828700160787783, 1.2898358734066657, \
-  1.2968395546510096, 1.3038812651919358, 1.3109612115247644, 1.318079601266064, \
-  1.3252366431597413, 1.3324325470831615, 1.3396675240533029, 1.3469417862329458, \
-  1.3542555469368927, 1.3616090206382248, 1.3690024229745905, 1.3764359707545302, \
-  1.383909881963832, 1.3914243757719262, 1.3989796725383112, 1.4065759938190154, \
-  1.4142135623730951, 1.4218926021691656, 1.42961333839197, 1.4373759974489824, \
-  1.4451808069770467, 1.4530279958490526, 1.460917794180647, 1.4688504333369818, \
-  1.4768261459394993, 1.4848451658727524, 1.4929077282912648, 1.5010140696264256, \
-  1.5091644275934228, 1.5173590411982147, 1.5255981507445384, 1.5338819978409559, \
-  1.5422108254079407, 1.550584877685, 1.5590044002378369, 1.567469639965553, \
-  1.5759808451078865, 1.5845382652524937, 1.593142151342267, 1.6017927556826934, \
-  1.6104903319492543, 1.6192351351948637, 1.6280274218573478, 1.6368674497669644, \
-  1.6457554781539649, 1.6546917676561943, 1.6636765803267364, 1.6727101796415966, \
-  1.681792830507429, 1.6909247992693053, 1.7001063537185235, 1.7093377631004629, \
-  1.7186192981224779, 1.7279512309618377, 1.7373338352737062, 1.746767386199169, \
-  1.7562521603732995, 1.7657884359332727, 1.7753764925265212, 1.785016611318935, \
-  1.7947090750031072, 1.8044541678066239, 1.8142521755003989, 1.8241033854070534, \
-  1.8340080864093424, 1.843966568958626, 1.8539791250833855, 1.864046048397789, \
-  1.8741676341103, 1.8843441790323345, 1.8945759815869656, 1.9048633418176741, \
-  1.9152065613971474, 1.925605943636125, 1.9360617934922943, 1.9465744175792332, \
-  1.9571441241754002, 1.9677712232331759, 1.9784560263879509, 1.9891988469672663}
+  0x3ff0000000000000ull, 0x3feff63da9fb3335ull, 0x3fefec9a3e778061ull, 0x3fefe315e86e7f85ull, \
+  0x3fefd9b0d3158574ull, 0x3fefd06b29ddf6deull, 0x3fefc74518759bc8ull, 0x3fefbe3ecac6f383ull, \
+  0x3fefb5586cf9890full, 0x3fefac922b7247f7ull, 0x3fefa3ec32d3d1a2ull, 0x3fef9b66affed31bull, \
+  0x3fef9301d0125b51ull, 0x3fef8abdc06c31ccull, 0x3fef829aaea92de0ull, 0x3fef7a98c8a58e51ull, \
+  0x3fef72b83c7d517bull, 0x3fef6af9388c8deaull, 0x3fef635beb6fcb75ull, 0x3fef5be084045cd4ull, \
+  0x3fef54873168b9aaull, 0x3fef4d5022fcd91dull, 0x3fef463b88628cd6ull, 0x3fef3f49917ddc96ull, \
+  0x3fef387a6e756238ull, 0x3fef31ce4fb2a63full, 0x3fef2b4565e27cddull, 0x3fef24dfe1f56381ull, \
+  0x3fef1e9df51fdee1ull, 0x3fef187fd0dad990ull, 0x3fef1285a6e4030bull, 0x3fef0cafa93e2f56ull, \
+  0x3fef06fe0a31b715ull, 0x3fef0170fc4cd831ull, 0x3feefc08b26416ffull, 0x3feef6c55f929ff1ull, \
+  0x3feef1a7373aa9cbull, 0x3feeecae6d05d866ull, 0x3feee7db34e59ff7ull, 0x3feee32dc313a8e5ull, \
+  0x3feedea64c123422ull, 0x3feeda4504ac801cull, 0x3feed60a21f72e2aull, 0x3feed1f5d950a897ull, \
+  0x3feece086061892dull, 0x3feeca41ed1d0057ull, 0x3feec6a2b5c13cd0ull, 0x3feec32af0d7d3deull, \
+  0x3feebfdad5362a27ull, 0x3feebcb299fddd0dull, 0x3feeb9b2769d2ca7ull, 0x3feeb6daa2cf6642ull, \
+  0x3feeb42b569d4f82ull, 0x3feeb1a4ca5d920full, 0x3feeaf4736b527daull, 0x3feead12d497c7fdull, \
+  0x3feeab07dd485429ull, 0x3feea9268a5946b7ull, 0x3feea76f15ad2148ull, 0x3feea5e1b976dc09ull, \
+  0x3feea47eb03a5585ull, 0x3feea34634ccc320ull, 0x3feea23882552225ull, 0x3feea155d44ca973ull, \
+  0x3feea09e667f3bcdull, 0x3feea012750bdabfull, 0x3fee9fb23c651a2full, 0x3fee9f7df9519484ull, \
+  0x3fee9f75e8ec5f74ull, 0x3fee9f9a48a58174ull, 0x3fee9feb564267c9ull, 0x3feea0694fde5d3full, \
+  0x3feea11473eb0187ull, 0x3feea1ed0130c132ull, 0x3feea2f336cf4e62ull, 0x3feea427543e1a12ull, \
+  0x3feea589994cce13ull, 0x3feea71a4623c7adull, 0x3feea8d99b4492edull, 0x3feeaac7d98a6699ull, \
+  0x3feeace5422aa0dbull, 0x3feeaf3216b5448cull, 0x3feeb1ae99157736ull, 0x3feeb45b0b91ffc6ull, \
+  0x3feeb737b0cdc5e5ull, 0x3feeba44cbc8520full, 0x3feebd829fde4e50ull, 0x3feec0f170ca07baull, \
+  0x3feec49182a3f090ull, 0x3feec86319e32323ull, 0x3feecc667b5de565ull, 0x3feed09bec4a2d33ull, \
+  0x3feed503b23e255dull, 0x3feed99e1330b358ull, 0x3feede6b5579fdbfull, 0x3feee36bbfd3f37aull, \
+  0x3feee89f995ad3adull, 0x3feeee07298db666ull, 0x3feef3a2b84f15fbull, 0x3feef9728de5593aull, \
+  0x3feeff76f2fb5e47ull, 0x3fef05b030a1064aull, 0x3fef0c1e904bc1d2ull, 0x3fef12c25bd71e09ull, \
+  0x3fef199bdd85529cull, 0x3fef20ab5fffd07aull, 0x3fef27f12e57d14bull, 0x3fef2f6d9406e7b5ull, \
+  0x3fef3720dcef9069ull, 0x3fef3f0b555dc3faull, 0x3fef472d4a07897cull, 0x3fef4f87080d89f2ull, \
+  0x3fef5818dcfba487ull, 0x3fef60e316c98398ull, 0x3fef69e603db3285ull, 0x3fef7321f301b460ull, \
+  0x3fef7c97337b9b5full, 0x3fef864614f5a129ull, 0x3fef902ee78b3ff6ull, 0x3fef9a51fbc74c83ull, \
+  0x3fefa4afa2a490daull, 0x3fefaf482d8e67f1ull, 0x3fefba1bee615a27ull, 0x3fefc52b376bba97ull, \
+  0x3fefd0765b6e4540ull, 0x3fefdbfdad9cbe14ull, 0x3fefe7c1819e90d8ull, 0x3feff3c22b8f71f1ull}
 #define PIMDK_EXP_COEFS {0.008333333333333333, 0.041666666666666664, 0.16666666666666666, 0.5}
 #define PIMDK_LOG_COEFS {0.08695652173913043, 0.09523809523809523, 0.10526315789473684, 0.11764705882352941, \
   0.13333333333333333, 0.15384615384615385, 0.18181818181818182, 0.2222222222222222, 0.2857142857142857, 0.4, \
@@ -105,14 +106,23 @@
 #if defined(__CUDACC__)
 static __constant__ double pimdk_dc_exp[4] = PIMDK_EXP_COEFS;
 /* the 2^(j/128) table is indexed per lane: global memory through the read-only path (L1-resident, 1 KB) */
-static __device__ const double pimdk_dg_exp2[128] = PIMDK_EXP2_TAB;
+static __device__ const unsigned long long pimdk_dg_exp2[128] = PIMDK_EXP2_TAB;
+#if defined(PIMDK_EXP2_SHARED)
+/* a translation unit that defines PIMDK_EXP2_SHARED also gets pimdk_exp_nonpos_sh(), which reads the table from shared
+ * memory (a 32-bit address, no 64-bit address arithmetic per call); a kernel that uses it calls pimdk_exp2_stage() first */
+__shared__ unsigned long long pimdk_sh_exp2[128];
+static __device__ __forceinline__ void pimdk_exp2_stage() {
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) pimdk_sh_exp2[i] = pimdk_dg_exp2[i];
+  __syncthreads();
+}
+#endif
 static __constant__ double pimdk_dc_log[11] = PIMDK_LOG_COEFS;
 static __constant__ double pimdk_dc_sin[9] = PIMDK_SIN_COEFS;
 static __constant__ double pimdk_dc_cos[10] = PIMDK_COS_COEFS;
 static __constant__ double pimdk_dc_asin[28] = PIMDK_ASIN_COEFS;
 #endif
 static const double pimdk_hc_exp[4] = PIMDK_EXP_COEFS;
-static const double pimdk_hc_exp2[128] = PIMDK_EXP2_TAB;
+static const uint64_t pimdk_hc_exp2[128] = PIMDK_EXP2_TAB;
 static const double pimdk_hc_log[11] = PIMDK_LOG_COEFS;
 static const double pimdk_hc_sin[9] = PIMDK_SIN_COEFS;
 static const double pimdk_hc_cos[10] = PIMDK_COS_COEFS;
@@ -150,14 +160,14 @@ PIMDK_HD double pimdk_u2d(uint64_t u) {
  * ten FP64 operations in all (the degree-13 Taylor form this replaces took nineteen), < 1 ulp (table 0.5 + final
  * rounding 0.5).  Returns 0 at or below -708 and +inf above 709; on (-708, 709] every intermediate is a normal
  * number, so the scaling is exact.  NaN propagates through the arithmetic (fma(T', NaN, T')). */
-#define PIMDK_EXP_CORE(x, res)                                                        \
+#define PIMDK_EXP_CORE(x, res, T2K)                                                       \
   do {                                                                                \
     const double pimdk_t = PIMDK_FMA((x), 184.66496523378731, 6755399441055744.0);    \
     const int32_t pimdk_ki = (int32_t)(uint32_t)(pimdk_d2u(pimdk_t) & 0xffffffffull); \
     const double pimdk_kd = PIMDK_SUB(pimdk_t, 6755399441055744.0);                   \
     double pimdk_r = PIMDK_FMA(pimdk_kd, -5.41521234663377981633e-03, (x)); /* ln2 high part / 128 (fdlibm split) */ \
     pimdk_r = PIMDK_FMA(pimdk_kd, -1.49079291349264664064e-12, pimdk_r);    /* ln2 low part / 128 */ \
-    const double pimdk_T = pimdk_exp2_scaled(pimdk_ki);                               \
+    const double pimdk_T = T2K(pimdk_ki);                                             \
     const double pimdk_r2 = PIMDK_MUL(pimdk_r, pimdk_r);                              \
     double pimdk_p = PIMDK_FMA(PIMDK_TAB(exp)[0], pimdk_r, PIMDK_TAB(exp)[1]);        \
     pimdk_p = PIMDK_FMA(pimdk_p, pimdk_r, PIMDK_TAB(exp)[2]);                         \
@@ -165,14 +175,14 @@ PIMDK_HD double pimdk_u2d(uint64_t u) {
     const double pimdk_q = PIMDK_FMA(pimdk_r2, pimdk_p, pimdk_r);                     \
     (res) = PIMDK_FMA(pimdk_T, pimdk_q, pimdk_T);                                     \
   } while (0)
-/* 2^(ki >> 7) * 2^((ki & 127)/128): the table entry with ki >> 7 added to its exponent field (integer pipe).  For
- * arguments outside (-708, 709] the result is garbage that the callers' range tests discard. */
+/* 2^(ki >> 7) * 2^((ki & 127)/128): the (pre-biased) table entry with ki << 13 added to its high word — one integer
+ * multiply-add.  For arguments outside (-708, 709] the result is garbage that the callers' range tests discard. */
 PIMDK_HD double pimdk_exp2_scaled(int32_t ki) {
 #if defined(__CUDA_ARCH__)
-  const double T = __ldg(&pimdk_dg_exp2[ki & 127]);
-  return __hiloint2double(__double2hiint(T) + (int)((uint32_t)(ki >> 7) << 20), __double2loint(T));
+  const unsigned long long b = __ldg(&pimdk_dg_exp2[ki & 127]);
+  return __hiloint2double((int)((unsigned)(b >> 32) + ((unsigned)ki << 13)), (int)(unsigned)b);
 #else
-  return pimdk_u2d(pimdk_d2u(pimdk_hc_exp2[ki & 127]) + ((uint64_t)((uint32_t)(ki >> 7) << 20) << 32));
+  return pimdk_u2d(pimdk_hc_exp2[ki & 127] + ((uint64_t)(uint32_t)ki << 45));
 #endif
 }
 PIMDK_HD double pimdk_exp(double x) {
@@ -180,14 +190,14 @@ PIMDK_HD double pimdk_exp(double x) {
 #if defined(__CUDA_ARCH__)
   /* branch-free: no convergence barrier around every exp, so the independent exps of neighbouring site pairs
    * interleave in the FP64 pipe instead of running one after the other */
-  PIMDK_EXP_CORE(x, res);
+  PIMDK_EXP_CORE(x, res, pimdk_exp2_scaled);
   res = (x > 709.0) ? __longlong_as_double(0x7ff0000000000000ll) : res;
   res = (x <= -708.0) ? 0.0 : res;
   return res;
 #else
   if (!(x > -708.0)) return (x != x) ? x : 0.0;
   if (x > 709.0) return pimdk_u2d(0x7ff0000000000000ull);
-  PIMDK_EXP_CORE(x, res);
+  PIMDK_EXP_CORE(x, res, pimdk_exp2_scaled);
   return res;
 #endif
 }
@@ -197,12 +207,25 @@ PIMDK_HD double pimdk_exp(double x) {
 PIMDK_HD double pimdk_exp_nonpos(double x) {
 #if defined(__CUDA_ARCH__)
   double res;
-  PIMDK_EXP_CORE(x, res);
+  PIMDK_EXP_CORE(x, res, pimdk_exp2_scaled);
   return (x <= -708.0) ? 0.0 : res;
 #else
   return pimdk_exp(x);
 #endif
 }
+
+#if defined(__CUDACC__) && defined(PIMDK_EXP2_SHARED)
+/* pimdk_exp_nonpos with the table read from shared memory (kernels that called pimdk_exp2_stage()): same bits */
+static __device__ __forceinline__ double pimdk_exp2_scaled_sh(int32_t ki) {
+  const unsigned long long b = pimdk_sh_exp2[ki & 127];
+  return __hiloint2double((int)((unsigned)(b >> 32) + ((unsigned)ki << 13)), (int)(unsigned)b);
+}
+static __device__ __forceinline__ double pimdk_exp_nonpos_sh(double x) {
+  double res;
+  PIMDK_EXP_CORE(x, res, pimdk_exp2_scaled_sh);
+  return (x <= -708.0) ? 0.0 : res;
+}
+#endif
 
 /* log(x), x > 0 finite normal: x = 2^e m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s),
  * s = (m-1)/(m+1), odd series to s^23; e ln2 added in two parts. */

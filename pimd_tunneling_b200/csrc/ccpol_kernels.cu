@@ -20,6 +20,8 @@
 #else
 #define PIMDK_CCPOL_NS ccpol_fast_impl
 #endif
+// the sweep kernel reads the exp table from shared memory (pimdk_exp_nonpos_sh); the other kernels through the read-only path
+#define PIMDK_EXP2_SHARED 1
 #include "ccpol_device.cuh"
 #include "kernels.h"
 
@@ -279,7 +281,7 @@ __device__ __forceinline__ void sweep_chunk(const double* sA, const double* sB, 
     r12 = ra[64] - rb[64];
     d = d + r12 * r12;
     R[q] = fast_sqrt(d);
-    e[q] = pimdk_exp_nonpos(-beta * R[q]);   // beta >= 0 (checked when the tables are built), R >= 0
+    e[q] = pimdk_exp_nonpos_sh(-beta * R[q]);   // beta >= 0 (checked when the tables are built), R >= 0
   }
 #pragma unroll
   for (int q = 0; q < N; ++q) {
@@ -304,7 +306,7 @@ __device__ __forceinline__ void sweep_row4(const double* ra, const double* sB, i
     r12 = az - rb[64];
     d = d + r12 * r12;
     R[q] = fast_sqrt(d);
-    e[q] = pimdk_exp_nonpos(-beta * R[q]);   // beta >= 0 (checked when the tables are built), R >= 0
+    e[q] = pimdk_exp_nonpos_sh(-beta * R[q]);   // beta >= 0 (checked when the tables are built), R >= 0
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -334,6 +336,7 @@ __device__ __forceinline__ void sweep_block(const double* sA, const double* sB, 
 
 __global__ void __launch_bounds__(kSweepBlock, PIMDK_SWEEP_MINB)
 KNAME(ccpol_sweep_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
+  pimdk_exp2_stage();
   extern __shared__ __align__(16) unsigned char smem[];
   const CcpolDev& T = stage_tables<kRigidTableBytes>(tab, smem);
   double* slots = reinterpret_cast<double*>(smem + kRigidTableBytes);
