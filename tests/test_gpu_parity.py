@@ -510,6 +510,41 @@ def test_ti_averages_agree_with_oracle_within_error_bars(pk, orc):
     assert abs(res["deltaA"]) < 5.0 * np.sqrt(np.sum(res["weights"] ** 2 * sg ** 2)) + 1e-12
 
 
+@pytest.mark.parametrize("name,n,beta,thermostat", [("1d", 16, 3.0, 2), ("1d", 64, 10.0, 2), ("2dtest", 15, 4.0, 1), ("2dtest", 15, 4.0, 2)])
+def test_ti_ratio_matches_exact_path_integral(pk, name, n, beta, thermostat):
+    """Known-answer test for the whole TI path (init_path, PILE / Andersen propagation, estimator, statistics),
+    independent of the oracle: q/q0 = exp(-betan DeltaA) is a ratio of n-bead discretised density-matrix elements,
+    which tests/exact_pi.py evaluates deterministically by transfer matrices.  The GPU run must reproduce ln(q/q0)
+    within 4.5 standard errors of its own estimate (and the standard error must be small enough to mean something:
+    the 2D value is -1.15, the 1D values -0.34 and -0.0014).  tools/dev/ti_exact_scan.py repeats this for three time
+    steps, both thermostats and 1024 repetitions: 12 runs, |z| <= 2.6, mean z = -0.1 (dt = 5e-3 shows the integrator's
+    O(dt^2) bias at the 2-sigma level with PILE, so the test runs at 2e-3)."""
+    import exact_pi
+    from pimd_tunneling_b200.ti_driver import MCData, run_ti
+
+    if name == "1d":
+        a, b = np.array([[-1.0]]), np.array([[1.0]])
+        exact = exact_pi.log_ratio_1d(-1.0, 1.0, n, beta)
+        mc = MCData(n=n, beta=beta, NMC=60000, imin=5000, dt=2e-3, nintegral=12, nrep=256, thermostat=thermostat, ndim=1,
+                    natom=1, seed=31337)
+        tol_se = 0.02
+    else:
+        a = np.array([[3.0], [0.0]])
+        b = np.array([[3.0 * np.cos(np.pi / 3)], [3.0 * np.sin(np.pi / 3)]])
+        exact = exact_pi.log_ratio_2d(a[:, 0], b[:, 0], n, beta)
+        mc = MCData(n=n, beta=beta, NMC=60000, imin=5000, dt=2e-3, nintegral=12, nrep=256, thermostat=thermostat, ndim=2,
+                    natom=1, Noutput=750, seed=4711)
+        tol_se = 0.03
+    res = run_ti(name, mc, a, b, [1.0])
+    betan = beta / (n + 1)
+    got = -betan * res["deltaA"]
+    se = betan * np.sqrt(res["sigmaA"] / mc.nrep)          # pimd_par.f90:420: sqrt(sigmaA/nrep)
+    print("ln(q/q0): run %.5f +/- %.5f, exact %.5f" % (got, se, exact))
+    assert se < tol_se, se
+    assert abs(got - exact) < 4.5 * se, (got, exact, se)
+    assert abs(np.log(res["q_over_q0"]) - got) < 1e-12
+
+
 # ---------------------------------------------------------------- second derivatives (row N2) -----
 def test_vdoubleprime_bit_exact(pk, orc):
     """Vdoubleprime of the three plugins against the oracle's literal restatement, including the in-place drift"""

@@ -276,3 +276,33 @@ def test_second_derivatives_restatement(orc):
     mask[0, 1] = mask[1, 0] = False
     assert np.abs(dense - num)[mask].max() < 1e-5 * np.abs(num).max()
     assert dense[1, 0] == 0.0 and abs(num[1, 0] + 1.0 / betan ** 2) < 1e-5 / betan ** 2
+
+
+def test_oracle_ti_ratio_matches_exact_path_integral(orc):
+    """The oracle's verletint restatement (init_path, PILE step, estimator) is parity-unpinned by the reference (no
+    fixtures, clock-seeded RNG); this pins it to the mathematics instead: ln(q/q0) of a 1D run against the transfer-
+    matrix value of tests/exact_pi.py, within 4.5 standard errors."""
+    import exact_pi
+    from pimd_tunneling_b200 import path as P
+
+    orc.select("1d")
+    n, beta, dt, NMC, imin, nint, nrep = 16, 3.0, 5e-3, 20000, 1000, 8, 20
+    betan = beta / (n + 1)
+    a, b = np.array([[-1.0]]), np.array([[1.0]])
+    lam, path, spl = P.build_path(np.stack([a, b], axis=0))
+    xi, w = np.polynomial.legendre.leggauss(nint)
+    xi, w = (xi + 1) / 2, w / 2
+    xint, dbd = P.endpoints(lam, path, spl, xi)
+    I = np.empty((nint, nrep))
+    for k in range(nint):
+        for r in range(nrep):
+            orc.nm_setup(n, [1.0], betan, 1.0, 1.0, dt)
+            orc.init_nm(a, xint[..., k])
+            orc.set_rng(99, 5000 + k * nrep + r)
+            x0, p0 = orc.init_path(float(xi[k]), lam, path, spl)
+            _, _, d = orc.propagate(2, x0, p0, dbd[..., k], NMC, imin)
+            I[k, r] = d / betan ** 2
+    m, s = I.mean(axis=1), I.std(axis=1, ddof=1) / np.sqrt(nrep)
+    got, se = -betan * np.sum(w * m), betan * np.sqrt(np.sum(w ** 2 * s ** 2))
+    exact = exact_pi.log_ratio_1d(-1.0, 1.0, n, beta)
+    assert se < 0.12 and abs(got - exact) < 4.5 * se, (got, exact, se)
