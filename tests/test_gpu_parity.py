@@ -659,6 +659,35 @@ def test_rpi_splitting_closes_the_instanton_calculation(pk, orc):
     orc.set_V0(0.0)
 
 
+def test_rpi_splitting_matches_the_analytic_instanton(pk):
+    """Known answer for the instanton rows (UM, UMprime, L-BFGS-B on the GPU gradient, UMhessian, detJ, the closing
+    formulas of `program rpi`), independent of the oracle: for V = (x^2-1)^2 and mass m the kink action is
+    S = (4/3) sqrt(2m) and the one-loop splitting is 2 w sqrt(6 S/pi) exp(-S), w = sqrt(8/m).  With m = 20, n = 512,
+    beta = 40 the ring-polymer values converge to these to 3e-5 and 1.2e-4."""
+    from scipy.optimize import fmin_l_bfgs_b
+
+    m, n, beta = 20.0, 512, 40.0
+    pes = pk.McmodMass("1d").V_init()
+    pes.set_V0(0.0)
+    a, b = np.array([[-1.0]]), np.array([[1.0]])
+    im = pk.InstantonMod(pes, [m], beta, n, fixedends=True, rpi=True)
+    x0 = np.empty((n, 1, 1), order="F")
+    for i in range(n):
+        x0[i] = a + (b - a) * i / (n - 1)
+
+    def fg(v):
+        g_, f_ = im.UMforceenergy(v.reshape(x0.shape, order="F"), a, b)
+        return f_, g_.reshape(-1, order="F")
+
+    xs, _, info = fmin_l_bfgs_b(fg, x0.reshape(-1, order="F"), m=8, factr=1e6, pgtol=1e-7, maxls=40, maxiter=20000)
+    r = im.rpi_splitting(np.asfortranarray(xs.reshape(x0.shape, order="F")), a, b)
+    S = 4.0 / 3.0 * np.sqrt(2.0 * m)
+    delta = 2.0 * np.sqrt(8.0 / m) * np.sqrt(6.0 * S / np.pi) * np.exp(-S)
+    assert r["skipped"] == 0 and r["skipped0"] == 0
+    assert abs(r["s_kink"] - S) < 1e-4 * S, (r["s_kink"], S)
+    assert abs(r["delta"] - delta) < 5e-4 * delta, (r["delta"], delta)
+
+
 def test_full_size_c4_step_is_partition_invariant(pk):
     """BASELINE config C4 at its full size (512 beads x 8192 trajectories, CCpol-8sf, PILE): one step of the whole
     batch, then 12 sampled trajectories re-run alone and in a different order.  Results are keyed by the global

@@ -306,3 +306,38 @@ def test_oracle_ti_ratio_matches_exact_path_integral(orc):
     got, se = -betan * np.sum(w * m), betan * np.sqrt(np.sum(w ** 2 * s ** 2))
     exact = exact_pi.log_ratio_1d(-1.0, 1.0, n, beta)
     assert se < 0.12 and abs(got - exact) < 4.5 * se, (got, exact, se)
+
+
+def test_oracle_instanton_matches_the_analytic_kink(orc):
+    """UM / UMprime / UMhessian of the oracle (parity-unpinned by the reference) pinned to the analytic instanton of
+    V = (x^2-1)^2: kink action (4/3) sqrt(2m), one-loop splitting 2 w sqrt(6 S/pi) exp(-S)."""
+    from scipy.linalg import eigvals_banded
+    from scipy.optimize import fmin_l_bfgs_b
+
+    orc.select("1d")
+    orc.set_V0(0.0)
+    m, n, beta = 20.0, 256, 40.0
+    betan = beta / n
+    a, b = np.array([[-1.0]]), np.array([[1.0]])
+    orc.nm_setup(n, [m], betan, 1.0, 1.0, 1e-3, False, True)
+    x0 = np.empty((n, 1, 1), order="F")
+    for i in range(n):
+        x0[i] = a + (b - a) * i / (n - 1)
+
+    def fg(v):
+        g_, f_ = orc.UMforceenergy(v.reshape(x0.shape, order="F"), a, b)
+        return f_, g_.reshape(-1, order="F")
+
+    xs, _, _ = fmin_l_bfgs_b(fg, x0.reshape(-1, order="F"), m=8, factr=1e6, pgtol=1e-7, maxls=40, maxiter=20000)
+    xt = np.asfortranarray(xs.reshape(x0.shape, order="F"))
+    xh = np.empty_like(xt)
+    xh[:] = a.reshape(1, 1, 1)
+    e0 = eigvals_banded(orc.UMhessian(xh, True), lower=True)
+    e1 = eigvals_banded(orc.UMhessian(xt, False), lower=True)[1:]
+    assert (e0 > 0).all() and (e1 > 0).all()
+    phi = np.exp(0.5 * (np.sum(np.log(e1)) - np.sum(np.log(e0))))
+    sk = betan * orc.UM(xt, a, b)
+    delta = 2.0 * np.exp(-sk) * np.sqrt(sk / (2.0 * np.pi)) / phi
+    S = 4.0 / 3.0 * np.sqrt(2.0 * m)
+    exact = 2.0 * np.sqrt(8.0 / m) * np.sqrt(6.0 * S / np.pi) * np.exp(-S)
+    assert abs(sk - S) < 2e-4 * S and abs(delta - exact) < 2e-3 * exact, (sk, S, delta, exact)
