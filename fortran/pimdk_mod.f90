@@ -77,6 +77,10 @@ module pimdk
      integer(c_int64_t) function pimdk_last_nan_trajectory() bind(C, name="pimdk_last_nan_trajectory")
        import
      end function
+     ! trajectories per chunk of the copy-overlapped host-buffer propagate (0 = automatic)
+     integer(c_int) function pimdk_set_propagate_chunk(ntraj_per_chunk) bind(C, name="pimdk_set_propagate_chunk")
+       import; integer(c_int64_t), value :: ntraj_per_chunk
+     end function
      integer(c_int) function pimdk_gauleg(x1, x2, n, x, w) bind(C, name="pimdk_gauleg")
        import; real(c_double), value :: x1, x2; integer(c_int64_t), value :: n; real(c_double) :: x(*), w(*)
      end function

@@ -48,6 +48,7 @@ _SIGS = {
     "pimdk_propagate": [_i64, _i64, _pd, _pd, _pd, _pd, _pd, _dbl, _dbl, _i64, _i64, _i64, _i64, _u64, _pi, _pd],
     "pimdk_propagate_dev": [_i64, _i64, _pd, _pd, _pd, _pd, _pd, _dbl, _dbl, _i64, _i64, _i64, _i64, _u64, _pi, _pd],
     "pimdk_set_restart": [_i64, _i64],
+    "pimdk_set_propagate_chunk": [_i64],
     "pimdk_get_dhdr_sums": [_i64, _pd],
     "pimdk_ti_partial_sums": [_i64, _pd, _pi, _i64, _i64, _dbl, _pd],
     "pimdk_ti_finish": [_i64, _pd, _pd, _dbl, _pd, _pd, _pd, _pd, _pd],

@@ -79,6 +79,10 @@ struct Ctx {
   bool fused = true;  // small systems: one persistent warp-per-ring-polymer kernel
   long restart = 0, restartnmc = 0;  // module verletint's restart / restartnmc (verletmodule.f90:10)
   long sums_n = 0;                   // trajectories in wDhSum (running sums of the last propagate call)
+  long chunk_traj = 0;               // pimdk_set_propagate_chunk: trajectories per chunk of the host-buffer propagate (0 = automatic)
+  long sum_off = 0, sum_total = 0;   // chunked host-buffer propagate: this chunk's offset into wDhSum / whole batch
+  cudaStream_t copy_stream = nullptr; // host<->device copies of the chunked propagate, overlapped with compute
+  cudaEvent_t ev_in[2] = {nullptr, nullptr};
   // PES
   PesKind pes = PES_NONE;
   int ndim = 0, natom = 0;
@@ -94,7 +98,7 @@ struct Ctx {
   std::vector<double> mass, lam, beadmass, T;
   DevBuf dT, dsA, dsB, dlamb2, dmass, dtabs;  // dtabs: 8 per-call (natom,n) tables
   // workspaces
-  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wUmIn, wUmOut, wHgp, wHgm, wHess, wBand, wDense, wEig, wWork;
+  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wX2, wPp2, wUmIn, wUmOut, wHgp, wHgm, wHess, wBand, wDense, wEig, wWork;
   PinBuf hUm;
   // profiling
   bool profiling = false;
@@ -355,10 +359,16 @@ int pimdk_finalize(void) {
   resolve_spans();
   DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
-                    &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wUmIn, &g.wUmOut, &g.wHgp, &g.wHgm, &g.wHess, &g.wBand,
+                    &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wX2, &g.wPp2, &g.wUmIn, &g.wUmOut, &g.wHgp, &g.wHgm, &g.wHess, &g.wBand,
                     &g.wDense, &g.wEig, &g.wWork};
   for (DevBuf* b : bufs) b->release();
   g.hUm.release();
+  if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
+  g.copy_stream = nullptr;
+  for (cudaEvent_t& e : g.ev_in) {
+    if (e) cudaEventDestroy(e);
+    e = nullptr;
+  }
   g.inited = false;
   g.nm_ready = false;
   g.pes = PES_NONE;
@@ -889,8 +899,9 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   if (NMC < 0 || imin < 0 || NMC - imin <= 0) return fail(PIMDK_EINVAL, "need NMC > imin >= 0");
   const int keep_sum = g.restart == 2;                 // restart = 2: dHdr arrives holding the running sums
   const long step0 = keep_sum ? g.restartnmc : 0;      // steps already done; also offsets the RNG step counter
-  CU(g.wDhSum.ensure(sizeof(double) * ntraj));
-  g.sums_n = ntraj;
+  CU(g.wDhSum.ensure(sizeof(double) * (g.sum_total > 0 ? g.sum_total : ntraj)));   // (the chunked caller sized it before its first chunk)
+  g.sums_n = g.sum_total > 0 ? g.sum_total : ntraj;
+  double* dsum = g.wDhSum.as<double>() + (g.sum_total > 0 ? g.sum_off : 0);
   const int n = g.n, ndof = g.nm_ndim * g.nm_natom;
   const long rows = (long)ntraj * ndof;
   const size_t tot = (size_t)rows * n;
@@ -912,7 +923,7 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
     {
       Scope s("fused");
       CU(launch_fused_small(nm, g.pes, g.sp, (int)thermostat, ntraj, x, p, a, b, dbdl, dt, NMC, imin, (double)Noutput, seed,
-                            dgid, dHdr, g.wFlags.as<int>(), step0, keep_sum, g.wDhSum.as<double>(), g.stream));
+                            dgid, dHdr, g.wFlags.as<int>(), step0, keep_sum, dsum, g.stream));
     }
     rc = check_flags(false);
     g.last_nan_traj = -1;
@@ -993,7 +1004,7 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   {
     Scope s("estimator");
     // the running sum is what write_restart stores (:171, 246, 412); then dHdr/dble(NMC+restartnmc-imin) (:247,413)
-    CU(cudaMemcpyAsync(g.wDhSum.p, dHdr, sizeof(double) * ntraj, cudaMemcpyDeviceToDevice, g.stream));
+    CU(cudaMemcpyAsync(dsum, dHdr, sizeof(double) * ntraj, cudaMemcpyDeviceToDevice, g.stream));
     CU(launch_scale(dHdr, (double)(NMC + step0 - imin), ntraj, g.stream));
   }
   rc = check_flags(false);
@@ -1014,6 +1025,86 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   return rc;
 }
 
+// Host-buffer form.  Large batches are cut into chunks of whole trajectories (independent units; results depend on the
+// global trajectory id only) and pipelined: while chunk c is propagated on the compute stream, chunk c+1 is copied in and
+// chunk c-1 copied out on a second stream, through two device buffers.  Only the first copy-in and the last copy-out
+// are exposed.
+static int propagate_chunked(pimdk_int thermostat, pimdk_int ntraj, long chunk, double* x, double* p, const double* a,
+                             const double* b, const double* dbdl, double dt, double gamma, pimdk_int NMC, pimdk_int imin,
+                             pimdk_int Noutput, pimdk_int cayley, uint64_t seed, const pimdk_int* traj_gid, double* dHdr) {
+  const int ndof = g.nm_ndim * g.nm_natom;
+  const size_t per = (size_t)ndof * g.n;                       // doubles of x (or p) per trajectory
+  const size_t nb = (size_t)ntraj * ndof;
+  if (!g.copy_stream) CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : g.ev_in)
+    if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  DevBuf* bx[2] = {&g.wX, &g.wX2};
+  DevBuf* bp[2] = {&g.wPp, &g.wPp2};
+  for (int i = 0; i < 2; ++i) {
+    CU(bx[i]->ensure((size_t)chunk * per * sizeof(double)));
+    CU(bp[i]->ensure((size_t)chunk * per * sizeof(double)));
+  }
+  CU(g.wA.ensure(ndof * sizeof(double)));
+  CU(g.wB.ensure(nb * sizeof(double)));
+  CU(g.wDbdl.ensure(nb * sizeof(double)));
+  CU(g.wDhdr.ensure(ntraj * sizeof(double)));
+  CU(g.wDhSum.ensure(sizeof(double) * ntraj));
+  CU(cudaMemcpyAsync(g.wA.p, a, ndof * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.wB.p, b, nb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.wDbdl.p, dbdl, nb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  if (g.restart == 2) CU(cudaMemcpyAsync(g.wDhdr.p, dHdr, ntraj * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  const int64_t* dgid;
+  int rc = upload_gid(traj_gid, ntraj, &dgid);
+  if (rc) return rc;
+  const long nchunk = (ntraj + chunk - 1) / chunk;
+  auto copy_in = [&](long c) -> cudaError_t {
+    const long t0 = c * chunk, nt = (ntraj - t0 < chunk) ? ntraj - t0 : chunk;
+    cudaError_t e = cudaMemcpyAsync(bx[c & 1]->p, x + (size_t)t0 * per, (size_t)nt * per * sizeof(double), cudaMemcpyHostToDevice, g.copy_stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(bp[c & 1]->p, p + (size_t)t0 * per, (size_t)nt * per * sizeof(double), cudaMemcpyHostToDevice, g.copy_stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(g.ev_in[c & 1], g.copy_stream);
+  };
+  int result = PIMDK_OK;
+  long first_nan = -1;
+  std::string keep;
+  CU(copy_in(0));
+  g.sum_total = ntraj;
+  for (long c = 0; c < nchunk; ++c) {
+    const long t0 = c * chunk, nt = (ntraj - t0 < chunk) ? ntraj - t0 : chunk;
+    if (c + 1 < nchunk) {
+      cudaError_t e = copy_in(c + 1);   // behind the copy-out of chunk c-1 in stream order: its buffer is free by then
+      if (e != cudaSuccess) { g.sum_total = 0; return fail(PIMDK_ECUDA, "%s", cudaGetErrorString(e)); }
+    }
+    cudaStreamWaitEvent(g.stream, g.ev_in[c & 1], 0);
+    g.sum_off = t0;
+    rc = pimdk_propagate_dev(thermostat, nt, bx[c & 1]->as<double>(), bp[c & 1]->as<double>(), g.wA.as<double>(),
+                             g.wB.as<double>() + (size_t)t0 * ndof, g.wDbdl.as<double>() + (size_t)t0 * ndof, dt, gamma, NMC,
+                             imin, Noutput, cayley, seed, dgid ? reinterpret_cast<const pimdk_int*>(dgid + t0) : nullptr,
+                             g.wDhdr.as<double>() + t0);   // returns with the compute stream drained
+    if (rc != PIMDK_OK && rc != PIMDK_ENAN) { g.sum_total = 0; return rc; }
+    if (rc == PIMDK_ENAN && result == PIMDK_OK) {
+      result = rc;
+      keep = g.err;
+      first_nan = g.last_nan_traj >= 0 ? t0 + g.last_nan_traj : -1;
+    }
+    cudaError_t e = cudaMemcpyAsync(x + (size_t)t0 * per, bx[c & 1]->p, (size_t)nt * per * sizeof(double), cudaMemcpyDeviceToHost, g.copy_stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(p + (size_t)t0 * per, bp[c & 1]->p, (size_t)nt * per * sizeof(double), cudaMemcpyDeviceToHost, g.copy_stream);
+    if (e != cudaSuccess) { g.sum_total = 0; return fail(PIMDK_ECUDA, "%s", cudaGetErrorString(e)); }
+  }
+  g.sum_total = 0;
+  g.sum_off = 0;
+  CU(cudaMemcpyAsync(dHdr, g.wDhdr.p, ntraj * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.copy_stream));
+  CU(cudaStreamSynchronize(g.stream));
+  if (result == PIMDK_ENAN) {
+    g.err = keep;
+    g.last_nan_traj = first_nan;
+  }
+  return result;
+}
+
 int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p, const double* a, const double* b,
                     const double* dbdl, double dt, double gamma, pimdk_int NMC, pimdk_int imin, pimdk_int Noutput,
                     pimdk_int cayley, uint64_t seed, const pimdk_int* traj_gid, double* dHdr) {
@@ -1022,6 +1113,23 @@ int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p,
   if (ntraj <= 0) return PIMDK_OK;
   const int ndof = g.nm_ndim * g.nm_natom;
   const size_t tot = (size_t)ntraj * ndof * g.n, nb = (size_t)ntraj * ndof;
+  {
+    // automatic: chunks of >= 128 MB of state (x and p) and >= 256 trajectories, rounded up to whole PES passes
+    // (32768 beads) where the bead count allows; worth it from three chunks on
+    long chunk = g.chunk_traj;
+    if (chunk <= 0) {
+      const size_t per_traj = 2 * (size_t)ndof * g.n * sizeof(double);
+      chunk = (long)(((size_t)128 << 20) / per_traj) + 1;
+      if (chunk < 256) chunk = 256;
+      long m = 32768, r = g.n;
+      while (r) { const long t = m % r; m = r; r = t; }   // m = gcd(32768, n)
+      m = 32768 / m;                                       // trajectories per whole pass
+      if (m <= chunk) chunk = (chunk + m - 1) / m * m;
+    }
+    if ((long)ntraj >= 3 * chunk)
+      return propagate_chunked(thermostat, ntraj, chunk, x, p, a, b, dbdl, dt, gamma, NMC, imin, Noutput, cayley, seed,
+                               traj_gid, dHdr);
+  }
   CU(g.wX.ensure(tot * sizeof(double)));
   CU(g.wPp.ensure(tot * sizeof(double)));
   CU(g.wA.ensure(ndof * sizeof(double)));
@@ -1051,6 +1159,12 @@ int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p,
 }
 
 pimdk_int pimdk_last_nan_trajectory(void) { return g.last_nan_traj; }
+
+int pimdk_set_propagate_chunk(pimdk_int ntraj_per_chunk) {
+  if (ntraj_per_chunk < 0) return fail(PIMDK_EINVAL, "chunk size must be >= 0 (0 = automatic)");
+  g.chunk_traj = (long)ntraj_per_chunk;
+  return PIMDK_OK;
+}
 
 int pimdk_set_restart(pimdk_int restart, pimdk_int restartnmc) {
   if (restart < 0 || restart > 2 || restartnmc < 0) return fail(PIMDK_EINVAL, "restart must be 0, 1 or 2 and restartnmc >= 0");

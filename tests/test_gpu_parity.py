@@ -342,6 +342,41 @@ def test_partition_invariance_and_imin(pk):
     assert not np.array_equal(d0, vi.propagate_pimd_pile(x, p, a, bt, dbdl, traj_gid=gid)[2])
 
 
+@pytest.mark.parametrize("name,n,mass,beta,sigma", [("1d", 32, [1.0], 10.0, 0.05), ("2dtest", 160, [1.0], 10.0, 0.05),
+                                                   ("ccpol8sf", 8, DIMER_MASS, 200.0, 0.01)])
+@pytest.mark.parametrize("thermostat", [1, 2])
+def test_chunked_host_propagate_equals_single_shot(pk, name, n, mass, beta, sigma, thermostat):
+    """pimdk_propagate (host buffers) pipelines large batches in chunks of whole trajectories with the copies
+    overlapped; every bit of x, p, dHdr and of the running sums must equal the single-shot call (11 trajectories in
+    chunks of 3: a ragged last chunk; fused and streamed paths; restart = 2 continuing the sums)."""
+    from pimd_tunneling_b200._lib import check, lib
+
+    pes = pk.McmodMass(name).V_init()
+    a, b = _wells(name)
+    ntraj, steps = 11, 12 if name != "ccpol8sf" else 4
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, sigma, mass)
+    gid = np.arange(ntraj, dtype=np.int64) * 3 + 5
+    vi = pk.VerletInt(pes, n, mass, beta, dt=1e-3, NMC=steps, imin=1, Noutput=5, seed=77).init_nm()
+    fn = vi.propagate_pimd_pile if thermostat == 2 else vi.propagate_pimd_nm
+    try:
+        check(lib().pimdk_set_propagate_chunk(10 ** 6))      # one shot
+        ref = fn(x, p, a, bt, dbdl, traj_gid=gid)
+        sums_ref = vi.last_sums.copy()
+        check(lib().pimdk_set_propagate_chunk(3))            # chunks 3, 3, 3, 2
+        got = fn(x, p, a, bt, dbdl, traj_gid=gid)
+        assert all(np.array_equal(u, v) for u, v in zip(ref, got)) and np.array_equal(sums_ref, vi.last_sums)
+        # restart = 2: the incoming dHdr holds running sums and is continued, chunk by chunk
+        vi.restart, vi.restartnmc = 2, steps
+        check(lib().pimdk_set_propagate_chunk(10 ** 6))
+        ref2 = fn(ref[0], ref[1], a, bt, dbdl, traj_gid=gid, dHdr0=sums_ref.copy())
+        check(lib().pimdk_set_propagate_chunk(3))
+        got2 = fn(ref[0], ref[1], a, bt, dbdl, traj_gid=gid, dHdr0=sums_ref.copy())
+        assert all(np.array_equal(u, v) for u, v in zip(ref2, got2))
+    finally:
+        check(lib().pimdk_set_propagate_chunk(0))
+        check(lib().pimdk_set_restart(0, 0))
+
+
 @pytest.mark.parametrize("name,n,mass,beta,sigma", [("2dtest", 32, [1.0], 10.0, 0.05), ("2dtest", 160, [1.0], 10.0, 0.05),
                                                    ("ccpol8sf", 8, DIMER_MASS, 200.0, 0.01)])
 @pytest.mark.parametrize("thermostat", [1, 2])
