@@ -157,8 +157,8 @@ pimdk_int pimdk_last_nan_trajectory(void);
 /* The host-buffer pimdk_propagate cuts large batches into chunks of whole trajectories and overlaps the copy-in of
  * chunk c+1 and the copy-out of chunk c-1 with the propagation of chunk c (two streams, two device buffers; pass
  * page-locked host arrays for the copies to be asynchronous).  Results do not depend on the chunking: they are keyed
- * by the global trajectory id.  ntraj_per_chunk = 0 (default): automatic (>= 128 MB of state per chunk, whole PES
- * passes, used from three chunks on); > 0: that many trajectories per chunk. */
+ * by the global trajectory id.  ntraj_per_chunk = 0 (default): automatic (>= 128 MB of state per chunk, used from
+ * three chunks on); > 0: that many trajectories per chunk. */
 int pimdk_set_propagate_chunk(pimdk_int ntraj_per_chunk);
 
 /* Per-lambda statistics of pimd_par.f90:397-409 for the local shard:

@@ -440,6 +440,13 @@ size_t KNAME(ccpol_work_bytes)(long ngeom, int grad) {
   return (size_t)(n < 1 ? 1 : n) * kFields * 8 * (grad ? 36 : 1);
 }
 
+// kernel launches of one launch_ccpol call (7 per pass: setup, sites, dipind, sapt, rigid, sweep, combine)
+long KNAME(ccpol_launches)(long ngeom, int grad, size_t work_bytes) {
+  const long chunk = (long)(work_bytes / ((size_t)kFields * 8 * (grad ? 36 : 1)));
+  if (chunk < 1 || ngeom < 1) return 0;
+  return 7 * ((ngeom + chunk - 1) / chunk);
+}
+
 cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, double V0, GeomLayout L, double* x, double* v,
                                 double* grad, long ngeom, int write_drift, int* flags, double* work, size_t work_bytes,
                                 cudaStream_t st) {

@@ -211,9 +211,7 @@ int pes_eval_dev(GeomLayout L, double* x, double* v, double* grad, long ngeom, i
       if (!vv && !gg) continue;
       const size_t wb = fast ? ccpol_work_bytes_fast(ngeom, gg != nullptr) : ccpol_work_bytes_strict(ngeom, gg != nullptr);
       CU(g.wCc.ensure(wb));
-      const long per = (long)(42 * 8 * (gg ? 36 : 1));
-      const long npass = (ngeom + (long)(g.wCc.cap / per) - 1) / (long)(g.wCc.cap / per);
-      Scope s("pes", (int)(5 * npass));
+      Scope s("pes", (int)(fast ? ccpol_launches_fast(ngeom, gg != nullptr, g.wCc.cap) : ccpol_launches_strict(ngeom, gg != nullptr, g.wCc.cap)));
       CU(fast ? launch_ccpol_fast(tab, g.hdev.iemonomer, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
                                   g.wCc.as<double>(), g.wCc.cap, g.stream)
               : launch_ccpol_strict(tab, g.hdev.iemonomer, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
@@ -1114,17 +1112,13 @@ int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p,
   const int ndof = g.nm_ndim * g.nm_natom;
   const size_t tot = (size_t)ntraj * ndof * g.n, nb = (size_t)ntraj * ndof;
   {
-    // automatic: chunks of >= 128 MB of state (x and p) and >= 256 trajectories, rounded up to whole PES passes
-    // (32768 beads) where the bead count allows; worth it from three chunks on
+    // automatic: chunks of >= 128 MB of state (x and p) and >= 256 trajectories; worth it from three chunks on
     long chunk = g.chunk_traj;
     if (chunk <= 0) {
       const size_t per_traj = 2 * (size_t)ndof * g.n * sizeof(double);
       chunk = (long)(((size_t)128 << 20) / per_traj) + 1;
       if (chunk < 256) chunk = 256;
-      long m = 32768, r = g.n;
-      while (r) { const long t = m % r; m = r; r = t; }   // m = gcd(32768, n)
-      m = 32768 / m;                                       // trajectories per whole pass
-      if (m <= chunk) chunk = (chunk + m - 1) / m * m;
+      chunk = (chunk + 63) / 64 * 64;
     }
     if ((long)ntraj >= 3 * chunk)
       return propagate_chunked(thermostat, ntraj, chunk, x, p, a, b, dbdl, dt, gamma, NMC, imin, Noutput, cayley, seed,
