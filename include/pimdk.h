@@ -65,7 +65,9 @@ int pimdk_set_gemm(pimdk_int kind);
  * pimdk_pes_select  = V_init  (mcmod_1d.f90:8, mcmod_2dtest.f90:11, mcmod_waterdimer_ccpol.f90:9
  *                     -> init_ccpol(3,1,1,0), main_CCpol-8sf.f:1-173)
  *   name: "1d" | "2dtest" | "ccpol8sf".  pes_params (optional): "1d": {Vheight, x0};
- *   "2dtest": {a0, b0, rho0}; "ccpol8sf": {iemonomer (default 1)}.
+ *   "2dtest": {a0, b0, rho0}; "ccpol8sf": {iemonomer (default 1), isurf (default 3; 1..10 select the surfaces of
+ *   init_ccpol, main_CCpol-8sf.f:14-107: SAPT data file, Eckart or Radau embedding, potparts or potparts_old,
+ *   with or without the CCpol-8s correction)}.
  * pimdk_pes_set_v0  = assignment to module variable V0 (pimd_par.f90:166, rpi_ser.f90:95)
  * pimdk_pes_eval    = V (function) and Vprime (subroutine) over a batch x(ndim,natom,nbatch);
  *                     v (nbatch) and/or grad (ndim,natom,nbatch) may be NULL.  grad = +dV/dx.

@@ -340,6 +340,26 @@ PIMDK_HD double pimdk_acos(double x) {
   return PIMDK_SUB(pio2_hi, PIMDK_SUB(pimdk_asin_k(x), pio2_lo));
 }
 
+/* atan(x): t = |x| or 1/|x| in [0, 1]; atan t = asin(y), y = t / sqrt(1 + t^2) <= 0.7072, with
+ * asin(y) = pi/2 - 2 asin(sqrt((1 - y)/2)) above 0.5; atan|x| = pi/2 - atan(1/|x|) for |x| > 1 (<= 3 ulp).
+ * Used by the Eckart embedding (eck_rad_tst, main_CCpol-8sf.f:597-716) only: one call per monomer and energy. */
+PIMDK_HD double pimdk_atan(double x) {
+  const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+  const double ax = x < 0.0 ? -x : x;
+  const int inv = ax > 1.0;
+  const double t = inv ? PIMDK_DIV(1.0, ax) : ax;
+  const double y = PIMDK_DIV(t, PIMDK_SQRT(PIMDK_FMA(t, t, 1.0)));
+  double a;
+  if (y > 0.5) {
+    const double s = PIMDK_SQRT(PIMDK_MUL(PIMDK_SUB(1.0, y), 0.5));
+    a = PIMDK_ADD(PIMDK_SUB(pio2_hi, PIMDK_MUL(2.0, pimdk_asin_k(s))), pio2_lo);
+  } else {
+    a = pimdk_asin_k(y);
+  }
+  if (inv) a = PIMDK_ADD(PIMDK_SUB(pio2_hi, a), pio2_lo);
+  return x < 0.0 ? -a : a;
+}
+
 /* expm1 on |r| <= 0.35: r (1 + r/2 + ... + r^13/14!) */
 PIMDK_HD double pimdk_expm1_k(double r) {
   double p = 1.1470745597729725e-11;           /* 1/14! */

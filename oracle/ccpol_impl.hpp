@@ -27,8 +27,7 @@ namespace oracle {
 
 // Elementary functions: the shared deterministic math policy (include/pimdk_detmath.h) stands in
 // for the reference's (unknown) Intel libm; sqrt, fabs are IEEE; atan is used by the Eckart
-// embedding only (surfaces other than 3/10, oracle-side golden check only).
-using std::atan;
+// embedding only (surfaces other than 3/10).
 using std::fabs;
 using std::sqrt;
 inline double exp(double x) { return pimdk_exp(x); }
@@ -36,6 +35,7 @@ inline double pow(double x, double y) { return pimdk_pow(x, y); }
 inline double sin(double x) { return pimdk_sin(x); }
 inline double cos(double x) { return pimdk_cos(x); }
 inline double acos(double x) { return pimdk_acos(x); }
+inline double atan(double x) { return pimdk_atan(x); }
 inline double tanh(double x) { return pimdk_tanh(x); }
 
 template <class R>

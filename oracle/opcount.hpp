@@ -38,7 +38,7 @@ inline Counted fabs(Counted a) { return Counted(std::fabs(a.v)); }
 inline Counted sin(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_sin(a.v)); }
 inline Counted cos(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_cos(a.v)); }
 inline Counted acos(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_acos(a.v)); }
-inline Counted atan(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(std::atan(a.v)); }
+inline Counted atan(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_atan(a.v)); }
 inline Counted tanh(Counted a) { Counted::cnt[Counted::TRIG]++; return Counted(pimdk_tanh(a.v)); }
 
 }  // namespace oracle

@@ -81,7 +81,7 @@ __device__ __forceinline__ const CcpolDev& stage_tables(const CcpolDev* __restri
 // j=atom inner: c = i*6 + j), s = 0 for +eps, 1 for -eps; components already visited by the reference's
 // loop carry its round-off drift x+eps-2eps+eps (mcmod_waterdimer_ccpol.f90:48-52).
 __global__ void __launch_bounds__(kSetupBlock)
-KNAME(ccpol_setup_kernel)(int iemonomer, GeomLayout L, const double* __restrict__ x, long geom0, long ne, int grad,
+KNAME(ccpol_setup_kernel)(int iemonomer, int iembed, GeomLayout L, const double* __restrict__ x, long geom0, long ne, int grad,
                           double* __restrict__ buf) {
   const long e = (long)blockIdx.x * kSetupBlock + threadIdx.x;
   if (e >= ne) return;
@@ -107,7 +107,7 @@ KNAME(ccpol_setup_kernel)(int iemonomer, GeomLayout L, const double* __restrict_
     xb[d] = val;
   }
   double A[3][3], B[3][3], rg[6][3], emon;
-  ccpol_setup(iemonomer, xb, A, B, rg, emon);
+  ccpol_setup(iemonomer, iembed, xb, A, B, rg, emon);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -191,6 +191,7 @@ KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __
 // FP64 code, more than the instruction cache, and every thread follows the same path through it; warps that
 // start together stay close enough in the code that one warp's instruction fetch serves the others (measured:
 // 128-thread CTAs at equal or higher occupancy are 11% slower and stall on instruction fetch).
+template <bool OLD>
 __global__ void __launch_bounds__(kSaptBlock, PIMDK_SAPT_MINB)
 KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -214,7 +215,7 @@ KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __re
   const double sa[3] = {S[48], S[49], S[50]};
   const double sb[3] = {S[51], S[52], S[53]};
   Scratch<kSaptBlock> qb{reinterpret_cast<double*>(smem + kSaptTableBytes) + 24 * kSaptBlock + threadIdx.x};
-  const double val = sapt_pair_sum(T, S, sitesB, qb, sa, sb);
+  const double val = sapt_pair_sum<OLD>(T, S, sitesB, qb, sa, sb);
   buf[(which ? F_VALL : F_VAL) * ne + e] = val + buf[(F_FCIND + which) * ne + e];
 }
 
@@ -395,22 +396,22 @@ KNAME(ccpol_sweep_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __r
 
 // ---- stage 3 ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-KNAME(ccpol_combine_kernel)(int iemonomer, double V0, GeomLayout L, double* __restrict__ x, long geom0, long ne, int grad,
+KNAME(ccpol_combine_kernel)(int iemonomer, int icc, double V0, GeomLayout L, double* __restrict__ x, long geom0, long ne, int grad,
                             const double* __restrict__ buf, double* __restrict__ v, double* __restrict__ gradout,
                             int write_drift, int* __restrict__ flags) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const double eps = 1e-4;
   if (!grad) {
     if (i >= ne) return;
-    v[geom0 + i] = ccpol_combine(iemonomer, V0, buf[F_ERIG * ne + i], buf[F_VAL * ne + i], buf[F_VALL * ne + i],
+    v[geom0 + i] = ccpol_combine(iemonomer, icc, V0, icc ? buf[F_ERIG * ne + i] : 0.0, buf[F_VAL * ne + i], buf[F_VALL * ne + i],
                                  buf[F_EMON * ne + i]);
     return;
   }
   if (i >= ne / 2) return;  // one thread per (geometry, component)
   const long ep = 2 * i, em = ep + 1;
-  const double vp = ccpol_combine(iemonomer, V0, buf[F_ERIG * ne + ep], buf[F_VAL * ne + ep], buf[F_VALL * ne + ep],
+  const double vp = ccpol_combine(iemonomer, icc, V0, icc ? buf[F_ERIG * ne + ep] : 0.0, buf[F_VAL * ne + ep], buf[F_VALL * ne + ep],
                                   buf[F_EMON * ne + ep]);
-  const double vm = ccpol_combine(iemonomer, V0, buf[F_ERIG * ne + em], buf[F_VAL * ne + em], buf[F_VALL * ne + em],
+  const double vm = ccpol_combine(iemonomer, icc, V0, icc ? buf[F_ERIG * ne + em] : 0.0, buf[F_VAL * ne + em], buf[F_VALL * ne + em],
                                   buf[F_EMON * ne + em]);
   const long g = geom0 + i / 18;
   const int c = (int)(i % 18);
@@ -441,18 +442,20 @@ size_t KNAME(ccpol_work_bytes)(long ngeom, int grad) {
 }
 
 // kernel launches of one launch_ccpol call (7 per pass: setup, sites, dipind, sapt, rigid, sweep, combine)
-long KNAME(ccpol_launches)(long ngeom, int grad, size_t work_bytes) {
+long KNAME(ccpol_launches)(long ngeom, int grad, int icc, size_t work_bytes) {
   const long chunk = (long)(work_bytes / ((size_t)kFields * 8 * (grad ? 36 : 1)));
   if (chunk < 1 || ngeom < 1) return 0;
-  return 7 * ((ngeom + chunk - 1) / chunk);
+  return (icc ? 7 : 5) * ((ngeom + chunk - 1) / chunk);
 }
 
-cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, double V0, GeomLayout L, double* x, double* v,
+cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, int icc, int potparts_old, double V0, GeomLayout L, double* x, double* v,
                                 double* grad, long ngeom, int write_drift, int* flags, double* work, size_t work_bytes,
                                 cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(KNAME(ccpol_sapt_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sapt_smem());
+    cudaError_t e = cudaFuncSetAttribute(KNAME(ccpol_sapt_kernel)<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sapt_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(KNAME(ccpol_sapt_kernel)<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sapt_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(KNAME(ccpol_rigid_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rigid_smem());
     if (e != cudaSuccess) return e;
@@ -466,14 +469,17 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, double V0, G
   for (long g0 = 0; g0 < ngeom; g0 += chunk) {
     const long ng = (ngeom - g0 < chunk) ? ngeom - g0 : chunk;
     const long ne = ng * (g ? 36 : 1);
-    KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, L, x, g0, ne, g, work);
+    KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, iembed, L, x, g0, ne, g, work);
     KNAME(ccpol_sites_kernel)<<<(unsigned)((4 * ne + 127) / 128), 128, 0, st>>>(ne, work);
     KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, dipind_smem(), st>>>(tab, ne, work);
-    KNAME(ccpol_sapt_kernel)<<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
-    KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, rigid_smem(), st>>>(tab, ne, work, flags);
-    KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + 31) / 32), kSweepBlock, sweep_smem(), st>>>(tab, ne, work);
+    if (potparts_old) KNAME(ccpol_sapt_kernel)<true><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
+    else KNAME(ccpol_sapt_kernel)<false><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
+    if (icc) {   // CCpol-8s rigid model of the embedded monomers; surfaces 5..9 are SAPT-5s'f alone
+      KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, rigid_smem(), st>>>(tab, ne, work, flags);
+      KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + 31) / 32), kSweepBlock, sweep_smem(), st>>>(tab, ne, work);
+    }
     const long nt = g ? ne / 2 : ne;
-    KNAME(ccpol_combine_kernel)<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(iemonomer, V0, L, x, g0, ne, g, work, v, grad, write_drift, flags);
+    KNAME(ccpol_combine_kernel)<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(iemonomer, icc, V0, L, x, g0, ne, g, work, v, grad, write_drift, flags);
   }
   return cudaGetLastError();
 }

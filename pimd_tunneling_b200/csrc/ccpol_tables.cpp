@@ -226,29 +226,43 @@ bool from_packed(const std::string& sapt, const std::string& cc, CcpolHost* h) {
 
 }  // namespace
 
-const char* load_ccpol_tables(const char* dir, CcpolHost* out) {
+const char* load_ccpol_tables(const char* dir, int isurf, CcpolHost* out) {
   std::memset(out, 0, sizeof(*out));
   g_msg.clear();
-  std::string d(dir ? dir : ".");
+  // main_CCpol-8sf.f:28-107: embedding, potparts variant, SAPT data file, CCpol-8s correction on/off
+  struct Row { int iembed, ipotparts; const char* f; int icc; };
+  static const Row rows[10] = {
+      {1, 1, "SAPT5spf_2014", 1},   {1, 1, "SAPT5spfIR_2014", 1}, {2, 1, "SAPT5spfIR_2006", 1}, {1, 1, "SAPT5spfIR_2006", 1},
+      {1, 1, "SAPT5spf_2014", 0},   {1, 1, "SAPT5spfIR_2014", 0}, {1, 1, "SAPT5spfIR_2006", 0}, {1, 0, "SAPT5spf_2006", 0},
+      {1, 0, "SAPT5spfIR_2006", 0}, {2, 1, "SAPT5spfIR_2014", 1}};
+  if (isurf < 1 || isurf > 10) {
+    g_msg = "wrong value of isurf";
+    return g_msg.c_str();
+  }
+  const Row& r = rows[isurf - 1];
+  std::string d(dir ? dir : "."), f(r.f);
   bool ok;
-  if (exists(d + "/data_SAPT5spfIR_2006") && exists(d + "/data_CCpol8s") && exists(d + "/data_ccdata")) {
-    ok = sapt_from_text(d + "/data_SAPT5spfIR_2006", out) &&
-         cc8s_from_text(d + "/data_CCpol8s", d + "/data_ccdata", out);
-  } else if (exists(d + "/sapt_SAPT5spfIR_2006.tbl") && exists(d + "/ccpol8s.tbl")) {
-    ok = from_packed(d + "/sapt_SAPT5spfIR_2006.tbl", d + "/ccpol8s.tbl", out);
+  if (exists(d + "/data_" + f) && exists(d + "/data_CCpol8s") && exists(d + "/data_ccdata")) {
+    ok = sapt_from_text(d + "/data_" + f, out) && cc8s_from_text(d + "/data_CCpol8s", d + "/data_ccdata", out);
+  } else if (exists(d + "/sapt_" + f + ".tbl") && exists(d + "/ccpol8s.tbl")) {
+    ok = from_packed(d + "/sapt_" + f + ".tbl", d + "/ccpol8s.tbl", out);
   } else {
-    g_msg = "no CCpol-8sf data files (data_SAPT5spfIR_2006/data_CCpol8s/data_ccdata or *.tbl) in " + d;
+    g_msg = "no CCpol-8sf data files (data_" + f + "/data_CCpol8s/data_ccdata or *.tbl) in " + d;
     ok = false;
   }
   if (!ok && g_msg.empty()) g_msg = "failed to read CCpol-8sf data files in " + d;
+  out->isurf = isurf;
+  out->iembed = r.iembed;
+  out->ipotparts = r.ipotparts;
+  out->icc = r.icc;
   return ok ? "" : g_msg.c_str();
 }
 
 const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
   std::memset(o, 0, sizeof(*o));
   g_msg.clear();
-  if (h.numlin != 568 || h.nlin0 != 144 || h.nparsall != 134) {
-    g_msg = "unexpected CCpol-8sf table sizes (need 568 / 144 / 134)";
+  if (h.numlin < 1 || h.numlin > 568 || h.nlin0 != 144 || h.nparsall != 134) {
+    g_msg = "unexpected CCpol-8sf table sizes (need <= 568 / 144 / 134)";
     return g_msg.c_str();
   }
   for (int t = 0; t < kNType; ++t)
@@ -259,7 +273,10 @@ const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* o) {
   // type 6 must be unused for the trimming above to be valid
   for (int k = 0; k < 18; ++k)
     if (h.param[5 * 18 + k] != 0.0) { g_msg = "site type 6 carries parameters; not supported"; return g_msg.c_str(); }
-  std::memcpy(o->c, h.c, 568 * sizeof(double));
+  std::memcpy(o->c, h.c, 568 * sizeof(double));   // (zero beyond numlin)
+  o->iembed = (uint8_t)h.iembed;
+  o->icc = (uint8_t)h.icc;
+  o->potparts_old = (uint8_t)(h.ipotparts == 0);
   std::memcpy(o->cc, h.cc, 144 * sizeof(double));
   std::memcpy(o->params, h.params, 134 * sizeof(double));
   std::memcpy(o->sites, h.sites, 75 * sizeof(double));

@@ -25,7 +25,9 @@ struct CcpolDev {
   // CCpol-8s site classes: runs of consecutive sites with identical ind_beta rows (8 classes of
   // sizes 1,2,2,4,4,4,4,4 for data_ccdata); cls_start[c]..cls_start[c+1]-1 are the sites of class c
   uint8_t cls_start[26];
-  uint8_t pad0_[5];
+  uint8_t iembed;                            // 1 Eckart, 2 Radau f=1 (main_CCpol-8sf.f:28-107)
+  uint8_t icc;                               // 1: Erigid + (val - vall); 0: SAPT-5s'f alone
+  uint8_t pad0_[3];
   int32_t ncls;
   int32_t iemonomer;
   double bin_beta[37];                       // beta of each bin (params(ind_beta) of its site pairs); [36] unused
@@ -46,7 +48,8 @@ struct CcpolDev {
   // exactly zero evaluates to +-0 in the reference (function d returns 0 for br == 0,
   // proc_sapt5sf_new_ncd.f:1234-1237) and adding +-0 changes no bits, so the kernels skip it.
   uint8_t pairflags[kNType * kNType];
-  uint8_t pad1_[3];
+  uint8_t potparts_old;                      // ipotparts = 0: potparts_old (surfaces 8, 9)
+  uint8_t pad1_[2];
 };
 // bytes of the leading rigid-model block = offset of the first SAPT member (a multiple of 16)
 #define PIMDK_RIGID_TABLE_BYTES (offsetof(::pimdk::CcpolDev, param))
@@ -65,12 +68,13 @@ struct CcpolHost {
   double sites[75];
   int ind_charge[25];
   int ind_beta[625], ind_d1[625], ind_d6[625], ind_d8[625], ind_d10[625], ind_c6[625], ind_c8[625], ind_c10[625];
+  int isurf, iembed, ipotparts, icc;   // surface switches of init_ccpol (main_CCpol-8sf.f:28-107)
 };
 
-// Loads from `dir`: first the reference's own text files (data_SAPT5spfIR_2006, data_CCpol8s,
-// data_ccdata — the names the reference opens from its CWD), else the packed *.tbl files shipped
-// in pimd_tunneling_b200/data.  Returns empty string on success, else an error message.
-const char* load_ccpol_tables(const char* dir, CcpolHost* out);
+// Loads the tables of surface `isurf` (1..10, main_CCpol-8sf.f:14-107; the plugin uses 3) from `dir`: first the
+// reference's own text files (data_SAPT5spf*_20*, data_CCpol8s, data_ccdata — the names the reference opens from its
+// CWD), else the packed *.tbl files shipped in pimd_tunneling_b200/data.  Returns "" on success, else a message.
+const char* load_ccpol_tables(const char* dir, int isurf, CcpolHost* out);
 // Builds the device image (static index map, byte-sized index tables).  Returns error or "".
 const char* build_ccpol_dev(const CcpolHost& h, int iemonomer, CcpolDev* out);
 

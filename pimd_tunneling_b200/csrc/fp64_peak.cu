@@ -83,6 +83,7 @@ __global__ void math_eval_kernel(int kind, long n, const double* __restrict__ x,
     case 6: r = pimdk_pow(v, -1.5); break;
     case 7: r = pimdk_pow(v, -3.0); break;
     case 8: r = pimdk_pow(v, 0.66666666666666666); break;
+    case 9: r = pimdk_atan(v); break;
     default: r = v;
   }
   y[i] = r;

@@ -182,9 +182,10 @@ int clear_flags() {
   return PIMDK_OK;
 }
 
-int ensure_ccpol_tables() {
-  if (g.tab_loaded) return PIMDK_OK;
-  const char* m = load_ccpol_tables(g.data_dir.c_str(), &g.htab);
+int ensure_ccpol_tables(int isurf) {
+  if (g.tab_loaded && g.htab.isurf == isurf) return PIMDK_OK;
+  g.tab_loaded = false;
+  const char* m = load_ccpol_tables(g.data_dir.c_str(), isurf, &g.htab);
   if (m[0]) return fail(PIMDK_EDATA, "%s", m);
   g.tab_loaded = true;
   return PIMDK_OK;
@@ -211,10 +212,10 @@ int pes_eval_dev(GeomLayout L, double* x, double* v, double* grad, long ngeom, i
       if (!vv && !gg) continue;
       const size_t wb = fast ? ccpol_work_bytes_fast(ngeom, gg != nullptr) : ccpol_work_bytes_strict(ngeom, gg != nullptr);
       CU(g.wCc.ensure(wb));
-      Scope s("pes", (int)(fast ? ccpol_launches_fast(ngeom, gg != nullptr, g.wCc.cap) : ccpol_launches_strict(ngeom, gg != nullptr, g.wCc.cap)));
-      CU(fast ? launch_ccpol_fast(tab, g.hdev.iemonomer, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
+      Scope s("pes", (int)(fast ? ccpol_launches_fast(ngeom, gg != nullptr, g.hdev.icc, g.wCc.cap) : ccpol_launches_strict(ngeom, gg != nullptr, g.hdev.icc, g.wCc.cap)));
+      CU(fast ? launch_ccpol_fast(tab, g.hdev.iemonomer, g.hdev.iembed, g.hdev.icc, g.hdev.potparts_old, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
                                   g.wCc.as<double>(), g.wCc.cap, g.stream)
-              : launch_ccpol_strict(tab, g.hdev.iemonomer, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
+              : launch_ccpol_strict(tab, g.hdev.iemonomer, g.hdev.iembed, g.hdev.icc, g.hdev.potparts_old, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
                                     g.wCc.as<double>(), g.wCc.cap, g.stream));
     }
   } else {
@@ -428,10 +429,12 @@ int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
     return PIMDK_OK;
   }
   if (s == "ccpol8sf") {  // mcmod_waterdimer_ccpol.f90:9-16 -> init_ccpol(3,1,1,0)
-    int rc = ensure_ccpol_tables();
-    if (rc) return rc;
     const int iemon = np > 0 ? (int)pp[0] : 1;
+    const int isurf = np > 1 ? (int)pp[1] : 3;
     if (iemon != 0 && iemon != 1) return fail(PIMDK_EINVAL, "wrong value of iemonomer");
+    if (isurf < 1 || isurf > 10) return fail(PIMDK_EINVAL, "wrong value of isurf");
+    int rc = ensure_ccpol_tables(isurf);
+    if (rc) return rc;
     const char* m = build_ccpol_dev(g.htab, iemon, &g.hdev);
     if (m[0]) return fail(PIMDK_EDATA, "%s", m);
     rc = upload_ccpol_dev();
@@ -1270,7 +1273,7 @@ int pimdk_selftest_fastmath(pimdk_int* mismatches) {
 }
 int pimdk_selftest_math(pimdk_int kind, pimdk_int n, const double* x, double* y) {
   NEED_INIT();
-  if (kind < 0 || kind > 8 || n <= 0 || !x || !y) return fail(PIMDK_EINVAL, "bad selftest_math arguments");
+  if (kind < 0 || kind > 9 || n <= 0 || !x || !y) return fail(PIMDK_EINVAL, "bad selftest_math arguments");
   CU(math_eval((int)kind, (long)n, x, y, g.stream));
   return PIMDK_OK;
 }

@@ -19,10 +19,16 @@ class McmodMass:
     potforcepresent = True    # potforce is provided for every PES here
     atom1, atom2, atom3 = 1, 2, 3
 
-    def __init__(self, name, params=None, n=0):
+    def __init__(self, name, params=None, n=0, isurf=None, iemonomer=None):
+        """params: "1d" {Vheight, x0}; "2dtest" {a0, b0, rho0}; "ccpol8sf" {iemonomer, isurf} — the first two arguments
+        of init_ccpol(isurf, iemon, iembedang, ixyz) (main_CCpol-8sf.f:1; the plugin calls init_ccpol(3,1,1,0)), also
+        settable by keyword."""
         if name not in _SHAPES:
             raise ValueError("unknown PES %r (1d, 2dtest, ccpol8sf)" % name)
         self.name = name
+        if name == "ccpol8sf" and (isurf is not None or iemonomer is not None):
+            p0 = [1.0, 3.0] if params is None else (list(np.asarray(params, dtype=np.float64)) + [3.0])[:2]
+            params = [p0[0] if iemonomer is None else float(iemonomer), p0[1] if isurf is None else float(isurf)]
         self.params = None if params is None else np.asarray(params, dtype=np.float64)
         self.ndim, self.natom = _SHAPES[name]
         self.ndof = self.ndim * self.natom

@@ -15,7 +15,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle_lib import GOLDEN_GEOM_ANG, Oracle, thermal_dimer_geometries
+from oracle_lib import GOLDEN_GEOM_ANG, GOLDEN_VAL, GOLDEN_VALM, Oracle, thermal_dimer_geometries
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -52,6 +52,30 @@ def test_ccpol_known_answer(pk):
     pes0 = pk.McmodMass("ccpol8sf", params=[0]).V_init()   # iemonomer = 0
     e0 = pes0.V((GOLDEN_GEOM_ANG / 0.529177).reshape(6, 3).T) * 627.510
     assert abs(e0 - (-1.34676)) < 5.1e-6
+
+
+# main_CCpol-8sf.f:180-183 (test_parameters): the reference's only golden vectors, 10 surfaces x {interaction, + monomers}
+@pytest.mark.parametrize("isurf", range(1, 11))
+def test_ccpol_all_surfaces_golden_and_bit_exact(pk, orc, isurf):
+    """All ten surfaces of init_ccpol through the C ABI (Eckart or Radau embedding, potparts or potparts_old, four
+    SAPT data files, with and without the CCpol-8s correction): the interaction energy of the known-answer geometry
+    within the printed precision of val(isurf); with monomers within 3e-5 of valm(isurf) (printed by a build without
+    -r8, see test_oracle.py); energies and finite-difference gradients of 40 thermal geometries bit-exact against
+    the oracle."""
+    xg = (GOLDEN_GEOM_ANG / 0.529177).reshape(6, 3).T
+    pes0 = pk.McmodMass("ccpol8sf", isurf=isurf, iemonomer=0).V_init()
+    assert abs(pes0.V(xg) * 627.510 - GOLDEN_VAL[isurf - 1]) < 5.1e-6
+    pes = pk.McmodMass("ccpol8sf", isurf=isurf).V_init()
+    assert abs(pes.V(xg) * 627.510 - GOLDEN_VALM[isurf - 1]) < 3e-5
+    orc.load_ccpol(isurf, 1)
+    orc.L.orc_pes_select(b"ccpol8sf")
+    orc.ndim, orc.natom = 3, 6
+    x = thermal_dimer_geometries(40, seed=100 + isurf)
+    v, g = pes.eval_batch(x)
+    vo, go, _ = orc.pes_eval(x)
+    assert np.array_equal(v, vo) and np.array_equal(g, go), (np.abs(v - vo).max(), np.abs(g - go).max())
+    pk.McmodMass("ccpol8sf").V_init()      # back to the plugin's surface
+    orc.load_ccpol(3, 1)
 
 
 @pytest.mark.parametrize("nbatch", [1, 7, 252, 1000])
@@ -159,7 +183,7 @@ def test_math_policy_host_equals_device(pk):
                 "void dm(int kind, long n, const double* x, double* y){ for(long i=0;i<n;++i){ double v=x[i], r=v; switch(kind){\n"
                 "case 0: r=pimdk_exp(v);break; case 1: r=pimdk_log(v);break; case 2: r=pimdk_sin(v);break; case 3: r=pimdk_cos(v);break;\n"
                 "case 4: r=pimdk_acos(v);break; case 5: r=pimdk_tanh(v);break; case 6: r=pimdk_pow(v,-1.5);break;\n"
-                "case 7: r=pimdk_pow(v,-3.0);break; case 8: r=pimdk_pow(v,0.66666666666666666);break;} y[i]=r; } }\n")
+                "case 7: r=pimdk_pow(v,-3.0);break; case 8: r=pimdk_pow(v,0.66666666666666666);break; case 9: r=pimdk_atan(v);break;} y[i]=r; } }\n")
     so = src[:-2] + ".so"
     subprocess.run(["gcc", "-O2", "-march=native", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
                     "-o", so, src, "-lm"], check=True)
@@ -171,7 +195,9 @@ def test_math_policy_host_equals_device(pk):
     args = {0: np.concatenate([edges, rng.uniform(-750, 720, 200000), rng.uniform(-60, 30, 200000)]),
             1: np.exp(rng.uniform(-40, 40, 100000)), 2: rng.uniform(-50, 50, 100000), 3: rng.uniform(-50, 50, 100000),
             4: np.concatenate([[1.0, -1.0, 0.5, -0.5, 0.0], rng.uniform(-1, 1, 100000)]), 5: rng.uniform(-25, 25, 100000),
-            6: np.exp(rng.uniform(-10, 10, 100000)), 7: np.exp(rng.uniform(-10, 10, 100000)), 8: np.exp(rng.uniform(-10, 10, 100000))}
+            6: np.exp(rng.uniform(-10, 10, 100000)), 7: np.exp(rng.uniform(-10, 10, 100000)), 8: np.exp(rng.uniform(-10, 10, 100000)),
+            9: np.concatenate([[0.0, -0.0, 1.0, -1.0, 1e300, -1e300, np.inf, -np.inf, np.nan], rng.uniform(-5, 5, 100000),
+                               rng.uniform(-1e6, 1e6, 20000)])}
     for kind, x in args.items():
         x = np.ascontiguousarray(x, dtype=np.float64)
         yd, yh = np.empty_like(x), np.empty_like(x)

@@ -105,12 +105,12 @@ def test_detmath_accuracy():
                 "double dm_exp(double x){return pimdk_exp(x);} double dm_log(double x){return pimdk_log(x);}\n"
                 "double dm_pow(double x,double y){return pimdk_pow(x,y);} double dm_sin(double x){return pimdk_sin(x);}\n"
                 "double dm_cos(double x){return pimdk_cos(x);} double dm_acos(double x){return pimdk_acos(x);}\n"
-                "double dm_tanh(double x){return pimdk_tanh(x);}\n")
+                "double dm_tanh(double x){return pimdk_tanh(x);} double dm_atan(double x){return pimdk_atan(x);}\n")
     so = src[:-2] + ".so"
     subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(root, "include"), "-o", so,
                     src, "-lm"], check=True)
     L = ctypes.CDLL(so)
-    for f in "exp log sin cos acos tanh".split():
+    for f in "exp log sin cos acos tanh atan".split():
         getattr(L, "dm_" + f).restype = ctypes.c_double
         getattr(L, "dm_" + f).argtypes = [ctypes.c_double]
     L.dm_pow.restype = ctypes.c_double
@@ -122,7 +122,8 @@ def test_detmath_accuracy():
 
     cases = [("exp", mp.exp, rng.uniform(-200, 50, 600), 1.0), ("log", mp.log, np.exp(rng.uniform(-30, 30, 600)), 2.0),
              ("sin", mp.sin, rng.uniform(-7, 7, 600), 2.0), ("cos", mp.cos, rng.uniform(-7, 7, 600), 2.0),
-             ("acos", mp.acos, rng.uniform(-1, 1, 600), 2.0), ("tanh", mp.tanh, rng.uniform(-3, 3, 600), 4.0)]
+             ("acos", mp.acos, rng.uniform(-1, 1, 600), 2.0), ("tanh", mp.tanh, rng.uniform(-3, 3, 600), 4.0),
+             ("atan", mp.atan, np.concatenate([rng.uniform(-3, 3, 400), rng.uniform(-1e4, 1e4, 200)]), 3.0)]
     for name, ref, xs, tol in cases:
         worst = max(ulps(getattr(L, "dm_" + name)(float(x)), ref(mp.mpf(float(x)))) for x in xs)
         assert worst < tol, (name, worst)
