@@ -9,6 +9,9 @@ pes = pk.McmodMass("ccpol8sf").V_init()
 x = thermal_dimer_geometries(37, seed=11)          # ragged: 37*36 energies, not a multiple of 32
 v, g = pes.eval_batch(x)
 h = pes.Vdoubleprime_batch(np.asfortranarray(x[..., :2].copy()))
+for isurf in (1, 7, 8):   # Eckart embedding, SAPT-only (rigid/sweep stages skipped), potparts_old
+    pk.McmodMass("ccpol8sf", isurf=isurf).V_init().eval_batch(x[..., :5])
+pes = pk.McmodMass("ccpol8sf").V_init()
 a, b, mass = wells("ccpol8sf")
 for n, th in ((7, 2), (5, 1)):
     vi = pk.VerletInt(pes, n, mass, 160.0, dt=1e-3, NMC=2, Noutput=1, seed=7).init_nm()
