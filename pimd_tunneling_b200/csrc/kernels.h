@@ -96,6 +96,8 @@ cudaError_t launch_andersen_init(long ntraj, uint64_t seed, uint64_t step0, doub
 cudaError_t launch_sample_momenta(const NmTables& nm, double* P, long ntraj, uint64_t seed, int stream, uint64_t step,
                                   const int64_t* gid, cudaStream_t st);
 // estimator: dHdr[traj] += sum_{dim,atom} mass*(-x(n,dim,atom))*dbdl(dim,atom,traj)   (verletmodule.f90:397-403)
+cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const double* a, const double* b,
+                                   const double* dbdl, double* dHdr, long ntraj, cudaStream_t st);
 cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* dbdl, double* dHdr, long ntraj,
                              cudaStream_t st);
 cudaError_t launch_scale(double* v, double s, long n, cudaStream_t st);

@@ -319,6 +319,58 @@ __global__ void estimator_kernel(NmTables nm, const double* __restrict__ x, cons
   dHdr[t] = dHdr[t] + contr;
 }
 
+// The estimator needs the LAST bead only: x(n,dof) = sum_j T(n,j) (Q_j + beadvec_j), the last column of the
+// back-transform.  The Andersen step (NM(dt/2) V(dt) NM(dt/2)) has no other use for the positions at the end of a
+// step, so this kernel replaces its third n x n transform per step by one length-n contraction per (trajectory, dof):
+// the same fma chain, j ascending from zero, that the GEMM kernels run for that column — identical bits.
+// A CTA owns whole trajectories (kEmRows / ndof of them): the rows' modes are staged through shared memory in
+// coalesced 32-column tiles, thread = row runs the chain, then one thread per trajectory adds the ndof terms in the
+// reference's order (j = dim outer, k = atom inner; verletmodule.f90:236-244).
+constexpr int kEmRows = 32, kEmThreads = 256;
+__global__ void __launch_bounds__(kEmThreads)
+estimator_modes_kernel(NmTables nm, const double* __restrict__ Q, const double* __restrict__ a,
+                       const double* __restrict__ b, const double* __restrict__ dbdl, double* __restrict__ dHdr,
+                       long ntraj) {
+  extern __shared__ double em_smem[];
+  const int n = nm.n, ndof = nm.ndof;
+  double* tcol = em_smem;                 // T(:, n): n doubles
+  double* tile = em_smem + n;             // [kEmRows][33]
+  double* xl = tile + kEmRows * 33;       // last-bead positions of the CTA's rows
+  const int tpc = kEmRows / ndof;         // trajectories per CTA
+  const long traj0 = (long)blockIdx.x * tpc;
+  const int nrow = (int)(((ntraj - traj0 < tpc) ? ntraj - traj0 : tpc) * ndof);   // active rows
+  const long row0 = traj0 * ndof;
+  for (int m = threadIdx.x; m < n; m += kEmThreads) tcol[m] = nm.T[(long)m * n + (n - 1)];
+  const int r = threadIdx.x;              // chain phase: thread = row (first warp)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int m0 = 0; m0 < n; m0 += 32) {
+    __syncthreads();
+    for (int rr = warp; rr < nrow; rr += kEmThreads / 32) {   // Q + beadvec, formed lane-parallel by all warps
+      const int m = m0 + lane, tl = rr / ndof;
+      tile[rr * 33 + lane] = m < n ? Q[(row0 + rr) * (long)n + m] + beadvec_at(nm, a, b, traj0 + tl, rr - tl * ndof, m) : 0.0;
+    }
+    __syncthreads();
+    if (r < nrow) {
+      const int mm = (n - m0 < 32) ? n - m0 : 32;
+      for (int q = 0; q < mm; ++q) acc = fma(tile[r * 33 + q], tcol[m0 + q], acc);
+    }
+  }
+  if (r < kEmRows) xl[r] = acc;
+  __syncthreads();
+  if (threadIdx.x < nrow / ndof) {
+    const long t = traj0 + threadIdx.x;
+    const double* xt = xl + threadIdx.x * ndof;
+    double contr = 0.0;
+    for (int j = 0; j < nm.ndim; ++j)
+      for (int k = 0; k < nm.natom; ++k) {
+        const int d = k * nm.ndim + j;
+        contr = contr + nm.mass[k] * (-xt[d]) * dbdl[t * ndof + d];
+      }
+    dHdr[t] = dHdr[t] + contr;
+  }
+}
+
 __global__ void scale_kernel(double* v, double s, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = v[i] / s;
@@ -405,6 +457,19 @@ cudaError_t launch_sample_momenta(const NmTables& nm, double* P, long ntraj, uin
 cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* dbdl, double* dHdr, long ntraj,
                              cudaStream_t st) {
   estimator_kernel<<<(unsigned)((ntraj + 127) / 128), 128, 0, st>>>(nm, x, dbdl, dHdr, ntraj);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const double* a, const double* b,
+                                   const double* dbdl, double* dHdr, long ntraj, cudaStream_t st) {
+  const int tpc = kEmRows / nm.ndof;     // (ndof <= 18 for every surface here)
+  if (tpc < 1) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(nm.n + kEmRows * 33 + kEmRows) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(estimator_modes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  estimator_modes_kernel<<<(unsigned)((ntraj + tpc - 1) / tpc), kEmThreads, smem, st>>>(nm, Q, a, b, dbdl, dHdr, ntraj);
   return cudaGetLastError();
 }
 

@@ -988,14 +988,14 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
         Scope s("update");
         CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream));
       }
-      {
-        Scope s("gemm");
-        CU(launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream));
-      }
-      if (ii > imin) {
+      if (ii > imin) {   // the estimator reads the last bead only: one contraction per (trajectory, dof), not a transform
         Scope s("estimator");
-        CU(launch_estimator(nm, x, dbdl, dHdr, ntraj, g.stream));
+        CU(launch_estimator_modes(nm, Q, a, b, dbdl, dHdr, ntraj, g.stream));
       }
+    }
+    {
+      Scope s("gemm");   // positions at the end of the call
+      CU(launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream));
     }
   }
   {
