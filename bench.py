@@ -199,6 +199,9 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries the one JSON line; NCCL's version banner (NCCL_DEBUG=VERSION) would go there too
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pk.init(local_rank)
     L = lib()
