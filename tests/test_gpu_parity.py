@@ -78,6 +78,20 @@ def test_ccpol_all_surfaces_golden_and_bit_exact(pk, orc, isurf):
     orc.load_ccpol(3, 1)
 
 
+def test_ccpol_far_separated_dimers_underflow_exactly(pk, orc):
+    """Monomers 150 ... 400 bohr apart, mixed with bound dimers inside one 32-energy group of the sweep: the
+    exponentials e^{-beta R} reach the policy's flush-to-zero range (below -708) and must agree with the oracle bit
+    for bit, like everything else."""
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    orc.select("ccpol8sf")
+    x = thermal_dimer_geometries(24, seed=5)
+    x[2, 3:, :] += np.linspace(150.0, 400.0, 24)[None, :]     # monomer B (atoms 4-6) moved along z
+    x[2, 3:, ::3] -= np.linspace(150.0, 400.0, 24)[None, ::3]  # every third one back to the bound geometry
+    v, g = pes.eval_batch(x)
+    vo, go, _ = orc.pes_eval(x)
+    assert np.array_equal(v, vo) and np.array_equal(g, go), (np.abs(v - vo).max(), np.abs(g - go).max())
+
+
 @pytest.mark.parametrize("nbatch", [1, 7, 252, 1000])
 def test_ccpol_energy_gradient_bit_exact(pk, orc, nbatch):
     pes = pk.McmodMass("ccpol8sf").V_init()
