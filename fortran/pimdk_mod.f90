@@ -67,6 +67,12 @@ module pimdk
        import; integer(c_int64_t), value :: n, ndim, natom, singlewell; real(c_double), value :: betan
        real(c_double) :: x(*), mass(*), etasquared(*); type(c_ptr), value :: eigvecs
      end function
+     ! the readhess branch of init_path (verletmodule.f90:49-88) for one ring polymer
+     integer(c_int) function pimdk_readhess_displace(n, ndim, natom, x, mass, betan, beta, seed, traj_gid, etasquared) &
+          bind(C, name="pimdk_readhess_displace")
+       import; integer(c_int64_t), value :: n, ndim, natom, seed, traj_gid
+       real(c_double) :: x(*), etasquared(*); real(c_double), intent(in) :: mass(*); real(c_double), value :: betan, beta
+     end function
      ! module variables restart / restartnmc (verletmodule.f90:10) and the running sums write_restart stores (:171)
      integer(c_int) function pimdk_set_restart(restart, restartnmc) bind(C, name="pimdk_set_restart")
        import; integer(c_int64_t), value :: restart, restartnmc

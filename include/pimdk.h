@@ -105,6 +105,14 @@ int pimdk_um_hessian(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, co
                      pimdk_int singlewell, double* band);
 int pimdk_detj(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
                pimdk_int singlewell, double* etasquared, double* eigvecs);
+/* The `readhess` branch of init_path (verletmodule.f90:49-88) for ONE ring polymer x(n,ndim,natom) that already sits on
+ * the path: totdof normals N(0, sqrt(1/beta)) (Philox stream 4, keyed by seed and traj_gid), eigenvectors of the
+ * ring-polymer Hessian (detJ(x, etasquared, .false., interphess, eigvecs): the interpolated Hessian is accepted and
+ * ignored by the reference, instantonmod.f90:813, so UMhessian calls Vdoubleprime on every bead), and
+ *   x(i2,j2,k2) += sum over modes 2..totdof with etasquared >= 0 of sqrt(1/(etasquared mass(k2))) tempx eigvecs(idof2, mode),
+ * idof2 = natom*(j2-1 + ndim*(i2-1)) + k2 as written there.  x in/out; etasquared (totdof) optional out. */
+int pimdk_readhess_displace(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+                            double beta, uint64_t seed, pimdk_int traj_gid, double* etasquared);
 
 /* ---- module verletint -----------------------------------------------------------------------
  * pimdk_nm_setup = alloc_nm + the a,b-independent part of init_nm (verletmodule.f90:306-338):

@@ -41,6 +41,7 @@ _SIGS = {
     "pimdk_pes_hessian": [_i64, _i64, _i64, _pd, _pd],
     "pimdk_um_hessian": [_i64, _i64, _i64, _pd, _pd, _dbl, _i64, _pd],
     "pimdk_detj": [_i64, _i64, _i64, _pd, _pd, _dbl, _i64, _pd, _pd],
+    "pimdk_readhess_displace": [_i64, _i64, _i64, _pd, _pd, _dbl, _dbl, _u64, _i64, _pd],
     "pimdk_nm_setup": [_i64, _i64, _i64, _pd, _dbl, _dbl],
     "pimdk_nm_get": [_pd, _pd, _pd],
     "pimdk_nm_transform": [_i64, _i64, _pd, _pd, _pd],

@@ -6,6 +6,7 @@
 // hess[g*ndof*ndof + dof2*ndof + dof1] = d grad(dof2) / d x(dof1).  Built with -fmad=false: the central
 // differences reproduce the reference's operation order, including the in-place perturbation drift of x.
 #include "kernels.h"
+#include "philox.cuh"
 #include "pes_simple_device.cuh"
 
 namespace pimdk {
@@ -116,7 +117,41 @@ __global__ void band_to_dense_kernel(long N, int kd, const double* __restrict__ 
   A[t] = (hi - lo <= kd) ? band[(hi - lo) + (long)(kd + 1) * lo] : 0.0;
 }
 
+// init_path's readhess branch (verletmodule.f90:49-88): totdof normals N(0, sqrt(1/beta)) ...
+__global__ void readhess_normals_kernel(long N, double stdev, uint64_t seed, uint32_t gid, double* __restrict__ tempx) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) tempx[i] = stdev * normal_at(seed, STREAM_READHESS, 0, gid, (uint64_t)i);
+}
+// ... and the displacement along the eigenvectors of the ring-polymer Hessian (:75-87), literally: modes 2..totdof
+// with a non-negative eigenvalue, added in that order;  x(i2,j2,k2) += sqrt(1/(eta2(m) mass(k2))) tempx(m) Z(idof2, m)
+// with the reference's row index idof2 = natom*(j2-1 + ndim*(i2-1)) + k2 (atom fastest, whereas UMhessian numbers the
+// degrees of freedom dimension fastest: the two agree for natom = 1 or ndim = 1 only — restated, not repaired).
+__global__ void readhess_displace_kernel(int n, int ndim, int natom, const double* __restrict__ eta,
+                                         const double* __restrict__ Z, const double* __restrict__ mass,
+                                         const double* __restrict__ tempx, double* __restrict__ x) {
+  const long N = (long)n * ndim * natom;
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;   // x(n,ndim,natom), bead fastest
+  if (e >= N) return;
+  const int i2 = (int)(e % n), j2 = (int)((e / n) % ndim), k2 = (int)(e / ((long)n * ndim));
+  const long idof2 = (long)natom * (j2 + (long)ndim * i2) + k2;
+  double acc = x[e];
+  for (long m = 1; m < N; ++m) {
+    const double et = eta[m];
+    if (et < 0.0) continue;
+    acc = acc + sqrt(1.0 / (et * mass[k2])) * tempx[m] * Z[idof2 + N * m];
+  }
+  x[e] = acc;
+}
+
 }  // namespace
+
+cudaError_t launch_readhess_displace(int n, int ndim, int natom, const double* eta, const double* Z, const double* mass,
+                                     double stdev, uint64_t seed, uint32_t gid, double* tempx, double* x, cudaStream_t st) {
+  const long N = (long)n * ndim * natom;
+  readhess_normals_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, stdev, seed, gid, tempx);
+  readhess_displace_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(n, ndim, natom, eta, Z, mass, tempx, x);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_simple_hessian(PesKind kind, const SimplePesParams& P, int ndim, int natom, GeomLayout L, double* x,
                                   double* hess, long ngeom, cudaStream_t st) {

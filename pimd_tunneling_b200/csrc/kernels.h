@@ -118,6 +118,8 @@ cudaError_t launch_hess_column(GeomLayout L, const double* gp, const double* gm,
 cudaError_t launch_um_band(int n, int ndim, int natom, const double* hess, const double* mass, double betan, int singlewell,
                            double* band, cudaStream_t st);
 cudaError_t launch_band_to_dense(long N, int kd, const double* band, double* A, cudaStream_t st);
+cudaError_t launch_readhess_displace(int n, int ndim, int natom, const double* eta, const double* Z, const double* mass,
+                                     double stdev, uint64_t seed, uint32_t gid, double* tempx, double* x, cudaStream_t st);
 
 // ---- ring-polymer potential (um_kernels.cu): instantonmod.f90:17-151 ----
 cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double* a, const double* b,

@@ -12,7 +12,7 @@
 
 namespace pimdk {
 
-enum { STREAM_INIT = 0, STREAM_LANGEVIN = 1, STREAM_ANDERSEN = 2, STREAM_POISSON = 3 };
+enum { STREAM_INIT = 0, STREAM_LANGEVIN = 1, STREAM_ANDERSEN = 2, STREAM_POISSON = 3, STREAM_READHESS = 4 };
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t* out) {

@@ -720,10 +720,11 @@ int cusolver_load() {
 }
 }  // namespace
 
-int pimdk_detj(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
-               pimdk_int singlewell, double* etasquared, double* eigvecs) {
-  NEED_INIT();
-  if (!etasquared) return fail(PIMDK_EINVAL, "etasquared must not be NULL");
+// detJ's work on the device: UMhessian (x comes back with the Hessian's finite-difference drift, like the reference's),
+// dense symmetric eigensolver.  Leaves the eigenvalues (ascending) in wEig and, if asked, the eigenvectors (column-major,
+// one per column) in wDense; the stream is drained on return.
+static int detj_core(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+                     pimdk_int singlewell, bool vectors) {
   int rc = um_hessian_dev(n, ndim, natom, x, mass, betan, singlewell);   // "Hessian is cooked."
   if (rc) return rc;
   rc = cusolver_load();
@@ -737,7 +738,7 @@ int pimdk_detj(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const do
     CU(launch_band_to_dense(N, (int)nd, g.wBand.as<double>(), g.wDense.as<double>(), g.stream));
   }
   // DSBEVD(jobz, 'L', totdof, ndof, H, ndof+1, etasquared, ...) (instantonmod.f90:819-823): all eigenvalues, ascending
-  const int jobz = eigvecs ? 1 : 0;   // CUSOLVER_EIG_MODE_VECTOR / NOVECTOR
+  const int jobz = vectors ? 1 : 0;   // CUSOLVER_EIG_MODE_VECTOR / NOVECTOR
   const int uplo = 0;                 // CUBLAS_FILL_MODE_LOWER
   int lwork = 0;
   if (cs.set_stream(cs.handle, g.stream) != 0) return fail(PIMDK_ECUDA, "cusolverDnSetStream failed");
@@ -750,10 +751,42 @@ int pimdk_detj(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const do
   if (st != 0) return fail(PIMDK_ECUDA, "cusolverDnDsyevd failed (status %d)", st);
   int info = 0;
   CU(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  if (info != 0) return fail(PIMDK_ECUDA, "eigensolver did not converge (info = %d)", info);
+  return PIMDK_OK;
+}
+
+int pimdk_detj(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+               pimdk_int singlewell, double* etasquared, double* eigvecs) {
+  NEED_INIT();
+  if (!etasquared) return fail(PIMDK_EINVAL, "etasquared must not be NULL");
+  int rc = detj_core(n, ndim, natom, x, mass, betan, singlewell, eigvecs != nullptr);
+  if (rc) return rc;
+  const long N = (long)n * ndim * natom;
   CU(cudaMemcpyAsync(etasquared, g.wEig.p, sizeof(double) * N, cudaMemcpyDeviceToHost, g.stream));
   if (eigvecs) CU(cudaMemcpyAsync(eigvecs, g.wDense.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
-  if (info != 0) return fail(PIMDK_ECUDA, "eigensolver did not converge (info = %d)", info);
+  return PIMDK_OK;
+}
+
+int pimdk_readhess_displace(pimdk_int n, pimdk_int ndim, pimdk_int natom, double* x, const double* mass, double betan,
+                            double beta, uint64_t seed, pimdk_int traj_gid, double* etasquared) {
+  NEED_INIT();
+  if (!(beta > 0.0)) return fail(PIMDK_EINVAL, "beta must be positive");
+  int rc = detj_core(n, ndim, natom, x, mass, betan, 0, true);   // detJ(x, etasquared, .false., interphess, eigvecs)
+  if (rc) return rc;
+  const long N = (long)n * ndim * natom;
+  CU(g.wAux.ensure(sizeof(double) * N));
+  {
+    Scope s("hess", 2);
+    // wX holds x as UMhessian left it; wMisc the masses (um_hessian_dev)
+    CU(launch_readhess_displace((int)n, (int)ndim, (int)natom, g.wEig.as<double>(), g.wDense.as<double>(),
+                                g.wMisc.as<double>(), std::sqrt(1.0 / beta), seed, (uint32_t)traj_gid, g.wAux.as<double>(),
+                                g.wX.as<double>(), g.stream));
+  }
+  CU(cudaMemcpyAsync(x, g.wX.p, sizeof(double) * N, cudaMemcpyDeviceToHost, g.stream));
+  if (etasquared) CU(cudaMemcpyAsync(etasquared, g.wEig.p, sizeof(double) * N, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
   return PIMDK_OK;
 }
 

@@ -103,7 +103,16 @@ class VerletInt:
         return out
 
     # init_path (verletmodule.f90:32-119)
-    def init_path(self, xi, lampath, path, splinepath, traj_gid=None):
+    def init_path(self, xi, lampath, path, splinepath, traj_gid=None, readhess=False):
+        """x on the spline path, momenta sampled in normal-mode space.  readhess=True adds the thermal displacement of
+        the reference's `readhess` branch (verletmodule.f90:49-88), one ring polymer at a time (an eigen-decomposition
+        of order n*ndof each)."""
+        if readhess:
+            x, p = self.init_path(xi, lampath, path, splinepath, traj_gid=traj_gid)
+            gid = np.arange(x.shape[3], dtype=np.int64) if traj_gid is None else np.asarray(traj_gid, dtype=np.int64)
+            for t in range(x.shape[3]):
+                x[..., t] = self.readhess_displace(x[..., t], int(gid[t]))[0]
+            return x, p
         self._need()
         xi = f64(np.atleast_1d(np.asarray(xi, dtype=np.float64)))
         ntraj = xi.size
@@ -117,6 +126,16 @@ class VerletInt:
         check(lib().pimdk_init_path(ntraj, npath, hptr(lam), hptr(path), hptr(spl), hptr(xi), self.seed, hptr(gid),
                                     hptr(x), hptr(p)))
         return x, p
+
+    def readhess_displace(self, x, traj_gid=0):
+        """One ring polymer x(n,ndim,natom) displaced along the eigenvectors of its ring-polymer Hessian with
+        N(0, 1/(beta eta^2 m)) amplitudes (verletmodule.f90:52-87).  Returns (x, etasquared)."""
+        self._need()
+        xw = np.array(f64(x, (self.n, self.ndim, self.natom)), order="F")
+        eta = np.empty(self.n * self.ndim * self.natom)
+        check(lib().pimdk_readhess_displace(self.n, self.ndim, self.natom, hptr(xw), hptr(self.mass), self.betan,
+                                            self.beta, self.seed, int(traj_gid), hptr(eta)))
+        return xw, eta
 
     def _propagate(self, thermostat, x, p, a, b, dbdl, traj_gid, dHdr0=None):
         self._need()

@@ -734,6 +734,45 @@ def test_rpi_splitting_closes_the_instanton_calculation(pk, orc):
     orc.set_V0(0.0)
 
 
+@pytest.mark.parametrize("name,n,mass,beta", [("1d", 24, [1.3], 8.0), ("2dtest", 16, [1.0], 6.0)])
+def test_readhess_displacement_matches_oracle_composition(pk, orc, name, n, mass, beta):
+    """init_path's `readhess` branch (verletmodule.f90:49-88) on the GPU against the same steps composed from the oracle:
+    UMhessian band -> LAPACK eigenvectors, Philox normals (stream 4), the literal displacement formula.  Eigenvectors are
+    defined up to sign, so the comparison is made mode by mode: the GPU displacement, mass-weighted and projected on the
+    LAPACK eigenvectors, must have the amplitudes |tempx_m| / sqrt(eta2_m) (modes 2..totdof with eta2 >= 0; nothing along
+    mode 1), and the eigenvalues must agree."""
+    import ctypes
+    from scipy.linalg import eig_banded
+    from pimd_tunneling_b200 import path as P
+
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    a, b = _wells(name)
+    vi = pk.VerletInt(pes, n, mass, beta, seed=2718).init_nm()
+    orc.nm_setup(n, mass, vi.betan, 1.0, 1.0, 1e-3, False, True)
+    lam, path, spl = P.build_path(np.stack([a, b], axis=0))
+    x0, _ = vi.init_path([0.7], lam, path, spl, traj_gid=[9])
+    x0 = np.asfortranarray(x0[..., 0])
+    band = orc.UMhessian(x0.copy(), False)
+    xd = x0.copy(order="F")                          # x as UMhessian leaves it (1D/2D Vdoubleprime: no drift)
+    w, Z = eig_banded(band, lower=True)
+    xg, eta = vi.readhess_displace(x0, traj_gid=9)
+    N = n * pes.ndof
+    assert np.abs(eta - w).max() <= 1e-9 * np.abs(w).max()
+    orc.L.orc_normal.restype = ctypes.c_double
+    orc.L.orc_normal.argtypes = [ctypes.c_ulonglong, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_ulonglong]
+    tempx = np.sqrt(1.0 / beta) * np.array([orc.L.orc_normal(2718, 4, 0, 9, m) for m in range(N)])
+    # UMhessian numbers a degree of freedom as ndof*(bead-1) + dof; natom = 1 here, so idof2 is the same index
+    dx = (xg - xd).reshape(n, pes.ndof, order="F").reshape(-1) * np.sqrt(mass[0])
+    c = Z.T @ dx
+    expect = np.where(w >= 0.0, np.abs(tempx) / np.sqrt(np.where(w > 0, w, 1.0)), 0.0)
+    expect[0] = 0.0
+    assert np.abs(np.abs(c) - expect).max() <= 1e-7 * max(expect.max(), 1e-300), (np.abs(c)[:4], expect[:4])
+    # through the mirror of init_path: same polymer, same global id -> same bits
+    x1, _ = vi.init_path([0.7], lam, path, spl, traj_gid=[9], readhess=True)
+    assert np.array_equal(x1[..., 0], xg)
+
+
 def test_rpi_splitting_matches_the_analytic_instanton(pk):
     """Known answer for the instanton rows (UM, UMprime, L-BFGS-B on the GPU gradient, UMhessian, detJ, the closing
     formulas of `program rpi`), independent of the oracle: for V = (x^2-1)^2 and mass m the kink action is
