@@ -31,6 +31,8 @@ for n in (33, 200):
     x0, p0 = vi.init_path(xi, lam, path, spl)
     bt, dbdl = P.endpoints(lam, path, spl, xi)
     vi.propagate_pimd_pile(x0, p0, a2, bt, dbdl); vi.propagate_pimd_nm(x0, p0, a2, bt, dbdl)
+    if n == 33:
+        vi.init_path(xi[:2], lam, path, spl, readhess=True)   # readhess thermal initialisation
     # the chunked, copy-overlapped host-buffer path (chunks of 2, 2, 1 trajectories)
     from pimd_tunneling_b200._lib import check, lib
     check(lib().pimdk_set_propagate_chunk(2))
