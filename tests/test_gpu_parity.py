@@ -172,6 +172,29 @@ def test_edge_cases(pk):
     assert ei.value.code in (5, 6)
 
 
+def test_nan_trap_reports_the_trajectory_single_shot_and_chunked(pk):
+    """The reference STOPs with "NaN in pot propagation" (verletmodule.f90:533-536, 577-580); the library returns
+    PIMDK_ENAN and the index of the first offending trajectory in the caller's batch — also when the host-buffer call
+    is pipelined in chunks (the index is the batch index, not the chunk-local one) — and still returns the others."""
+    from pimd_tunneling_b200._lib import check, lib
+
+    pes = pk.McmodMass("2dtest").V_init()
+    a, b = _wells("2dtest")
+    n, ntraj = 160, 7
+    vi = pk.VerletInt(pes, n, [1.0], 10.0, NMC=3, Noutput=10 ** 9, seed=5).init_nm()
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, 0.05, [1.0])
+    x[3, 1, 0, 4] = np.nan
+    try:
+        for chunk in (10 ** 6, 3):
+            check(lib().pimdk_set_propagate_chunk(chunk))
+            with pytest.raises(pk.PimdkError) as ei:
+                vi.propagate_pimd_pile(x, p, a, bt, dbdl)
+            assert ei.value.code == 5 and "NaN" in str(ei.value)
+            assert int(lib().pimdk_last_nan_trajectory()) == 4
+    finally:
+        check(lib().pimdk_set_propagate_chunk(0))
+
+
 def test_division_by_small_integers(pk):
     """the damping series divides by 1..10 with a 3-instruction correctly rounded sequence: 0 mismatches vs '/'"""
     import ctypes
