@@ -449,6 +449,18 @@ def run_instanton(args, cfg, rank):
     dt = time.perf_counter() - t0
     launches = int(lib().pimdk_launch_count()) - l0
     nbytes = x0.nbytes
+    # the solid-angle loop's shape (rpi_par.f90:209-281): many independent polymers per f/g call
+    batch = {}
+    for npoly in (8, 64, 512):
+        X = np.asfortranarray(np.repeat(x0[..., None], npoly, axis=3))
+        B = np.asfortranarray(np.repeat(b[..., None], npoly, axis=2))
+        for _ in range(5):
+            im.UMforceenergy_batch(X, a, B)
+        reps = max(20, K // 4)
+        tb = time.perf_counter()
+        for _ in range(reps):
+            im.UMforceenergy_batch(X, a, B)
+        batch[str(npoly)] = reps * npoly / (time.perf_counter() - tb)
     # one complete optimisation driven by the GPU gradient, iterate count and final action against the oracle's
     def fg_gpu(v):
         g_, f_ = im.UMforceenergy(v.reshape(x0.shape, order="F"), a, b)
@@ -471,6 +483,7 @@ def run_instanton(args, cfg, rank):
     rpi = im.rpi_splitting(xg.reshape(x0.shape, order="F"), a, b)
     rpi["seconds"] = time.perf_counter() - t2
     line.update({"value": K / dt, "ms_per_step": 1e3 * dt / K, "gpu_launches": launches, "rpi": rpi,
+                 "batched_evaluations_per_s": batch,
                  "e2e": {"value": K / dt, "unit": "evaluations/s", "h2d_bytes_per_step": nbytes + 2 * a.nbytes + mass.nbytes,
                          "d2h_bytes_per_step": nbytes + 8,
                          "note": "host-buffer C ABI call per evaluation, as L-BFGS-B on the host needs it; value == e2e"},

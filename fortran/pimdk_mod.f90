@@ -67,6 +67,12 @@ module pimdk
        import; integer(c_int64_t), value :: n, ndim, natom, singlewell; real(c_double), value :: betan
        real(c_double) :: x(*), mass(*), etasquared(*); type(c_ptr), value :: eigvecs
      end function
+     ! UMforceenergy for npoly independent ring polymers (the solid-angle loop of rpi_par.f90:209-281)
+     integer(c_int) function pimdk_um_forceenergy_batch(npoly, n, ndim, natom, x, a, b, mass, betan, fixedends, f, g) &
+          bind(C, name="pimdk_um_forceenergy_batch")
+       import; integer(c_int64_t), value :: npoly, n, ndim, natom, fixedends; real(c_double), value :: betan
+       real(c_double), intent(in) :: x(*), a(*), b(*), mass(*); real(c_double) :: f(*), g(*)
+     end function
      ! the readhess branch of init_path (verletmodule.f90:49-88) for one ring polymer
      integer(c_int) function pimdk_readhess_displace(n, ndim, natom, x, mass, betan, beta, seed, traj_gid, etasquared) &
           bind(C, name="pimdk_readhess_displace")

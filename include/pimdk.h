@@ -86,6 +86,13 @@ int pimdk_pes_eval_dev(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, const 
  * This is the f/g evaluation `instanton` hands to setulb on task 'FG' (instantonmod.f90:748-765). */
 int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x, const double* a,
                          const double* b, const double* mass, double betan, pimdk_int fixedends, double* f, double* g);
+/* The same for npoly independent ring polymers in one call: x, g (n,ndim,natom,npoly); b (ndim,natom,npoly), one end
+ * point per polymer; a (ndim,natom) shared; f (npoly).  This is the batch of the solid-angle loop of `program rpi`
+ * (rpi_par.f90:209-281: npoints**3 instanton optimisations that differ in the rotated end point only): every polymer's
+ * values are bit-identical to the single-polymer call. */
+int pimdk_um_forceenergy_batch(pimdk_int npoly, pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x,
+                               const double* a, const double* b, const double* mass, double betan, pimdk_int fixedends,
+                               double* f, double* g);
 
 /* ---- second derivatives and the fluctuation factor -------------------------------
  * pimdk_pes_hessian = Vdoubleprime(x, hess) of the selected plugin over a batch (mcmod_1d.f90:37-57: central

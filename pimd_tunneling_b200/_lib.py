@@ -38,6 +38,7 @@ _SIGS = {
     "pimdk_pes_vprime_inplace": [_i64, _i64, _i64, _pd, _pd],
     "pimdk_pes_eval_dev": [_i64, _i64, _i64, _pd, _pd, _pd],
     "pimdk_um_forceenergy": [_i64, _i64, _i64, _pd, _pd, _pd, _pd, _dbl, _i64, _pd, _pd],
+    "pimdk_um_forceenergy_batch": [_i64, _i64, _i64, _i64, _pd, _pd, _pd, _pd, _dbl, _i64, _pd, _pd],
     "pimdk_pes_hessian": [_i64, _i64, _i64, _pd, _pd],
     "pimdk_um_hessian": [_i64, _i64, _i64, _pd, _pd, _dbl, _i64, _pd],
     "pimdk_detj": [_i64, _i64, _i64, _pd, _pd, _dbl, _i64, _pd, _pd],

@@ -122,7 +122,7 @@ cudaError_t launch_readhess_displace(int n, int ndim, int natom, const double* e
                                      double stdev, uint64_t seed, uint32_t gid, double* tempx, double* x, cudaStream_t st);
 
 // ---- ring-polymer potential (um_kernels.cu): instantonmod.f90:17-151 ----
-cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double* a, const double* b,
+cudaError_t launch_um(int npoly, int n, int ndim, int natom, const double* x, const double* a, const double* b,
                       const double* mass, double betan, int fixedends, const double* vbead /*n or NULL*/,
                       const double* gbead /*(n,ndim,natom) or NULL*/, double* um_out /*1, may be NULL*/,
                       double* grad_out /*(n,ndim,natom) or NULL*/, cudaStream_t st);

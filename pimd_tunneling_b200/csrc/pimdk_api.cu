@@ -529,37 +529,40 @@ int pimdk_pes_vprime_inplace(pimdk_int nbatch, pimdk_int ndim, pimdk_int natom, 
   return pes_eval_host(nbatch, ndim, natom, x, nullptr, grad, 1);
 }
 
-int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x, const double* a,
-                         const double* b, const double* mass, double betan, pimdk_int fixedends, double* f,
-                         double* gout) {
-  NEED_INIT();
+// UMforceenergy for npoly independent ring polymers x(n,ndim,natom,npoly) with end points a (shared) and
+// b(ndim,natom,npoly): one PES pass over all npoly*n beads, spring terms and the ordered UM sum per polymer.
+static int um_forceenergy_impl(pimdk_int npoly, pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x,
+                               const double* a, const double* b, const double* mass, double betan, pimdk_int fixedends,
+                               double* f, double* gout) {
   int rc = check_dims(ndim, natom);
   if (rc) return rc;
   if (n < 2) return fail(PIMDK_EINVAL, "n must be >= 2");
+  if (npoly < 1 || npoly > 65535) return fail(PIMDK_EINVAL, "npoly must be in 1..65535");
   if (fixedends && (!a || !b)) return fail(PIMDK_EINVAL, "fixedends needs a and b");
-  // This call sits inside L-BFGS-B's reverse-communication loop (instantonmod.f90:741-767): one small problem per
-  // call, so its cost is latency.  Inputs are packed into one page-locked block (one H2D copy), outputs and the
-  // flag word come back through it as well, and there is a single stream synchronisation.
+  // This call sits inside L-BFGS-B's reverse-communication loop (instantonmod.f90:741-767): small problems, so its
+  // cost is latency.  Inputs are packed into one page-locked block (one H2D copy), outputs and the flag word come
+  // back through it as well, and there is a single stream synchronisation.
   const long ndof = ndim * natom;
-  const size_t nx = (size_t)n * ndof;
-  const size_t nin = nx + 2 * ndof + natom, nout = nx + 2;   // [x | a | b | mass]  /  [g | UM | flags]
+  const size_t nx = (size_t)n * ndof, nxt = nx * (size_t)npoly;
+  const size_t nin = nxt + ndof + (size_t)npoly * ndof + natom, nout = nxt + (size_t)npoly + 1;
+  //   [x | a | b | mass]  /  [g | UM(npoly) | flags]
   CU(g.wUmIn.ensure(nin * sizeof(double)));
   CU(g.wUmOut.ensure(nout * sizeof(double)));
-  CU(g.wG.ensure(nx * sizeof(double)));
-  CU(g.wV.ensure((size_t)n * sizeof(double)));
+  CU(g.wG.ensure(nxt * sizeof(double)));
+  CU(g.wV.ensure((size_t)n * npoly * sizeof(double)));
   CU(g.hUm.ensure((nin + nout) * sizeof(double)));
   double* hin = g.hUm.as<double>();
   double* hout = hin + nin;
-  std::memcpy(hin, x, nx * sizeof(double));
+  std::memcpy(hin, x, nxt * sizeof(double));
   if (fixedends) {
-    std::memcpy(hin + nx, a, ndof * sizeof(double));
-    std::memcpy(hin + nx + ndof, b, ndof * sizeof(double));
+    std::memcpy(hin + nxt, a, ndof * sizeof(double));
+    std::memcpy(hin + nxt + ndof, b, (size_t)npoly * ndof * sizeof(double));
   }
-  std::memcpy(hin + nx + 2 * ndof, mass, natom * sizeof(double));
+  std::memcpy(hin + nxt + ndof + (size_t)npoly * ndof, mass, natom * sizeof(double));
   double* dx = g.wUmIn.as<double>();
-  double *da = dx + nx, *db = da + ndof, *dm = db + ndof;
+  double *da = dx + nxt, *db = da + ndof, *dm = db + (size_t)npoly * ndof;
   double* dg = g.wUmOut.as<double>();
-  double* dum = dg + nx;
+  double* dum = dg + nxt;
   CU(cudaMemcpyAsync(dx, hin, nin * sizeof(double), cudaMemcpyHostToDevice, g.stream));
   rc = clear_flags();
   if (rc) return rc;
@@ -567,27 +570,41 @@ int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const dou
   // x is intent(in) in UM*: the FD perturbation of ccpol works on a copy and its drift is dropped
   double* xw = dx;
   if (gout && g.pes == PES_CCPOL) {
-    CU(g.wAux.ensure(nx * sizeof(double)));
-    CU(cudaMemcpyAsync(g.wAux.p, dx, nx * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    CU(g.wAux.ensure(nxt * sizeof(double)));
+    CU(cudaMemcpyAsync(g.wAux.p, dx, nxt * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
     xw = g.wAux.as<double>();
   }
-  rc = pes_eval_dev(L, xw, f ? g.wV.as<double>() : nullptr, gout ? g.wG.as<double>() : nullptr, n, 0);
+  rc = pes_eval_dev(L, xw, f ? g.wV.as<double>() : nullptr, gout ? g.wG.as<double>() : nullptr, (long)n * npoly, 0);
   if (rc) return rc;
   {
     Scope s("um", (f ? 1 : 0) + (gout ? 1 : 0));
-    CU(launch_um((int)n, (int)ndim, (int)natom, dx, da, db, dm, betan, fixedends != 0, g.wV.as<double>(),
-                 g.wG.as<double>(), f ? dum : nullptr, gout ? dg : nullptr, g.stream));
+    CU(launch_um((int)npoly, (int)n, (int)ndim, (int)natom, dx, da, fixedends ? db : nullptr, dm, betan, fixedends != 0,
+                 g.wV.as<double>(), g.wG.as<double>(), f ? dum : nullptr, gout ? dg : nullptr, g.stream));
   }
-  CU(cudaMemcpyAsync(hout, dg, (nx + 1) * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CU(cudaMemcpyAsync(hout + nx + 1, g.wFlags.p, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaMemcpyAsync(hout, dg, (nxt + npoly) * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaMemcpyAsync(hout + nxt + npoly, g.wFlags.p, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
-  if (f) *f = hout[nx];
-  if (gout) std::memcpy(gout, hout, nx * sizeof(double));
+  if (f) std::memcpy(f, hout + nxt, (size_t)npoly * sizeof(double));
+  if (gout) std::memcpy(gout, hout, nxt * sizeof(double));
   int fl = 0;
-  std::memcpy(&fl, hout + nx + 1, sizeof(int));
+  std::memcpy(&fl, hout + nxt + npoly, sizeof(int));
   if (fl & PIMDK_FLAG_NOCONV) return fail(PIMDK_ENOCONV, "No convergence in indN_iter");
   if (fl & PIMDK_FLAG_NAN) return fail(PIMDK_ENAN, "NaN in pot propagation");
   return PIMDK_OK;
+}
+
+int pimdk_um_forceenergy(pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x, const double* a,
+                         const double* b, const double* mass, double betan, pimdk_int fixedends, double* f,
+                         double* gout) {
+  NEED_INIT();
+  return um_forceenergy_impl(1, n, ndim, natom, x, a, b, mass, betan, fixedends, f, gout);
+}
+
+int pimdk_um_forceenergy_batch(pimdk_int npoly, pimdk_int n, pimdk_int ndim, pimdk_int natom, const double* x,
+                               const double* a, const double* b, const double* mass, double betan, pimdk_int fixedends,
+                               double* f, double* gout) {
+  NEED_INIT();
+  return um_forceenergy_impl(npoly, n, ndim, natom, x, a, b, mass, betan, fixedends, f, gout);
 }
 
 // ---- second derivatives: Vdoubleprime, UMhessian, detJ ------------------------------------------

@@ -14,6 +14,11 @@ um_grad_kernel(int n, int ndim, int natom, const double* __restrict__ x, const d
                const double* __restrict__ b, const double* __restrict__ mass, double betan, int fixedends,
                const double* __restrict__ gbead, double* __restrict__ grad) {
   const long total = (long)n * ndim * natom;
+  // polymer blockIdx.y of a batch: its own x, gradient and end point b; a and the masses are shared
+  x += blockIdx.y * total;
+  gbead += blockIdx.y * total;
+  grad += blockIdx.y * total;
+  if (b) b += (long)blockIdx.y * ndim * natom;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int i = (int)(e % n);         // bead (0-based)
     const int dof = (int)(e / n);       // atom*ndim + dim
@@ -43,6 +48,10 @@ um_energy_kernel(int n, int ndim, int natom, const double* __restrict__ x, const
                  const double* __restrict__ vbead, double* __restrict__ um_out) {
   extern __shared__ double terms[];   // [kUmTile][1 + ndof]
   const int ndof = ndim * natom, w = 1 + ndof;
+  x += (long)blockIdx.y * n * ndof;   // polymer blockIdx.y of a batch
+  vbead += (long)blockIdx.y * n;
+  um_out += blockIdx.y;
+  if (b) b += (long)blockIdx.y * ndof;
   const double bn2 = betan * betan;
   double um = 0.0;
   for (int i0 = 0; i0 < n; i0 += kUmTile) {
@@ -95,18 +104,21 @@ um_energy_kernel(int n, int ndim, int natom, const double* __restrict__ x, const
 
 }  // namespace
 
-cudaError_t launch_um(int n, int ndim, int natom, const double* x, const double* a, const double* b,
+// npoly ring polymers x(n,ndim,natom,npoly) with their own end points b(ndim,natom,npoly); a shared
+cudaError_t launch_um(int npoly, int n, int ndim, int natom, const double* x, const double* a, const double* b,
                       const double* mass, double betan, int fixedends, const double* vbead, const double* gbead,
                       double* um_out, double* grad_out, cudaStream_t st) {
+  if (npoly < 1 || npoly > 65535) return cudaErrorInvalidValue;
   if (grad_out) {
     long total = (long)n * ndim * natom;
     long blocks = (total + 255) / 256;
     if (blocks > 148L * 8) blocks = 148L * 8;
-    um_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(n, ndim, natom, x, a, b, mass, betan, fixedends, gbead, grad_out);
+    um_grad_kernel<<<dim3((unsigned)blocks, (unsigned)npoly), 256, 0, st>>>(n, ndim, natom, x, a, b, mass, betan, fixedends, gbead,
+                                                                           grad_out);
   }
   if (um_out)
-    um_energy_kernel<<<1, 256, (size_t)kUmTile * (1 + ndim * natom) * sizeof(double), st>>>(n, ndim, natom, x, a, b, mass, betan,
-                                                                                          fixedends, vbead, um_out);
+    um_energy_kernel<<<dim3(1, (unsigned)npoly), 256, (size_t)kUmTile * (1 + ndim * natom) * sizeof(double), st>>>(
+        n, ndim, natom, x, a, b, mass, betan, fixedends, vbead, um_out);
   return cudaGetLastError();
 }
 

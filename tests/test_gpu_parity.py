@@ -572,6 +572,75 @@ def test_instanton_lbfgs_iterates_match(pk, orc):
     assert ig.shape == io.shape and relmax(ig, io) < RTOL and abs(fgpu - fcpu) <= RTOL * abs(fcpu)
 
 
+@pytest.mark.parametrize("name,n,beta,mass", [("2dtest", 48, 30.0, [1.0]), ("ccpol8sf", 6, 300.0, DIMER_MASS)])
+def test_um_forceenergy_batch_is_bit_identical_per_polymer(pk, name, n, beta, mass):
+    """pimdk_um_forceenergy_batch (the solid-angle loop's batch, rpi_par.f90:252-255): every polymer's UM and gradient
+    equal the single-polymer call bit for bit, whatever its neighbours in the batch are."""
+    pes = pk.McmodMass(name).V_init()
+    a, b = _wells(name)
+    im = pk.InstantonMod(pes, mass, beta, n, fixedends=True, rpi=True)
+    rng = np.random.default_rng(8)
+    npoly = 5
+    X = np.empty((n, pes.ndim, pes.natom, npoly), order="F")
+    B = np.empty((pes.ndim, pes.natom, npoly), order="F")
+    for k in range(npoly):
+        B[..., k] = b + 0.02 * rng.normal(size=b.shape)
+        for i in range(n):
+            X[i, :, :, k] = a + (B[..., k] - a) * i / (n - 1) + 0.01 * rng.normal(size=a.shape)
+    G, F = im.UMforceenergy_batch(X, a, B)
+    for k in range(npoly):
+        g1, f1 = im.UMforceenergy(X[..., k], a, B[..., k])
+        assert f1 == F[k] and np.array_equal(g1, G[..., k])
+
+
+def test_instanton_batch_takes_the_iterates_of_separate_runs(pk):
+    """instanton_batch runs one L-BFGS-B optimisation per end point side by side, their f/g requests coalesced into
+    batched GPU calls: path, action and iteration count of every optimisation equal those of a run on its own."""
+    from scipy.optimize import fmin_l_bfgs_b
+
+    name, n, beta, mass = "2dtest", 64, 30.0, [1.0]
+    pes = pk.McmodMass(name).V_init()
+    a, b = _wells(name)
+    pes.set_V0(pes.V(a))
+    im = pk.InstantonMod(pes, mass, beta, n, fixedends=True, rpi=True)
+    x0 = np.empty((n, 2, 1), order="F")
+    for i in range(n):
+        x0[i] = a + (b - a) * i / (n - 1)
+    ends = np.array([b + d for d in ([[0.0], [0.0]], [[0.05], [-0.02]], [[-0.1], [0.04]], [[0.0], [0.15]])])
+    xs, fs, infos = im.instanton_batch(x0, a, ends)
+    for k in range(ends.shape[0]):
+        def fg(v, k=k):
+            g_, f_ = im.UMforceenergy(v.reshape(x0.shape, order="F"), a, ends[k])
+            return f_, g_.reshape(-1, order="F")
+        x1, f1, i1 = fmin_l_bfgs_b(fg, x0.reshape(-1, order="F"), m=8, factr=1e6, pgtol=pes.eps2, maxls=40, maxiter=15000)
+        assert f1 == fs[k] and np.array_equal(x1.reshape(x0.shape, order="F"), xs[..., k])
+        assert i1["nit"] == infos[k]["nit"] and i1["funcalls"] == infos[k]["funcalls"]
+    pes.set_V0(0.0)
+
+
+def test_angular_sweep_water_dimer_pipeline(pk):
+    """The solid-angle loop of rpi_par.f90:209-300 end to end on the water dimer at a toy size (6 beads, 2 angles per
+    axis = 8 rotated end points, 25 L-BFGS-B iterations each): rotate_atoms, batched instanton, detJ, I(beta)."""
+    from pimd_tunneling_b200.instantonmod import rotate_atoms
+
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    a, b = _wells("ccpol8sf")
+    pes.set_V0(pes.V(a))
+    n = 6
+    im = pk.InstantonMod(pes, DIMER_MASS, 3000.0, n, fixedends=True, rpi=True)
+    x0 = np.empty((n, 3, 6), order="F")
+    for i in range(n):
+        x0[i] = a
+    r = im.angular_sweep(x0, a, a, 2, cutofftheta=0.02, cutoffphi=0.02, maxiter=25)
+    assert r["Ibeta"].shape == (8,) and np.all(np.isfinite(r["Ibeta"])) and np.all((r["Ibeta"] >= 0) & (r["Ibeta"] <= 1))
+    assert abs(r["weight"].sum() - 0.02 ** 3) < 1e-15
+    # the first end point by hand: eta(1), phi(1), theta(1) about axes 1, 3, 1
+    w = rotate_atoms(rotate_atoms(rotate_atoms(a, 1, r["eta"][0]), 3, r["phi"][0]), 1, r["theta"][0])
+    g1, f1 = im.UMforceenergy(r["x"][..., 0], a, w)
+    assert f1 == r["UM"][0]
+    pes.set_V0(0.0)
+
+
 # ---------------------------------------------------------------- stochastic agreement ------------
 def test_ti_averages_agree_with_oracle_within_error_bars(pk, orc):
     """north_star: stochastic TI averages must agree with the reference within combined statistical error bars.
