@@ -5,6 +5,7 @@
 #include <string>
 
 #include "ccpol_impl.hpp"
+#include "dual.hpp"
 #include "opcount.hpp"
 #include "pes.hpp"
 #include "tables.hpp"
@@ -81,6 +82,23 @@ int orc_ccpol_opcount(const double* xyz18, double* counts, int ncounts, double* 
   Counted e = ccpol<Counted>(g_tab, w);
   if (E) *E = e.v;
   for (int i = 0; i < ncounts && i < Counted::NKIND; ++i) counts[i] = (double)Counted::cnt[i];
+  return 0;
+}
+// V (Hartree) and its ANALYTIC gradient (Hartree/bohr) at x(3,6) in bohr by forward-mode dual numbers (dual.hpp)
+// through the same templates: V = ccpol(x * 0.529177)/627.510 (mcmod_waterdimer_ccpol.f90:18-37, V0 not subtracted).
+int orc_ccpol_analytic_gradient(const double* x_bohr18, double* V, double* grad18) {
+  if (!g_tab_loaded) { g_err = "tables not loaded"; return 1; }
+  Dual w[18];
+  for (int i = 0; i < 18; ++i) {
+    Dual xi(x_bohr18[i]);
+    xi.d[i] = 1.0;
+    w[i] = xi * Dual(0.529177);
+  }
+  bool conv = true;
+  Dual e = ccpol<Dual>(g_tab, w, &conv) / Dual(627.510);
+  if (!conv) { g_err = "No convergence in indN_iter"; return 2; }
+  if (V) *V = e.v;
+  for (int i = 0; i < 18; ++i) grad18[i] = e.d[i];
   return 0;
 }
 int orc_opcount_kinds() { return Counted::NKIND; }

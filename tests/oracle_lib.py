@@ -122,6 +122,15 @@ class Oracle:
         self._chk(self.L.orc_ccpol_energy_ang(_p(x), ctypes.byref(e)))
         return e.value
 
+    def ccpol_analytic_gradient(self, x):
+        """x(3,6) bohr -> (V Hartree without V0, grad(3,6) Hartree/bohr): forward-mode dual numbers through the oracle's
+        templates (oracle/dual.hpp) — the analytic gradient the reference does not have"""
+        xk = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(3, 6).T.reshape(-1))
+        v = ctypes.c_double()
+        g = np.zeros(18)
+        self._chk(self.L.orc_ccpol_analytic_gradient(_p(xk), ctypes.byref(v), _p(g)))
+        return v.value, g.reshape(6, 3).T.copy()
+
     def ccpol_opcount(self, xyz18):
         nk = self.L.orc_opcount_kinds()
         cnt = np.zeros(nk)
