@@ -7,6 +7,7 @@ import ctypes
 import numpy as np
 
 from ._lib import check, f64, hptr, lib
+from .path import rotate_atoms  # noqa: F401  (instantonmod.f90:346-376; re-exported)
 
 
 class InstantonMod:
@@ -218,18 +219,3 @@ class InstantonMod:
         return {"lndetj0": lndetj0, "lndetj": lndetj, "skipped0": int(np.sum(eta0 <= 0.0)), "skipped": int(np.sum(tail <= 0.0)),
                 "phi": phi, "s_kink": float(s_kink), "theta": float(theta), "delta": float(2.0 * theta / self.betan)}
 
-
-def rotate_atoms(atoms, axis, theta):
-    """instantonmod.f90:346-376: rotation of (3, natom) coordinates about `axis` (1, 2 or 3) by theta; the identity for
-    |theta| <= 1e-10 like the reference"""
-    atoms = np.array(atoms, dtype=np.float64)
-    if abs(theta) <= 1e-10:
-        return atoms
-    j, k = {1: (1, 2), 2: (0, 2), 3: (0, 1)}[axis]
-    r = np.zeros((3, 3))
-    r[axis - 1, axis - 1] = 1.0
-    r[j, j] = np.cos(theta)
-    r[k, k] = np.cos(theta)
-    r[k, j] = -np.sin(theta)
-    r[j, k] = np.sin(theta)
-    return r @ atoms

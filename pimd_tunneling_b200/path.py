@@ -136,3 +136,64 @@ def acceptor_switch_path(well1, well2, npath=9):
         g[:, 5] = O + rot(H2 - O, s * np.pi)
         pts[k] = g + s * (w2 - end)
     return pts
+
+
+# ---- alignment of the wells (instantonmod.f90:222-376), host side, O(natom) ---------------------------------------
+def rotate_atoms(atoms, axis, theta):
+    """instantonmod.f90:346-376: (3, natom) coordinates rotated about `axis` (1, 2, 3) by theta; identity for
+    |theta| <= 1e-10 like the reference"""
+    atoms = np.array(atoms, dtype=np.float64)
+    if abs(theta) <= 1e-10:
+        return atoms
+    j, k = {1: (1, 2), 2: (0, 2), 3: (0, 1)}[axis]
+    r = np.zeros((3, 3))
+    r[axis - 1, axis - 1] = 1.0
+    r[j, j] = np.cos(theta)
+    r[k, k] = np.cos(theta)
+    r[k, j] = -np.sin(theta)
+    r[j, k] = np.sin(theta)
+    return r @ atoms
+
+
+def get_align(atomsin, atom1=1, atom2=2, atom3=3):
+    """get_align (instantonmod.f90:222-264): angles that put atom1 at the origin, atom1->atom2 on the x axis and atom3
+    in the xz plane, and the origin shift.  atoms (3, natom); atom indices 1-based like mcmod_mass's atom1..3."""
+    atomsin = np.asarray(atomsin, dtype=np.float64)
+    if atomsin.shape[0] != 3:
+        raise ValueError("Wrong number of dimensions; change align_atoms subroutine!")
+    i1, i2, i3 = atom1 - 1, atom2 - 1, atom3 - 1
+    origin = atomsin[:, i1].copy()
+    atoms = atomsin - origin[:, None]
+    w = atoms[:, i2] - atoms[:, i1]
+    theta1 = float(np.arctan2(w[1], w[0]))
+    atoms = rotate_atoms(atoms, 3, theta1)
+    w = atoms[:, i2] - atoms[:, i1]
+    theta2 = float(np.arctan2(w[2], w[0]))
+    atoms = rotate_atoms(atoms, 2, theta2)
+    w = atoms[:, i3] - atoms[:, i1]
+    theta3 = float(-np.arctan2(w[1], w[2]))
+    return theta1, theta2, theta3, origin
+
+
+def align_atoms(atomsin, theta1, theta2, theta3, origin=None, atom1=1):
+    """align_atoms (instantonmod.f90:269-312): atom1 to the origin (its own position, as in the reference — `origin`
+    is accepted and unused there), then the three rotations; the input unchanged if all angles are below 1e-10"""
+    atomsin = np.asarray(atomsin, dtype=np.float64)
+    if atomsin.shape[0] != 3:
+        raise ValueError("Wrong number of dimensions; change align_atoms subroutine!")
+    if not any(abs(t) > 1e-10 for t in (theta1, theta2, theta3)):
+        return atomsin.copy()
+    out = atomsin - atomsin[:, atom1 - 1][:, None]
+    out = rotate_atoms(out, 3, theta1)
+    out = rotate_atoms(out, 2, theta2)
+    return rotate_atoms(out, 1, theta3)
+
+
+def align_wells(well1, well2, alignwell=False, atoms=(1, 2, 3)):
+    """pimd_par.f90:159-165: well1 aligned by its own angles; well2 by the same angles, or by its own if alignwell"""
+    t = get_align(well1, *atoms)
+    w1 = align_atoms(well1, t[0], t[1], t[2], t[3], atoms[0])
+    if alignwell:
+        t = get_align(well2, *atoms)
+    w2 = align_atoms(well2, t[0], t[1], t[2], t[3], atoms[0])
+    return np.asfortranarray(w1), np.asfortranarray(w2)

@@ -3,7 +3,7 @@
 masses files (:119-165), V0 = V(well1) (:166), spline path (read_path), Gauss-Legendre nodes and end points
 (:212-221), the (lambda x repetition) task layout (:243-257, 281-295), ONE batched propagate call instead of
 the task loop (:321-381), and the statistics (:397-424) with one all-reduce instead of MPI_Gather (:389).
-Alignment of the wells (get_align/align_atoms) is the identity here (out of scope).  All
+The wells are aligned like pimd_par.f90:159-165 (get_align/align_atoms, path.py) for ndim = 3 and used as given otherwise.  All
 numerical work is done by libpimdk.so."""
 import re
 from dataclasses import dataclass, field
@@ -36,6 +36,7 @@ class MCData:
     cayley: bool = False
     fixedends: bool = True
     dHdrlimit: float = -1.0
+    alignwell: bool = False
     seed: int = 0
     extra: dict = field(default_factory=dict)
 
@@ -85,6 +86,8 @@ def run_ti(pes_name, mc, well1, well2, mass, path_points=None, rank=0, world=1, 
     pes = McmodMass(pes_name).V_init()
     well1 = np.asfortranarray(well1, dtype=np.float64)
     well2 = np.asfortranarray(well2, dtype=np.float64)
+    if pes.ndim == 3:   # pimd_par.f90:159-165 (the reference STOPs for ndim != 3; there the wells are used as given)
+        well1, well2 = P.align_wells(well1, well2, mc.alignwell, (pes.atom1, pes.atom2, pes.atom3))
     pes.set_V0(0.0)
     pes.set_V0(pes.V(well1))                                   # V0 = V(well1), pimd_par.f90:166
     if path_points is None:

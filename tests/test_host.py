@@ -170,3 +170,27 @@ def test_multiwell_waterdimer_postprocessing():
     assert abs(out["E-"]["level_cm"] - ref) <= 1e-12 * abs(ref)
     lv = [out[k]["level_cm"] for k in out]
     assert all(np.isfinite(lv)) and lv[3] > lv[0] and lv[4] > 0      # acceptor-tunnelling partners lie above A1+
+
+
+def test_alignment_of_the_wells():
+    """get_align / align_atoms / rotate_atoms (instantonmod.f90:222-376) as pimd_par.f90:159-165 uses them: atom1 to the
+    origin, atom1->atom2 on the x axis, atom3 in the xz plane; rigid motion (distances kept); well2 carried by well1's
+    angles unless alignwell; identity below the reference's 1e-10 angle threshold."""
+    from pimd_tunneling_b200 import path as P
+
+    rng = np.random.default_rng(3)
+    w1, w2 = rng.normal(size=(3, 6)), rng.normal(size=(3, 6))
+    a1, a2 = P.align_wells(w1, w2)
+    assert np.abs(a1[:, 0]).max() == 0.0 and np.abs(a1[1:, 1]).max() < 1e-15 and abs(a1[1, 2]) < 1e-15 and a1[0, 1] > 0
+    dist = lambda a: np.linalg.norm(a[:, :, None] - a[:, None, :], axis=0)
+    assert np.abs(dist(a1) - dist(w1)).max() < 1e-14 and np.abs(dist(a2) - dist(w2)).max() < 1e-14
+    # well2 moved by well1's rotation: relative orientation of the two wells is kept
+    t = P.get_align(w1)
+    r = lambda x: P.rotate_atoms(P.rotate_atoms(P.rotate_atoms(x, 3, t[0]), 2, t[1]), 1, t[2])
+    assert np.abs(a2 - r(w2 - w2[:, :1])).max() < 1e-14
+    b1, b2 = P.align_wells(w1, w2, alignwell=True)
+    assert np.array_equal(b1, a1) and np.abs(b2[1:, 1]).max() < 1e-15 and abs(b2[1, 2]) < 1e-15
+    # already aligned: all three angles below 1e-10 -> the reference copies the input (no shift to atom1 either)
+    assert np.array_equal(P.align_atoms(a1 + 5.0, 0.0, 0.0, 0.0), a1 + 5.0)
+    with pytest.raises(ValueError):
+        P.get_align(np.zeros((2, 3)))
