@@ -59,6 +59,25 @@ class InstantonMod:
                                                self.betan, 1 if self.fixedends else 0, hptr(f), hptr(g)))
         return g, f
 
+    def instanton(self, xtilde, a=None, b=None, m=8, factr=1e6, pgtol=None, maxls=40, maxiter=15000):
+        """`call instanton(xtilde[, a, b])` (instantonmod.f90:679-777): L-BFGS-B (m = 8, factr = 1e6, pgtol = eps2, the
+        reference's settings; scipy's implementation of lbfgsb.f) on the GPU action and gradient.  Returns the
+        optimised xtilde(n,ndim,natom)."""
+        from scipy.optimize import fmin_l_bfgs_b
+
+        p = self.pes
+        shape = (self.n, p.ndim, p.natom)
+        x0 = np.asarray(xtilde, dtype=np.float64).reshape(shape, order="F")
+
+        def fg(v):
+            g_, f_ = self.UMforceenergy(v.reshape(shape, order="F"), a, b)
+            return f_, g_.reshape(-1, order="F")
+
+        xs, self.last_UM, self.last_info = fmin_l_bfgs_b(fg, x0.reshape(-1, order="F"), m=m, factr=factr,
+                                                         pgtol=p.eps2 if pgtol is None else pgtol, maxls=maxls,
+                                                         maxiter=maxiter)
+        return np.asfortranarray(xs.reshape(shape, order="F"))
+
     def instanton_batch(self, xtilde0, well1, endpoints, m=8, factr=1e6, pgtol=None, maxls=40, maxiter=15000):
         """`call instanton(xtilderot, well1, endpoints(ii,:,:))` (instantonmod.f90:679-777) for every end point of
         the solid-angle loop (rpi_par.f90:252-255), run side by side.  Each optimisation is an ordinary L-BFGS-B run

@@ -197,3 +197,111 @@ def align_wells(well1, well2, alignwell=False, atoms=(1, 2, 3)):
         t = get_align(well2, *atoms)
     w2 = align_atoms(well2, t[0], t[1], t[2], t[3], atoms[0])
     return np.asfortranarray(w1), np.asfortranarray(w2)
+
+
+# ---- read_path (instantonmod.f90:895-1035) -------------------------------------------------------------------------
+def read_xyz_frames(filename, ndim, natom, xunit=1):
+    """path.xyz: per frame a count line, a comment line, natom lines `label x [y [z]]` (instantonmod.f90:917-926);
+    xunit = 2: Angstrom -> bohr by /0.529177.  Returns points(npath, ndim, natom)."""
+    frames = []
+    with open(filename) as f:
+        lines = [l for l in f.read().splitlines()]
+    i = 0
+    while i < len(lines):
+        if not lines[i].strip():
+            i += 1
+            continue
+        int(lines[i].split()[0])            # `read(15,*) dummy`
+        rows = lines[i + 2:i + 2 + natom]
+        if len(rows) < natom:
+            raise ValueError("truncated frame in %s" % filename)
+        pt = np.array([[float(t.lower().replace("d", "e")) for t in r.split()[1:1 + ndim]] for r in rows]).T
+        frames.append(pt / 0.529177 if xunit == 2 else pt)
+        i += 2 + natom
+    return np.array(frames)
+
+
+def findmiddle(x1, x2, lampath, vpath):
+    """findmiddle (instantonmod.f90:832-871): bisection (40 steps, 1e-6) for the zero of dV/dlambda of the splined
+    V(lambda) between x1 and x2 — the top of the barrier along the path"""
+    lampath, vpath = np.asarray(lampath, dtype=np.float64), np.asarray(vpath, dtype=np.float64)
+    spl = spline(lampath, vpath)
+    fmid = splin_grad(lampath, vpath, spl, x2)
+    f = splin_grad(lampath, vpath, spl, x1)
+    if f * fmid >= 0.0:
+        raise ValueError("root must be bracketed in findmiddle")
+    if f < 0.0:
+        mid, dx = x1, x2 - x1
+    else:
+        mid, dx = x2, x1 - x2
+    for _ in range(40):
+        dx = dx * 0.5
+        xm = mid + dx
+        fm = splin_grad(lampath, vpath, spl, xm)
+        if fm <= 0.0:
+            mid = xm
+        if abs(dx) < 1e-6 or fm == 0.0:
+            return mid
+    raise ValueError("too many bisections in findmiddle")
+
+
+def centre_lampath(lampath, vpath):
+    """the `centre` branch of read_path (:996-1010): reparametrise lambda so that the barrier top sits at 1/2"""
+    lampath = np.asarray(lampath, dtype=np.float64)
+    xmiddle = findmiddle(0.3, 0.7, lampath, vpath)
+    a = 2.0 - 4.0 * xmiddle
+    b = 4.0 * xmiddle - 1.0
+    if a >= 0:
+        out = -0.5 * b / a + np.sqrt((lampath / a) + (0.5 * b / a) ** 2)
+    else:
+        out = -0.5 * b / a - np.sqrt((lampath / a) + (0.5 * b / a) ** 2)
+    return out, a, b, xmiddle
+
+
+def read_path(points, V_batch, n, align=True, instanton=None, well1=None, well2=None, fixedends=True, centre=False,
+              atoms=(1, 2, 3)):
+    """read_path (instantonmod.f90:895-1035) on frames already parsed (read_xyz_frames):
+      * frames aligned by the FIRST frame's angles (:927-931; for ndim != 3 the reference STOPs in get_align — there the
+        frames are used as given),
+      * lampath = cumulative Euclidean distance / total (:932, 936), Vpath = V along the path (V_batch: callable on
+        (ndim, natom, npath) -> energies; the PES plugin's batched V),
+      * xtilde(k) = path(lambda = (k-1)/(n-1)) (:947-949),
+      * instanton (callable xtilde -> optimised xtilde; InstantonMod.instanton) refines the path (:953-990): new path =
+        well1, xtilde, well2 (fixedends) or xtilde, re-parametrised by arc length,
+      * centre: barrier top moved to lambda = 1/2 (:996-1010),
+      * natural splines of every coordinate (:1014-1022).
+    Returns dict(lampath, path, splinepath, Vpath, xtilde[, centre=(a, b, xmiddle)])."""
+    pts = np.asarray(points, dtype=np.float64)
+    if align and pts.shape[1] == 3:
+        t = get_align(pts[0], *atoms)
+        pts = np.array([align_atoms(f, t[0], t[1], t[2], t[3], atoms[0]) for f in pts])
+    lam, path, spl = build_path(pts)
+    nd, na = path.shape[1], path.shape[2]
+
+    def beads(lam, path, spl):
+        xt = np.empty((n, nd, na), order="F")
+        for i in range(nd):
+            for j in range(na):
+                for k in range(n):
+                    xt[k, i, j] = splint(lam, path[:, i, j], spl[:, i, j], k / (n - 1.0))
+        return xt
+
+    xtilde = beads(lam, path, spl)
+    if instanton is not None:
+        xtilde = np.asfortranarray(instanton(xtilde))
+        if fixedends:
+            pts = np.concatenate([np.asarray(well1, dtype=np.float64)[None], xtilde, np.asarray(well2, dtype=np.float64)[None]])
+        else:
+            pts = np.array(xtilde)
+        lam, path, spl = build_path(pts)
+    vpath = np.asarray(V_batch(np.asfortranarray(np.moveaxis(path, 0, 2))), dtype=np.float64)
+    out = {"Vpath": vpath, "xtilde": xtilde}
+    if centre:
+        lam, a, b, xm = centre_lampath(lam, vpath)
+        out["centre"] = (a, b, xm)
+        spl = np.zeros_like(path, order="F")
+        for i in range(nd):
+            for j in range(na):
+                spl[:, i, j] = spline(lam, path[:, i, j])
+    out.update({"lampath": lam, "path": path, "splinepath": spl})
+    return out

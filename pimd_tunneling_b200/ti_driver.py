@@ -37,6 +37,14 @@ class MCData:
     fixedends: bool = True
     dHdrlimit: float = -1.0
     alignwell: bool = False
+    npath: int = 0
+    readpath: bool = True
+    instapath: bool = False
+    centre: bool = False
+    readhess: bool = False
+    atom1: int = 1
+    atom2: int = 2
+    atom3: int = 3
     seed: int = 0
     extra: dict = field(default_factory=dict)
 
@@ -80,19 +88,34 @@ def read_wells(path1, path2, masses_path, ndim, natom, xunit=1):
     return np.asfortranarray(w1), np.asfortranarray(w2), np.array(mass[:natom]), labels[:natom]
 
 
-def run_ti(pes_name, mc, well1, well2, mass, path_points=None, rank=0, world=1, max_traj_per_call=None):
+def run_ti(pes_name, mc, well1, well2, mass, path_points=None, rank=0, world=1, max_traj_per_call=None, path_file=None):
     """One TI run.  Returns the statistics of pimd_par.f90:397-424 plus the per-trajectory integrands of this
-    rank.  With world > 1 (torch.distributed initialised) the estimator sums are all-reduced."""
+    rank.  With world > 1 (torch.distributed initialised) the estimator sums are all-reduced.
+    The path: `path_file` (the reference's path.xyz, read like read_path with mc.xunit, mc.instapath, mc.centre) or
+    `path_points` (frames already in bohr) or, with neither, the straight line between the wells."""
     pes = McmodMass(pes_name).V_init()
     well1 = np.asfortranarray(well1, dtype=np.float64)
     well2 = np.asfortranarray(well2, dtype=np.float64)
+    atoms = (mc.atom1, mc.atom2, mc.atom3)
     if pes.ndim == 3:   # pimd_par.f90:159-165 (the reference STOPs for ndim != 3; there the wells are used as given)
-        well1, well2 = P.align_wells(well1, well2, mc.alignwell, (pes.atom1, pes.atom2, pes.atom3))
+        well1, well2 = P.align_wells(well1, well2, mc.alignwell, atoms)
     pes.set_V0(0.0)
     pes.set_V0(pes.V(well1))                                   # V0 = V(well1), pimd_par.f90:166
+    if path_file is not None:
+        path_points = P.read_xyz_frames(path_file, pes.ndim, pes.natom, mc.xunit)
     if path_points is None:
         path_points = np.stack([well1, well2], axis=0)
-    lam, path, spl = P.build_path(path_points)
+        lam, path, spl = P.build_path(path_points)
+    else:
+        refine = None
+        if mc.instapath:   # read_path :953-990: the instanton found from the splined guess becomes the path
+            from .instantonmod import InstantonMod
+
+            im = InstantonMod(pes, mass, mc.beta, mc.n, fixedends=mc.fixedends, rpi=False)
+            refine = (lambda xt: im.instanton(xt, well1, well2)) if mc.fixedends else (lambda xt: im.instanton(xt))
+        rp = P.read_path(path_points, pes.V_batch, mc.n, align=True, instanton=refine, well1=well1, well2=well2,
+                         fixedends=mc.fixedends, centre=mc.centre, atoms=atoms)
+        lam, path, spl = rp["lampath"], rp["path"], rp["splinepath"]
     vi = VerletInt(pes, mc.n, mass, mc.beta, tau=mc.tau, gamma=mc.gamma, dt=mc.dt, NMC=mc.NMC, imin=mc.imin,
                    Noutput=mc.Noutput, cayley=mc.cayley, seed=mc.seed).init_nm()
     xi, weights = vi.gauleg(0.0, 1.0, mc.nintegral)
@@ -106,7 +129,7 @@ def run_ti(pes_name, mc, well1, well2, mass, path_points=None, rank=0, world=1, 
     step = max_traj_per_call or gid.size or 1
     for s in range(0, gid.size, step):
         sl = slice(s, min(gid.size, s + step))
-        x, p = vi.init_path(xi[il[sl]], lam, path, spl, traj_gid=gid[sl])
+        x, p = vi.init_path(xi[il[sl]], lam, path, spl, traj_gid=gid[sl], readhess=mc.readhess)
         b = np.asfortranarray(xint[:, :, il[sl]])
         dbdl = np.asfortranarray(dbdxi[:, :, il[sl]])
         fn = vi.propagate_pimd_pile if mc.thermostat == PILE else vi.propagate_pimd_nm

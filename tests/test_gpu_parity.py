@@ -712,6 +712,32 @@ def test_ti_ratio_matches_exact_path_integral(pk, name, n, beta, thermostat):
     assert abs(np.log(res["q_over_q0"]) - got) < 1e-12
 
 
+def test_ti_along_a_curved_path_file_gives_the_same_ratio(pk, tmp_path):
+    """q/q0 depends on the end points only, not on the path b(xi) between them: a TI run along a curved path read from a
+    path.xyz file (read_xyz_frames -> read_path: arc-length lampath, natural splines, xint/dbdxi on the curve) must
+    reproduce the same exact ln(q/q0) = -1.147 as the straight line.  The frames lie on the arc of radius 3 between the
+    two wells; the second run refines that guess to the instanton first (instapath, read_path :953-990)."""
+    import exact_pi
+    from pimd_tunneling_b200.ti_driver import MCData, run_ti
+
+    n, beta = 15, 4.0
+    a = np.array([[3.0], [0.0]])
+    b = np.array([[3.0 * np.cos(np.pi / 3)], [3.0 * np.sin(np.pi / 3)]])
+    f = tmp_path / "path.xyz"
+    ang = np.linspace(0.0, np.pi / 3, 11)
+    f.write_text("".join("1\npoint %d\nX %.12f %.12f\n" % (i, 3.0 * np.cos(t), 3.0 * np.sin(t)) for i, t in enumerate(ang)))
+    exact = exact_pi.log_ratio_2d(a[:, 0], b[:, 0], n, beta)
+    betan = beta / (n + 1)
+    for instapath, seed in ((False, 11), (True, 12)):
+        mc = MCData(n=n, beta=beta, NMC=60000, imin=5000, dt=2e-3, nintegral=12, nrep=256, thermostat=2, ndim=2, natom=1,
+                    instapath=instapath, seed=seed)
+        res = run_ti("2dtest", mc, a, b, [1.0], path_file=str(f))
+        got = -betan * res["deltaA"]
+        se = betan * np.sqrt(res["sigmaA"] / mc.nrep)
+        print("curved path%s: ln(q/q0) %.5f +/- %.5f, exact %.5f" % (" (instanton)" if instapath else "", got, se, exact))
+        assert se < 0.03 and abs(got - exact) < 4.5 * se, (instapath, got, exact, se)
+
+
 # ---------------------------------------------------------------- second derivatives (row N2) -----
 def test_vdoubleprime_bit_exact(pk, orc):
     """Vdoubleprime of the three plugins against the oracle's literal restatement, including the in-place drift"""

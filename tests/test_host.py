@@ -194,3 +194,35 @@ def test_alignment_of_the_wells():
     assert np.array_equal(P.align_atoms(a1 + 5.0, 0.0, 0.0, 0.0), a1 + 5.0)
     with pytest.raises(ValueError):
         P.get_align(np.zeros((2, 3)))
+
+
+def test_read_path_pieces(tmp_path):
+    """read_path (instantonmod.f90:895-1035) on the host: xyz frames (xunit = 2 converts from Angstrom), arc-length
+    lampath, findmiddle's bisection for the barrier top, the `centre` reparametrisation that moves it to 1/2, and the
+    instanton refinement hook (path = well1, xtilde, well2)."""
+    from pimd_tunneling_b200 import path as P
+
+    xs = np.array([-1.0, -0.8, -0.55, -0.2, 0.25, 0.5, 0.7, 0.9, 1.0])
+    f = tmp_path / "path.xyz"
+    f.write_text("".join("1\nframe %d\nX %.10f\n" % (i, x * 0.529177) for i, x in enumerate(xs)))
+    pts = P.read_xyz_frames(str(f), 1, 1, xunit=2)
+    assert pts.shape == (9, 1, 1) and np.abs(pts[:, 0, 0] - xs).max() < 1e-9
+    V = lambda x: (x[0, 0, :] ** 2 - 1.0) ** 2
+    r = P.read_path(pts, V, n=7)
+    assert np.abs(r["lampath"] - (xs + 1.0) / 2.0).max() < 1e-9 and np.abs(r["Vpath"] - (xs ** 2 - 1) ** 2).max() < 1e-9
+    assert np.abs(r["xtilde"][:, 0, 0] - np.linspace(-1, 1, 7)).max() < 1e-3
+    xm = P.findmiddle(0.3, 0.7, r["lampath"], r["Vpath"])
+    assert abs(xm - 0.5) < 2e-2                         # top of the splined barrier: x = 0 <-> lambda = 1/2
+    # an asymmetric parametrisation is pulled back to the middle
+    lam2 = r["lampath"] ** 1.6
+    lam2 /= lam2[-1]
+    xm2 = P.findmiddle(0.2, 0.8, lam2, r["Vpath"])
+    lamc, a, b, xmid = P.centre_lampath(lam2, r["Vpath"]) if 0.3 < xm2 < 0.7 else (None, 0, 0, xm2)
+    if lamc is not None:
+        assert abs(a * 0.25 + b * 0.5 - xmid) < 1e-12      # the quadratic map sends 1/2 to the old barrier position
+        assert lamc[0] == 0.0 and abs(lamc[-1] - 1.0) < 1e-12 and np.all(np.diff(lamc) > 0)
+    # instanton hook with fixed ends: new path = well1, refined beads, well2
+    w1, w2 = np.array([[-1.0]]), np.array([[1.0]])
+    r2 = P.read_path(pts, V, n=7, instanton=lambda xt: xt * 0.9, well1=w1, well2=w2)
+    assert r2["path"].shape == (9, 1, 1) and r2["path"][0, 0, 0] == -1.0 and r2["path"][-1, 0, 0] == 1.0
+    assert np.abs(r2["path"][1:-1, 0, 0] - 0.9 * r["xtilde"][:, 0, 0]).max() < 1e-15
