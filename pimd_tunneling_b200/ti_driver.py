@@ -49,12 +49,13 @@ class MCData:
     extra: dict = field(default_factory=dict)
 
 
-def read_namelist(text):
-    """&MCDATA key=value, ... /   (Fortran logicals .true./.false., d-exponents)"""
-    body = re.search(r"&\s*MCDATA(.*?)(/|&end)", text, flags=re.S | re.I)
+def read_namelist(text, group="MCDATA", into=None):
+    """&MCDATA key=value, ... /   (Fortran logicals .true./.false., d-exponents); `group`/`into` select another
+    namelist group and its dataclass (rpi_driver reads &RPIDATA with this)"""
+    body = re.search(r"&\s*" + group + r"(.*?)(/|&end)", text, flags=re.S | re.I)
     if not body:
-        raise ValueError("no &MCDATA namelist found")
-    mc = MCData()
+        raise ValueError("no &%s namelist found" % group)
+    mc = MCData() if into is None else into
     for key, val in re.findall(r"(\w+)\s*=\s*([^,\n/]+)", body.group(1)):
         v = val.strip().strip("'\"")
         lk = {f.lower(): f for f in mc.__dataclass_fields__}

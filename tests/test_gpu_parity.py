@@ -920,6 +920,26 @@ def test_rpi_splitting_matches_the_analytic_instanton(pk):
     assert abs(r["delta"] - delta) < 5e-4 * delta, (r["delta"], delta)
 
 
+def test_rpi_front_end_reproduces_the_analytic_instanton(pk):
+    """`program rpi` through the native front end (namelist RPIDATA, linear-interpolation guess, instanton, V0 shift,
+    single-well Q_0, closing formulas): the quartic double well with m = 20 again, now from a namelist."""
+    from pimd_tunneling_b200.rpi_driver import read_rpidata, run_rpi
+
+    rd = read_rpidata("&RPIDATA\n n=512, beta=40.0d0, ndim=1, natom=1, readpath=.false., fixedends=.true.\n/\n")
+    assert (rd.n, rd.beta, rd.ndim, rd.readpath, rd.npoints) == (512, 40.0, 1, False, 10)
+    pes = pk.McmodMass("1d")
+    eps2 = pes.eps2
+    pk.McmodMass.eps2 = 1e-7          # pgtol (module variable eps2 of mcmod_mass) for a converged kink
+    try:
+        r = run_rpi("1d", rd, np.array([[-1.0]]), np.array([[1.0]]), [20.0])
+    finally:
+        pk.McmodMass.eps2 = eps2
+    S = 4.0 / 3.0 * np.sqrt(40.0)
+    delta = 2.0 * np.sqrt(8.0 / 20.0) * np.sqrt(6.0 * S / np.pi) * np.exp(-S)
+    assert abs(r["s_kink"] - S) < 1e-4 * S and abs(r["delta"] - delta) < 5e-4 * delta, (r["s_kink"], S, r["delta"], delta)
+    assert r["Vpath"].min() >= 0.0 and abs(r["lampath"][-1] - 1.0) < 1e-15
+
+
 def test_full_size_c4_step_is_partition_invariant(pk):
     """BASELINE config C4 at its full size (512 beads x 8192 trajectories, CCpol-8sf, PILE): one step of the whole
     batch, then 12 sampled trajectories re-run alone and in a different order.  Results are keyed by the global
