@@ -82,3 +82,23 @@ def run_rpi(pes_name, rd, well1, well2, mass, path_points=None, path_file=None):
     else:
         out.update(im.rpi_splitting(xtilde, well1, well2))
     return out
+
+
+def crossover(pes, tstate, mass):
+    """`program crossover` (crossover.f90): mass-weighted Hessian of the transition state (Vdoubleprime on the GPU),
+    its eigenvalues, and the crossover inverse temperature 2 pi / sqrt(-eta2_1) below which the instanton exists.
+    (The reference fills hessmat with `do j2 = 1, ndim` where natom is meant (crossover.f90:51), so for natom != ndim
+    part of its matrix is never assigned; the full matrix is formed here.)  Returns (beta_c, etasquared)."""
+    mass = np.asarray(mass, dtype=np.float64).reshape(pes.natom)
+    h = pes.Vdoubleprime(np.asarray(tstate, dtype=np.float64).reshape(pes.ndim, pes.natom))
+    nd = pes.ndim * pes.natom
+    m = np.empty((nd, nd))
+    for i1 in range(pes.ndim):
+        for j1 in range(pes.natom):
+            for i2 in range(pes.ndim):
+                for j2 in range(pes.natom):
+                    m[j1 * pes.ndim + i1, j2 * pes.ndim + i2] = h[i1, j1, i2, j2] / np.sqrt(mass[j1] * mass[j2])
+    eta = np.linalg.eigvalsh(0.5 * (m + m.T))
+    if not eta[0] < 0.0:
+        raise ValueError("no negative Hessian eigenvalue: not a transition state")
+    return 2.0 * np.pi / np.sqrt(-eta[0]), eta

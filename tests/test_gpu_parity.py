@@ -940,6 +940,24 @@ def test_rpi_front_end_reproduces_the_analytic_instanton(pk):
     assert r["Vpath"].min() >= 0.0 and abs(r["lampath"][-1] - 1.0) < 1e-15
 
 
+def test_crossover_temperature(pk):
+    """`program crossover`: V = (x^2-1)^2 has V''(0) = -4, so beta_c = 2 pi / sqrt(4/m) = pi sqrt(m); the 2D surface's
+    saddle between two wells (on the ring, at the half angle) has exactly one negative eigenvalue."""
+    from pimd_tunneling_b200.rpi_driver import crossover
+
+    pes = pk.McmodMass("1d").V_init()
+    bc, eta = crossover(pes, [[0.0]], [7.0])
+    assert abs(bc - np.pi * np.sqrt(7.0)) < 1e-6 * bc and abs(eta[0] + 4.0 / 7.0) < 1e-6   # Vdoubleprime is a finite difference (mcmod_1d.f90:37-57)
+    pes2 = pk.McmodMass("2dtest").V_init()
+    # radial position of the saddle on the 30-degree ray: maximum along the ring direction, minimum radially
+    r = np.linspace(2.0, 4.0, 4001)
+    ts = np.zeros((2, 1, r.size), order="F")
+    ts[0, 0], ts[1, 0] = r * np.cos(np.pi / 6), r * np.sin(np.pi / 6)
+    rs = r[np.argmin(pes2.V_batch(ts))]
+    bc2, eta2 = crossover(pes2, [[rs * np.cos(np.pi / 6)], [rs * np.sin(np.pi / 6)]], [1.0])
+    assert eta2[0] < 0.0 < eta2[1] and np.isfinite(bc2)
+
+
 def test_full_size_c4_step_is_partition_invariant(pk):
     """BASELINE config C4 at its full size (512 beads x 8192 trajectories, CCpol-8sf, PILE): one step of the whole
     batch, then 12 sampled trajectories re-run alone and in a different order.  Results are keyed by the global
