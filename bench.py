@@ -378,6 +378,19 @@ def run_ours(args, cfg, rank, world, local_rank):
                          "achieved_sass_note": "2*DFMA+DMUL+DADD executed per bead-gradient (ncu, profiles/) / kernel time"},
             "clocks": sampler.summary(),
         }
+        # the same step seen from the memory side (not its bound): DRAM bytes of the PES pipeline per step (ncu, profiles/)
+        # plus the streamed state traffic, against the measured copy bandwidth of MEASURED_PEAKS.json
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            hbm_peak, hbm_src = 6500.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+        if cfg["pes"] == "ccpol8sf":
+            gb = CCPOL_DRAM_BYTES_PER_BEAD * ntraj * n / 1e9 + 10 * 8 * ndof * ntraj * n / 1e9
+            line["roofline_hbm"] = {"bound": "hbm", "achieved": gb / (ms / K * 1e-3), "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": gb / (ms / K * 1e-3) / hbm_peak, "traffic": gb, "peak_source": hbm_src,
+                                    "note": "supplementary view: the step is FP64-bound (roofline above); its DRAM traffic uses "
+                                            "this fraction of the HBM bandwidth"}
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             per_step = 12 if cfg["pes"] == "ccpol8sf" else 400
