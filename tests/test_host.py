@@ -226,3 +226,103 @@ def test_read_path_pieces(tmp_path):
     r2 = P.read_path(pts, V, n=7, instanton=lambda xt: xt * 0.9, well1=w1, well2=w2)
     assert r2["path"].shape == (9, 1, 1) and r2["path"][0, 0, 0] == -1.0 and r2["path"][-1, 0, 0] == 1.0
     assert np.abs(r2["path"][1:-1, 0, 0] - 0.9 * r["xtilde"][:, 0, 0]).max() < 1e-15
+
+
+def _c_prototypes():
+    """{name: (return kind, [argument kinds])} of include/pimdk.h; kinds: i64 / f64 by value, ptr"""
+    hdr = open(os.path.join(ROOT, "include", "pimdk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"^((?:const\s+)?[A-Za-z_0-9]+\s*\*?)\s*(pimdk_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr, flags=re.M):
+        kinds = []
+        for a in [s.strip() for s in args.replace("\n", " ").split(",")]:
+            if a in ("void", ""):
+                continue
+            if "*" in a:
+                kinds.append("ptr")
+            elif re.match(r"(pimdk_int|uint64_t|int64_t)\b", a):
+                kinds.append("i64")
+            elif re.match(r"double\b", a):
+                kinds.append("f64")
+            else:
+                raise AssertionError("unclassified C argument %r of %s" % (a, name))
+        r = ret.replace(" ", "")
+        protos[name] = ({"int": "int", "pimdk_int": "i64", "constchar*": "ptr"}[r], kinds)
+    return protos
+
+
+def _fortran_interfaces():
+    """the same from the interface block of fortran/pimdk_mod.f90 (no Fortran compiler exists in this image, so the
+    shim cannot be compiled here: this is the check that it at least agrees with the header argument by argument)"""
+    src = open(os.path.join(ROOT, "fortran", "pimdk_mod.f90")).read()
+    block = src[src.index("interface"):src.index("end interface")]
+    block = re.sub(r"&\s*\n\s*", " ", block)
+    out = {}
+    for m in re.finditer(r"^\s*(integer\(c_int\)|integer\(c_int64_t\)|type\(c_ptr\))\s+function\s+(\w+)\s*\(([^)]*)\)\s*"
+                         r"bind\(C,\s*name=\"(\w+)\"\)(.*?)end function", block, flags=re.S | re.M | re.I):
+        ret, fname, dummies, cname, body = m.groups()
+        assert fname == cname
+        dummies = [d.strip().lower() for d in dummies.split(",") if d.strip()]
+        kind = {}
+        body = "\n".join(l.split("!")[0] for l in body.splitlines())
+        for stmt in re.split(r"[;\n]", body):
+            stmt = stmt.strip()
+            if "::" not in stmt:
+                continue
+            decl, names = stmt.split("::")
+            decl = decl.lower()
+            byval = "value" in decl
+            for nm in re.split(r",\s*(?![^()]*\))", names):
+                nm = nm.strip().lower()
+                arr = nm.endswith("(*)")
+                nm = nm.replace("(*)", "")
+                if decl.startswith("type(c_ptr)"):
+                    assert byval and not arr, (fname, nm)
+                    kind[nm] = "ptr"
+                elif decl.startswith("integer(c_int64_t)"):
+                    kind[nm] = "i64" if byval else "ptr"
+                    assert byval != arr, (fname, nm)
+                elif decl.startswith("real(c_double)"):
+                    kind[nm] = "f64" if byval else "ptr"
+                    assert byval != arr, (fname, nm)   # a non-value scalar would still be a pointer, but none is meant
+                elif decl.startswith("character(kind=c_char)"):
+                    assert arr and not byval, (fname, nm)
+                    kind[nm] = "ptr"
+                else:
+                    raise AssertionError("unclassified Fortran declaration %r in %s" % (stmt, fname))
+        assert set(kind) == set(dummies), (fname, sorted(kind), dummies)
+        r = {"integer(c_int)": "int", "integer(c_int64_t)": "i64", "type(c_ptr)": "ptr"}[ret.lower()]
+        out[cname] = (r, [kind[d] for d in dummies])
+    return out
+
+
+def test_fortran_shim_agrees_with_the_c_header():
+    c = _c_prototypes()
+    f = _fortran_interfaces()
+    assert len(f) >= 22 and len(c) >= 40
+    for name, sig in f.items():
+        assert name in c, "%s bound in fortran/pimdk_mod.f90 but not declared in include/pimdk.h" % name
+        assert sig == c[name], (name, sig, c[name])
+    # every entry point the shim's executable part calls is in its interface block
+    src = open(os.path.join(ROOT, "fortran", "pimdk_mod.f90")).read()
+    body = src[src.index("end interface"):]
+    body = "\n".join(l.split("!")[0] for l in body.splitlines())
+    called = set(re.findall(r"\b(pimdk_[a-z0-9_]+)\s*\(", body)) - {"pimdk_check", "pimdk_propagate_tasks"}
+    assert called and called <= set(f), called - set(f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/pimdk.h is the drop-in boundary: it must compile as C99 (no C++, no torch types) and a C program
+    must link against libpimdk.so through it"""
+    from pimd_tunneling_b200._lib import LIB_PATH
+
+    src = tmp_path / "t.c"
+    src.write_text('#include "pimdk.h"\n#include <stdio.h>\nint main(void) {\n'
+                   '  double x[2], w[2];\n  int rc = pimdk_gauleg(0.0, 1.0, 2, x, w);\n'
+                   '  printf("%d %.17g %.17g\\n", rc, x[0] + x[1], w[0] + w[1]);\n'
+                   '  return pimdk_last_error() == 0;\n}\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), LIB_PATH, "-Wl,-rpath," + os.path.dirname(LIB_PATH)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "0" and abs(float(out[1]) - 1.0) < 1e-15 and abs(float(out[2]) - 1.0) < 1e-15

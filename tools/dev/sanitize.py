@@ -33,6 +33,10 @@ for n in (33, 200):
     vi.propagate_pimd_pile(x0, p0, a2, bt, dbdl); vi.propagate_pimd_nm(x0, p0, a2, bt, dbdl)
     if n == 33:
         vi.init_path(xi[:2], lam, path, spl, readhess=True)   # readhess thermal initialisation
+        # the solid-angle loop's batched UMforceenergy (grid.y = polymer; 3 polymers, ragged against the 32-wide tiles)
+        im2 = pk.InstantonMod(pes2, m2, 10.0, n)
+        im2.UMforceenergy_batch(x0[..., :3], a2, bt[..., :3])
+        pes2.Vdoubleprime(np.asfortranarray(a2))                # program crossover's transition-state Hessian
     # the chunked, copy-overlapped host-buffer path (chunks of 2, 2, 1 trajectories)
     from pimd_tunneling_b200._lib import check, lib
     check(lib().pimdk_set_propagate_chunk(2))
