@@ -526,6 +526,13 @@ def main():
     ap.add_argument("--quick", action="store_true", help="device-resident value only (no profiling, e2e or CPU legs)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    # stdout carries exactly ONE JSON line.  Libraries write banners to the C-level stdout (NCCL prints its version at
+    # any NCCL_DEBUG level from VERSION up, WARN included): point file descriptor 1 at stderr for the whole run and keep
+    # the real stdout for Python's own prints.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -539,7 +546,7 @@ def main():
         # launched without torchrun: re-exec under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=real_stdout))
     run_ours(args, cfg, rank, world, local_rank)
 
 

@@ -9,4 +9,5 @@ done
 cat $OUT | python -c "
 import sys, json
 for l in sys.stdin:
+    if not l.startswith('{'): continue
     d = json.loads(l); print('%6d traj  %8.1f ms/step  %.3e bead-steps/s' % (d['config']['trajectories_per_gpu'], d['ms_per_step'], d['value']))"
