@@ -435,15 +435,52 @@ size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepSlots * 32 * sizeo
 
 }  // namespace
 
+// Passes.  A gradient pass holds at most 32768 geometries (1.18 M energies, 377 MB of staging).  With
+// PIMDK_CCPOL_STREAMS = N > 1 a call of more than one pass deals its passes round-robin to the caller's stream and
+// N - 1 further ones, each with its own slice of the staging buffer: the block scheduler then fills the tail of one pass's
+// kernels (and the idle slots of the low-occupancy stages) with CTAs of the other pass.  Passes are independent, so
+// the results are the same bits either way.
+#ifndef PIMDK_CCPOL_STREAMS
+#define PIMDK_CCPOL_STREAMS 2
+#endif
+namespace {
+#ifndef PIMDK_GRAD_PASS
+#define PIMDK_GRAD_PASS 32768
+#endif
+constexpr long kGradPass = PIMDK_GRAD_PASS, kEnergyPass = 1048576;
+constexpr int kPassStreams = PIMDK_CCPOL_STREAMS;
+inline size_t geom_bytes(int grad) { return (size_t)kFields * 8 * (grad ? 36 : 1); }
+// geometries per pass and number of staging halves in use for a buffer of work_bytes
+inline long pass_geoms(long ngeom, int grad, size_t work_bytes, int* nbuf) {
+  const long slots = (long)(work_bytes / geom_bytes(grad));
+  *nbuf = 1;
+  if (kPassStreams > 1 && grad && ngeom > kGradPass) {
+    const long npass = (ngeom + kGradPass - 1) / kGradPass;
+    const int want = npass < kPassStreams ? (int)npass : kPassStreams;
+    if (slots >= want * kGradPass) {
+      *nbuf = want;
+      return kGradPass;
+    }
+  }
+  return slots;
+}
+}  // namespace
+
 size_t KNAME(ccpol_work_bytes)(long ngeom, int grad) {
-  const long cap = grad ? 32768 : 1048576;  // geometries per pass (grad: 1.18 M energies, 377 MB)
+  const long cap = grad ? kGradPass : kEnergyPass;
   const long n = ngeom < cap ? ngeom : cap;
-  return (size_t)(n < 1 ? 1 : n) * kFields * 8 * (grad ? 36 : 1);
+  long nbuf = 1;
+  if (kPassStreams > 1 && grad && ngeom > cap) {
+    nbuf = (ngeom + cap - 1) / cap;
+    if (nbuf > kPassStreams) nbuf = kPassStreams;
+  }
+  return (size_t)(n < 1 ? 1 : n) * geom_bytes(grad) * (size_t)nbuf;
 }
 
 // kernel launches of one launch_ccpol call (7 per pass: setup, sites, dipind, sapt, rigid, sweep, combine)
 long KNAME(ccpol_launches)(long ngeom, int grad, int icc, size_t work_bytes) {
-  const long chunk = (long)(work_bytes / ((size_t)kFields * 8 * (grad ? 36 : 1)));
+  int nbuf;
+  const long chunk = pass_geoms(ngeom, grad, work_bytes, &nbuf);
   if (chunk < 1 || ngeom < 1) return 0;
   return (icc ? 7 : 5) * ((ngeom + chunk - 1) / chunk);
 }
@@ -464,11 +501,32 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
     attr = true;
   }
   const int g = grad != nullptr;
-  const long chunk = (long)(work_bytes / ((size_t)kFields * 8 * (g ? 36 : 1)));
+  int nbuf;
+  const long chunk = pass_geoms(ngeom, g, work_bytes, &nbuf);
   if (chunk < 1) return cudaErrorInvalidValue;
-  for (long g0 = 0; g0 < ngeom; g0 += chunk) {
+  static cudaStream_t st_x[kPassStreams > 1 ? kPassStreams : 2] = {};
+  static cudaEvent_t ev_fork = nullptr, ev_join[kPassStreams > 1 ? kPassStreams : 2] = {};
+  cudaStream_t const st_a = st;
+  double* const work_a = work;
+  if (nbuf > 1) {
+    if (!ev_fork) {
+      cudaError_t e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+      for (int k = 1; k < kPassStreams && e == cudaSuccess; ++k) {
+        e = cudaStreamCreateWithFlags(&st_x[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming);
+      }
+      if (e != cudaSuccess) return e;
+    }
+    cudaEventRecord(ev_fork, st_a);      // the other streams start after everything queued before this call
+    for (int k = 1; k < nbuf; ++k) cudaStreamWaitEvent(st_x[k], ev_fork, 0);
+  }
+  long ipass = 0;
+  for (long g0 = 0; g0 < ngeom; g0 += chunk, ++ipass) {
     const long ng = (ngeom - g0 < chunk) ? ngeom - g0 : chunk;
     const long ne = ng * (g ? 36 : 1);
+    const int slice = nbuf > 1 ? (int)(ipass % nbuf) : 0;
+    st = slice ? st_x[slice] : st_a;
+    work = work_a + (size_t)slice * kGradPass * (geom_bytes(1) / sizeof(double));
     KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, iembed, L, x, g0, ne, g, work);
     KNAME(ccpol_sites_kernel)<<<(unsigned)((4 * ne + 127) / 128), 128, 0, st>>>(ne, work);
     KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, dipind_smem(), st>>>(tab, ne, work);
@@ -480,6 +538,10 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
     }
     const long nt = g ? ne / 2 : ne;
     KNAME(ccpol_combine_kernel)<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(iemonomer, icc, V0, L, x, g0, ne, g, work, v, grad, write_drift, flags);
+  }
+  for (int k = 1; k < nbuf; ++k) {       // join: the caller's stream continues after the other streams' passes
+    cudaEventRecord(ev_join[k], st_x[k]);
+    cudaStreamWaitEvent(st_a, ev_join[k], 0);
   }
   return cudaGetLastError();
 }

@@ -124,6 +124,24 @@ def test_ccpol_frozen_vectors_and_v0(pk):
     pes.set_V0(0.0)
 
 
+def test_ccpol_multi_pass_gradient_bit_identical(pk, orc):
+    """A gradient call of more than 32768 geometries runs as several passes of the seven-kernel pipeline, dealt
+    alternately to two streams with separate staging slices (PIMDK_CCPOL_STREAMS): 70 replicas of 1000 thermal
+    geometries (70 000 geometries, 3 passes; twice, so that streams and slices are reused) must carry, replica by
+    replica, the bits of a single-pass call — which is bit-exact against the oracle on a sample."""
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    nd, rep = 1000, 70
+    x = thermal_dimer_geometries(nd, seed=5)                       # (3, 6, nd)
+    v1, g1 = pes.eval_batch(x)
+    vo, go, _ = orc.pes_eval(x[..., :16])
+    assert np.array_equal(g1[..., :16], go) and np.array_equal(v1[:16], vo)
+    xb = np.asfortranarray(np.tile(x, (1, 1, rep)))
+    for _ in range(2):
+        vb, gb = pes.eval_batch(xb)
+        assert np.array_equal(gb.reshape(3, 6, rep, nd), np.broadcast_to(g1[:, :, None, :], (3, 6, rep, nd)))
+        assert np.array_equal(vb.reshape(rep, nd), np.broadcast_to(v1[None, :], (rep, nd)))
+
+
 def test_ccpol_fast_mode_within_contraction_noise(pk, orc):
     from pimd_tunneling_b200._lib import check, lib
 
