@@ -38,6 +38,12 @@ namespace {
 #ifndef PIMDK_SAPT_MINB
 #define PIMDK_SAPT_MINB 1
 #endif
+#ifndef PIMDK_SETUP_MINB
+#define PIMDK_SETUP_MINB 1
+#endif
+#ifndef PIMDK_DIPIND_MINB
+#define PIMDK_DIPIND_MINB 1
+#endif
 #ifndef PIMDK_RIGID_MINB
 #define PIMDK_RIGID_MINB 5
 #endif
@@ -80,7 +86,7 @@ __device__ __forceinline__ const CcpolDev& stage_tables(const CcpolDev* __restri
 // grad = 1: energy e = 36*g + 2*c + s is the displaced geometry for component c (loop order i=dim outer,
 // j=atom inner: c = i*6 + j), s = 0 for +eps, 1 for -eps; components already visited by the reference's
 // loop carry its round-off drift x+eps-2eps+eps (mcmod_waterdimer_ccpol.f90:48-52).
-__global__ void __launch_bounds__(kSetupBlock)
+__global__ void __launch_bounds__(kSetupBlock, PIMDK_SETUP_MINB)
 KNAME(ccpol_setup_kernel)(int iemonomer, int iembed, GeomLayout L, const double* __restrict__ x, long geom0, long ne, int grad,
                           double* __restrict__ buf) {
   const long e = (long)blockIdx.x * kSetupBlock + threadIdx.x;
@@ -163,7 +169,7 @@ struct GlobalSites {  // slot k of the item in the staging buffer: sites of A, s
     return __ldg(p + (long)f * stride);
   }
 };
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PIMDK_DIPIND_MINB)
 KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
   {
@@ -508,8 +514,13 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
   static cudaEvent_t ev_fork = nullptr, ev_join[kPassStreams > 1 ? kPassStreams : 2] = {};
   cudaStream_t const st_a = st;
   double* const work_a = work;
+  static int st_dev = -1;                // device the extra streams live on (a process may re-initialise on another)
   if (nbuf > 1) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (ev_fork && dev != st_dev) ev_fork = nullptr;   // handles of the other device are left to its context
     if (!ev_fork) {
+      st_dev = dev;
       cudaError_t e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
       for (int k = 1; k < kPassStreams && e == cudaSuccess; ++k) {
         e = cudaStreamCreateWithFlags(&st_x[k], cudaStreamNonBlocking);
