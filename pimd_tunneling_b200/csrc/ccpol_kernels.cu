@@ -65,8 +65,15 @@ constexpr int kSweepBlock = PIMDK_SWEEP_BLOCK;            // warps that share 32
 // SAPT-5s'f sites: 4 blocks (flexible A, flexible B, rigid A, rigid B) of 24 site coordinates + 3 symmetry coordinates
 constexpr int kSiteFields = 27;
 constexpr int kFrameFields = 24;                 // body frames of the two rigid monomers (ex, ey, ez, com) x 2
-constexpr int kFields = 44 + 4 * kSiteFields + kFrameFields;
-enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39, F_EIND = 40, F_A0U = 41, F_FCIND = 42, F_SITES = 44, F_FRAME = 44 + 4 * kSiteFields };
+// PIMDK_DIPIND_SPLIT: stage 1a also forms dipind's per-monomer dipole sum and polarisability (4 values per monomer
+// geometry, appended to the staging buffer), so that stage 1b reads 14 values per item instead of 54
+#ifndef PIMDK_DIPIND_SPLIT
+#define PIMDK_DIPIND_SPLIT 1
+#endif
+constexpr int kDipFields = PIMDK_DIPIND_SPLIT ? 16 : 0;
+constexpr int kFields = 44 + 4 * kSiteFields + kFrameFields + kDipFields;
+enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39, F_EIND = 40, F_A0U = 41, F_FCIND = 42, F_SITES = 44, F_FRAME = 44 + 4 * kSiteFields,
+       F_DIP = 44 + 4 * kSiteFields + kFrameFields };
 constexpr int kTabBytes = (int)((sizeof(CcpolDev) + 15) / 16 * 16);
 constexpr int kRigidTableBytes = (int)PIMDK_RIGID_TABLE_BYTES;
 constexpr int kSaptTableBytes = kTabBytes - kRigidTableBytes;
@@ -136,8 +143,21 @@ struct GlobalSlots {  // set_sites' output sink: slot k of this thread's block l
   long stride;
   __device__ __forceinline__ double& operator[](int k) const { return p[k * stride]; }
 };
+#if PIMDK_DIPIND_SPLIT
+struct TeeSlots {  // set_sites' sink that also keeps the values in registers for dipind's per-monomer part
+  double* p;
+  long stride;
+  double* loc;
+  struct Ref {
+    double* g;
+    double* l;
+    __device__ __forceinline__ void operator=(double v) const { *g = v; *l = v; }
+  };
+  __device__ __forceinline__ Ref operator[](int k) const { return Ref{p + k * stride, loc + k}; }
+};
+#endif
 __global__ void __launch_bounds__(128)
-KNAME(ccpol_sites_kernel)(long ne, double* __restrict__ buf) {
+KNAME(ccpol_sites_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   const long i = (long)blockIdx.x * 128 + threadIdx.x;
   if (i >= 4 * ne) return;
   const int blk = (int)(i / ne);             // 0 flexible A, 1 flexible B, 2 rigid A, 3 rigid B
@@ -149,11 +169,27 @@ KNAME(ccpol_sites_kernel)(long ne, double* __restrict__ buf) {
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int k = 0; k < 3; ++k) c[a][k] = fast_div(buf[(f0 + a * 3 + k) * ne + e], a0);
+#if PIMDK_DIPIND_SPLIT
+  double loc[24];
+  TeeSlots out{buf + (long)(F_SITES + blk * kSiteFields) * ne + e, ne, loc};
+  set_sites(c, out, 0, s);
+  buf[(long)(F_SITES + blk * kSiteFields + 24) * ne + e] = s[0];
+  buf[(long)(F_SITES + blk * kSiteFields + 25) * ne + e] = s[1];
+  buf[(long)(F_SITES + blk * kSiteFields + 26) * ne + e] = s[2];
+  double dm[3], polis;
+  dipind_monomer(*tab, [&](int k) { return loc[k]; }, blk & 1, s, dm, polis);
+  double* dip = buf + (long)(F_DIP + blk * 4) * ne + e;
+  dip[0] = dm[0];
+  dip[ne] = dm[1];
+  dip[2 * ne] = dm[2];
+  dip[3 * ne] = polis;
+#else
   GlobalSlots out{buf + (long)(F_SITES + blk * kSiteFields) * ne + e, ne};
   set_sites(c, out, 0, s);
   out[24] = s[0];
   out[25] = s[1];
   out[26] = s[2];
+#endif
 }
 
 // ---- stage 1b -----------------------------------------------------------------------------------
@@ -171,6 +207,25 @@ struct GlobalSites {  // slot k of the item in the staging buffer: sites of A, s
 };
 __global__ void __launch_bounds__(128, PIMDK_DIPIND_MINB)
 KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
+#if PIMDK_DIPIND_SPLIT
+  const long j = (long)blockIdx.x * 128 + threadIdx.x;
+  if (j >= 2 * ne) return;
+  const int which = j >= ne;
+  const long e = which ? j - ne : j;
+  const double* sitesA = buf + (long)(F_SITES + which * 2 * kSiteFields) * ne + e;   // O is site 0 of a block
+  const double* sitesB = sitesA + (long)kSiteFields * ne;
+  const double* dipA = buf + (long)(F_DIP + which * 8) * ne + e;
+  const double* dipB = dipA + 4 * ne;
+  double Oa[3], Ob[3], dma[3], dmb[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    Oa[k] = __ldg(sitesA + k * ne);
+    Ob[k] = __ldg(sitesB + k * ne);
+    dma[k] = __ldg(dipA + k * ne);
+    dmb[k] = __ldg(dipB + k * ne);
+  }
+  buf[(F_FCIND + which) * ne + e] = dipind_pair(__ldg(&tab->parab[10 - 1]), Oa, Ob, dma, dmb, __ldg(dipA + 3 * ne), __ldg(dipB + 3 * ne));
+#else
   extern __shared__ __align__(16) unsigned char smem[];
   {
     const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + kRigidTableBytes);
@@ -187,6 +242,7 @@ KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __
   const double sa[3] = {__ldg(S.p + 24 * ne), __ldg(S.p + 25 * ne), __ldg(S.p + 26 * ne)};
   const double sb[3] = {__ldg(S.p + 51 * ne), __ldg(S.p + 52 * ne), __ldg(S.p + 53 * ne)};
   buf[(F_FCIND + which) * ne + e] = dipind(T, S, sa, sb);
+#endif
 }
 
 // ---- stage 1c -----------------------------------------------------------------------------------
@@ -539,8 +595,8 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
     st = slice ? st_x[slice] : st_a;
     work = work_a + (size_t)slice * kGradPass * (geom_bytes(1) / sizeof(double));
     KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, iembed, L, x, g0, ne, g, work);
-    KNAME(ccpol_sites_kernel)<<<(unsigned)((4 * ne + 127) / 128), 128, 0, st>>>(ne, work);
-    KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, dipind_smem(), st>>>(tab, ne, work);
+    KNAME(ccpol_sites_kernel)<<<(unsigned)((4 * ne + 127) / 128), 128, 0, st>>>(tab, ne, work);
+    KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, PIMDK_DIPIND_SPLIT ? 0 : dipind_smem(), st>>>(tab, ne, work);
     if (potparts_old) KNAME(ccpol_sapt_kernel)<true><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
     else KNAME(ccpol_sapt_kernel)<false><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
     if (icc) {   // CCpol-8s rigid model of the embedded monomers; surfaces 5..9 are SAPT-5s'f alone
