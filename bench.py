@@ -40,12 +40,12 @@ M_O, M_H = 15.9949146221 * 1822.888486, 1.0078250321 * 1822.888486
 FLOP_PER_ENERGY = 25156 + 33156 + 1760 + 806 + 1129 + 33 + 28
 FLOP_PER_BEAD_GRAD = {"ccpol8sf": 36 * FLOP_PER_ENERGY + 36, "2dtest": 6 * (2 + 14) + 12, "1d": 8}
 # DRAM bytes per bead-gradient of the CCpol pipeline, dram__bytes_read.sum + dram__bytes_write.sum summed over
-# its seven kernels in one `ncu --set full` capture of a 32 768-bead pass (profiles/r1_ccpol_pipeline_v20.md)
-CCPOL_DRAM_BYTES_PER_BEAD = 136471
+# its seven kernels in one `ncu --set full` capture of a 32 768-bead pass (profiles/r1_ccpol_pipeline_v23.md)
+CCPOL_DRAM_BYTES_PER_BEAD = 117995
 # SASS-level FP64 flop per bead-gradient (2*DFMA + DMUL + DADD thread instructions of the seven kernels, same
 # capture): what the FP64 pipe actually executes for the 2 234 484 source-level operations, because exp, division
 # and square root expand to ~20, ~10 and ~10 pipe instructions and strict mode issues no contracted FMAs
-CCPOL_SASS_FLOP_PER_BEAD = 2715480
+CCPOL_SASS_FLOP_PER_BEAD = 2716920
 
 CONFIGS = {
     # name: pes, n, nintegral, nrep, thermostat, beta, Noutput
