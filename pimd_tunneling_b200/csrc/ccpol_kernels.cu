@@ -497,7 +497,7 @@ size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepSlots * 32 * sizeo
 
 }  // namespace
 
-// Passes.  A gradient pass holds at most 32768 geometries (1.18 M energies, 377 MB of staging).  With
+// Passes.  A gradient pass holds at most 32768 geometries (1.18 M energies x 192 staging fields = 1.8 GB).  With
 // PIMDK_CCPOL_STREAMS = N > 1 a call of more than one pass deals its passes round-robin to the caller's stream and
 // N - 1 further ones, each with its own slice of the staging buffer: the block scheduler then fills the tail of one pass's
 // kernels (and the idle slots of the low-occupancy stages) with CTAs of the other pass.  Passes are independent, so
