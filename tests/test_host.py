@@ -326,3 +326,20 @@ def test_header_is_plain_c(tmp_path):
                     "-o", str(exe), LIB_PATH, "-Wl,-rpath," + os.path.dirname(LIB_PATH)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out[0] == "0" and abs(float(out[1]) - 1.0) < 1e-15 and abs(float(out[2]) - 1.0) < 1e-15
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: stdout carries ONE JSON line (library banners go to stderr: file descriptor 1 is pointed at
+    stderr for the run).  The reference arm needs no GPU: it times the CPU oracle on a bounded sample."""
+    import json
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "bead-steps/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert d["config"]["workload"].startswith("C4:")
