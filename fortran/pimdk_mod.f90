@@ -117,7 +117,7 @@ end module pimdk
 
 !---------------------------------------------------------------------------------------------------------
 ! Replacement plugin: same module name and procedures as mcmod_waterdimer_ccpol.f90:1-80, in the CURRENT
-! plugin interface (mcmod_waterdimer.f90:1-105): V_init(iproc), V, Vprime, potforce, module variables.
+! plugin interface (mcmod_waterdimer.f90:1-105): V_init(iproc), V, Vprime, potforce, Vdoubleprime, module variables.
 module mcmod_mass
   use iso_c_binding
   use pimdk
@@ -163,7 +163,17 @@ contains
     call pimdk_check(pimdk_pes_eval(1_c_int64_t, int(ndim,c_int64_t), int(natom,c_int64_t), xc, c_loc(vv), c_loc(gc)))
     grad(:,:) = gc(:,:); energy = vv(1)
   end subroutine potforce
-  ! Vdoubleprime: unchanged from mcmod_waterdimer_ccpol.f90:60-77 (finite difference of Vprime), not on the hot path
+
+  ! Vdoubleprime (mcmod_waterdimer_ccpol.f90:60-77: central difference of Vprime, eps = 1d-5, x perturbed in place and
+  ! left with the drift of 2*ndof nested Vprime calls): the 36 gradient passes run on the device in one call
+  subroutine Vdoubleprime(x, hess)
+    double precision :: x(:,:), hess(:,:,:,:)
+    double precision :: xc(ndim,natom), hc(ndim,natom,ndim,natom)
+    xc(:,:) = x(:,:)
+    call pimdk_check(pimdk_pes_hessian(1_c_int64_t, int(ndim,c_int64_t), int(natom,c_int64_t), xc, hc))
+    x(:,:) = xc(:,:)
+    hess(:,:,:,:) = hc(:,:,:,:)
+  end subroutine Vdoubleprime
 end module mcmod_mass
 
 !---------------------------------------------------------------------------------------------------------
