@@ -128,12 +128,15 @@ module mcmod_mass
   logical::                        potforcepresent=.true.
   character, allocatable::         label(:)
   character(len=20)::              basename
+  ! which in-repo surface this plugin stands for: "ccpol8sf" (mcmod_waterdimer_ccpol.f90), "2dtest" (mcmod_2dtest.f90)
+  ! or "1d" (mcmod_1d.f90); set before V_init (the reference has one mcmod_<PES>.f90 per surface and picks at link time)
+  character(len=16)::              pimdk_pes_name = "ccpol8sf"
 contains
   subroutine V_init(iproc)
     integer, intent(in) :: iproc
     ! data files are opened from the CWD like the reference (main_CCpol-8sf.f:49,115)
     call pimdk_check(pimdk_init(-1_c_int64_t, "."//c_null_char))
-    call pimdk_check(pimdk_pes_select("ccpol8sf"//c_null_char, c_null_ptr, 0_c_int64_t))
+    call pimdk_check(pimdk_pes_select(trim(pimdk_pes_name)//c_null_char, c_null_ptr, 0_c_int64_t))
     write(*,*) "Potential initializaton complete"
     V0=0.0d0
   end subroutine V_init
