@@ -39,13 +39,41 @@ M_O, M_H = 15.9949146221 * 1822.888486, 1.0078250321 * 1822.888486
 # exp 1129, pow 33, trig 28
 FLOP_PER_ENERGY = 25156 + 33156 + 1760 + 806 + 1129 + 33 + 28
 FLOP_PER_BEAD_GRAD = {"ccpol8sf": 36 * FLOP_PER_ENERGY + 36, "2dtest": 6 * (2 + 14) + 12, "1d": 8}
-# DRAM bytes per bead-gradient of the CCpol pipeline, dram__bytes_read.sum + dram__bytes_write.sum summed over
-# its seven kernels in one `ncu --set full` capture of a 32 768-bead pass (profiles/r1_ccpol_pipeline_v23.md)
-CCPOL_DRAM_BYTES_PER_BEAD = 117995
-# SASS-level FP64 flop per bead-gradient (2*DFMA + DMUL + DADD thread instructions of the seven kernels, same
-# capture): what the FP64 pipe actually executes for the 2 234 484 source-level operations, because exp, division
-# and square root expand to ~20, ~10 and ~10 pipe instructions and strict mode issues no contracted FMAs
-CCPOL_SASS_FLOP_PER_BEAD = 2716920
+# Counters that only a profiler can give (DRAM bytes and executed FP64 flop per bead-gradient of the CCpol pipeline)
+# are NOT pasted here: they are read from the committed summary of the `ncu --set full` capture
+# (profiles/ccpol_counters.json, written by tools/ncu_pipeline_summary.py) together with the hash of the kernel
+# sources the capture was taken on; a summary whose hash differs from the tree's is reported as stale and not used.
+CCPOL_SOURCES = ["pimd_tunneling_b200/csrc/ccpol_kernels.cu", "pimd_tunneling_b200/csrc/ccpol_device.cuh",
+                 "pimd_tunneling_b200/csrc/ccpol_grad.cuh", "pimd_tunneling_b200/csrc/ccpol_tables.h", "include/pimdk_detmath.h"]
+
+
+def ccpol_source_hash():
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in CCPOL_SOURCES:
+        path = os.path.join(ROOT, f)
+        if os.path.exists(path):
+            with open(path, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
+def ccpol_counters(mode):
+    """{"dram_bytes_per_bead", "sass_flop_per_bead", "source"} for `mode`, or None with the reason"""
+    path = os.path.join(ROOT, "profiles", "ccpol_counters.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except Exception:
+        return None, "profiles/ccpol_counters.json absent"
+    ent = d.get(mode)
+    if not ent:
+        return None, "no ncu capture of mode %s in profiles/ccpol_counters.json" % mode
+    if ent.get("source_sha256") != ccpol_source_hash():
+        return None, "stale: %s was captured on other kernel sources (%s...)" % (ent.get("capture"), str(ent.get("source_sha256"))[:12])
+    return ent, "profiles/ccpol_counters.json <- %s" % ent.get("capture")
+
 
 CONFIGS = {
     # name: pes, n, nintegral, nrep, thermostat, beta, Noutput
@@ -189,106 +217,207 @@ def run_reference(args, cfg, rank):
 
 
 # ------------------------------------------------------------------------------------------------
+class Workload:
+    """State of `ntraj` ring polymers of config `cfg` on this rank: pinned host copies (the e2e leg starts from them) and
+    device copies (the device-resident leg), end points b(lambda) and dbdl per trajectory, global ids."""
+
+    def __init__(self, pk, cfg, pes, vi, gid, nrep_glob, dev):
+        import torch
+
+        from pimd_tunneling_b200 import path as P
+
+        self.cfg, self.vi, self.gid, self.nrep_glob = cfg, vi, gid, nrep_glob
+        n, nd, na = cfg["n"], pes.ndim, pes.natom
+        ndof = nd * na
+        self.n, self.nd, self.na, self.ndof, self.ntraj = n, nd, na, ndof, gid.size
+        nintegral = cfg["nintegral"]
+        a, b, mass = wells(cfg["pes"])
+        self.a = a
+        self.xi, self.wts = vi.gauleg(0.0, 1.0, nintegral)
+        il = (gid // nrep_glob) % nintegral
+        lam, path, spl = ti_path(cfg["pes"], a, b)
+        xint, dbdxi = P.endpoints(lam, path, spl, self.xi)       # pimd_par.f90:214-221
+        self.bt = np.asfortranarray(xint[:, :, il])              # endpoints(ii,:,:)
+        self.dbdl = np.asfortranarray(dbdxi[:, :, il])           # gradpoints(ii,:,:)
+        ntraj = self.ntraj
+        # init_path in chunks (host staging of the full state is 2 x ntraj*n*ndof*8 bytes)
+        self.x_h = torch.empty((ntraj, ndof, n), dtype=torch.float64).pin_memory()
+        self.p_h = torch.empty((ntraj, ndof, n), dtype=torch.float64).pin_memory()
+        chunk = max(1, min(ntraj, (1 << 27) // (n * ndof)))
+        for lo in range(0, ntraj, chunk):
+            hi = min(ntraj, lo + chunk)
+            xc, pc = vi.init_path(self.xi[il[lo:hi]], lam, path, spl, traj_gid=gid[lo:hi])
+            self.x_h[lo:hi] = torch.from_numpy(np.ascontiguousarray(xc.reshape(-1, order="F").reshape(hi - lo, ndof, n)))
+            self.p_h[lo:hi] = torch.from_numpy(np.ascontiguousarray(pc.reshape(-1, order="F").reshape(hi - lo, ndof, n)))
+        self.x_d, self.p_d = self.x_h.to(dev), self.p_h.to(dev)
+        self.a_d = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))).to(dev)
+        self.b_d = torch.from_numpy(np.ascontiguousarray(self.bt.reshape(-1, order="F"))).to(dev)
+        self.dbdl_d = torch.from_numpy(np.ascontiguousarray(self.dbdl.reshape(-1, order="F"))).to(dev)
+        self.gid_d = torch.from_numpy(gid).to(dev)
+        self.dH_d = torch.zeros(max(1, ntraj), dtype=torch.float64, device=dev)
+        self.sums = None
+
+    def call_dev(self, nsteps, seed):
+        """nsteps steps of every local ring polymer (state resident in HBM), then the path's single collective: per-lambda
+        estimator sums formed on the device and all-reduced by the library's own NCCL communicator"""
+        from pimd_tunneling_b200 import ti
+
+        cfg, vi = self.cfg, self.vi
+        vi.seed = seed
+        if self.ntraj > 0:
+            vi.propagate_dev(cfg["thermostat"], self.ntraj, self.x_d.data_ptr(), self.p_d.data_ptr(), self.a_d.data_ptr(),
+                             self.b_d.data_ptr(), self.dbdl_d.data_ptr(), self.gid_d.data_ptr(), self.dH_d.data_ptr(), NMC=nsteps)
+        self.sums = ti.reduce_dev(self.ntraj, self.dH_d.data_ptr(), self.gid_d.data_ptr(), self.nrep_glob, cfg["nintegral"], vi.betan)
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6500.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def fast_vs_strict(pk, L, check, mode_id, nsample=256):
+    """Measured parity of a non-default arithmetic mode against strict on `nsample` thermal dimer geometries:
+    max relative energy error and max gradient error over max|grad| (both modes on the GPU, through the C ABI)."""
+    rng = np.random.default_rng(3)
+    a, _, _ = wells("ccpol8sf")
+    x = np.asfortranarray(a[:, :, None] + rng.normal(0.0, 0.05, size=(3, 6, nsample)))
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    check(L.pimdk_set_mode(0))
+    v0, g0 = pes.eval_batch(x)
+    check(L.pimdk_set_mode(mode_id))
+    v1, g1 = pes.eval_batch(x)
+    return {"geometries": nsample, "energy_max_rel": float(np.max(np.abs(v1 - v0) / np.abs(v0))),
+            "gradient_max_over_maxgrad": float(np.max(np.abs(g1 - g0).reshape(18, -1).max(0) / np.abs(g0).reshape(18, -1).max(0)))}
+
+
+MODES = {"strict": 0, "fast": 1, "analytic": 2}
+
+
 def run_ours(args, cfg, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
     import pimd_tunneling_b200 as pk
     from pimd_tunneling_b200 import ti
-    from pimd_tunneling_b200._lib import check, lib
+    from pimd_tunneling_b200._lib import check, hptr, lib
 
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
         # stdout carries the one JSON line; NCCL's version banner (NCCL_DEBUG=VERSION) would go there too
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # torch.distributed is plumbing here: the barrier of the timing contract and the hand-over of the library
+        # communicator's unique id.  The path's collective itself is the library's (pimdk_ti_reduce_dev).
+        dist.init_process_group("nccl", device_id=dev)
     pk.init(local_rank)
     L = lib()
-    if args.mode == "fast":
-        check(L.pimdk_set_mode(1))
+    ti.comm_init(rank, world)
+    mode_id = MODES[args.mode]
+    parity = None
+    if mode_id and cfg["pes"] == "ccpol8sf" and rank == 0 and not args.quick and not args.sweep:
+        parity = fast_vs_strict(pk, L, check, mode_id)
+    check(L.pimdk_set_mode(mode_id if cfg["pes"] == "ccpol8sf" else 0))
     pes = pk.McmodMass(cfg["pes"]).V_init()
     a, b, mass = wells(cfg["pes"])
     n, nd, na = cfg["n"], pes.ndim, pes.natom
     ndof = nd * na
-    nintegral, nrep = cfg["nintegral"], cfg["nrep"]
-    if args.ntraj:
-        nrep = max(1, args.ntraj // nintegral)
-    ntraj = nintegral * nrep                     # per GPU (weak scaling)
+    nintegral = cfg["nintegral"]
     K, W = args.steps, args.warmup
     vi = pk.VerletInt(pes, n, mass, cfg["beta"], dt=1e-3, gamma=1.0, NMC=1, imin=0, Noutput=cfg["Noutput"],
                       seed=0x5EED0000).init_nm()
-    xi, wts = vi.gauleg(0.0, 1.0, nintegral)
-    # global ids: rank r owns ids [r*ntraj, (r+1)*ntraj) of a (world*nrep)-repetition job
-    gid = np.arange(ntraj, dtype=np.int64) + rank * ntraj
-    nrep_glob = nrep * world
-    il = (gid // nrep_glob) % nintegral
-    from pimd_tunneling_b200 import path as P
+    strong = args.scaling == "strong"
 
-    lam, path, spl = ti_path(cfg["pes"], a, b)
-    xint, dbdxi = P.endpoints(lam, path, spl, xi)       # pimd_par.f90:214-221
-    bt = np.asfortranarray(xint[:, :, il])              # endpoints(ii,:,:)
-    dbdl = np.asfortranarray(dbdxi[:, :, il])           # gradpoints(ii,:,:)
-    # init_path in chunks (host staging of the full state is 2 x ntraj*n*ndof*8 bytes)
-    x_h = torch.empty((ntraj, ndof, n), dtype=torch.float64).pin_memory()
-    p_h = torch.empty((ntraj, ndof, n), dtype=torch.float64).pin_memory()
-    chunk = max(1, min(ntraj, (1 << 27) // (n * ndof)))
-    for lo in range(0, ntraj, chunk):
-        hi = min(ntraj, lo + chunk)
-        xc, pc = vi.init_path(xi[il[lo:hi]], lam, path, spl, traj_gid=gid[lo:hi])
-        x_h[lo:hi] = torch.from_numpy(np.ascontiguousarray(xc.reshape(-1, order="F").reshape(hi - lo, ndof, n)))
-        p_h[lo:hi] = torch.from_numpy(np.ascontiguousarray(pc.reshape(-1, order="F").reshape(hi - lo, ndof, n)))
-    dev = torch.device("cuda", local_rank)
-    x_d, p_d = x_h.to(dev), p_h.to(dev)
-    a_d = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))).to(dev)
-    b_d = torch.from_numpy(np.ascontiguousarray(bt.reshape(-1, order="F"))).to(dev)
-    dbdl_d = torch.from_numpy(np.ascontiguousarray(dbdl.reshape(-1, order="F"))).to(dev)
-    gid_d = torch.from_numpy(gid).to(dev)
-    dH_d = torch.zeros(ntraj, dtype=torch.float64, device=dev)
-    sums_d = torch.zeros(3 * nintegral, dtype=torch.float64, device=dev)
+    def layout(total_or_per_gpu):
+        """-> (global ids of this rank, repetitions per lambda of the whole job).  weak: every rank holds `total_or_per_gpu`
+        trajectories (the job grows with N); strong: the job is `total_or_per_gpu` trajectories, block-partitioned by
+        global id (pimd_par.f90:109-110, 281-295)."""
+        if strong:
+            nrep_glob = max(1, total_or_per_gpu // nintegral)
+            lo, hi = ti.shard(nintegral * nrep_glob, rank, world)
+            return np.arange(lo, hi, dtype=np.int64), nrep_glob
+        nrep = max(1, total_or_per_gpu // nintegral)
+        nt = nintegral * nrep
+        return np.arange(nt, dtype=np.int64) + rank * nt, nrep * world
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_call(nsteps, seed_off=0):
-        vi.seed = 0x5EED0000 + seed_off
-        vi.propagate_dev(cfg["thermostat"], ntraj, x_d.data_ptr(), p_d.data_ptr(), a_d.data_ptr(), b_d.data_ptr(),
-                         dbdl_d.data_ptr(), gid_d.data_ptr(), dH_d.data_ptr(), NMC=nsteps)
-        if world > 1:   # the single collective of the path: estimator sums per lambda
-            I = dH_d / (vi.betan ** 2)
-            s = torch.stack([torch.zeros(nintegral, dtype=torch.float64, device=dev).index_add_(0, torch.from_numpy(il).to(dev), I),
-                             torch.zeros(nintegral, dtype=torch.float64, device=dev).index_add_(0, torch.from_numpy(il).to(dev), I * I),
-                             torch.bincount(torch.from_numpy(il).to(dev), minlength=nintegral).double()], dim=1).reshape(-1)
-            dist.all_reduce(s)
-            sums_d.copy_(s)
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(wl, nsteps, seed):
+        """device time of one call of nsteps steps on this rank's stream, max over ranks [ms]"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        wl.call_dev(nsteps, seed)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    base_traj = args.ntraj if args.ntraj else nintegral * cfg["nrep"]
+
+    # ---- batch-scaling sweep (C5): one JSON line per batch size, device-resident value only ----
+    if args.sweep:
+        for tot in [int(t) for t in args.sweep.split(",")]:
+            gid, nrep_glob = layout(tot)
+            wl = Workload(pk, cfg, pes, vi, gid, nrep_glob, dev)
+            wl.call_dev(W, 0x5EED0001)
+            barrier()
+            check(L.pimdk_profile_reset())
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            ms = timed(wl, K, 0x5EED0002)
+            sampler.stop_flag = True
+            ntot = nintegral * nrep_glob
+            if rank == 0:
+                print(json.dumps({"metric": "ring-polymer bead-steps/sec", "value": ntot * n * K / (ms * 1e-3), "unit": "bead-steps/s",
+                                  "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "scaling": args.scaling,
+                                  "config": {"workload": cfg["label"], "beads": n, "trajectories_total": ntot,
+                                             "trajectories_this_gpu": int(gid.size), "mode": args.mode},
+                                  "gpu_launches": int(L.pimdk_launch_count()), "clocks": sampler.summary(), "quick": True}), flush=True)
+            del wl
+            torch.cuda.empty_cache()
+        ti.comm_finalize()
+        if world > 1:
+            dist.destroy_process_group()
+        pk.finalize()
+        return
+
+    gid, nrep_glob = layout(base_traj)
+    ntraj = int(gid.size)
+    ntot = nintegral * nrep_glob                     # trajectories of the whole job
+    wl = Workload(pk, cfg, pes, vi, gid, nrep_glob, dev)
 
     # ---- device-resident timing ("value"): CUDA events on the launching stream, no per-kernel profiling ----
-    one_call(W, 1)                                     # W untimed warm-up steps
+    wl.call_dev(W, 0x5EED0001)                         # W untimed warm-up steps
     barrier()
     check(L.pimdk_profile(0))
     check(L.pimdk_profile_reset())
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    one_call(K, 2)                                     # exactly K timed steps
-    e1.record()
-    barrier()
+    ms = timed(wl, K, 0x5EED0002)                      # exactly K timed steps
     sampler.stop_flag = True
-    ms = e0.elapsed_time(e1)
     launches = int(L.pimdk_launch_count())
-    if args.quick:   # batch-scaling sweeps (C5): device-resident value only
-        tq = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+    units_total = ntot * n * K
+    value = units_total / (ms * 1e-3)
+    if args.quick:
         if rank == 0:
-            print(json.dumps({"metric": "ring-polymer bead-steps/sec", "value": world * ntraj * n * K / (float(tq.item()) * 1e-3),
-                              "unit": "bead-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": float(tq.item()) / K,
-                              "config": {"workload": cfg["label"], "beads": n, "trajectories_per_gpu": ntraj, "mode": args.mode},
+            print(json.dumps({"metric": "ring-polymer bead-steps/sec", "value": value, "unit": "bead-steps/s", "n_gpus": world,
+                              "steps": K, "warmup": W, "ms_per_step": ms / K, "scaling": args.scaling,
+                              "config": {"workload": cfg["label"], "beads": n, "trajectories_total": ntot,
+                                         "trajectories_this_gpu": ntraj, "mode": args.mode},
                               "gpu_launches": launches, "clocks": sampler.summary(), "quick": True}), flush=True)
+        ti.comm_finalize()
         if world > 1:
             dist.destroy_process_group()
         pk.finalize()
@@ -298,97 +427,119 @@ def run_ours(args, cfg, rank, world, local_rank):
     check(L.pimdk_profile_reset())
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
-    one_call(K, 3)
+    wl.call_dev(K, 0x5EED0003)
     p1.record()
     torch.cuda.synchronize()
     ms_prof = p0.elapsed_time(p1)
-    pes_ms, pes_n = ctypes.c_double(), ctypes.c_int64()
-    check(L.pimdk_profile_get(b"pes", ctypes.byref(pes_ms), ctypes.byref(pes_n)))
     fam = {}
-    for f in ("gemm", "update", "estimator"):
+    for f in ("pes", "gemm", "update", "estimator", "fused"):
         m_, c_ = ctypes.c_double(), ctypes.c_int64()
         check(L.pimdk_profile_get(f.encode(), ctypes.byref(m_), ctypes.byref(c_)))
         fam[f] = {"ms": m_.value, "launches": int(c_.value)}
     check(L.pimdk_profile(0))
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax.item())
-    units_total = world * ntraj * n * K
-    value = units_total / (ms * 1e-3)
 
     # ---- end-to-end through the host-buffer C ABI ("e2e") ----
-    xw = x_h.numpy().reshape(-1).reshape((n, nd, na, ntraj), order="F")
-    pw = p_h.numpy().reshape(-1).reshape((n, nd, na, ntraj), order="F")
-    dH_h = np.zeros(ntraj)
+    xw = wl.x_h.numpy().reshape(-1).reshape((n, nd, na, ntraj), order="F")
+    pw = wl.p_h.numpy().reshape(-1).reshape((n, nd, na, ntraj), order="F")
+    dH_h = np.zeros(max(1, ntraj))
     Ke = K
-    from pimd_tunneling_b200._lib import hptr
 
     def e2e_call(nsteps):
-        check(L.pimdk_propagate(cfg["thermostat"], ntraj, hptr(xw), hptr(pw), hptr(a), hptr(bt), hptr(dbdl), 1e-3, 1.0,
-                                nsteps, 0, cfg["Noutput"], 0, 0x5EED0003, hptr(gid), hptr(dH_h)))
-        sums = ti.partial_sums(dH_h, gid % (nintegral * nrep_glob), nrep_glob, nintegral, vi.betan)
-        return ti.allreduce_sums(sums)
+        if ntraj > 0:
+            check(L.pimdk_propagate(cfg["thermostat"], ntraj, hptr(xw), hptr(pw), hptr(a), hptr(wl.bt), hptr(wl.dbdl), 1e-3, 1.0,
+                                    nsteps, 0, cfg["Noutput"], 0, 0x5EED0003, hptr(gid), hptr(dH_h)))
+        sums = ti.partial_sums(dH_h[:ntraj], gid, nrep_glob, nintegral, vi.betan)
+        return ti.allreduce_sums(sums)             # pimdk_ti_allreduce: the library's communicator
 
     barrier()
     t0 = time.perf_counter()
     sums = e2e_call(Ke)
     torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * ntraj * n * Ke / float(te.item())
-    stats = ti.finish(sums, wts, vi.betan)
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = ntot * n * Ke / t_e2e
+    stats = ti.finish(sums, wl.wts, vi.betan)
     state_bytes = 2 * ntraj * n * ndof * 8
     small = ndof * 8 + 2 * ntraj * ndof * 8 + ntraj * 8
 
     if rank == 0:
         peak = ctypes.c_double()
         check(L.pimdk_fp64_peak(ctypes.byref(peak)))
-        # the PES gradient of all beads is one pipeline run per step (4 kernels per 32768-bead pass for CCpol)
-        flop_total = FLOP_PER_BEAD_GRAD[cfg["pes"]] * ntraj * n * K
-        achieved = flop_total / (pes_ms.value * 1e-3) / 1e12 if pes_ms.value > 0 else None
+        peak_note = ("DFMA probe measured in this run by pimdk_fp64_peak (csrc/fp64_peak.cu: 8 independent fma chains per thread, "
+                     "148 x 8 x 256 threads, 2 flop per fma, best of 5, CUDA events); MEASURED_PEAKS.json has no FP64 entry; "
+                     "theoretical 148 SM x 64 lanes x 2 x sm clock")
+        rows_per_gpu = ntraj * ndof
+        roof = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak.value, "peak_source": peak_note, "traffic": None,
+                "other_kernels_ms": fam, "step_ms_under_profiling": ms_prof / K}
+        if cfg["pes"] == "ccpol8sf":
+            pes_ms = fam["pes"]["ms"]
+            flop_bead = FLOP_PER_BEAD_GRAD["ccpol8sf"]
+            achieved = flop_bead * ntraj * n * K / (pes_ms * 1e-3) / 1e12 if pes_ms > 0 else None
+            cnt, cnt_src = ccpol_counters(args.mode)
+            roof.update({"achieved": achieved, "frac": achieved / peak.value if achieved else None,
+                         "kernel": "ccpol_{setup,sites,dipind,sapt,rigid,sweep,combine}_kernel_%s (one PES-gradient pipeline)" % args.mode,
+                         "kernel_ms_per_step": pes_ms / K, "kernel_launches": fam["pes"]["launches"],
+                         "kernel_share_of_step": pes_ms / ms_prof,
+                         "flop_per_bead_gradient": flop_bead,
+                         "flop_note": "source-level FP64 operation census of the REFERENCE's finite-difference gradient (36 energies; "
+                                      "oracle/opcount.hpp); exp, division and square root count as one operation each",
+                         "algorithmic_bytes": 32 * ndof * ntraj * n / 1e9, "counters_source": cnt_src})
+            if cnt:
+                roof["traffic"] = cnt["dram_bytes_per_bead"] * ntraj * n / 1e9
+                roof["traffic_unit"] = "GB per step (all beads of this GPU): ncu dram__bytes_read+write per bead-gradient x beads"
+                if pes_ms > 0:
+                    roof["achieved_sass"] = cnt["sass_flop_per_bead"] * ntraj * n * K / (pes_ms * 1e-3) / 1e12
+                    roof["achieved_sass_note"] = "2*DFMA+DMUL+DADD executed per bead-gradient (ncu source page) / kernel time of this run"
+        elif fam["fused"]["launches"] > 0:
+            # C1: the whole step loop is ONE kernel; per bead-step it runs two n-point transforms per dof (G = T g, x = T(Q + beadvec)),
+            # the surface's gradient, kick + 2 rotations + O-step and its share of the estimator
+            flop_bead = 4 * ndof * n + FLOP_PER_BEAD_GRAD[cfg["pes"]] + 30 * ndof
+            fms = fam["fused"]["ms"]
+            achieved = flop_bead * ntraj * n * K / (fms * 1e-3) / 1e12 if fms > 0 else None
+            roof.update({"achieved": achieved, "frac": achieved / peak.value if achieved else None,
+                         "kernel": "fused_small_kernel (persistent warp per ring polymer, all steps in one launch)",
+                         "kernel_ms_per_step": fms / K, "kernel_launches": fam["fused"]["launches"],
+                         "kernel_share_of_step": fms / ms_prof, "flop_per_bead_step": flop_bead,
+                         "note": "256 ring polymers = 256 warps on 148 SMs: the configuration is latency/occupancy-bound by size; "
+                                 "the fraction is the honest statement of that"})
+        else:
+            # C2: the two n x n transforms per step dominate: 2 * rows * n^2 flop per launch against the FP64 peak
+            gms, gl = fam["gemm"]["ms"], fam["gemm"]["launches"]
+            flop = 2.0 * rows_per_gpu * n * n * gl
+            achieved = flop / (gms * 1e-3) / 1e12 if gms > 0 else None
+            hp, hsrc = hbm_peak()
+            ums, ul = fam["update"]["ms"], fam["update"]["launches"]
+            roof.update({"achieved": achieved, "frac": achieved / peak.value if achieved else None,
+                         "kernel": "nm_gemm_pipe_kernel (FP64 tensor-core transform, cp.async 3-stage)",
+                         "kernel_ms_per_step": gms / K, "kernel_launches": gl, "kernel_share_of_step": gms / ms_prof,
+                         "flop_per_launch": 2.0 * rows_per_gpu * n * n,
+                         "algorithmic_bytes": 32 * ndof * ntraj * n / 1e9,
+                         "update_kernels_hbm": {"ms": ums, "launches": ul, "peak_gbs": hp, "peak_source": hsrc,
+                                                "note": "nm_update2 / sample_momenta2 / andersen_clock; 32-48 B per element per launch"}})
         line = {
             "metric": "ring-polymer bead-steps/sec", "value": value, "unit": "bead-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["label"], "pes": cfg["pes"], "beads": n, "trajectories_per_gpu": ntraj,
+            "config": {"workload": cfg["label"], "pes": cfg["pes"], "beads": n, "trajectories_total": ntot, "trajectories_per_gpu": ntraj,
                        "lambda_points": nintegral, "thermostat": "PILE" if cfg["thermostat"] == 2 else "Andersen",
                        "beta": cfg["beta"], "dt": 1e-3, "mode": args.mode,
-                       "l2": "state per step (x,p,P,Q,G: %.2f GB) exceeds the 126 MB L2" % (5 * state_bytes / 2 / 1e9),
-                       "parallelism": "independent trajectories sharded by global id; 1 all-reduce of %d doubles" % (3 * nintegral)},
+                       "l2": "state per step (x,p,P,Q,G: %.3f GB) %s the 126 MB L2" % (5 * state_bytes / 2 / 1e9, "exceeds" if 5 * state_bytes / 2 > 126e6 else "fits; inputs of consecutive steps differ (the state evolves), nothing is cached across steps but the tables"),
+                       "parallelism": "independent trajectories sharded by global id; 1 ncclAllReduce of %d doubles inside libpimdk (NCCL %s, %d ranks)" % ((3 * nintegral,) + ti.comm_info()[2:0:-1])},
             "e2e": {"value": e2e_value, "unit": "bead-steps/s", "h2d_bytes_per_step": (state_bytes + small) / Ke,
                     "d2h_bytes_per_step": (state_bytes + ntraj * 8) / Ke, "steps_per_call": Ke,
                     "deltaA": stats["deltaA"], "sigmaA": stats["sigmaA"]},
             "gpu_launches": launches,
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                         "frac": (achieved / peak.value) if achieved else None,
-                         "traffic": (CCPOL_DRAM_BYTES_PER_BEAD * ntraj * n / 1e9) if (CCPOL_DRAM_BYTES_PER_BEAD and cfg["pes"] == "ccpol8sf") else None,
-                         "traffic_unit": "GB per step (all beads), from ncu dram__bytes_read+write per bead",
-                         "algorithmic_bytes": 32 * ndof * ntraj * n / 1e9,
-                         "kernel": ("ccpol_{setup,sites,dipind,sapt,rigid,sweep,combine}_kernel_" + args.mode + " (one PES-gradient pipeline)")
-                         if cfg["pes"] == "ccpol8sf" else "simple_pes_kernel",
-                         "kernel_ms_per_step": pes_ms.value / K, "kernel_launches": int(pes_n.value),
-                         "kernel_share_of_step": pes_ms.value / ms_prof,
-                         "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "flop_per_bead_gradient": FLOP_PER_BEAD_GRAD[cfg["pes"]], "other_kernels_ms": fam,
-                         "achieved_sass": (CCPOL_SASS_FLOP_PER_BEAD * ntraj * n * K / (pes_ms.value * 1e-3) / 1e12)
-                         if (cfg["pes"] == "ccpol8sf" and args.mode == "strict" and pes_ms.value > 0) else None,
-                         "achieved_sass_note": "2*DFMA+DMUL+DADD executed per bead-gradient (ncu, profiles/) / kernel time"},
+            "roofline": roof,
             "clocks": sampler.summary(),
         }
-        # the same step seen from the memory side (not its bound): DRAM bytes of the PES pipeline per step (ncu, profiles/)
-        # plus the streamed state traffic, against the measured copy bandwidth of MEASURED_PEAKS.json
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-        except Exception:
-            hbm_peak, hbm_src = 6500.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
-        if cfg["pes"] == "ccpol8sf":
-            gb = CCPOL_DRAM_BYTES_PER_BEAD * ntraj * n / 1e9 + 10 * 8 * ndof * ntraj * n / 1e9
-            line["roofline_hbm"] = {"bound": "hbm", "achieved": gb / (ms / K * 1e-3), "peak": hbm_peak, "unit": "GB/s",
-                                    "frac": gb / (ms / K * 1e-3) / hbm_peak, "traffic": gb, "peak_source": hbm_src,
+        if parity is not None:
+            line["config"]["mode_parity_vs_strict"] = parity
+        if cfg["pes"] == "ccpol8sf" and roof.get("traffic"):
+            # the same step seen from the memory side (not its bound): DRAM bytes of the PES pipeline per step (ncu, profiles/)
+            # plus the streamed state traffic, against the measured copy bandwidth of MEASURED_PEAKS.json
+            hp, hsrc = hbm_peak()
+            gb = roof["traffic"] + 10 * 8 * ndof * ntraj * n / 1e9
+            line["roofline_hbm"] = {"bound": "hbm", "achieved": gb / (ms / K * 1e-3), "peak": hp, "unit": "GB/s",
+                                    "frac": gb / (ms / K * 1e-3) / hp, "traffic": gb, "peak_source": hsrc,
                                     "note": "supplementary view: the step is FP64-bound (roofline above); its DRAM traffic uses "
                                             "this fraction of the HBM bandwidth"}
         if not args.no_cpu and world == 1:
@@ -398,6 +549,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             line["cpu_baseline"] = {"value": v, "unit": "bead-steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d cores x 1 trajectory x %d beads x %d steps (%.1f s)" % (cores, n, per_step, wall)}
         print(json.dumps(line), flush=True)
+    ti.comm_finalize()
     if world > 1:
         dist.destroy_process_group()
     pk.finalize()
@@ -521,7 +673,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--ntraj", type=int, default=0, help="override trajectories per GPU (testing)")
-    ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--mode", default="strict", choices=sorted(MODES),
+                    help="CCpol arithmetic: strict = the reference's finite-difference gradient, bit-faithful (the headline); "
+                         "fast = the same with FMA contraction; analytic = opt-in analytic gradient (NOT the reference's arithmetic)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: trajectories per GPU fixed; strong: the config's trajectories split over the GPUs")
+    ap.add_argument("--sweep", default="", help="comma-separated trajectory counts (per GPU if weak, in total if strong): "
+                                                 "one JSON line per count, device-resident value only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="device-resident value only (no profiling, e2e or CPU legs)")
     args = ap.parse_args()

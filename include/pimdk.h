@@ -12,7 +12,9 @@
  * library stream without synchronising.  Every call returns 0 on success or a PIMDK_E* code;
  * pimdk_last_error() gives the text.  The library never calls exit(); the Fortran shim turns a
  * non-zero code into the reference's `write(*,*) msg; stop`.  Not thread-safe (neither is the
- * reference: module globals and COMMON /ddaattaa/).
+ * reference: module globals and COMMON /ddaattaa/).  Like the reference's linked-in mcmod_<PES>.o there is ONE
+ * selected PES, one V0 and one set of normal-mode tables per process: pimdk_pes_select / pimdk_pes_set_v0 /
+ * pimdk_nm_setup replace the previous selection for every later call.
  *
  * There is no CPU fallback: without a CUDA device every compute call fails with PIMDK_ENODEV.
  */
@@ -151,7 +153,8 @@ int pimdk_init_path(pimdk_int ntraj, pimdk_int npath, const double* lampath, con
  *   Noutput   Andersen: mean collision interval (Poisson); PILE: unused (print cadence)
  *   seed, traj_gid: RNG contract: Philox4x32-10 keyed by seed, counter carries the
  *             global trajectory id so results do not depend on how trajectories are sharded.
- *             traj_gid == NULL means 0..ntraj-1.
+ *             traj_gid == NULL means 0..ntraj-1.  The counter carries 32 bits of the id: ids outside
+ *             0 .. 2^32-1 are rejected with PIMDK_EINVAL (they would alias RNG streams).
  * Requires pimdk_pes_select and pimdk_nm_setup with matching n, ndim, natom. */
 int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p, const double* a, const double* b,
                     const double* dbdl, double dt, double gamma, pimdk_int NMC, pimdk_int imin, pimdk_int Noutput,
@@ -168,6 +171,12 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
  * pimdk_get_dhdr_sums returns the running (un-normalised) sums of the last propagate call: the dHdr that
  * write_restart stores (verletmodule.f90:162-185, called at :206, 246, 394, 412). */
 int pimdk_set_restart(pimdk_int restart, pimdk_int restartnmc);
+/* Andersen thermostat, a run cut into several propagate calls (restart = 1 writes its files every Noutput steps from
+ * inside the loop, verletmodule.f90:205-207, without touching the collision clock `count` / `rkick(1)`, :199-202,208-234):
+ * enable = 1 makes the following Andersen calls continue the per-trajectory clocks left by the previous call (same
+ * number of trajectories; PIMDK_EINVAL otherwise) instead of starting at count = 0 with a new Poisson interval.
+ * enable = 0 (default): every call starts its clocks like a fresh propagate_pimd_nm. */
+int pimdk_set_andersen_carry(pimdk_int enable);
 int pimdk_get_dhdr_sums(pimdk_int ntraj, double* sums);
 /* index (0-based, into the last call's batch) of the first trajectory that tripped the NaN trap, or -1 */
 pimdk_int pimdk_last_nan_trajectory(void);
@@ -186,6 +195,27 @@ int pimdk_ti_partial_sums(pimdk_int ntraj, const double* dHdr, const pimdk_int* 
                           pimdk_int nintegral, double betan, double* sums);
 int pimdk_ti_finish(pimdk_int nintegral, const double* sums, const double* weights, double betan, double* mean,
                     double* var, double* deltaA, double* sigmaA, double* q_over_q0);
+/* ---- multi-GPU: one rank (process) per GPU, independent trajectories sharded by global id (pimd_par.f90:109-110,
+ * 281-295), ONE collective per run ------------------------------------------------------------------------------
+ * The reference gathers every rank's integrands on the root (MPI_Gather, pimd_par.f90:389) and forms the per-lambda mean
+ * and variance there (:397-409).  Here the library owns an NCCL communicator (bound at run time; PIMDK_NCCL_LIB names the
+ * library if libnccl.so.2 is not on the loader path) and all-reduces {sum I, sum I**2, count} per lambda point, 3*nintegral
+ * doubles, on the library stream.
+ *   pimdk_comm_unique_id : rank 0 creates the 128-byte id (ncclGetUniqueId) and hands it to the other ranks by whatever
+ *                          means the host program has (MPI_Bcast in the Fortran drivers, a file, a socket)
+ *   pimdk_comm_init      : every rank, after pimdk_init on its own device (ncclCommInitRank); nranks = 1 needs no id/NCCL
+ *   pimdk_ti_allreduce   : sums(3,nintegral) on the host (from pimdk_ti_partial_sums), summed over ranks in place
+ *   pimdk_ti_reduce_dev  : the same for dHdr / traj_gid that are still on the device (dHdr as pimdk_propagate_dev left
+ *                          it): per-lambda partial sums formed by a device kernel, all-reduced, copied to sums (host);
+ *                          feed pimdk_ti_finish with the result.  Works with one rank too (no NCCL involved). */
+#define PIMDK_UNIQUE_ID_BYTES 128
+int pimdk_comm_unique_id(void* id);
+int pimdk_comm_init(pimdk_int rank, pimdk_int nranks, const void* id);
+int pimdk_comm_finalize(void);
+int pimdk_comm_info(pimdk_int* rank, pimdk_int* nranks, pimdk_int* nccl_version);
+int pimdk_ti_allreduce(pimdk_int nintegral, double* sums);
+int pimdk_ti_reduce_dev(pimdk_int ntraj, const double* dHdr, const pimdk_int* traj_gid, pimdk_int nrep, pimdk_int nintegral,
+                        double betan, double* sums);
 /* gauleg (verletmodule.f90:124-160) */
 int pimdk_gauleg(double x1, double x2, pimdk_int nintegral, double* x, double* w);
 

@@ -50,11 +50,18 @@ _SIGS = {
     "pimdk_propagate": [_i64, _i64, _pd, _pd, _pd, _pd, _pd, _dbl, _dbl, _i64, _i64, _i64, _i64, _u64, _pi, _pd],
     "pimdk_propagate_dev": [_i64, _i64, _pd, _pd, _pd, _pd, _pd, _dbl, _dbl, _i64, _i64, _i64, _i64, _u64, _pi, _pd],
     "pimdk_set_restart": [_i64, _i64],
+    "pimdk_set_andersen_carry": [_i64],
     "pimdk_set_propagate_chunk": [_i64],
     "pimdk_get_dhdr_sums": [_i64, _pd],
     "pimdk_ti_partial_sums": [_i64, _pd, _pi, _i64, _i64, _dbl, _pd],
     "pimdk_ti_finish": [_i64, _pd, _pd, _dbl, _pd, _pd, _pd, _pd, _pd],
     "pimdk_gauleg": [_dbl, _dbl, _i64, _pd, _pd],
+    "pimdk_comm_unique_id": [ctypes.c_void_p],
+    "pimdk_comm_init": [_i64, _i64, ctypes.c_void_p],
+    "pimdk_comm_finalize": [],
+    "pimdk_comm_info": [ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64)],
+    "pimdk_ti_allreduce": [_i64, _pd],
+    "pimdk_ti_reduce_dev": [_i64, _pd, _pi, _i64, _i64, _dbl, _pd],
     "pimdk_profile": [_i64],
     "pimdk_profile_get": [ctypes.c_char_p, ctypes.POINTER(_dbl), ctypes.POINTER(_i64)],
     "pimdk_profile_reset": [],
@@ -128,3 +135,8 @@ def finalize():
     if _lib is not None:
         _lib.pimdk_finalize()
     _initialised = False
+    # selections made before finalize are gone with the context
+    from . import mcmod_mass, verletint
+
+    mcmod_mass.McmodMass._owner = None
+    verletint.VerletInt._owner = None

@@ -550,8 +550,12 @@ long KNAME(ccpol_launches)(long ngeom, int grad, int icc, size_t work_bytes) {
 cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, int icc, int potparts_old, double V0, GeomLayout L, double* x, double* v,
                                 double* grad, long ngeom, int write_drift, int* flags, double* work, size_t work_bytes,
                                 cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  // function attributes are per device: one bit per device ordinal (a process may drive several GPUs, or re-initialise on another)
+  static unsigned long long attr_mask = 0;
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  const unsigned long long dev_bit = 1ull << (cur_dev & 63);
+  if (!(attr_mask & dev_bit)) {
     cudaError_t e = cudaFuncSetAttribute(KNAME(ccpol_sapt_kernel)<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sapt_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(KNAME(ccpol_sapt_kernel)<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sapt_smem());
@@ -560,7 +564,7 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(KNAME(ccpol_sweep_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem());
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr_mask |= dev_bit;
   }
   const int g = grad != nullptr;
   int nbuf;

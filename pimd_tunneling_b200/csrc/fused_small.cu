@@ -46,7 +46,8 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
                    double* __restrict__ pg, const double* __restrict__ a, const double* __restrict__ b,
                    const double* __restrict__ dbdl, double dt, long NMC, long imin, double lambda, uint64_t seed,
                    const int64_t* __restrict__ gid, double* __restrict__ dHdr, int* __restrict__ flags, long step0,
-                   int keep_sum, double* __restrict__ dHsum) {
+                   int keep_sum, double* __restrict__ dHsum, int* __restrict__ clk_count, int* __restrict__ clk_kick,
+                   int carry) {
   extern __shared__ __align__(16) double sm[];
   const int n = nm.n;
   double* Ts = sm;                                   // transmatrix, n x n
@@ -164,8 +165,9 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
       if (ii > imin) estimator();
     }
   } else {                // propagate_pimd_nm (:190-250) / time_step_nm (:291-302)
-    int count = 0;
-    int rkick = poisson_norm(seed, (uint64_t)step0, g, lambda);
+    // collision clock: fresh (:199-202) or continued from the previous call of a run cut into segments
+    int count = carry ? clk_count[traj] : 0;
+    int rkick = carry ? clk_kick[traj] : poisson_norm(seed, (uint64_t)step0, g, lambda);
     for (long ii = 1; ii <= NMC; ++ii) {
       count = count + 1;
       if (count >= rkick) {
@@ -193,6 +195,10 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
       kick_and_rotate(false, 1, (uint64_t)(ii + step0));
       to_beads();
       if (ii > imin) estimator();
+    }
+    if (lane == 0 && clk_count) {
+      clk_count[traj] = count;
+      clk_kick[traj] = rkick;
     }
   }
   // back to bead space: p = T P ; x is current
@@ -226,14 +232,14 @@ template <int NDOF, int S>
 cudaError_t launch_t(const NmTables& nm, int kind, const SimplePesParams& pp, int thermostat, long ntraj, double* x,
                      double* p, const double* a, const double* b, const double* dbdl, double dt, long NMC, long imin,
                      double lambda, uint64_t seed, const int64_t* gid, double* dHdr, int* flags, long step0, int keep_sum,
-                     double* dHsum, cudaStream_t st) {
+                     double* dHsum, int* clk_count, int* clk_kick, int carry, cudaStream_t st) {
   const size_t smem = ((size_t)nm.n * nm.n + (size_t)kWarpsPerBlock * nm.n) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(fused_small_kernel<NDOF, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned blocks = (unsigned)((ntraj + kWarpsPerBlock - 1) / kWarpsPerBlock);
   fused_small_kernel<NDOF, S><<<blocks, kWarpsPerBlock * 32, smem, st>>>(nm, kind, pp, thermostat, ntraj, x, p, a, b, dbdl,
                                                                         dt, NMC, imin, lambda, seed, gid, dHdr, flags, step0,
-                                                                        keep_sum, dHsum);
+                                                                        keep_sum, dHsum, clk_count, clk_kick, carry);
   return cudaGetLastError();
 }
 
@@ -249,12 +255,13 @@ bool fused_small_supported(PesKind kind, int n, int ndim, int natom) {
 cudaError_t launch_fused_small(const NmTables& nm, PesKind kind, const SimplePesParams& pp, int thermostat, long ntraj,
                                double* x, double* p, const double* a, const double* b, const double* dbdl, double dt,
                                long NMC, long imin, double lambda, uint64_t seed, const int64_t* gid, double* dHdr,
-                               int* flags, long step0, int keep_sum, double* dHsum, cudaStream_t st) {
+                               int* flags, long step0, int keep_sum, double* dHsum, int* clk_count, int* clk_kick, int carry,
+                               cudaStream_t st) {
   const int S = (nm.n + 31) / 32;
 #define PIMDK_FUSED_CASE(ND, SS)                                                                                        \
   if (nm.ndof == ND && S == SS)                                                                                         \
     return launch_t<ND, SS>(nm, (int)kind, pp, thermostat, ntraj, x, p, a, b, dbdl, dt, NMC, imin, lambda, seed, gid, \
-                            dHdr, flags, step0, keep_sum, dHsum, st);
+                            dHdr, flags, step0, keep_sum, dHsum, clk_count, clk_kick, carry, st);
   PIMDK_FUSED_CASE(1, 1) PIMDK_FUSED_CASE(1, 2) PIMDK_FUSED_CASE(1, 3) PIMDK_FUSED_CASE(1, 4)
   PIMDK_FUSED_CASE(2, 1) PIMDK_FUSED_CASE(2, 2) PIMDK_FUSED_CASE(2, 3) PIMDK_FUSED_CASE(2, 4)
 #undef PIMDK_FUSED_CASE

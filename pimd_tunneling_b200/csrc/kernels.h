@@ -8,7 +8,7 @@
 
 namespace pimdk {
 
-enum { PIMDK_FLAG_NAN = 1, PIMDK_FLAG_NOCONV = 2 };
+enum { PIMDK_FLAG_NAN = 1, PIMDK_FLAG_NOCONV = 2, PIMDK_FLAG_BADGID = 4 };
 
 // Where geometry g (one bead of one ring polymer, or one batch entry) lives in a coordinate array.
 //   ABI batch   x(ndim,natom,nbatch):          n_inner=1, stride_outer=ndof, stride_dof=1
@@ -79,14 +79,22 @@ enum GemmMode {
   GEMM_ADD_BEADVEC = 2, // Y = (A + beadvec) T          (nmtransform_backward, bead>0)
 };
 void set_nm_gemm_dmma(int on);
+// BV (optional): beadvec(k, dof) of every row, precomputed by launch_beadvec; with it (and n even) GEMM_PLAIN and
+// GEMM_SUB_BEADVEC run the cp.async-pipelined tensor-core kernel, and the backward form is a GEMM_PLAIN of Q + beadvec
+// (written by launch_nm_update / launch_add) instead of GEMM_ADD_BEADVEC.
 cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, double* Y, long rows,
-                           const double* a /*(ndof)*/, const double* b /*(ndof,ntraj)*/, cudaStream_t st);
+                           const double* a /*(ndof)*/, const double* b /*(ndof,ntraj)*/, cudaStream_t st,
+                           const double* BV = nullptr);
+bool nm_uses_beadvec_array(const NmTables& nm);
+cudaError_t launch_beadvec(const NmTables& nm, const double* a, const double* b, long rows, double* BV, cudaStream_t st);
+cudaError_t launch_add(const double* x, const double* y, double* z, long total, cudaStream_t st);
 
 // P <- P - dt*G ; then rotate(dt/2) . O-step(Philox) . rotate(dt/2) on (P,Q) in normal-mode space (PILE), or
 // rotate only (thermostat handled by the caller for Andersen).
 cudaError_t launch_nm_update(const NmTables& nm, double* P, double* Q, const double* G, double dt, long ntraj,
                              int do_kick, int nrot, int do_langevin, uint64_t seed, uint64_t step,
-                             const int64_t* gid, int* flags, cudaStream_t st);
+                             const int64_t* gid, int* flags, cudaStream_t st, const double* BV = nullptr,
+                             double* QB = nullptr /* receives Q + BV */);
 // Andersen: P <- N(0, sqrt(1/betan))*sqrt(beadmass) for trajectories whose counter fired; updates counters.
 cudaError_t launch_andersen(const NmTables& nm, double* P, long ntraj, uint64_t seed, uint64_t step, double lambda,
                             const int64_t* gid, int* count, int* rkick, cudaStream_t st);
@@ -97,7 +105,8 @@ cudaError_t launch_sample_momenta(const NmTables& nm, double* P, long ntraj, uin
                                   const int64_t* gid, cudaStream_t st);
 // estimator: dHdr[traj] += sum_{dim,atom} mass*(-x(n,dim,atom))*dbdl(dim,atom,traj)   (verletmodule.f90:397-403)
 cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const double* a, const double* b,
-                                   const double* dbdl, double* dHdr, long ntraj, cudaStream_t st);
+                                   const double* dbdl, double* dHdr, long ntraj, cudaStream_t st,
+                                   const double* BV = nullptr);
 cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* dbdl, double* dHdr, long ntraj,
                              cudaStream_t st);
 cudaError_t launch_scale(double* v, double s, long n, cudaStream_t st);
@@ -107,7 +116,8 @@ bool fused_small_supported(PesKind kind, int n, int ndim, int natom);
 cudaError_t launch_fused_small(const NmTables& nm, PesKind kind, const SimplePesParams& pp, int thermostat, long ntraj,
                                double* x, double* p, const double* a, const double* b, const double* dbdl, double dt,
                                long NMC, long imin, double lambda, uint64_t seed, const int64_t* gid, double* dHdr,
-                               int* flags, long step0, int keep_sum, double* dHsum, cudaStream_t st);
+                               int* flags, long step0, int keep_sum, double* dHsum, int* clk_count, int* clk_kick, int carry,
+                               cudaStream_t st);
 
 // ---- second derivatives (hess_kernels.cu): Vdoubleprime, UMhessian (instantonmod.f90:155-217) ----
 cudaError_t launch_simple_hessian(PesKind kind, const SimplePesParams& P, int ndim, int natom, GeomLayout L, double* x,

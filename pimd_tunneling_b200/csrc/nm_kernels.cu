@@ -241,6 +241,130 @@ nm_gemm_dmma_kernel(NmTables nm, const double* __restrict__ A, double* __restric
   }
 }
 
+
+// ---- the production transform: DMMA tiles fed by a 3-stage cp.async pipeline ------------------------------------------------
+// Same tile shape, fragment layout and fma/k order as nm_gemm_dmma_kernel above (identical bits), but the k-tiles of A and
+// T travel global -> shared memory asynchronously (cp.async.cg, 16 bytes = 2 doubles per request, zero-filled outside the
+// matrix), three tiles in flight, ONE barrier per k-tile: the tensor pipe no longer waits for a store-after-compute
+// hand-over twice per tile.  The beadvec shift is not formed inside the main loop any more: the forward form subtracts a
+// precomputed beadvec array E in the epilogue (MODE = GEMM_SUB_BEADVEC), the backward form is a plain product of the
+// array Q + beadvec that the update kernel wrote (the reference's order: add, then transform; verletmodule.f90:274-279).
+// Needs n even (16-byte alignment of every row); odd n takes the register-staged kernels above.
+constexpr int kStages = 3;
+template <int NT>
+constexpr size_t pipe_smem_bytes() { return (size_t)kStages * (BM * LDA + DK * (16 * NT + 4)) * sizeof(double); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled, the source is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MODE, int NT>
+__global__ void __launch_bounds__(GT, NT == 4 ? 2 : 1)
+nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restrict__ Y, long rows,
+                    const double* __restrict__ E) {
+  constexpr int TN = 16 * NT, LDB = TN + 4, STAGE = BM * LDA + DK * LDB;
+  extern __shared__ __align__(16) double pipe_smem[];
+  const int n = nm.n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const long row0 = (long)blockIdx.y * BM;
+  const int col0 = blockIdx.x * TN;
+  const int ktiles = (n + DK - 1) / DK;
+  auto issue = [&](int kt) {
+    if (kt < ktiles) {
+      double* As = pipe_smem + (kt % kStages) * STAGE;
+      double* Bs = As + BM * LDA;
+      const int k0 = kt * DK;
+#pragma unroll
+      for (int c = tid; c < BM * (DK / 2); c += GT) {       // A tile: 128 rows x 8 requests
+        const int r = c >> 3, ch = c & 7;
+        const long gr = row0 + r;
+        const int gk = k0 + 2 * ch;
+        const bool ok = gr < rows && gk < n;
+        cp_async16(As + r * LDA + 2 * ch, ok ? A + gr * n + gk : A, ok);
+      }
+#pragma unroll
+      for (int c = tid; c < DK * (TN / 2); c += GT) {       // T tile: 16 rows x TN/2 requests
+        const int r = c / (TN / 2), ch = c - r * (TN / 2);
+        const int gk = k0 + r, gc = col0 + 2 * ch;
+        const bool ok = gk < n && gc < n;
+        cp_async16(Bs + r * LDB + 2 * ch, ok ? nm.T + (long)gk * n + gc : nm.T, ok);
+      }
+    }
+    cp_async_commit();   // an empty group keeps the wait count uniform in the tail
+  };
+  double acc[4][NT][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) issue(s);
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<kStages - 2>();   // tile kt has landed (for this thread's requests) ...
+    __syncthreads();                // ... and for everybody's; also: everybody is done with the stage issued next
+    issue(kt + kStages - 1);
+    const double* As = pipe_smem + (kt % kStages) * STAGE;
+    const double* Af = As + (wm * 32 + (lane >> 2)) * LDA + (lane & 3);
+    const double* Bf = As + BM * LDA + (lane & 3) * LDB + wn * 8 * NT + (lane >> 2);
+#pragma unroll
+    for (int kk = 0; kk < DK; kk += 4) {
+      double af[4], bf[NT];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = Af[i * 8 * LDA + kk];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bf[j] = Bf[kk * LDB + j * 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(af[i]), "d"(bf[j]));
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
+    if (r >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int c = col0 + wn * 8 * NT + j * 8 + 2 * (lane & 3);
+      if (c >= n) continue;          // n is even: c and c + 1 are inside or outside together
+      double y0 = acc[i][j][0], y1 = acc[i][j][1];
+      if (MODE == GEMM_SUB_BEADVEC) {
+        const double2 e = *reinterpret_cast<const double2*>(&E[r * n + c]);
+        y0 = y0 - e.x;
+        y1 = y1 - e.y;
+      }
+      *reinterpret_cast<double2*>(&Y[r * n + c]) = make_double2(y0, y1);
+    }
+  }
+}
+
+// beadvec(k, dof) of every (trajectory, dof) row, once per propagate call (a and b do not change during it): init_nm
+// (verletmodule.f90:328-333) for the whole batch
+__global__ void __launch_bounds__(256)
+beadvec_kernel(NmTables nm, const double* __restrict__ a, const double* __restrict__ b, long rows, double* __restrict__ BV) {
+  const long total = rows * nm.n;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long r = e / nm.n;
+    const int k = (int)(e - r * nm.n);
+    const long traj = r / nm.ndof;
+    BV[e] = beadvec_at(nm, a, b, traj, (int)(r - traj * nm.ndof), k);
+  }
+}
+__global__ void __launch_bounds__(256)
+add_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ z, long total) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) z[e] = x[e] + y[e];
+}
+
 __global__ void __launch_bounds__(256)
 nm_update_kernel(NmTables nm, double* __restrict__ Pn, double* __restrict__ Qn, const double* __restrict__ G,
                  double dt, long ntraj, int ops, uint64_t seed, uint64_t step, const int64_t* __restrict__ gid,
@@ -265,6 +389,91 @@ nm_update_kernel(NmTables nm, double* __restrict__ Pn, double* __restrict__ Qn, 
     if (P != P) atomicOr(flags, PIMDK_FLAG_NAN);
     Pn[e] = P;
     Qn[e] = Q;
+  }
+}
+
+// The same update for even n, two consecutive modes (k, k+1) of one (trajectory, dof) row per thread: the two modes are
+// the two normals of ONE Box-Muller pair (RNG contract: normal #idx lives in pair idx >> 1), so one Philox block, one log
+// and one sincos serve both (the per-element kernel above evaluates them twice and drops half); 16-byte loads and
+// stores; row -> (trajectory, dof) by one 32-bit division per thread instead of two 64-bit ones per element.  Same
+// arithmetic per element, identical bits.  QB (optional) receives Q + beadvec for the back-transform that follows.
+__global__ void __launch_bounds__(256)
+nm_update2_kernel(NmTables nm, double* __restrict__ Pn, double* __restrict__ Qn, const double* __restrict__ G,
+                  double dt, unsigned rows, int ops, uint64_t seed, uint64_t step, const int64_t* __restrict__ gid,
+                  int* __restrict__ flags, const double* __restrict__ BV, double* __restrict__ QB) {
+  const int n = nm.n;
+  const unsigned half = (unsigned)n >> 1;
+  const unsigned rpc = (2 * blockDim.x >= (unsigned)n) ? (2 * blockDim.x) / (unsigned)n : 1;   // rows per CTA pass
+  const unsigned tl = (2 * threadIdx.x) / (unsigned)n;            // this thread's row within the pass (0 when n >= 512)
+  const unsigned k_first = 2 * threadIdx.x - tl * (unsigned)n;
+  if (tl >= rpc) return;
+  for (unsigned long long row0 = (unsigned long long)blockIdx.x * rpc; row0 < rows; row0 += (unsigned long long)gridDim.x * rpc) {
+    const unsigned row = (unsigned)row0 + tl;
+    if (row >= rows) continue;
+    const unsigned traj = row / (unsigned)nm.ndof;
+    const int dof = (int)(row - traj * (unsigned)nm.ndof);
+    const int akb = (dof / nm.ndim) * n;
+    const uint32_t g = gid ? (uint32_t)gid[traj] : traj;
+    const size_t base = (size_t)row * n;
+    for (unsigned k = k_first; k < (unsigned)n; k += 2 * blockDim.x) {
+      const size_t e = base + k;
+      double2 P = *reinterpret_cast<const double2*>(Pn + e);
+      double2 Q = *reinterpret_cast<const double2*>(Qn + e);
+      const int ak = akb + (int)k;
+      if (ops & OP_KICK) {
+        const double2 gg = *reinterpret_cast<const double2*>(G + e);
+        P.x = P.x - gg.x * dt;
+        P.y = P.y - gg.y * dt;
+      }
+      if (ops & OP_ROT1) {
+        rotate(nm, ak, P.x, Q.x);
+        rotate(nm, ak + 1, P.y, Q.y);
+      }
+      if (ops & OP_LANGEVIN) {
+        double z0, z1;
+        normal_pair_at(seed, STREAM_LANGEVIN, step, g, (uint64_t)(((unsigned)dof * (unsigned)n + k) >> 1), z0, z1);
+        P.x = nm.c1sq[ak] * P.x + nm.cnoise[ak] * z0;
+        P.y = nm.c1sq[ak + 1] * P.y + nm.cnoise[ak + 1] * z1;
+      }
+      if (ops & OP_ROT2) {
+        rotate(nm, ak, P.x, Q.x);
+        rotate(nm, ak + 1, P.y, Q.y);
+      }
+      if (P.x != P.x || P.y != P.y) atomicOr(flags, PIMDK_FLAG_NAN);
+      *reinterpret_cast<double2*>(Pn + e) = P;
+      *reinterpret_cast<double2*>(Qn + e) = Q;
+      if (QB) {
+        const double2 bv = *reinterpret_cast<const double2*>(BV + e);
+        *reinterpret_cast<double2*>(QB + e) = make_double2(Q.x + bv.x, Q.y + bv.y);
+      }
+    }
+  }
+}
+
+// momenta for even n, one Box-Muller pair per thread (see nm_update2_kernel)
+__global__ void __launch_bounds__(256)
+sample_momenta2_kernel(NmTables nm, double* __restrict__ Pn, unsigned rows, uint64_t seed, int stream, uint64_t step,
+                       const int64_t* __restrict__ gid, const int* __restrict__ count, const int* __restrict__ rkick) {
+  const int n = nm.n;
+  const unsigned rpc = (2 * blockDim.x >= (unsigned)n) ? (2 * blockDim.x) / (unsigned)n : 1;
+  const unsigned tl = (2 * threadIdx.x) / (unsigned)n;
+  const unsigned k_first = 2 * threadIdx.x - tl * (unsigned)n;
+  if (tl >= rpc) return;
+  for (unsigned long long row0 = (unsigned long long)blockIdx.x * rpc; row0 < rows; row0 += (unsigned long long)gridDim.x * rpc) {
+    const unsigned row = (unsigned)row0 + tl;
+    if (row >= rows) continue;
+    const unsigned traj = row / (unsigned)nm.ndof;
+    if (count && !(count[traj] + 1 >= rkick[traj])) continue;
+    const int dof = (int)(row - traj * (unsigned)nm.ndof);
+    const int akb = (dof / nm.ndim) * n;
+    const uint32_t g = gid ? (uint32_t)gid[traj] : traj;
+    const size_t base = (size_t)row * n;
+    for (unsigned k = k_first; k < (unsigned)n; k += 2 * blockDim.x) {
+      double z0, z1;
+      normal_pair_at(seed, stream, step, g, (uint64_t)(((unsigned)dof * (unsigned)n + k) >> 1), z0, z1);
+      *reinterpret_cast<double2*>(Pn + base + k) =
+          make_double2((0.0 + nm.stdev * z0) * nm.sigp[akb + (int)k], (0.0 + nm.stdev * z1) * nm.sigp[akb + (int)k + 1]);
+    }
   }
 }
 
@@ -330,7 +539,7 @@ constexpr int kEmRows = 32, kEmThreads = 256;
 __global__ void __launch_bounds__(kEmThreads)
 estimator_modes_kernel(NmTables nm, const double* __restrict__ Q, const double* __restrict__ a,
                        const double* __restrict__ b, const double* __restrict__ dbdl, double* __restrict__ dHdr,
-                       long ntraj) {
+                       long ntraj, const double* __restrict__ BV) {
   extern __shared__ double em_smem[];
   const int n = nm.n, ndof = nm.ndof;
   double* tcol = em_smem;                 // T(:, n): n doubles
@@ -348,7 +557,10 @@ estimator_modes_kernel(NmTables nm, const double* __restrict__ Q, const double* 
     __syncthreads();
     for (int rr = warp; rr < nrow; rr += kEmThreads / 32) {   // Q + beadvec, formed lane-parallel by all warps
       const int m = m0 + lane, tl = rr / ndof;
-      tile[rr * 33 + lane] = m < n ? Q[(row0 + rr) * (long)n + m] + beadvec_at(nm, a, b, traj0 + tl, rr - tl * ndof, m) : 0.0;
+      // beadvec: the call's precomputed array when there is one (the same expression, evaluated once per call)
+      tile[rr * 33 + lane] = m < n ? Q[(row0 + rr) * (long)n + m] +
+                                         (BV ? BV[(row0 + rr) * (long)n + m] : beadvec_at(nm, a, b, traj0 + tl, rr - tl * ndof, m))
+                                   : 0.0;
     }
     __syncthreads();
     if (r < nrow) {
@@ -390,9 +602,32 @@ static int g_gemm_dmma = 1;   // default: tensor-core path (1.5x the FMA-pipe ke
 void set_nm_gemm_dmma(int on) { g_gemm_dmma = on; }
 
 cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, double* Y, long rows, const double* a,
-                           const double* b, cudaStream_t st) {
+                           const double* b, cudaStream_t st, const double* BV) {
   if (rows <= 0) return cudaSuccess;
   dim3 grid((nm.n + BN - 1) / BN, (unsigned)((rows + BM - 1) / BM));
+  // production path: cp.async-pipelined DMMA tiles (even n; the forward shift needs the precomputed beadvec array)
+  if (g_gemm_dmma && (nm.n & 1) == 0 && (mode == GEMM_PLAIN || (mode == GEMM_SUB_BEADVEC && BV))) {
+    static unsigned long long attr_mask = 0;   // the >48 KB dynamic shared memory opt-in is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_mask & (1ull << (dev & 63)))) {
+      cudaError_t e = cudaFuncSetAttribute(nm_gemm_pipe_kernel<GEMM_PLAIN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes<4>());
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes<4>());
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_gemm_pipe_kernel<GEMM_PLAIN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes<8>());
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes<8>());
+      if (e != cudaSuccess) return e;
+      attr_mask |= 1ull << (dev & 63);
+    }
+    if (g_gemm_dmma == 3) {
+      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV);
+      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV);
+    } else {
+      dim3 g4((nm.n + 63) / 64, (unsigned)((rows + BM - 1) / BM));
+      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV);
+      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV);
+    }
+    return cudaGetLastError();
+  }
   if (g_gemm_dmma) {
     const int nt = g_gemm_dmma == 3 ? 8 : 4;   // 128 x 64 CTA tiles (two CTAs per SM) measured faster on every shape
     if (nt == 4) {
@@ -419,24 +654,53 @@ cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, d
   return cudaGetLastError();
 }
 
+// true when the streamed path keeps a precomputed beadvec array for this shape (see nm_gemm_pipe_kernel)
+bool nm_uses_beadvec_array(const NmTables& nm) { return g_gemm_dmma != 0 && (nm.n & 1) == 0; }
+
+cudaError_t launch_beadvec(const NmTables& nm, const double* a, const double* b, long rows, double* BV, cudaStream_t st) {
+  beadvec_kernel<<<grid_for(rows * nm.n, 256), 256, 0, st>>>(nm, a, b, rows, BV);
+  return cudaGetLastError();
+}
+cudaError_t launch_add(const double* x, const double* y, double* z, long total, cudaStream_t st) {
+  add_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, z, total);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_nm_update(const NmTables& nm, double* P, double* Q, const double* G, double dt, long ntraj,
                              int do_kick, int nrot, int do_langevin, uint64_t seed, uint64_t step,
-                             const int64_t* gid, int* flags, cudaStream_t st) {
+                             const int64_t* gid, int* flags, cudaStream_t st, const double* BV, double* QB) {
   int ops = 0;
   if (do_kick) ops |= OP_KICK;
   if (nrot >= 1) ops |= OP_ROT1;
   if (do_langevin) ops |= OP_LANGEVIN;
   if (nrot >= 2) ops |= OP_ROT2;
-  const long total = ntraj * (long)nm.ndof * nm.n;
+  const long rows = ntraj * (long)nm.ndof;
+  const long total = rows * nm.n;
+  if ((nm.n & 1) == 0 && rows < 0xffffffffL) {
+    const long rpc = 512 >= nm.n ? 512 / nm.n : 1;
+    nm_update2_kernel<<<grid_for((rows + rpc - 1) / rpc, 1), 256, 0, st>>>(nm, P, Q, G, dt, (unsigned)rows, ops, seed, step, gid, flags,
+                                                                        QB ? BV : nullptr, QB);
+    return cudaGetLastError();
+  }
   nm_update_kernel<<<grid_for(total, 256), 256, 0, st>>>(nm, P, Q, G, dt, ntraj, ops, seed, step, gid, flags);
+  if (QB) add_kernel<<<grid_for(total, 256), 256, 0, st>>>(Q, BV, QB, total);
   return cudaGetLastError();
+}
+
+static void sample_momenta_any(const NmTables& nm, double* P, long ntraj, uint64_t seed, int stream, uint64_t step,
+                               const int64_t* gid, const int* count, const int* rkick, cudaStream_t st) {
+  const long rows = ntraj * (long)nm.ndof;
+  if ((nm.n & 1) == 0 && rows < 0xffffffffL) {
+    const long rpc = 512 >= nm.n ? 512 / nm.n : 1;
+    sample_momenta2_kernel<<<grid_for((rows + rpc - 1) / rpc, 1), 256, 0, st>>>(nm, P, (unsigned)rows, seed, stream, step, gid, count, rkick);
+  } else {
+    sample_momenta_kernel<<<grid_for(rows * nm.n, 256), 256, 0, st>>>(nm, P, ntraj, seed, stream, step, gid, count, rkick);
+  }
 }
 
 cudaError_t launch_andersen(const NmTables& nm, double* P, long ntraj, uint64_t seed, uint64_t step, double lambda,
                             const int64_t* gid, int* count, int* rkick, cudaStream_t st) {
-  const long total = ntraj * (long)nm.ndof * nm.n;
-  sample_momenta_kernel<<<grid_for(total, 256), 256, 0, st>>>(nm, P, ntraj, seed, STREAM_ANDERSEN, step, gid, count,
-                                                              rkick);
+  sample_momenta_any(nm, P, ntraj, seed, STREAM_ANDERSEN, step, gid, count, rkick, st);
   andersen_clock_kernel<<<(unsigned)((ntraj + 127) / 128), 128, 0, st>>>(ntraj, seed, step, lambda, gid, count, rkick, 0);
   return cudaGetLastError();
 }
@@ -449,8 +713,7 @@ cudaError_t launch_andersen_init(long ntraj, uint64_t seed, uint64_t step0, doub
 
 cudaError_t launch_sample_momenta(const NmTables& nm, double* P, long ntraj, uint64_t seed, int stream, uint64_t step,
                                   const int64_t* gid, cudaStream_t st) {
-  const long total = ntraj * (long)nm.ndof * nm.n;
-  sample_momenta_kernel<<<grid_for(total, 256), 256, 0, st>>>(nm, P, ntraj, seed, stream, step, gid, nullptr, nullptr);
+  sample_momenta_any(nm, P, ntraj, seed, stream, step, gid, nullptr, nullptr, st);
   return cudaGetLastError();
 }
 
@@ -461,7 +724,7 @@ cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* 
 }
 
 cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const double* a, const double* b,
-                                   const double* dbdl, double* dHdr, long ntraj, cudaStream_t st) {
+                                   const double* dbdl, double* dHdr, long ntraj, cudaStream_t st, const double* BV) {
   const int tpc = kEmRows / nm.ndof;     // (ndof <= 18 for every surface here)
   if (tpc < 1) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(nm.n + kEmRows * 33 + kEmRows) * sizeof(double);
@@ -469,7 +732,7 @@ cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const do
     cudaError_t e = cudaFuncSetAttribute(estimator_modes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  estimator_modes_kernel<<<(unsigned)((ntraj + tpc - 1) / tpc), kEmThreads, smem, st>>>(nm, Q, a, b, dbdl, dHdr, ntraj);
+  estimator_modes_kernel<<<(unsigned)((ntraj + tpc - 1) / tpc), kEmThreads, smem, st>>>(nm, Q, a, b, dbdl, dHdr, ntraj, BV);
   return cudaGetLastError();
 }
 

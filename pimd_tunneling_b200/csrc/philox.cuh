@@ -43,6 +43,25 @@ __device__ __forceinline__ double normal_at(uint64_t seed, int stream, uint64_t 
   return (idx & 1) ? rad * sn : rad * cs;
 }
 
+// Both normals of Box-Muller pair `pair` (normal #2*pair and #2*pair+1): one Philox block, one log, one sincos for two
+// numbers; bit-identical to normal_at(.., 2*pair) and normal_at(.., 2*pair + 1).
+__device__ __forceinline__ void normal_pair_at(uint64_t seed, int stream, uint64_t step, uint32_t gid, uint64_t pair,
+                                               double& z0, double& z1) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)pair, (uint32_t)(step & 0xffffffffu), gid,
+                ((uint32_t)stream << 24) | (uint32_t)((step >> 32) & 0xffffffu), (uint32_t)(seed & 0xffffffffu),
+                (uint32_t)(seed >> 32), r);
+  const double two53 = 1.0 / 9007199254740992.0;
+  const double u1 = ((double)((((uint64_t)r[0] << 32) | r[1]) >> 11) + 0.5) * two53;
+  const double u2 = ((double)((((uint64_t)r[2] << 32) | r[3]) >> 11) + 0.5) * two53;
+  const double rad = sqrt(-2.0 * pimdk_log(u1));
+  const double ang = 6.283185307179586 * u2;
+  double sn, cs;
+  pimdk_sincos(ang, &sn, &cs);
+  z0 = rad * cs;
+  z1 = rad * sn;
+}
+
 // Poisson(lambda), normal approximation (the reference requests VSL_RNG_METHOD_POISSON_POISNORM,
 // verletmodule.f90:361): floor(lambda + sqrt(lambda) z + 0.5), clamped at 0.
 __device__ __forceinline__ int poisson_norm(uint64_t seed, uint64_t step, uint32_t gid, double lambda) {

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -79,6 +80,8 @@ struct Ctx {
   bool fused = true;  // small systems: one persistent warp-per-ring-polymer kernel
   long restart = 0, restartnmc = 0;  // module verletint's restart / restartnmc (verletmodule.f90:10)
   long sums_n = 0;                   // trajectories in wDhSum (running sums of the last propagate call)
+  bool andersen_carry = false;       // pimdk_set_andersen_carry: the next Andersen call continues the collision clocks
+  long clock_n = 0;                  // trajectories whose (count, rkick) the last Andersen call left in wCount / wKick
   long chunk_traj = 0;               // pimdk_set_propagate_chunk: trajectories per chunk of the host-buffer propagate (0 = automatic)
   long sum_off = 0, sum_total = 0;   // chunked host-buffer propagate: this chunk's offset into wDhSum / whole batch
   cudaStream_t copy_stream = nullptr; // host<->device copies of the chunked propagate, overlapped with compute
@@ -98,7 +101,7 @@ struct Ctx {
   std::vector<double> mass, lam, beadmass, T;
   DevBuf dT, dsA, dsB, dlamb2, dmass, dtabs;  // dtabs: 8 per-call (natom,n) tables
   // workspaces
-  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wX2, wPp2, wUmIn, wUmOut, wHgp, wHgm, wHess, wBand, wDense, wEig, wWork;
+  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wX2, wPp2, wUmIn, wUmOut, wHgp, wHgm, wHess, wBand, wDense, wEig, wWork, wSums, wBV;
   PinBuf hUm;
   // profiling
   bool profiling = false;
@@ -176,8 +179,9 @@ int check_flags(bool sync_first) {
   return PIMDK_OK;
 }
 
+// wFlags: [int flags][int pad][long long slot] — the slot serves the NaN-trajectory lookup (no allocation on the error path)
 int clear_flags() {
-  CU(g.wFlags.ensure(sizeof(int)));
+  CU(g.wFlags.ensure(16));
   CU(cudaMemsetAsync(g.wFlags.p, 0, sizeof(int), g.stream));
   return PIMDK_OK;
 }
@@ -288,6 +292,12 @@ __global__ void first_nan_kernel(const double* __restrict__ p, long per_traj, lo
     if (p[e] != p[e]) atomicMin(out, (long long)(e / per_traj));
 }
 
+// RNG contract: the Philox counter carries the low 32 bits of the global trajectory id; larger ids would alias streams
+__global__ void check_gid_kernel(const int64_t* __restrict__ gid, long ntraj, int* __restrict__ flags) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ntraj && (gid[t] < 0 || gid[t] > 0xffffffffLL)) atomicOr(flags, PIMDK_FLAG_BADGID);
+}
+
 // init_path positions: x(k,dof,traj) = splint(lampath, path(:,dof), splinepath(:,dof), (k-1)*xi/(n-1))
 // (verletmodule.f90:39-48; splint/locate instantonmod.f90:500-524, 560-596)
 __global__ void init_path_kernel(int n, int ndof, int npath, const double* __restrict__ lampath,
@@ -322,6 +332,80 @@ __global__ void init_path_kernel(int n, int ndof, int npath, const double* __res
            ((aa * aa * aa - aa) * y2[klo - 1] + (bb * bb * bb - bb) * y2[khi - 1]) * (h * h) / 6.0;
   }
 }
+
+
+// Per-lambda statistics of the local shard on the device (pimd_par.f90:379, 397-409): one CTA per lambda point sums
+// I = dHdr/betan**2, I**2 and 1 over the shard's trajectories with that lambda index (global id / nrep) in a fixed
+// order (thread-strided partial sums, then a shared-memory tree), so a given shard always produces the same bits.
+constexpr int kTiThreads = 256;
+__global__ void __launch_bounds__(kTiThreads)
+ti_partial_sums_kernel(const double* __restrict__ dHdr, const int64_t* __restrict__ gid, long ntraj, long nrep, long nintegral,
+                       double betan, double* __restrict__ sums, int* __restrict__ flags) {
+  __shared__ double sh[3][kTiThreads];
+  const long il = blockIdx.x;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (long t = threadIdx.x; t < ntraj; t += kTiThreads) {
+    const long id = gid ? (long)gid[t] : t;
+    const long l = id / nrep;
+    if (il == 0 && (id < 0 || l >= nintegral)) atomicOr(flags, PIMDK_FLAG_BADGID);
+    if (l != il) continue;
+    const double I = dHdr[t] / (betan * betan);
+    s0 = s0 + I;
+    s1 = s1 + I * I;
+    s2 = s2 + 1.0;
+  }
+  sh[0][threadIdx.x] = s0;
+  sh[1][threadIdx.x] = s1;
+  sh[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int w = kTiThreads / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w)
+      for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] = sh[q][threadIdx.x] + sh[q][threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) sums[3 * il + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// NCCL is bound at run time (like cuSOLVER): libpimdk.so itself needs only the CUDA runtime, and a single-GPU user
+// needs no NCCL at all.  The communicator belongs to the library (SURVEY 8(b) ownership row).
+struct NcclId { char internal[128]; };
+struct Nccl {
+  void* lib = nullptr;
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+  int (*get_unique_id)(NcclId*) = nullptr;
+  int (*comm_init_rank)(void**, int, NcclId, int) = nullptr;
+  int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*comm_destroy)(void*) = nullptr;
+  const char* (*error_string)(int) = nullptr;
+  int (*get_version)(int*) = nullptr;
+} nc;
+int nccl_load() {
+  if (nc.lib) return PIMDK_OK;
+  const char* env = getenv("PIMDK_NCCL_LIB");
+  const char* names[] = {env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    nc.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (nc.lib) break;
+  }
+  if (!nc.lib) return fail(PIMDK_ECUDA, "multi-GPU needs NCCL (libnccl.so.2 not found: %s; set PIMDK_NCCL_LIB)", dlerror());
+  nc.get_unique_id = (int (*)(NcclId*))dlsym(nc.lib, "ncclGetUniqueId");
+  nc.comm_init_rank = (int (*)(void**, int, NcclId, int))dlsym(nc.lib, "ncclCommInitRank");
+  nc.all_reduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(nc.lib, "ncclAllReduce");
+  nc.comm_destroy = (int (*)(void*))dlsym(nc.lib, "ncclCommDestroy");
+  nc.error_string = (const char* (*)(int))dlsym(nc.lib, "ncclGetErrorString");
+  nc.get_version = (int (*)(int*))dlsym(nc.lib, "ncclGetVersion");
+  if (!nc.get_unique_id || !nc.comm_init_rank || !nc.all_reduce || !nc.comm_destroy || !nc.error_string) {
+    nc.lib = nullptr;
+    return fail(PIMDK_ECUDA, "NCCL symbols missing");
+  }
+  return PIMDK_OK;
+}
+#define NCCLCHK(call)                                                                                     \
+  do {                                                                                                    \
+    int r__ = (call);                                                                                     \
+    if (r__ != 0) return fail(PIMDK_ECUDA, "NCCL error %d at %s:%d (%s)", r__, __FILE__, __LINE__, nc.error_string(r__)); \
+  } while (0)
 
 }  // namespace
 
@@ -359,9 +443,15 @@ int pimdk_finalize(void) {
   DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
                     &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wX2, &g.wPp2, &g.wUmIn, &g.wUmOut, &g.wHgp, &g.wHgm, &g.wHess, &g.wBand,
-                    &g.wDense, &g.wEig, &g.wWork};
+                    &g.wDense, &g.wEig, &g.wWork, &g.wSums, &g.wBV};
   for (DevBuf* b : bufs) b->release();
   g.hUm.release();
+  if (nc.comm) {
+    nc.comm_destroy(nc.comm);
+    nc.comm = nullptr;
+    nc.rank = 0;
+    nc.nranks = 1;
+  }
   if (g.copy_stream) cudaStreamDestroy(g.copy_stream);
   g.copy_stream = nullptr;
   for (cudaEvent_t& e : g.ev_in) {
@@ -369,6 +459,8 @@ int pimdk_finalize(void) {
     e = nullptr;
   }
   g.inited = false;
+  g.andersen_carry = false;
+  g.clock_n = 0;
   g.nm_ready = false;
   g.pes = PES_NONE;
   g.tab_loaded = false;
@@ -960,21 +1052,40 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   CU(g.wQ.ensure(tot * sizeof(double)));
   CU(g.wG.ensure(tot * sizeof(double)));
   CU(g.wGn.ensure(tot * sizeof(double)));
+  // Andersen collision clocks (count, rkick per trajectory: verletmodule.f90:196-234).  They outlive the call so that a
+  // run cut into several calls (restart = 1 writes its files every Noutput steps) can continue them
+  // (pimdk_set_andersen_carry) instead of drawing a new interval at every cut, which the reference does not do.
+  const long clock_total = g.sum_total > 0 ? g.sum_total : (long)ntraj;
+  const long clock_off = g.sum_total > 0 ? g.sum_off : 0;
+  bool carry = false;
   if (thermostat == PIMDK_THERMOSTAT_ANDERSEN) {
-    CU(g.wCount.ensure(sizeof(int) * ntraj));
-    CU(g.wKick.ensure(sizeof(int) * ntraj));
+    carry = g.andersen_carry && g.clock_n == clock_total && g.wCount.cap >= sizeof(int) * clock_total;
+    if (g.andersen_carry && !carry)
+      return fail(PIMDK_EINVAL, "andersen carry: no collision clocks of a previous call for %ld trajectories", clock_total);
+    if (!carry) {
+      CU(g.wCount.ensure(sizeof(int) * clock_total));
+      CU(g.wKick.ensure(sizeof(int) * clock_total));
+    }
   }
+  if (!traj_gid && ntraj > 0x100000000LL) return fail(PIMDK_EINVAL, "more than 2^32 trajectories need explicit ids below 2^32");
   NmTables nm = nm_tables_base();
   rc = build_step_tables(&nm, dt, gamma, (int)cayley);
   if (rc) return rc;
   rc = clear_flags();
   if (rc) return rc;
   const int64_t* dgid = reinterpret_cast<const int64_t*>(traj_gid);
+  if (dgid) {
+    check_gid_kernel<<<(unsigned)((ntraj + 255) / 256), 256, 0, g.stream>>>(dgid, (long)ntraj, g.wFlags.as<int>());
+    CU(cudaGetLastError());
+  }
+  int* const clk_count = thermostat == PIMDK_THERMOSTAT_ANDERSEN ? g.wCount.as<int>() + clock_off : nullptr;
+  int* const clk_kick = thermostat == PIMDK_THERMOSTAT_ANDERSEN ? g.wKick.as<int>() + clock_off : nullptr;
+  if (thermostat == PIMDK_THERMOSTAT_ANDERSEN && (g.sum_total == 0 || clock_off + ntraj >= clock_total)) g.clock_n = clock_total;
   if (g.fused && fused_small_supported(g.pes, n, g.nm_ndim, g.nm_natom)) {
     {
       Scope s("fused");
       CU(launch_fused_small(nm, g.pes, g.sp, (int)thermostat, ntraj, x, p, a, b, dbdl, dt, NMC, imin, (double)Noutput, seed,
-                            dgid, dHdr, g.wFlags.as<int>(), step0, keep_sum, dsum, g.stream));
+                            dgid, dHdr, g.wFlags.as<int>(), step0, keep_sum, dsum, clk_count, clk_kick, carry ? 1 : 0, g.stream));
     }
     rc = check_flags(false);
     g.last_nan_traj = -1;
@@ -985,10 +1096,25 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   int* flags = g.wFlags.as<int>();
   GeomLayout L{n, (long)ndof * n, 1, n};
   if (!keep_sum) CU(cudaMemsetAsync(dHdr, 0, sizeof(double) * ntraj, g.stream));  // restart < 2: dHdr = 0 (:200,388)
+  // beadvec (init_nm :328-333) depends on a and b only: formed once per call for all rows; the update kernel then writes
+  // Q + beadvec next to Q (into G's buffer, which is dead between the gradient transform and the next gradient), and
+  // the back-transform is a plain product of that array
+  const bool use_bv = nm_uses_beadvec_array(nm);
+  double* BV = nullptr;
+  double* QB = use_bv ? G : nullptr;
+  if (use_bv) {
+    CU(g.wBV.ensure(tot * sizeof(double)));
+    BV = g.wBV.as<double>();
+    Scope s("update");
+    CU(launch_beadvec(nm, a, b, rows, BV, g.stream));
+  }
+  auto back_transform = [&]() -> cudaError_t {   // x = T (Q + beadvec)
+    return use_bv ? launch_nm_gemm(nm, GEMM_PLAIN, QB, x, rows, a, b, g.stream) : launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream);
+  };
   {
     Scope s("gemm", 2);
     CU(launch_nm_gemm(nm, GEMM_PLAIN, p, P, rows, a, b, g.stream));
-    CU(launch_nm_gemm(nm, GEMM_SUB_BEADVEC, x, Q, rows, a, b, g.stream));
+    CU(launch_nm_gemm(nm, GEMM_SUB_BEADVEC, x, Q, rows, a, b, g.stream, BV));
   }
   if (thermostat == PIMDK_THERMOSTAT_PILE) {
     for (pimdk_int ii = 1; ii <= NMC; ++ii) {
@@ -1000,11 +1126,11 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       }
       {
         Scope s("update");
-        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 2, 1, seed, (uint64_t)(ii + step0), dgid, flags, g.stream));
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 2, 1, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, BV, QB));
       }
       {
         Scope s("gemm");
-        CU(launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream));
+        CU(back_transform());
       }
       if (ii > imin) {
         Scope s("estimator");
@@ -1012,9 +1138,9 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       }
     }
   } else {
-    int* count = g.wCount.as<int>();
-    int* rkick = g.wKick.as<int>();
-    {
+    int* count = clk_count;
+    int* rkick = clk_kick;
+    if (!carry) {
       Scope s("update");
       CU(launch_andersen_init(ntraj, seed, (uint64_t)step0, (double)Noutput, dgid, count, rkick, g.stream));
     }
@@ -1022,11 +1148,11 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       {
         Scope s("update", 3);
         CU(launch_andersen(nm, P, ntraj, seed, (uint64_t)(ii + step0), (double)Noutput, dgid, count, rkick, g.stream));
-        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream));
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, BV, QB));
       }
       {
         Scope s("gemm");
-        CU(launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream));
+        CU(back_transform());
       }
       rc = pes_eval_dev(L, x, nullptr, G, (long)ntraj * n, 1);
       if (rc) return rc;
@@ -1040,12 +1166,13 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       }
       if (ii > imin) {   // the estimator reads the last bead only: one contraction per (trajectory, dof), not a transform
         Scope s("estimator");
-        CU(launch_estimator_modes(nm, Q, a, b, dbdl, dHdr, ntraj, g.stream));
+        CU(launch_estimator_modes(nm, Q, a, b, dbdl, dHdr, ntraj, g.stream, BV));
       }
     }
     {
-      Scope s("gemm");   // positions at the end of the call
-      CU(launch_nm_gemm(nm, GEMM_ADD_BEADVEC, Q, x, rows, a, b, g.stream));
+      Scope s("gemm", use_bv ? 2 : 1);   // positions at the end of the call
+      if (use_bv) CU(launch_add(Q, BV, QB, (long)tot, g.stream));
+      CU(back_transform());
     }
   }
   {
@@ -1060,15 +1187,17 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   }
   rc = check_flags(false);
   if (rc == PIMDK_ENAN) {
+    // everything on the library stream (a caller's non-blocking stream is not ordered against the legacy default stream)
     long long first = (long long)ntraj;
-    long long* dfirst = nullptr;
-    if (cudaMalloc(&dfirst, sizeof(long long)) == cudaSuccess) {
-      cudaMemcpy(dfirst, &first, sizeof(long long), cudaMemcpyHostToDevice);
+    long long* dfirst = reinterpret_cast<long long*>(g.wFlags.as<char>() + 8);
+    bool ok = cudaMemcpyAsync(dfirst, &first, sizeof(long long), cudaMemcpyHostToDevice, g.stream) == cudaSuccess;
+    if (ok) {
       first_nan_kernel<<<148, 256, 0, g.stream>>>(P, (long)ndof * n, ntraj, dfirst);
-      cudaMemcpy(&first, dfirst, sizeof(long long), cudaMemcpyDeviceToHost);
-      cudaFree(dfirst);
+      ok = cudaGetLastError() == cudaSuccess &&
+           cudaMemcpyAsync(&first, dfirst, sizeof(long long), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+           cudaStreamSynchronize(g.stream) == cudaSuccess;
     }
-    g.last_nan_traj = first < ntraj ? (long)first : -1;
+    g.last_nan_traj = (ok && first < ntraj) ? (long)first : -1;
   } else {
     g.last_nan_traj = -1;
   }
@@ -1213,6 +1342,11 @@ int pimdk_set_propagate_chunk(pimdk_int ntraj_per_chunk) {
   return PIMDK_OK;
 }
 
+int pimdk_set_andersen_carry(pimdk_int enable) {
+  g.andersen_carry = enable != 0;
+  return PIMDK_OK;
+}
+
 int pimdk_set_restart(pimdk_int restart, pimdk_int restartnmc) {
   if (restart < 0 || restart > 2 || restartnmc < 0) return fail(PIMDK_EINVAL, "restart must be 0, 1 or 2 and restartnmc >= 0");
   g.restart = (long)restart;
@@ -1261,6 +1395,110 @@ int pimdk_ti_finish(pimdk_int nintegral, const double* sums, const double* weigh
   if (deltaA) *deltaA = answer;
   if (sigmaA) *sigmaA = std::sqrt(sA);
   if (qq0) *qq0 = std::exp(-answer * betan);
+  return PIMDK_OK;
+}
+
+// ---- multi-GPU: the single collective of the path ------------------------------------------------------------------
+int pimdk_comm_unique_id(void* id) {
+  if (!id) return fail(PIMDK_EINVAL, "id must point to PIMDK_UNIQUE_ID_BYTES bytes");
+  int rc = nccl_load();
+  if (rc) return rc;
+  static_assert(sizeof(NcclId) == PIMDK_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+  NcclId u;
+  NCCLCHK(nc.get_unique_id(&u));
+  std::memcpy(id, &u, sizeof u);
+  return PIMDK_OK;
+}
+
+int pimdk_comm_init(pimdk_int rank, pimdk_int nranks, const void* id) {
+  NEED_INIT();
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(PIMDK_EINVAL, "need 0 <= rank < nranks");
+  if (nc.comm) return fail(PIMDK_EINVAL, "communicator already initialised (pimdk_comm_finalize first)");
+  if (nranks == 1) {   // a one-rank job needs no NCCL
+    nc.rank = 0;
+    nc.nranks = 1;
+    return PIMDK_OK;
+  }
+  if (!id) return fail(PIMDK_EINVAL, "id must not be NULL for nranks > 1");
+  int rc = nccl_load();
+  if (rc) return rc;
+  NcclId u;
+  std::memcpy(&u, id, sizeof u);
+  CU(cudaSetDevice(g.device));
+  NCCLCHK(nc.comm_init_rank(&nc.comm, (int)nranks, u, (int)rank));
+  nc.rank = (int)rank;
+  nc.nranks = (int)nranks;
+  return PIMDK_OK;
+}
+
+int pimdk_comm_finalize(void) {
+  if (nc.comm) {
+    cudaStreamSynchronize(g.stream);
+    nc.comm_destroy(nc.comm);
+  }
+  nc.comm = nullptr;
+  nc.rank = 0;
+  nc.nranks = 1;
+  return PIMDK_OK;
+}
+
+int pimdk_comm_info(pimdk_int* rank, pimdk_int* nranks, pimdk_int* nccl_version) {
+  if (rank) *rank = nc.rank;
+  if (nranks) *nranks = nc.nranks;
+  if (nccl_version) {
+    int v = 0;
+    if (nc.lib && nc.get_version) nc.get_version(&v);
+    *nccl_version = v;
+  }
+  return PIMDK_OK;
+}
+
+// sum over ranks of `count` doubles that live on the device, in place, on the library stream
+static int allreduce_dev(double* d, size_t count) {
+  if (nc.nranks == 1) return PIMDK_OK;
+  if (!nc.comm) return fail(PIMDK_EINVAL, "pimdk_comm_init has not been called");
+  NCCLCHK(nc.all_reduce(d, d, count, /*ncclDouble*/ 8, /*ncclSum*/ 0, nc.comm, g.stream));
+  g.launch_count += 1;
+  return PIMDK_OK;
+}
+
+int pimdk_ti_allreduce(pimdk_int nintegral, double* sums) {
+  NEED_INIT();
+  if (nintegral < 1 || !sums) return fail(PIMDK_EINVAL, "bad pimdk_ti_allreduce arguments");
+  if (nc.nranks == 1) return PIMDK_OK;
+  const size_t cnt = 3 * (size_t)nintegral;
+  CU(g.wSums.ensure(cnt * sizeof(double)));
+  CU(cudaMemcpyAsync(g.wSums.p, sums, cnt * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  int rc = allreduce_dev(g.wSums.as<double>(), cnt);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(sums, g.wSums.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return PIMDK_OK;
+}
+
+int pimdk_ti_reduce_dev(pimdk_int ntraj, const double* dHdr, const pimdk_int* traj_gid, pimdk_int nrep, pimdk_int nintegral,
+                        double betan, double* sums) {
+  NEED_INIT();
+  if (nrep <= 0 || nintegral <= 0 || ntraj < 0 || !sums || (ntraj > 0 && !dHdr) || !(betan > 0.0))
+    return fail(PIMDK_EINVAL, "bad pimdk_ti_reduce_dev arguments");
+  const size_t cnt = 3 * (size_t)nintegral;
+  CU(g.wSums.ensure(cnt * sizeof(double)));
+  int rc = clear_flags();
+  if (rc) return rc;
+  {
+    Scope s("estimator");
+    ti_partial_sums_kernel<<<(unsigned)nintegral, kTiThreads, 0, g.stream>>>(dHdr, reinterpret_cast<const int64_t*>(traj_gid), (long)ntraj,
+                                                                            (long)nrep, (long)nintegral, betan, g.wSums.as<double>(),
+                                                                            g.wFlags.as<int>());
+    CU(cudaGetLastError());
+  }
+  rc = allreduce_dev(g.wSums.as<double>(), cnt);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(sums, g.wSums.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  int fl = 0;
+  CU(cudaMemcpyAsync(&fl, g.wFlags.p, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  if (fl & PIMDK_FLAG_BADGID) return fail(PIMDK_EINVAL, "trajectory id outside nintegral*nrep");
   return PIMDK_OK;
 }
 

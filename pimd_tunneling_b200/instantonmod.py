@@ -22,6 +22,7 @@ class InstantonMod:
 
     def _call(self, x, a, b, want_f, want_g):
         p = self.pes
+        p._need()
         x = f64(x, (self.n, p.ndim, p.natom))
         a = None if a is None else f64(np.asarray(a, dtype=np.float64).reshape(p.ndim, p.natom))
         b = None if b is None else f64(np.asarray(b, dtype=np.float64).reshape(p.ndim, p.natom))
@@ -48,6 +49,7 @@ class InstantonMod:
         (ndim,natom,npoly); returns (answer(n,ndim,natom,npoly), UM(npoly)).  Bit-identical, polymer by polymer,
         to UMforceenergy."""
         p = self.pes
+        p._need()
         X = np.asarray(X, dtype=np.float64)
         npoly = X.shape[3]
         Xw = f64(np.array(X, order="F").reshape((self.n, p.ndim, p.natom, npoly), order="F"))
@@ -202,6 +204,7 @@ class InstantonMod:
         p = self.pes
         xw = np.array(f64(x, (self.n, p.ndim, p.natom)), order="F")
         band = np.empty((p.ndof + 1, self.n * p.ndof), order="F")
+        p._need()
         check(lib().pimdk_um_hessian(self.n, p.ndim, p.natom, hptr(xw), hptr(self.mass), self.betan,
                                      1 if singlewell else 0, hptr(band)))
         return band
@@ -214,6 +217,7 @@ class InstantonMod:
         N = self.n * p.ndof
         eta = np.empty(N)
         z = np.empty((N, N), order="F") if eigvecs else None
+        p._need()
         check(lib().pimdk_detj(self.n, p.ndim, p.natom, hptr(xw), hptr(self.mass), self.betan, 1 if singlewell else 0,
                                hptr(eta), hptr(z)))
         return (eta, z) if eigvecs else eta

@@ -39,12 +39,23 @@ class McmodMass:
         self.basename = ""
         self._selected = False
 
+    # The library holds ONE selected PES and one V0 per process (like the reference's single linked mcmod_<PES>.o).
+    # Several McmodMass objects may be alive: the one used last owns the selection, and an object that finds another
+    # owner re-selects its surface and pushes its V0 again before it computes anything.
+    _owner = None
+
+    def _select(self):
+        p = self.params
+        check(lib().pimdk_pes_select(self.name.encode(), hptr(p), 0 if p is None else p.size))
+        if self.V0 != 0.0:
+            check(lib().pimdk_pes_set_v0(float(self.V0)))
+        McmodMass._owner = self
+
     # subroutine V_init(iproc)
     def V_init(self, iproc=0):
         _lib.ensure_init()
-        p = self.params
-        check(lib().pimdk_pes_select(self.name.encode(), hptr(p), 0 if p is None else p.size))
         self.V0 = 0.0
+        self._select()
         self._selected = True
         return self
 
@@ -57,6 +68,9 @@ class McmodMass:
     def _need(self):
         if not self._selected:
             raise RuntimeError("V_init has not been called")
+        if McmodMass._owner is not self or not _lib._initialised:
+            _lib.ensure_init()
+            self._select()
 
     # function V(x)
     def V(self, x):

@@ -44,10 +44,16 @@ class VerletInt:
         _lib.ensure_init()
         check(lib().pimdk_nm_setup(self.n, self.ndim, self.natom, hptr(self.mass), self.betan, self.tau))
         self._ready = True
+        VerletInt._owner = self
         return self
 
+    # the library holds one set of normal-mode tables per process (module verletint's lam, beadmass, transmatrix):
+    # the VerletInt used last owns them, like McmodMass owns the PES selection
+    _owner = None
+
     def _need(self):
-        if not self._ready:
+        self.pes._need()
+        if not self._ready or VerletInt._owner is not self:
             self.init_nm()
 
     @property
@@ -200,8 +206,11 @@ class VerletInt:
         """-> x(n,ndim,natom), p(n,ndim,natom), dHdr (running sum), restartnmc   (pimd_par.f90:356-370)"""
         x = np.empty((self.n, self.ndim, self.natom), order="F")
         p = np.empty_like(x)
+        def num(t):   # Fortran list-directed reals may carry d/D exponents; atom labels are never converted
+            return float(t.replace("D", "E").replace("d", "e"))
+
         with open(path) as f:
-            tok = f.read().replace("D", "E").replace("d", "e").split()
+            tok = f.read().split()
         pos, second = 0, [None, None]
         for which, arr in enumerate((x, p)):
             for i in range(self.n):
@@ -209,11 +218,11 @@ class VerletInt:
                 second[which] = tok[pos]      # dHdr / restartnmc
                 pos += 1
                 for j in range(self.natom):
-                    pos += 1                  # dummychar
+                    pos += 1                  # dummychar (the label: skipped, whatever letters it holds)
                     for d in range(self.ndim):
-                        arr[i, d, j] = float(tok[pos])
+                        arr[i, d, j] = num(tok[pos])
                         pos += 1
-        return x, p, float(second[0]), int(float(second[1]))
+        return x, p, num(second[0]), int(num(second[1]))
 
     def propagate_restartable(self, thermostat, x, p, a, b, dbdl, traj_gid=None, iproc=0, directory="."):
         """The reference's restart protocol around one batched propagate call (verletmodule.f90:199-206, 246,
@@ -242,6 +251,9 @@ class VerletInt:
                 # one segment = a restarted run of k steps whose first `imin - local` steps are not sampled
                 self.NMC, self.imin = k, min(k - 1, max(0, imin - local)) if imin - local < k else k - 1
                 self.restart, self.restartnmc = (2, done + local) if (restart0 == 2 or local > 0) else (restart0, 0)
+                # the reference writes its files from inside ONE loop and never resets the Andersen collision clock
+                # (verletmodule.f90:199-234): segments after the first continue count / rkick of the previous call
+                check(lib().pimdk_set_andersen_carry(1 if (thermostat == ANDERSEN and local > 0) else 0))
                 if imin - local >= k:   # the whole segment lies before imin: propagate without sampling
                     keep = sums.copy()
                     x, p, _ = self._propagate(thermostat, x, p, a, b, dbdl, traj_gid, sums if self.restart == 2 else None)
@@ -256,6 +268,7 @@ class VerletInt:
                         self.write_restart(files[t], x[..., t], p[..., t], done + local, sums[t])
         finally:
             self.NMC, self.imin, self.restart, self.restartnmc = NMC, imin, restart0, 0
+            check(lib().pimdk_set_andersen_carry(0))
         return x, p, sums / float(NMC + done - imin)
 
     def propagate_dev(self, thermostat, ntraj, x_ptr, p_ptr, a_ptr, b_ptr, dbdl_ptr, gid_ptr, dHdr_ptr, NMC=None):

@@ -1005,3 +1005,106 @@ def test_full_size_c4_step_is_partition_invariant(pk):
     assert np.array_equal(xs, x1[..., pick]) and np.array_equal(ps, p1[..., pick]) and np.array_equal(ds, d1[pick])
     # and the thermostat did act: different repetitions of one lambda point have decorrelated
     assert not np.array_equal(p1[..., 0] - p0[..., 0], p1[..., 1] - p0[..., 1])
+
+
+# ---------------------------------------------------------------- BASELINE sizes against the oracle -----------------
+BASELINE_CASES = [
+    # name, n, ntraj, steps, thermostat, beta, mass, sigma, Noutput   (the bead counts of BASELINE.json's configs)
+    ("2dtest", 256, 2, 20, 1, 10.0, [1.0], 0.05, 7),            # C2: Andersen, streamed path (tensor-core transform,
+                                                                 #     paired-normal update, last-bead estimator)
+    ("2dtest", 256, 2, 20, 2, 10.0, [1.0], 0.05, 100000),       # the same beads through PILE
+    ("ccpol8sf", 512, 1, 2, 2, 12000.0, DIMER_MASS, 0.01, 100000),   # C4
+    ("ccpol8sf", 1024, 1, 1, 2, 12000.0, DIMER_MASS, 0.01, 100000),  # C5
+    ("1d", 64, 4, 50, 2, 10.0, [1.0], 0.05, 100000),            # C1 (fused kernel)
+]
+
+
+@pytest.mark.parametrize("case", BASELINE_CASES, ids=lambda c: "%s-n%d-th%d" % (c[0], c[1], c[4]))
+def test_propagate_matches_oracle_at_baseline_sizes(pk, orc, case):
+    """verletmodule.f90:190-250, 372-435 at the bead counts BASELINE.json quotes (C1 64, C2 256, C4 512, C5 1024), through
+    the path each of them takes in production, against the oracle's literal step sequence: 1e-10 relative."""
+    name, n, ntraj, steps, thermostat, beta, mass, sigma, Noutput = case
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    a, b = _wells(name)
+    vi = pk.VerletInt(pes, n, mass, beta, dt=1e-3, gamma=1.0, NMC=steps, Noutput=Noutput, seed=977).init_nm()
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, sigma, mass, seed=23)
+    gid = np.arange(ntraj, dtype=np.int64) * 5 + 2
+    fn = vi.propagate_pimd_pile if thermostat == 2 else vi.propagate_pimd_nm
+    xg, pg, dg = fn(x, p, a, bt, dbdl, traj_gid=gid)
+    for t in range(ntraj):
+        orc.nm_setup(n, mass, vi.betan, 1.0, 1.0, 1e-3, False, True)
+        orc.init_nm(a, bt[..., t])
+        orc.set_rng(977, int(gid[t]))
+        xo, po, do = orc.propagate(thermostat, x[..., t], p[..., t], dbdl[..., t], steps, 0, Noutput)
+        assert relmax(xg[..., t], xo) < RTOL
+        assert relmax(pg[..., t], po) < RTOL
+        assert abs(dg[t] - do) <= RTOL * abs(do)
+
+
+@pytest.mark.parametrize("name,n", [("2dtest", 32), ("2dtest", 160)])
+def test_andersen_restart_segments_keep_the_collision_clock(pk, tmp_path, name, n):
+    """restart = 1 with a FINITE Noutput under the Andersen thermostat: the reference writes its files from inside one
+    loop and never touches count / rkick (verletmodule.f90:199-234), so a run cut into Noutput-step calls must resample
+    momenta at the very steps of the uncut run.  (Fused kernel at n = 32, streamed path at n = 160.)"""
+    pes = pk.McmodMass(name).V_init()
+    a, b = _wells(name)
+    ntraj, steps, nout = 4, 60, 9
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, 0.05, [1.0])
+    gid = np.arange(ntraj, dtype=np.int64) + 3
+    vi = pk.VerletInt(pes, n, [1.0], 10.0, dt=1e-3, NMC=steps, imin=0, Noutput=nout, seed=5).init_nm()
+    x_ref, p_ref, d_ref = vi.propagate_pimd_nm(x, p, a, bt, dbdl, traj_gid=gid)
+    vs = pk.VerletInt(pes, n, [1.0], 10.0, dt=1e-3, NMC=steps, imin=0, Noutput=nout, seed=5).init_nm()
+    vs.restart = 1
+    xs, ps, ds = vs.propagate_restartable(1, x, p, a, bt, dbdl, traj_gid=gid, iproc=0, directory=str(tmp_path))
+    assert relmax(xs, x_ref) < RTOL and relmax(ps, p_ref) < RTOL and np.abs(ds - d_ref).max() <= RTOL * np.abs(d_ref).max()
+    # and the clock is NOT carried into an unrelated later call
+    x2, p2, d2 = vi.propagate_pimd_nm(x, p, a, bt, dbdl, traj_gid=gid)
+    assert np.array_equal(x2, x_ref) and np.array_equal(d2, d_ref)
+
+
+def test_trajectory_ids_beyond_32_bits_are_rejected(pk):
+    pes = pk.McmodMass("2dtest").V_init()
+    a, b = _wells("2dtest")
+    for n in (16, 160):   # fused and streamed
+        vi = pk.VerletInt(pes, n, [1.0], 10.0, dt=1e-3, NMC=2, seed=1).init_nm()
+        x, p, bt, dbdl, _ = _traj_inputs(pes, n, 2, a, b, 0.05, [1.0])
+        with pytest.raises(pk.PimdkError) as ei:
+            vi.propagate_pimd_pile(x, p, a, bt, dbdl, traj_gid=np.array([5, 2 ** 32], dtype=np.int64))
+        assert ei.value.code == 1
+        vi.propagate_pimd_pile(x, p, a, bt, dbdl, traj_gid=np.array([5, 2 ** 32 - 1], dtype=np.int64))
+
+
+def test_two_live_plugins_do_not_redirect_each_other(pk, orc):
+    """the library holds one PES selection and one V0; the Python mirror re-selects when another object owned it"""
+    p1 = pk.McmodMass("ccpol8sf", iemonomer=0).V_init()
+    p2 = pk.McmodMass("ccpol8sf", iemonomer=1).V_init()
+    p3 = pk.McmodMass("2dtest").V_init()
+    p3.set_V0(0.25)
+    x = (GOLDEN_GEOM_ANG / 0.529177).reshape(6, 3).T
+    e1, e2 = p1.V(x) * 627.510, p2.V(x) * 627.510
+    assert abs(e1 - GOLDEN_VAL[2]) < 5.1e-6 and abs(e2 - GOLDEN_VALM[2]) < 3e-5
+    v3 = p3.V(np.array([[3.0], [0.0]]))
+    p1.V(x)
+    assert p3.V(np.array([[3.0], [0.0]])) == v3 and p3.V0 == 0.25
+
+
+def test_device_side_estimator_sums_match_the_host_formulas(pk):
+    """pimdk_ti_reduce_dev (one rank: kernel + copy, no NCCL) against pimdk_ti_partial_sums (pimd_par.f90:397-409)"""
+    import torch
+
+    from pimd_tunneling_b200 import ti
+    rng = np.random.default_rng(8)
+    nintegral, nrep = 16, 37
+    gid = rng.permutation(nintegral * nrep).astype(np.int64)[:500]
+    dH = rng.normal(size=gid.size) * 3.0
+    betan = 0.37
+    ref = ti.partial_sums(dH, gid, nrep, nintegral, betan)
+    d = torch.from_numpy(dH).cuda()
+    gdev = torch.from_numpy(gid).cuda()
+    got = ti.reduce_dev(gid.size, d.data_ptr(), gdev.data_ptr(), nrep, nintegral, betan)
+    assert np.array_equal(got[:, 2], ref[:, 2])
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+    with pytest.raises(pk.PimdkError):
+        ti.reduce_dev(gid.size, d.data_ptr(), gdev.data_ptr(), nrep, nintegral - 1, betan)
+    assert ti.comm_info()[:2] == (0, 1)
