@@ -6,7 +6,8 @@
 !   module pimdk           raw interfaces, one per C entry point
 !   module mcmod_mass      drop-in replacement of mcmod_waterdimer_ccpol.f90 / mcmod_1d.f90 / mcmod_2dtest.f90
 !                          (same module name, same procedures; choose the PES with -DPIMDK_PES=...)
-!   subroutine pimdk_propagate_tasks   what the task loop of pimd_par.f90:321-381 collapses to
+!   subroutine pimdk_propagate_tasks   what the task loop of pimd_par.f90:321-381 collapses to (incl. the restart cadence)
+!   subroutine pimdk_ti_statistics     what the gather + root statistics of pimd_par.f90:383-424 collapse to (one NCCL all-reduce)
 module pimdk
   use iso_c_binding
   implicit none
@@ -92,6 +93,32 @@ module pimdk
      ! trajectories per chunk of the copy-overlapped host-buffer propagate (0 = automatic)
      integer(c_int) function pimdk_set_propagate_chunk(ntraj_per_chunk) bind(C, name="pimdk_set_propagate_chunk")
        import; integer(c_int64_t), value :: ntraj_per_chunk
+     end function
+     ! Andersen collision clocks continue across the calls of one segmented run (verletmodule.f90:199-234 never resets them)
+     integer(c_int) function pimdk_set_andersen_carry(enable) bind(C, name="pimdk_set_andersen_carry")
+       import; integer(c_int64_t), value :: enable
+     end function
+     ! multi-GPU: the library's NCCL communicator and the one collective of the path (replaces MPI_Gather, pimd_par.f90:389)
+     integer(c_int) function pimdk_comm_unique_id(id) bind(C, name="pimdk_comm_unique_id")
+       import; character(kind=c_char) :: id(*)
+     end function
+     integer(c_int) function pimdk_comm_init(rank, nranks, id) bind(C, name="pimdk_comm_init")
+       import; integer(c_int64_t), value :: rank, nranks; character(kind=c_char) :: id(*)
+     end function
+     integer(c_int) function pimdk_comm_finalize() bind(C, name="pimdk_comm_finalize")
+       import
+     end function
+     integer(c_int) function pimdk_ti_partial_sums(ntraj, dHdr, gid, nrep, nintegral, betan, sums) bind(C, name="pimdk_ti_partial_sums")
+       import; integer(c_int64_t), value :: ntraj, nrep, nintegral; real(c_double), value :: betan
+       real(c_double) :: dHdr(*), sums(*); type(c_ptr), value :: gid
+     end function
+     integer(c_int) function pimdk_ti_allreduce(nintegral, sums) bind(C, name="pimdk_ti_allreduce")
+       import; integer(c_int64_t), value :: nintegral; real(c_double) :: sums(*)
+     end function
+     integer(c_int) function pimdk_ti_finish(nintegral, sums, weights, betan, mean, var, deltaA, sigmaA, q_over_q0) &
+          bind(C, name="pimdk_ti_finish")
+       import; integer(c_int64_t), value :: nintegral; real(c_double), value :: betan
+       real(c_double) :: sums(*), weights(*), mean(*), var(*), deltaA(*), sigmaA(*), q_over_q0(*)
      end function
      integer(c_int) function pimdk_gauleg(x1, x2, n, x, w) bind(C, name="pimdk_gauleg")
        import; real(c_double), value :: x1, x2; integer(c_int64_t), value :: n; real(c_double) :: x(*), w(*)
@@ -182,30 +209,170 @@ end module mcmod_mass
 !---------------------------------------------------------------------------------------------------------
 ! The task loop of pimd_par.f90:321-381 (init_nm / init_path / propagate_pimd_* per task) as ONE batched call.
 ! endpoints, gradpoints: (ncalcs, ndim, natom) as in pimd_par.f90:243-257; integrand(ncalcs) out.
-subroutine pimdk_propagate_tasks(thermostat, ncalcs, first_gid, startpoint, endpoints, gradpoints, xipoints, &
-     lampath, path, splinepath, npath, mass, betan, tau, dt, gamma, NMC, imin, Noutput, cayley, seed, integrand)
+! restart / restartnmc are module verletint's (verletmodule.f90:10):
+!   restart = 0  one call of NMC steps
+!   restart = 1  the reference writes restart_proc<iproc>_<ii>.xyz every Noutput steps from inside its loop
+!                (verletmodule.f90:205-207, 394) and at the end (:246, 412): here the run is cut into calls of Noutput
+!                steps, each continuing the previous one's running sums, RNG step counters (pimdk_set_restart(2, done))
+!                and Andersen collision clocks (pimdk_set_andersen_carry), and the files are written between the calls
+!   restart = 2  x, p, dHdr and restartnmc are read from the files first (pimd_par.f90:356-370), then as restart = 1
+subroutine pimdk_propagate_tasks(thermostat, ncalcs, first_gid, iproc, startpoint, endpoints, gradpoints, xipoints, &
+     lampath, path, splinepath, npath, mass, label, betan, tau, dt, gamma, NMC, imin, Noutput, cayley, seed, &
+     restart, integrand)
   use iso_c_binding
   use pimdk
   use mcmod_mass, only: n, ndim, natom
   implicit none
-  integer :: thermostat, ncalcs, first_gid, npath, NMC, imin, Noutput, seed, ii
+  integer :: thermostat, ncalcs, first_gid, iproc, npath, NMC, imin, Noutput, seed, restart, ii, done, left, k, kmin, local
   logical :: cayley
   double precision :: startpoint(ndim,natom), endpoints(ncalcs,ndim,natom), gradpoints(ncalcs,ndim,natom)
   double precision :: xipoints(ncalcs), lampath(npath), path(npath,ndim,natom), splinepath(npath,ndim,natom)
   double precision :: mass(natom), betan, tau, dt, gamma, integrand(ncalcs)
-  double precision, allocatable :: x(:,:,:,:), p(:,:,:,:), b(:,:,:), dbdl(:,:,:), dHdr(:)
+  character :: label(natom)
+  double precision, allocatable :: x(:,:,:,:), p(:,:,:,:), b(:,:,:), dbdl(:,:,:), dHdr(:), sums(:)
   integer(c_int64_t), allocatable, target :: gid(:)
   allocate(x(n,ndim,natom,ncalcs), p(n,ndim,natom,ncalcs), b(ndim,natom,ncalcs), dbdl(ndim,natom,ncalcs))
-  allocate(dHdr(ncalcs), gid(ncalcs))
+  allocate(dHdr(ncalcs), sums(ncalcs), gid(ncalcs))
   do ii = 1, ncalcs
      b(:,:,ii) = endpoints(ii,:,:); dbdl(:,:,ii) = gradpoints(ii,:,:); gid(ii) = first_gid + ii - 1
   end do
   call pimdk_check(pimdk_nm_setup(int(n,c_int64_t), int(ndim,c_int64_t), int(natom,c_int64_t), mass, betan, tau))
-  call pimdk_check(pimdk_init_path(int(ncalcs,c_int64_t), int(npath,c_int64_t), lampath, path, splinepath, xipoints, &
-       int(seed,c_int64_t), c_loc(gid), x, p))
-  call pimdk_check(pimdk_propagate(int(thermostat,c_int64_t), int(ncalcs,c_int64_t), x, p, startpoint, b, dbdl, dt, gamma, &
-       int(NMC,c_int64_t), int(imin,c_int64_t), int(Noutput,c_int64_t), merge(1_c_int64_t,0_c_int64_t,cayley), &
-       int(seed,c_int64_t), c_loc(gid), dHdr))
-  integrand(:) = dHdr(:)/(betan**2)                     ! pimd_par.f90:379
-  deallocate(x, p, b, dbdl, dHdr, gid)
+  done = 0
+  sums(:) = 0.0d0
+  if (restart .lt. 2) then
+     call pimdk_check(pimdk_init_path(int(ncalcs,c_int64_t), int(npath,c_int64_t), lampath, path, splinepath, xipoints, &
+          int(seed,c_int64_t), c_loc(gid), x, p))
+  else
+     do ii = 1, ncalcs
+        call pimdk_read_restart(iproc, ii, x(:,:,:,ii), p(:,:,:,ii), sums(ii), done)
+     end do
+  end if
+  if (restart .eq. 0) then
+     call pimdk_check(pimdk_set_restart(0_c_int64_t, 0_c_int64_t))
+     call pimdk_check(pimdk_propagate(int(thermostat,c_int64_t), int(ncalcs,c_int64_t), x, p, startpoint, b, dbdl, dt, gamma, &
+          int(NMC,c_int64_t), int(imin,c_int64_t), int(Noutput,c_int64_t), merge(1_c_int64_t,0_c_int64_t,cayley), &
+          int(seed,c_int64_t), c_loc(gid), dHdr))
+     integrand(:) = dHdr(:)/(betan**2)                  ! pimd_par.f90:379
+  else
+     left = NMC; local = 0
+     do while (left .gt. 0)
+        k = min(max(1, Noutput), left)
+        kmin = max(0, min(k, imin - local))             ! steps of this segment that lie before imin
+        dHdr(:) = sums(:)
+        if (restart .eq. 2 .or. local .gt. 0) then
+           call pimdk_check(pimdk_set_restart(2_c_int64_t, int(done + local, c_int64_t)))
+        else
+           call pimdk_check(pimdk_set_restart(1_c_int64_t, 0_c_int64_t))
+        end if
+        call pimdk_check(pimdk_set_andersen_carry(merge(1_c_int64_t, 0_c_int64_t, thermostat .eq. 1 .and. local .gt. 0)))
+        if (kmin .ge. k) then                            ! the whole segment is equilibration: propagate, keep the sums
+           call pimdk_check(pimdk_propagate(int(thermostat,c_int64_t), int(ncalcs,c_int64_t), x, p, startpoint, b, dbdl, dt, &
+                gamma, int(k,c_int64_t), int(k-1,c_int64_t), int(Noutput,c_int64_t), merge(1_c_int64_t,0_c_int64_t,cayley), &
+                int(seed,c_int64_t), c_loc(gid), dHdr))
+        else
+           call pimdk_check(pimdk_propagate(int(thermostat,c_int64_t), int(ncalcs,c_int64_t), x, p, startpoint, b, dbdl, dt, &
+                gamma, int(k,c_int64_t), int(kmin,c_int64_t), int(Noutput,c_int64_t), merge(1_c_int64_t,0_c_int64_t,cayley), &
+                int(seed,c_int64_t), c_loc(gid), dHdr))
+           call pimdk_check(pimdk_get_dhdr_sums(int(ncalcs,c_int64_t), sums))
+        end if
+        local = local + k; left = left - k
+        do ii = 1, ncalcs                                ! write_restart (verletmodule.f90:162-185)
+           call pimdk_write_restart(iproc, ii, x(:,:,:,ii), p(:,:,:,ii), done + local, sums(ii), label)
+        end do
+     end do
+     call pimdk_check(pimdk_set_restart(0_c_int64_t, 0_c_int64_t))
+     call pimdk_check(pimdk_set_andersen_carry(0_c_int64_t))
+     integrand(:) = sums(:)/dble(NMC + done - imin)/(betan**2)      ! verletmodule.f90:247,413; pimd_par.f90:379
+  end if
+  deallocate(x, p, b, dbdl, dHdr, sums, gid)
 end subroutine pimdk_propagate_tasks
+
+! restart_proc<iproc>_<ii>.xyz in the layout of write_restart (verletmodule.f90:162-185) / the read side pimd_par.f90:356-370
+subroutine pimdk_restart_name(iproc, ii, fname)
+  implicit none
+  integer :: iproc, ii
+  character(len=64) :: fname, a, b
+  write(a,'(I0)') iproc; write(b,'(I0)') ii
+  fname = "restart_proc"//trim(a)//"_"//trim(b)//".xyz"
+end subroutine pimdk_restart_name
+
+subroutine pimdk_write_restart(iproc, ii, xprop, pprop, istep, dHdr, label)
+  use mcmod_mass, only: n, ndim, natom
+  implicit none
+  integer :: iproc, ii, istep, i, j, u
+  double precision :: xprop(n,ndim,natom), pprop(n,ndim,natom), dHdr
+  character :: label(natom)
+  character(len=64) :: fname
+  call pimdk_restart_name(iproc, ii, fname)
+  u = 600 + iproc
+  open(u, file=trim(fname))
+  do i = 1, n
+     write(u,*) natom
+     write(u,*) dHdr
+     do j = 1, natom
+        write(u,*) label(j), xprop(i,:,j)
+     end do
+  end do
+  do i = 1, n
+     write(u,*) natom
+     write(u,*) istep
+     do j = 1, natom
+        write(u,*) label(j), pprop(i,:,j)
+     end do
+  end do
+  close(u)
+end subroutine pimdk_write_restart
+
+subroutine pimdk_read_restart(iproc, ii, x, pinit, dHdr, restartnmc)
+  use mcmod_mass, only: n, ndim, natom
+  implicit none
+  integer :: iproc, ii, restartnmc, i, j, u, dummyint
+  double precision :: x(n,ndim,natom), pinit(n,ndim,natom), dHdr
+  character :: dummychar
+  character(len=64) :: fname
+  call pimdk_restart_name(iproc, ii, fname)
+  u = 600 + iproc
+  open(u, file=trim(fname))
+  do i = 1, n
+     read(u,*) dummyint
+     read(u,*) dHdr
+     do j = 1, natom
+        read(u,*) dummychar, x(i,:,j)
+     end do
+  end do
+  do i = 1, n
+     read(u,*) dummyint
+     read(u,*) restartnmc
+     do j = 1, natom
+        read(u,*) dummychar, pinit(i,:,j)
+     end do
+  end do
+  close(u)
+end subroutine pimdk_read_restart
+
+!---------------------------------------------------------------------------------------------------------
+! What pimd_par.f90:383-424 collapses to: no MPI_Gather of every rank's integrands, but ONE all-reduce (NCCL, inside the
+! library) of {sum I, sum I**2, count} per lambda point, after which EVERY rank holds the statistics.
+! The communicator is created once after V_init: rank 0 calls pimdk_comm_unique_id(id), the id (128 bytes) is broadcast
+! with the MPI the driver already has (call MPI_Bcast(id, 128, MPI_CHARACTER, 0, MPI_COMM_WORLD, ierr)), then every rank
+! calls pimdk_comm_init(iproc, nproc, id).  MPI is then needed for nothing else on this path.
+subroutine pimdk_ti_statistics(ncalcs, first_gid, integrand, nrep, nintegral, weights, betan, answer, sigmaA, finalI)
+  use iso_c_binding
+  use pimdk
+  implicit none
+  integer :: ncalcs, first_gid, nrep, nintegral, ii
+  double precision :: integrand(ncalcs), weights(nintegral), betan, answer, sigmaA, finalI
+  double precision :: sums(3,nintegral), mean(nintegral), var(nintegral), dA(1), sA(1), qq(1), dH(ncalcs)
+  integer(c_int64_t), allocatable, target :: gid(:)
+  allocate(gid(ncalcs))
+  do ii = 1, ncalcs
+     gid(ii) = first_gid + ii - 1
+  end do
+  dH(:) = integrand(:)*betan**2                         ! pimdk_ti_partial_sums divides by betan**2 like pimd_par.f90:379
+  call pimdk_check(pimdk_ti_partial_sums(int(ncalcs,c_int64_t), dH, c_loc(gid), int(nrep,c_int64_t), int(nintegral,c_int64_t), &
+       betan, sums))
+  call pimdk_check(pimdk_ti_allreduce(int(nintegral,c_int64_t), sums))
+  call pimdk_check(pimdk_ti_finish(int(nintegral,c_int64_t), sums, weights, betan, mean, var, dA, sA, qq))
+  answer = dA(1); sigmaA = sA(1)**2; finalI = qq(1)   ! sigmaA as the variance the reference carries (:420-423 take its sqrt)
+  deallocate(gid)
+end subroutine pimdk_ti_statistics

@@ -138,7 +138,14 @@ def run_ti(pes_name, mc, well1, well2, mass, path_points=None, rank=0, world=1, 
         b = np.asfortranarray(xint[:, :, il[sl]])
         dbdl = np.asfortranarray(dbdxi[:, :, il[sl]])
         fn = vi.propagate_pimd_pile if mc.thermostat == PILE else vi.propagate_pimd_nm
-        _, _, dH[sl] = fn(x, p, startpoint, b, dbdl, traj_gid=gid[sl])
+        # pimd_par.f90:323-326: a task whose end point is all zeros (the padding of the reference's block layout) is not
+        # propagated and contributes integrand 0
+        live = ~np.all(np.abs(b) < 1e-10, axis=(0, 1))
+        out_dH = np.zeros(live.size)
+        if live.any():
+            _, _, out_dH[live] = fn(np.asfortranarray(x[..., live]), np.asfortranarray(p[..., live]), startpoint,
+                                    np.asfortranarray(b[..., live]), np.asfortranarray(dbdl[..., live]), traj_gid=gid[sl][live])
+        dH[sl] = out_dH
     sums = ti.allreduce_sums(ti.partial_sums(dH, gid, mc.nrep, mc.nintegral, vi.betan))
     out = ti.finish(sums, weights, vi.betan)
     out.update({"xi": xi, "weights": weights, "integrand": dH / vi.betan ** 2, "traj_gid": gid, "betan": vi.betan,

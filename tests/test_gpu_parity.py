@@ -701,7 +701,7 @@ def test_ti_ratio_matches_exact_path_integral(pk, name, n, beta, thermostat):
     independent of the oracle: q/q0 = exp(-betan DeltaA) is a ratio of n-bead discretised density-matrix elements,
     which tests/exact_pi.py evaluates deterministically by transfer matrices.  The GPU run must reproduce ln(q/q0)
     within 4.5 standard errors of its own estimate (and the standard error must be small enough to mean something:
-    the 2D value is -1.15, the 1D values -0.34 and -0.0014).  tools/dev/ti_exact_scan.py repeats this for three time
+    the 2D value is -1.15, the 1D values -0.34 and -0.0014).  tools/ti_exact_scan.py repeats this for three time
     steps, both thermostats and 1024 repetitions: 12 runs, |z| <= 2.6, mean z = -0.1 (dt = 5e-3 shows the integrator's
     O(dt^2) bias at the 2-sigma level with PILE, so the test runs at 2e-3)."""
     import exact_pi

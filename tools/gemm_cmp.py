@@ -1,6 +1,6 @@
 """DFMA vs DMMA normal-mode transform on the C4 / C2 shapes: time, TFLOP/s, and agreement."""
 import sys, os, time, ctypes, numpy as np
-R=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, R)
+R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
 import torch
 import pimd_tunneling_b200 as pk
 from pimd_tunneling_b200._lib import lib, check, hptr

@@ -1,5 +1,5 @@
 import sys, os, numpy as np
-R=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, R); sys.path.insert(0, R+"/tests")
+R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R); sys.path.insert(0, R+"/tests")
 import pimd_tunneling_b200 as pk
 from bench import ti_path, wells
 from pimd_tunneling_b200 import path as P

@@ -1,5 +1,5 @@
 import sys, os, ctypes
-R=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, R)
+R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
 import pimd_tunneling_b200 as pk
 from pimd_tunneling_b200._lib import lib, check
 pk.init()
