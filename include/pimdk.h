@@ -40,7 +40,7 @@ enum {
 };
 
 enum { PIMDK_THERMOSTAT_ANDERSEN = 1, PIMDK_THERMOSTAT_PILE = 2 }; /* namelist `thermostat`, pimd_par.f90:68,371-378 */
-enum { PIMDK_MODE_STRICT = 0, PIMDK_MODE_FAST = 1 };
+enum { PIMDK_MODE_STRICT = 0, PIMDK_MODE_FAST = 1, PIMDK_MODE_ANALYTIC = 2 };
 
 /* Library / device lifetime.  device < 0 keeps the current CUDA device.  data_dir is where the
  * CCpol-8sf parameter files live: either the reference's own data_SAPT5spfIR_2006 / data_CCpol8s /
@@ -53,7 +53,13 @@ const char* pimdk_last_error(void);
 /* Launch everything on this cudaStream_t (default: the legacy default stream). */
 int pimdk_set_stream(void* cuda_stream);
 /* PIMDK_MODE_STRICT (default): CCpol arithmetic in the reference's operation order without FMA
- * contraction; PIMDK_MODE_FAST: same kernels with contraction. */
+ * contraction; PIMDK_MODE_FAST: same kernels with contraction.
+ * PIMDK_MODE_ANALYTIC (opt-in, NOT the reference's arithmetic): Vprime of ccpol8sf becomes the analytic gradient of the
+ * same energy expression (reverse-mode chain rule through the site-pair sums, about two energies per bead instead of
+ * the 36 of the central difference, mcmod_waterdimer_ccpol.f90:40-58).  It agrees with the oracle's dual-number
+ * gradient to ~1e-12 and with the finite-difference default to that difference's truncation error (~3e-8 of
+ * max|grad|); x is not perturbed, so no drift is left behind.  Energies (V) are still the strict ones.  Offered for
+ * the Radau-embedded surfaces with potparts (isurf 3 = the plugin's, and 10). */
 int pimdk_set_mode(pimdk_int mode);
 /* Small systems (1D/2D surfaces, n <= 128 beads) are propagated by one persistent warp-per-ring-polymer
  * kernel (default on); 0 forces the streamed multi-kernel path.  Both give bit-identical results. */

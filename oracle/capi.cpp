@@ -101,6 +101,36 @@ int orc_ccpol_analytic_gradient(const double* x_bohr18, double* V, double* grad1
   for (int i = 0; i < 18; ++i) grad18[i] = e.d[i];
   return 0;
 }
+// the same for the two site models alone (stage-wise yardsticks for the analytic-gradient kernels):
+// SAPT-5s'f(carta, cartb) in kcal/mol and its gradient with respect to the 18 Angstrom coordinates
+int orc_sapt5sf_dual(const double* a9, const double* b9, double* val, double* grad18) {
+  if (!g_tab_loaded) { g_err = "tables not loaded"; return 1; }
+  Dual ca[3][3], cb[3][3];
+  for (int i = 0; i < 9; ++i) {
+    ca[i / 3][i % 3] = Dual(a9[i]);
+    ca[i / 3][i % 3].d[i] = 1.0;
+    cb[i / 3][i % 3] = Dual(b9[i]);
+    cb[i / 3][i % 3].d[9 + i] = 1.0;
+  }
+  Dual e = sapt5sf<Dual>(g_tab, ca, cb);
+  *val = e.v;
+  for (int i = 0; i < 18; ++i) grad18[i] = e.d[i];
+  return 0;
+}
+// ccpol8s_dimer (kcal/mol) of six atoms in Angstrom and its gradient
+int orc_ccpol8s_dual(const double* xyz18, double* val, double* grad18) {
+  if (!g_tab_loaded) { g_err = "tables not loaded"; return 1; }
+  Dual w[18];
+  for (int i = 0; i < 18; ++i) {
+    w[i] = Dual(xyz18[i]);
+    w[i].d[i] = 1.0;
+  }
+  bool conv = true;
+  Dual e = ccpol8s_dimer<Dual>(g_tab, w, w + 3, w + 6, w + 9, w + 12, w + 15, &conv);
+  *val = e.v;
+  for (int i = 0; i < 18; ++i) grad18[i] = e.d[i];
+  return conv ? 0 : 2;
+}
 int orc_opcount_kinds() { return Counted::NKIND; }
 const char* orc_opcount_name(int i) { return Counted::name(i); }
 

@@ -3,7 +3,7 @@
 nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels to the GPU box.
 Every translation unit is built with -fmad=false (arithmetic in the reference's operation order; FMAs
 appear only where the source says fma()), except the second copy of the CCpol kernels, which is the
-opt-in "fast" mode.
+opt-in "fast" mode, and the analytic-gradient kernels (opt-in mode 2: no operation-order promise).
 """
 import os
 import shutil
@@ -21,6 +21,7 @@ UNITS = [
     # (source, object, extra flags)
     ("ccpol_kernels.cu", "ccpol_strict.o", ["-fmad=false", "-DPIMDK_CCPOL_STRICT=1"]),
     ("ccpol_kernels.cu", "ccpol_fast.o", ["-fmad=true", "-DPIMDK_CCPOL_STRICT=0"]),
+    ("ccpol_grad_kernels.cu", "ccpol_grad.o", ["-fmad=true"]),
     ("pes_simple.cu", "pes_simple.o", ["-fmad=false"]),
     ("nm_kernels.cu", "nm_kernels.o", ["-fmad=false"]),
     ("fused_small.cu", "fused_small.o", ["-fmad=false"]),

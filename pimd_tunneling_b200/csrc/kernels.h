@@ -46,6 +46,14 @@ PIMDK_DECL_CCPOL(strict)
 PIMDK_DECL_CCPOL(fast)
 #undef PIMDK_DECL_CCPOL
 
+// ---- CCpol analytic gradient (ccpol_grad_kernels.cu; opt-in mode PIMDK_MODE_ANALYTIC) ----
+namespace agrad { struct CcpolGradTab; }
+size_t ccpol_analytic_bytes_per_geom();
+long ccpol_analytic_launches(long ngeom, int icc, size_t work_bytes);
+cudaError_t launch_ccpol_analytic(const CcpolDev* tab, const agrad::CcpolGradTab* gt, int iemonomer, int icc, double V0, GeomLayout L,
+                                  const double* x, double* v, double* grad, long ngeom, int* flags, double* work, size_t work_bytes,
+                                  int num_sms, cudaStream_t st);
+
 // ---- 1D / 2D model surfaces (pes_simple.cu) ----
 cudaError_t launch_simple_pes(PesKind kind, const SimplePesParams& P, GeomLayout L, const double* x, double* v,
                               double* grad, long ngeom, int* flags, cudaStream_t st);

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/pimdk.h"
+#include "ccpol_grad.cuh"
 #include "kernels.h"
 
 using namespace pimdk;
@@ -93,7 +94,8 @@ struct Ctx {
   bool tab_loaded = false;
   CcpolHost htab;
   CcpolDev hdev;
-  DevBuf dtab;
+  agrad::CcpolGradTab hgrad;   // rigid-body coefficients and sweep tables of the analytic-gradient mode
+  DevBuf dtab, dgtab;
   // normal modes
   bool nm_ready = false;
   int n = 0, nm_ndim = 0, nm_natom = 0;
@@ -174,6 +176,8 @@ int check_flags(bool sync_first) {
   if (sync_first) CU(cudaStreamSynchronize(g.stream));
   CU(cudaMemcpyAsync(&fl, g.wFlags.p, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
+  if (fl & PIMDK_FLAG_BADGID)
+    return fail(PIMDK_EINVAL, "trajectory id outside 0 .. 2^32-1 (the Philox counter carries 32 bits of it: RNG contract, pimdk.h)");
   if (fl & PIMDK_FLAG_NOCONV) return fail(PIMDK_ENOCONV, "No convergence in indN_iter");
   if (fl & PIMDK_FLAG_NAN) return fail(PIMDK_ENAN, "NaN in pot propagation");
   return PIMDK_OK;
@@ -198,6 +202,8 @@ int ensure_ccpol_tables(int isurf) {
 int upload_ccpol_dev() {
   CU(g.dtab.ensure(sizeof(CcpolDev)));
   CU(cudaMemcpyAsync(g.dtab.p, &g.hdev, sizeof(CcpolDev), cudaMemcpyHostToDevice, g.stream));
+  CU(g.dgtab.ensure(sizeof(agrad::CcpolGradTab)));
+  CU(cudaMemcpyAsync(g.dgtab.p, &g.hgrad, sizeof(agrad::CcpolGradTab), cudaMemcpyHostToDevice, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   return PIMDK_OK;
 }
@@ -209,6 +215,18 @@ int pes_eval_dev(GeomLayout L, double* x, double* v, double* grad, long ngeom, i
   int* flags = g.wFlags.as<int>();
   if (g.pes == PES_CCPOL) {
     const CcpolDev* tab = g.dtab.as<CcpolDev>();
+    if (g.mode == PIMDK_MODE_ANALYTIC && grad) {
+      // opt-in: analytic gradient (and the energy with it) in one pipeline run; x is not perturbed, so there is no drift
+      if (g.hdev.iembed != 2 || g.hdev.potparts_old)
+        return fail(PIMDK_EINVAL, "the analytic-gradient mode covers the Radau-embedded surfaces with potparts (isurf 3 and 10)");
+      const long cap = 262144;
+      const size_t wb = (size_t)(ngeom < cap ? ngeom : cap) * ccpol_analytic_bytes_per_geom();
+      CU(g.wCc.ensure(wb));
+      Scope s("pes", (int)ccpol_analytic_launches(ngeom, g.hdev.icc, wb));
+      CU(launch_ccpol_analytic(tab, g.dgtab.as<agrad::CcpolGradTab>(), g.hdev.iemonomer, g.hdev.icc, g.hdev.V0, L, x, v, grad, ngeom,
+                               flags, g.wCc.as<double>(), wb, g.num_sms, g.stream));
+      return PIMDK_OK;
+    }
     const bool fast = g.mode == PIMDK_MODE_FAST;
     for (int pass = 0; pass < 2; ++pass) {  // energies, then gradients (two pipeline runs, like V then Vprime)
       double* vv = pass == 0 ? v : nullptr;
@@ -440,7 +458,7 @@ int pimdk_finalize(void) {
   if (!g.inited) return PIMDK_OK;
   cudaStreamSynchronize(g.stream);
   resolve_spans();
-  DevBuf* bufs[] = {&g.dtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
+  DevBuf* bufs[] = {&g.dtab, &g.dgtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
                     &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wX2, &g.wPp2, &g.wUmIn, &g.wUmOut, &g.wHgp, &g.wHgm, &g.wHess, &g.wBand,
                     &g.wDense, &g.wEig, &g.wWork, &g.wSums, &g.wBV};
@@ -485,7 +503,7 @@ int pimdk_set_fused(pimdk_int enable) {
 }
 
 int pimdk_set_mode(pimdk_int mode) {
-  if (mode != PIMDK_MODE_STRICT && mode != PIMDK_MODE_FAST) return fail(PIMDK_EINVAL, "unknown mode");
+  if (mode != PIMDK_MODE_STRICT && mode != PIMDK_MODE_FAST && mode != PIMDK_MODE_ANALYTIC) return fail(PIMDK_EINVAL, "unknown mode");
   g.mode = (int)mode;
   return PIMDK_OK;
 }
@@ -528,6 +546,8 @@ int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
     int rc = ensure_ccpol_tables(isurf);
     if (rc) return rc;
     const char* m = build_ccpol_dev(g.htab, iemon, &g.hdev);
+    if (m[0]) return fail(PIMDK_EDATA, "%s", m);
+    m = agrad::build_grad_tab(g.hdev, &g.hgrad);
     if (m[0]) return fail(PIMDK_EDATA, "%s", m);
     rc = upload_ccpol_dev();
     if (rc) return rc;

@@ -1108,3 +1108,69 @@ def test_device_side_estimator_sums_match_the_host_formulas(pk):
     with pytest.raises(pk.PimdkError):
         ti.reduce_dev(gid.size, d.data_ptr(), gdev.data_ptr(), nrep, nintegral - 1, betan)
     assert ti.comm_info()[:2] == (0, 1)
+
+
+# ---------------------------------------------------------------- opt-in analytic CCpol gradient (row N4) -----------
+@pytest.mark.parametrize("nbatch", [1, 7, 1000])
+def test_ccpol_analytic_gradient_mode(pk, orc, nbatch):
+    """pimdk_set_mode(PIMDK_MODE_ANALYTIC): Vprime of ccpol8sf as the analytic gradient of the same energy expression.
+    Parity gates: (i) against the oracle's dual-number gradient (oracle/dual.hpp), 1e-10 of max|grad| (energy 1e-12);
+    (ii) against the finite-difference default at ITS truncation error, < 2e-7 of max|grad|
+    (mcmod_waterdimer_ccpol.f90:40-58: eps = 1e-4 bohr; tests/test_oracle.py measures 2.6e-8 median); (iii) x untouched."""
+    from pimd_tunneling_b200._lib import check, lib
+
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    orc.select("ccpol8sf")
+    x = thermal_dimer_geometries(nbatch, seed=31, sigma=0.06)
+    v_fd, g_fd = pes.eval_batch(x)
+    check(lib().pimdk_set_mode(2))
+    try:
+        x0 = x.copy()
+        v, g = pes.eval_batch(x)
+        g_only = pes.Vprime_batch(x)
+        x_in = np.array(x, order="F")
+        g_inplace = pes.Vprime_batch_inplace(x_in)
+    finally:
+        check(lib().pimdk_set_mode(0))
+    assert np.array_equal(x, x0) and np.array_equal(x_in, x0)          # no finite-difference drift in this mode
+    assert np.array_equal(g_only, g) and np.array_equal(g_inplace, g)
+    assert np.abs(v - v_fd).max() <= 1e-12 * np.abs(v_fd).max()         # (energy-with-gradient is the analytic pipeline's own sum)
+    gmax = np.abs(g_fd).max(axis=(0, 1))
+    assert (np.abs(g - g_fd).max(axis=(0, 1)) / gmax).max() < 2e-7
+    for k in range(min(nbatch, 24)):
+        vo, go = orc.ccpol_analytic_gradient(x[:, :, k])
+        assert abs(v[k] - vo) <= 1e-12 * max(1.0, abs(vo))
+        assert np.abs(g[:, :, k] - go).max() <= 1e-10 * np.abs(go).max()
+
+
+def test_ccpol_analytic_mode_surfaces_and_propagation(pk, orc):
+    """the mode covers the Radau-embedded potparts surfaces (3 and 10) and refuses the others; a propagation in this mode
+    stays within the finite-difference truncation error of the default over a few steps"""
+    from pimd_tunneling_b200._lib import check, lib
+
+    x = thermal_dimer_geometries(5, seed=2)
+    check(lib().pimdk_set_mode(2))
+    try:
+        orc.load_ccpol(10, 0)
+        p10 = pk.McmodMass("ccpol8sf", isurf=10, iemonomer=0).V_init()
+        g10 = p10.Vprime_batch(x)
+        for k in range(5):
+            _, go = orc.ccpol_analytic_gradient(x[:, :, k])
+            assert np.abs(g10[:, :, k] - go).max() <= 1e-10 * np.abs(go).max()
+        with pytest.raises(pk.PimdkError):
+            pk.McmodMass("ccpol8sf", isurf=1).V_init().Vprime_batch(x)
+    finally:
+        orc.load_ccpol(3, 1)
+        check(lib().pimdk_set_mode(0))
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    a, b = _wells("ccpol8sf")
+    n, ntraj, steps = 16, 3, 5
+    vi = pk.VerletInt(pes, n, DIMER_MASS, 400.0, dt=1e-3, NMC=steps, seed=12).init_nm()
+    xx, pp, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, 0.01, DIMER_MASS)
+    x_fd, p_fd, d_fd = vi.propagate_pimd_pile(xx, pp, a, bt, dbdl)
+    check(lib().pimdk_set_mode(2))
+    try:
+        x_an, p_an, d_an = vi.propagate_pimd_pile(xx, pp, a, bt, dbdl)
+    finally:
+        check(lib().pimdk_set_mode(0))
+    assert relmax(x_an, x_fd) < 1e-9 and relmax(p_an, p_fd) < 1e-6 and np.abs(d_an - d_fd).max() <= 1e-8 * np.abs(d_fd).max()

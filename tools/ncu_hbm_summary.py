@@ -45,7 +45,7 @@ def main():
     raw = page(rep, "--page", "raw")
     h, units = raw[0], dict(zip(raw[0], raw[1]))
     rows = [dict(zip(h, r)) for r in raw[2:]]
-    out = ["| kernel | grid x block | regs | duration [ms] | DRAM read [MB] | DRAM write [MB] | DRAM GB/s | % of %.0f GB/s | algorithmic MB | traffic / algorithmic | FP64 pipe % | issue active % | warps active % | L2 hit % |" % peak,
+    out = ["| kernel | grid x block | regs | duration [ms] | DRAM read [MB] | DRAM write [MB] | DRAM GB/s | %% of %.0f GB/s | algorithmic MB | traffic / algorithmic | FP64 pipe %% | issue active %% | warps active %% | L2 hit %% |" % peak,
            "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for k in rows:
         name = k["Kernel Name"].split("(")[0].split("::")[-1]
