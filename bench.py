@@ -43,19 +43,21 @@ FLOP_PER_BEAD_GRAD = {"ccpol8sf": 36 * FLOP_PER_ENERGY + 36, "2dtest": 6 * (2 + 
 # are NOT pasted here: they are read from the committed summary of the `ncu --set full` capture
 # (profiles/ccpol_counters.json, written by tools/ncu_pipeline_summary.py) together with the hash of the kernel
 # sources the capture was taken on; a summary whose hash differs from the tree's is reported as stale and not used.
-CCPOL_SOURCES = ["pimd_tunneling_b200/csrc/ccpol_kernels.cu", "pimd_tunneling_b200/csrc/ccpol_device.cuh",
-                 "pimd_tunneling_b200/csrc/ccpol_grad.cuh", "pimd_tunneling_b200/csrc/ccpol_tables.h", "include/pimdk_detmath.h"]
+CCPOL_SOURCES = {
+    "fd": ["pimd_tunneling_b200/csrc/ccpol_kernels.cu", "pimd_tunneling_b200/csrc/ccpol_device.cuh",
+           "pimd_tunneling_b200/csrc/ccpol_tables.h", "include/pimdk_detmath.h"],
+    "analytic": ["pimd_tunneling_b200/csrc/ccpol_grad_kernels.cu", "pimd_tunneling_b200/csrc/ccpol_grad.cuh",
+                 "pimd_tunneling_b200/csrc/ccpol_tables.h", "include/pimdk_detmath.h"],
+}
 
 
-def ccpol_source_hash():
+def ccpol_source_hash(mode="strict"):
     import hashlib
 
     h = hashlib.sha256()
-    for f in CCPOL_SOURCES:
-        path = os.path.join(ROOT, f)
-        if os.path.exists(path):
-            with open(path, "rb") as fh:
-                h.update(fh.read())
+    for f in CCPOL_SOURCES["analytic" if mode == "analytic" else "fd"]:
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            h.update(fh.read())
     return h.hexdigest()
 
 
@@ -70,7 +72,7 @@ def ccpol_counters(mode):
     ent = d.get(mode)
     if not ent:
         return None, "no ncu capture of mode %s in profiles/ccpol_counters.json" % mode
-    if ent.get("source_sha256") != ccpol_source_hash():
+    if ent.get("source_sha256") != ccpol_source_hash(mode):
         return None, "stale: %s was captured on other kernel sources (%s...)" % (ent.get("capture"), str(ent.get("source_sha256"))[:12])
     return ent, "profiles/ccpol_counters.json <- %s" % ent.get("capture")
 
@@ -289,7 +291,7 @@ def fast_vs_strict(pk, L, check, mode_id, nsample=256):
     v0, g0 = pes.eval_batch(x)
     check(L.pimdk_set_mode(mode_id))
     v1, g1 = pes.eval_batch(x)
-    return {"geometries": nsample, "energy_max_rel": float(np.max(np.abs(v1 - v0) / np.abs(v0))),
+    return {"geometries": nsample, "energy_max_abs_over_max": float(np.max(np.abs(v1 - v0)) / np.max(np.abs(v0))),
             "gradient_max_over_maxgrad": float(np.max(np.abs(g1 - g0).reshape(18, -1).max(0) / np.abs(g0).reshape(18, -1).max(0)))}
 
 
@@ -472,21 +474,30 @@ def run_ours(args, cfg, rank, world, local_rank):
                 "other_kernels_ms": fam, "step_ms_under_profiling": ms_prof / K}
         if cfg["pes"] == "ccpol8sf":
             pes_ms = fam["pes"]["ms"]
-            flop_bead = FLOP_PER_BEAD_GRAD["ccpol8sf"]
-            achieved = flop_bead * ntraj * n * K / (pes_ms * 1e-3) / 1e12 if pes_ms > 0 else None
             cnt, cnt_src = ccpol_counters(args.mode)
+            if args.mode == "analytic":
+                # this mode does NOT run the reference's arithmetic, so the reference's operation census does not apply:
+                # its work is the FP64 flop its own kernels execute (2*DFMA+DMUL+DADD, ncu source page, profiles/)
+                flop_bead = cnt["sass_flop_per_bead"] if cnt else None
+                kern = "agrad_{prep,sapt,rigid,back}_kernel (analytic-gradient pipeline; opt-in, not the reference's finite difference)"
+                fnote = "executed FP64 flop per bead-gradient of the analytic pipeline (ncu); the reference's 36-energy census does not apply"
+            else:
+                flop_bead = FLOP_PER_BEAD_GRAD["ccpol8sf"]
+                kern = "ccpol_{setup,sites,dipind,sapt,rigid,sweep,combine}_kernel_%s (one PES-gradient pipeline)" % args.mode
+                fnote = ("source-level FP64 operation census of the REFERENCE's finite-difference gradient (36 energies; "
+                         "oracle/opcount.hpp); exp, division and square root count as one operation each")
+            achieved = flop_bead * ntraj * n * K / (pes_ms * 1e-3) / 1e12 if (pes_ms > 0 and flop_bead) else None
             roof.update({"achieved": achieved, "frac": achieved / peak.value if achieved else None,
-                         "kernel": "ccpol_{setup,sites,dipind,sapt,rigid,sweep,combine}_kernel_%s (one PES-gradient pipeline)" % args.mode,
+                         "kernel": kern,
                          "kernel_ms_per_step": pes_ms / K, "kernel_launches": fam["pes"]["launches"],
                          "kernel_share_of_step": pes_ms / ms_prof,
                          "flop_per_bead_gradient": flop_bead,
-                         "flop_note": "source-level FP64 operation census of the REFERENCE's finite-difference gradient (36 energies; "
-                                      "oracle/opcount.hpp); exp, division and square root count as one operation each",
+                         "flop_note": fnote,
                          "algorithmic_bytes": 32 * ndof * ntraj * n / 1e9, "counters_source": cnt_src})
             if cnt:
                 roof["traffic"] = cnt["dram_bytes_per_bead"] * ntraj * n / 1e9
                 roof["traffic_unit"] = "GB per step (all beads of this GPU): ncu dram__bytes_read+write per bead-gradient x beads"
-                if pes_ms > 0:
+                if pes_ms > 0 and args.mode != "analytic":
                     roof["achieved_sass"] = cnt["sass_flop_per_bead"] * ntraj * n * K / (pes_ms * 1e-3) / 1e12
                     roof["achieved_sass_note"] = "2*DFMA+DMUL+DADD executed per bead-gradient (ncu source page) / kernel time of this run"
         elif fam["fused"]["launches"] > 0:

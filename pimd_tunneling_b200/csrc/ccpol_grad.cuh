@@ -300,27 +300,32 @@ PIMDK_AG double pjt2_monomer(const double* A9, double* g9) {
 }
 
 // ---------------------------------------------------------------- damping -----------------
-// Tang-Toennies factor d(n, beta r) (function d / damp) and its derivative with respect to r.
-PIMDK_AG void tt_damp_d(int n, double beta, double r, double& dd, double& ddr) {
+// Tang-Toennies factor d(n, beta r) (function d / damp) and its derivative with respect to r.  The order is a template
+// parameter so that every i in term*br/i is a compile-time reciprocal; the reference's small-argument branch (series tail
+// summed until term/sum < 1e-8) is a fixed 12 further terms here, which is at least as many as that criterion takes for the
+// arguments that reach it (|d| < 1e-8 means br < 0.2 ... 0.9 for n = 1 ... 10).
+template <int N>
+PIMDK_AG void tt_damp_d(double beta, double r, double& dd, double& ddr) {
   const double br = beta * r;
-  if (br == 0.0) { dd = 0.0; ddr = 0.0; return; }
   double sum = 1.0, term = 1.0;
-  for (int i = 1; i <= n; ++i) {
-    term = term * br / (double)i;
+#pragma unroll
+  for (int i = 1; i <= N; ++i) {
+    term = term * br * (1.0 / (double)i);
     sum = sum + term;
   }
   const double e = pimdk_exp(-br);
   ddr = beta * e * term;                       // b e^{-br} (br)^n / n!
   dd = 1.0 - e * sum;
-  if (fabs(dd) < 1.0e-8) {                     // the reference's series branch
+  if (fabs(dd) < 1.0e-8) {
     double t = term, acc = 0.0;
-    for (int i = n + 1; i <= 1000; ++i) {
-      t = t * br / (double)i;
+#pragma unroll
+    for (int i = N + 1; i <= N + 12; ++i) {
+      t = t * br * (1.0 / (double)i);
       acc = acc + t;
-      if (t / acc < 1.0e-8) break;
     }
     dd = acc * e;
   }
+  if (br == 0.0) { dd = 0.0; ddr = 0.0; }
 }
 
 // ---------------------------------------------------------------- SAPT-5s'f pair sum with adjoints ----
@@ -379,7 +384,7 @@ PIMDK_AG void sapt_pair_adj(const CcpolDev& T, int ia, int ib, double r, const d
   const double rinv = 1.0 / r;
   if (flags & 2) {                               // damped electrostatics d(1, dmp1 r) qa qb / r
     double d1, d1r;
-    tt_damp_d(1, PB(6), r, d1, d1r);
+    tt_damp_d<1>(PB(6), r, d1, d1r);
     const double t = d1 * rinv;
     o.e += t * qa * qb;
     o.dqa += t * qb;
@@ -390,10 +395,13 @@ PIMDK_AG void sapt_pair_adj(const CcpolDev& T, int ia, int ib, double r, const d
     const double pm = (ta == tb) ? 0.0 : ((ta < tb) ? 1.0 : -1.0);
     const double r2i = rinv * rinv;
     double rni = r2i * r2i * r2i;                // r^-6
+#pragma unroll
     for (int q = 0; q < 3; ++q) {
       const int n = 6 + 2 * q;
       double dn, dnr;
-      tt_damp_d(n, PB(7 + q), r, dn, dnr);
+      if (q == 0) tt_damp_d<6>(PB(7), r, dn, dnr);
+      else if (q == 1) tt_damp_d<8>(PB(8), r, dn, dnr);
+      else tt_damp_d<10>(PB(9), r, dn, dnr);
       const double cn = PB(3 + q) + PB(11 + q) * (x3 + y3) + PB(14 + q) * (x1 + y1) + PB(17 + q) * (x2 + y2) +
                         PB(20 + q) * (x3 * y3) + PB(23 + q) * (x1 * y1) + PB(26 + q) * (x2 * y2) +
                         pm * (PB(29 + q) * (x3 - y3) + PB(32 + q) * (x1 - y1) + PB(35 + q) * (x2 - y2));
@@ -504,7 +512,7 @@ PIMDK_AG double dipind_pair_adj(double par, const double* Oa, const double* Ob, 
   const double r2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
   const double r = sqrt(r2);
   double dmp, dmpr;
-  tt_damp_d(6, par, r, dmp, dmpr);
+  tt_damp_d<6>(par, r, dmp, dmpr);
   const double r3i = 1.0 / (r2 * r), r5i = r3i / r2, r7i = r5i / r2;
   double etot = 0.0, av[3] = {0.0, 0.0, 0.0};
   for (int w = 0; w < 2; ++w) {
@@ -589,7 +597,7 @@ PIMDK_AG double sapt_item_adj(const CcpolDev& T, const double* sitesA, const dou
 // ---------------------------------------------------------------- CCpol-8s rigid model: pair functions ----
 // sweep pair (U0 :166-186 + the linear combination :105-110): E = e^{-beta R} (c0 + c1 R + c2 R^2 + c3 R^3)
 PIMDK_AG void sweep_pair(const double* b5, double R, double& e, double& dedR) {
-  const double ex = pimdk_exp(-b5[0] * R);
+  const double ex = pimdk_exp_nonpos(-b5[0] * R);   // beta >= 0 (checked when the tables are built), R >= 0
   const double p = b5[1] + R * (b5[2] + R * (b5[3] + R * b5[4]));
   const double dp = b5[2] + R * (2.0 * b5[3] + 3.0 * b5[4] * R);
   e = ex * p;
@@ -598,7 +606,7 @@ PIMDK_AG void sweep_pair(const double* b5, double R, double& e, double& dedR) {
 // damped electrostatics of one charged pair (:190-200)
 PIMDK_AG void elst_pair(double d1, double qq, double R, double& e, double& dedR) {
   double f, fr;
-  tt_damp_d(1, d1, R, f, fr);
+  tt_damp_d<1>(d1, R, f, fr);
   e = f * qq / R;
   dedR = qq * (fr - f / R) / R;
 }
@@ -608,10 +616,13 @@ PIMDK_AG void disp_pair(const double* dmp3, const double* c3, double R, double& 
   double rni = r2i * r2i * r2i;
   e = 0.0;
   dedR = 0.0;
+#pragma unroll
   for (int q = 0; q < 3; ++q) {
     const int n = 6 + 2 * q;
     double f, fr;
-    tt_damp_d(n, dmp3[q], R, f, fr);
+    if (q == 0) tt_damp_d<6>(dmp3[0], R, f, fr);
+    else if (q == 1) tt_damp_d<8>(dmp3[1], R, f, fr);
+    else tt_damp_d<10>(dmp3[2], R, f, fr);
     e -= f * c3[q] * rni;
     dedR -= c3[q] * (fr - (double)n * f * ri) * rni;
     rni *= r2i;

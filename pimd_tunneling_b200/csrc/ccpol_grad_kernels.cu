@@ -100,15 +100,24 @@ agrad_prep_kernel(const CcpolDev* __restrict__ tab, const CcpolGradTab* __restri
 }
 
 // ---- sapt ---------------------------------------------------------------------------------------
-constexpr int kSaptThreads = 128;
-__global__ void __launch_bounds__(kSaptThreads)
+// sapt_item_adj (ccpol_grad.cuh: the host-checked statement of this stage) laid out for the SM: one 512-thread CTA per SM,
+// the B sites and their adjoints in shared memory (slot-major, conflict-free), the A site of the current row and its adjoint
+// in registers (the row's adjoint goes straight to the staging buffer), charges and their chain to s1..s3 recomputed per pair
+// instead of being held in arrays — no local memory.
+constexpr int kSaptThreads = 512;
+template <int STRIDE>
+struct Slots {
+  double* p;   // &base[threadIdx.x]
+  __device__ __forceinline__ double& operator[](int k) const { return p[k * STRIDE]; }
+};
+__global__ void __launch_bounds__(kSaptThreads, 1)
 agrad_sapt_kernel(const CcpolDev* __restrict__ tab, const CcpolGradTab* __restrict__ gt, long nb, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int kSaptTab = (int)((sizeof(CcpolDev) - PIMDK_RIGID_TABLE_BYTES + 15) / 16 * 16);
   {  // the SAPT-5s'f members of the table (param .. pairflags) -> shared memory; T is a view whose leading members are not backed
     const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + PIMDK_RIGID_TABLE_BYTES);
     int4* dst = reinterpret_cast<int4*>(smem);
-    const int n16 = (int)((sizeof(CcpolDev) - PIMDK_RIGID_TABLE_BYTES + 15) / 16);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < kSaptTab / 16; i += blockDim.x) dst[i] = src[i];
     __syncthreads();
   }
   const CcpolDev& T = *reinterpret_cast<const CcpolDev*>(smem - PIMDK_RIGID_TABLE_BYTES);
@@ -118,22 +127,142 @@ agrad_sapt_kernel(const CcpolDev* __restrict__ tab, const CcpolGradTab* __restri
   const long e = which ? j - nb : j;
   const double* pa = buf + (long)(AF_SITES + 54 * which) * nb + e;
   const double* pb = pa + (long)27 * nb;
-  double sitesA[24], sitesB[24], sA[3], sB[3], adj[54];
-#pragma unroll
-  for (int k = 0; k < 24; ++k) {
-    sitesA[k] = pa[(long)k * nb];
-    sitesB[k] = pb[(long)k * nb];
-  }
+  Slots<kSaptThreads> sitesB{reinterpret_cast<double*>(smem + kSaptTab) + threadIdx.x};
+  Slots<kSaptThreads> adjB{reinterpret_cast<double*>(smem + kSaptTab) + 24 * kSaptThreads + threadIdx.x};
+  double sA[3], sB[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     sA[k] = which ? __ldg(&gt->s_rig[k]) : pa[(long)(24 + k) * nb];
     sB[k] = which ? __ldg(&gt->s_rig[k]) : pb[(long)(24 + k) * nb];
   }
-  const double val = sapt_item_adj(T, sitesA, sA, sitesB, sB, adj);
-  buf[(long)(which ? AF_VALL : AF_VAL) * nb + e] = val;
-  double* out = buf + (long)(which ? AF_ADJR : AF_ADJF) * nb + e;
-  const int nout = which ? 48 : 54;
-  for (int k = 0; k < nout; ++k) out[(long)k * nb] = adj[k];
+  // ---- dipole induction: dipole sums and polarisabilities of both monomers, pair part with adjoints
+  double dma[3] = {0.0, 0.0, 0.0}, dmb[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const double* prm = &T.param[site_type(i) * kNParam];
+    const double sg = dipind_sign(i);
+    const double qa = flex_charge(prm, sA[0], sA[1], sg * sA[2]) / 18.22262373;
+    const double qb = flex_charge(prm, sB[0], sB[1], sg * sB[2]) / 18.22262373;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double b = pb[(long)(i * 3 + k) * nb];
+      sitesB[i * 3 + k] = b;
+      dma[k] += qa * pa[(long)(i * 3 + k) * nb] / kA0;
+      dmb[k] += qb * b / kA0;
+    }
+  }
+  double pA, pB;
+  {
+    const double* prm = &T.param[0];
+    pA = prm[9] + prm[10] * sA[0] + prm[11] * sA[1] + prm[12] * sA[2] + prm[13] * sA[0] * sA[1] + prm[14] * sA[1] * sA[2] +
+         prm[15] * sA[0] * sA[0] + prm[16] * sA[1] * sA[1] + prm[17] * sA[2] * sA[2];
+    pB = prm[9] + prm[10] * sB[0] + prm[11] * sB[1] + prm[12] * sB[2] + prm[13] * sB[0] * sB[1] + prm[14] * sB[1] * sB[2] +
+         prm[15] * sB[0] * sB[0] + prm[16] * sB[1] * sB[1] + prm[17] * sB[2] * sB[2];
+  }
+  double aOa[3], aOb[3], adma[3], admb[3], apA, apB;
+  double E;
+  {
+    const double Oa[3] = {pa[0], pa[nb], pa[2 * nb]};
+    const double Ob[3] = {sitesB[0], sitesB[1], sitesB[2]};
+    E = dipind_pair_adj(T.parab[10 - 1], Oa, Ob, dma, dmb, pA, pB, aOa, aOb, adma, admb, apA, apB);
+  }
+  double asA[3], asB[3];    // adjoints of s1..s3 of A and of B
+  {
+    const double* prm = &T.param[0];
+    asA[0] = apA * (prm[10] + prm[13] * sA[1] + 2.0 * prm[15] * sA[0]);
+    asA[1] = apA * (prm[11] + prm[13] * sA[0] + prm[14] * sA[2] + 2.0 * prm[16] * sA[1]);
+    asA[2] = apA * (prm[12] + prm[14] * sA[1] + 2.0 * prm[17] * sA[2]);
+    asB[0] = apB * (prm[10] + prm[13] * sB[1] + 2.0 * prm[15] * sB[0]);
+    asB[1] = apB * (prm[11] + prm[13] * sB[0] + prm[14] * sB[2] + 2.0 * prm[16] * sB[1]);
+    asB[2] = apB * (prm[12] + prm[14] * sB[1] + 2.0 * prm[17] * sB[2]);
+  }
+  // B side of the dipole sums' adjoint: sites of B and, through the charges, s of B
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const double* prm = &T.param[site_type(i) * kNParam];
+    const double sg = dipind_sign(i);
+    const double q = flex_charge(prm, sB[0], sB[1], sg * sB[2]) / 18.22262373;
+    double aq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      adjB[i * 3 + k] = admb[k] * q / kA0 + (i == 0 ? aOb[k] : 0.0);
+      aq += admb[k] * sitesB[i * 3 + k] / kA0;
+    }
+    double g[3] = {0.0, 0.0, 0.0};
+    flex_charge_adj(prm, sB[0], sB[1], sg * sB[2], aq / 18.22262373, g);
+    asB[0] += g[0];
+    asB[1] += g[1];
+    asB[2] += sg * g[2];
+  }
+  // ---- the 8 x 8 site pairs, row by row
+  double* outA = buf + (long)(which ? AF_ADJR : AF_ADJF) * nb + e;
+#pragma unroll 1
+  for (int ia = 0; ia < 8; ++ia) {
+    const double* prmA = &T.param[site_type(ia) * kNParam];
+    const double ax = pa[(long)(ia * 3) * nb], ay = pa[(long)(ia * 3 + 1) * nb], az = pa[(long)(ia * 3 + 2) * nb];
+    // the row's adjoint starts with the dipole-sum part
+    const double sgd = dipind_sign(ia);
+    const double qd = flex_charge(prmA, sA[0], sA[1], sgd * sA[2]) / 18.22262373;
+    double gx = adma[0] * qd / kA0, gy = adma[1] * qd / kA0, gz = adma[2] * qd / kA0;
+    if (ia == 0) { gx += aOa[0]; gy += aOa[1]; gz += aOa[2]; }
+    {
+      double g[3] = {0.0, 0.0, 0.0};
+      flex_charge_adj(prmA, sA[0], sA[1], sgd * sA[2], (adma[0] * ax + adma[1] * ay + adma[2] * az) / kA0 / 18.22262373, g);
+      asA[0] += g[0];
+      asA[1] += g[1];
+      asA[2] += sgd * g[2];
+    }
+    const double sga = (ia == 2) ? -1.0 : 1.0;
+    const double qa = flex_charge(prmA, sA[0], sA[1], sga * sA[2]);
+    double aqa = 0.0;
+#pragma unroll 1
+    for (int ib = 0; ib < 8; ++ib) {
+      const double d0 = ax - sitesB[ib * 3], d1 = ay - sitesB[ib * 3 + 1], d2 = az - sitesB[ib * 3 + 2];
+      const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+      const double* prmB = &T.param[site_type(ib) * kNParam];
+      const double sgb = (ib == 2) ? -1.0 : 1.0;
+      const double qb = flex_charge(prmB, sB[0], sB[1], sgb * sB[2]);
+      PairOut o;
+      sapt_pair_adj(T, ia, ib, r, sA, sB, qa, qb, o);
+      E += o.e;
+      const double f = o.dr / r;
+      gx += f * d0; gy += f * d1; gz += f * d2;
+      adjB[ib * 3] -= f * d0; adjB[ib * 3 + 1] -= f * d1; adjB[ib * 3 + 2] -= f * d2;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        asA[k] += o.dx[k];
+        asB[k] += o.dy[k];
+      }
+      aqa += o.dqa;
+      if (o.dqb != 0.0) {
+        double g[3] = {0.0, 0.0, 0.0};
+        flex_charge_adj(prmB, sB[0], sB[1], sgb * sB[2], o.dqb, g);
+        asB[0] += g[0];
+        asB[1] += g[1];
+        asB[2] += sgb * g[2];
+      }
+    }
+    {
+      double g[3] = {0.0, 0.0, 0.0};
+      flex_charge_adj(prmA, sA[0], sA[1], sga * sA[2], aqa, g);
+      asA[0] += g[0];
+      asA[1] += g[1];
+      asA[2] += sga * g[2];
+    }
+    outA[(long)(ia * 3) * nb] = gx;
+    outA[(long)(ia * 3 + 1) * nb] = gy;
+    outA[(long)(ia * 3 + 2) * nb] = gz;
+  }
+  buf[(long)(which ? AF_VALL : AF_VAL) * nb + e] = E;
+#pragma unroll 1
+  for (int k = 0; k < 24; ++k) outA[(long)(24 + k) * nb] = adjB[k];
+  if (!which) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      outA[(long)(48 + k) * nb] = asA[k];
+      outA[(long)(51 + k) * nb] = asB[k];
+    }
+  }
 }
 
 // ---- rigid --------------------------------------------------------------------------------------
@@ -146,7 +275,7 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(kRigWarps * 32)
+__global__ void __launch_bounds__(kRigWarps * 32, 2)
 agrad_rigid_kernel(const CcpolDev* __restrict__ tab, const CcpolGradTab* __restrict__ gtab, long nb, double* __restrict__ buf,
                    int* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -199,22 +328,36 @@ agrad_rigid_kernel(const CcpolDev* __restrict__ tab, const CcpolGradTab* __restr
     }
     __syncwarp();
     double E = 0.0, adA[3] = {0.0, 0.0, 0.0}, adB[3] = {0.0, 0.0, 0.0};
-    // U0's exponential sweep: lane a meets B site (a + t) mod 25 at step t
+    // U0's exponential sweep: lane a meets B site (a + t) mod 25 at step t.  Five steps are evaluated together (independent
+    // instruction streams: the stage is bound by dependent-issue latency), then their B-side updates are applied one step
+    // at a time, a warp barrier between them, so that no two lanes ever update one B site at once.
 #pragma unroll 1
-    for (int t = 0; t < 25; ++t) {
-      if (site) {
-        int b = l + t;
+    for (int t0 = 0; t0 < 25; t0 += 5) {
+      double fx[5], fy[5], fz[5];
+      int bb[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        int b = l + t0 + q;
         if (b >= 25) b -= 25;
+        bb[q] = b;
         const double d0 = ra[0] - sB[b * 3], d1 = ra[1] - sB[b * 3 + 1], d2 = ra[2] - sB[b * 3 + 2];
-        const double R = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+        const double ri = rsqrt(r2);
+        const double R = r2 * ri;
         double pe, de;
         sweep_pair(G.bin5[G.pair_bin[b * 25 + l]], R, pe, de);
-        E += pe;
-        const double f = de / R;
-        adA[0] += f * d0; adA[1] += f * d1; adA[2] += f * d2;
-        aB[b * 3] -= f * d0; aB[b * 3 + 1] -= f * d1; aB[b * 3 + 2] -= f * d2;
+        const double f = site ? de * ri : 0.0;
+        E += site ? pe : 0.0;
+        fx[q] = f * d0; fy[q] = f * d1; fz[q] = f * d2;
+        adA[0] += fx[q]; adA[1] += fy[q]; adA[2] += fz[q];
       }
-      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        if (site) {
+          aB[bb[q] * 3] -= fx[q]; aB[bb[q] * 3 + 1] -= fy[q]; aB[bb[q] * 3 + 2] -= fz[q];
+        }
+        __syncwarp();
+      }
     }
     // damped electrostatics: pair (a, b) = (lane / 5, lane % 5); dispersion: (lane / 3, lane % 3)
     if (site) {
@@ -315,23 +458,25 @@ agrad_rigid_kernel(const CcpolDev* __restrict__ tab, const CcpolGradTab* __restr
         }
       }
     }
-    // reduce the site adjoints to the frames: site = COM + a I + b J + c K
+    // reduce the site adjoints to the frames (site = COM + a I + b J + c K): the 2 x 25 x 3 site adjoints go through shared
+    // memory and 24 lanes form one of the 24 frame adjoints each (25 multiply-adds) instead of 24 shuffle reductions
     const double Esum = warp_sum(E);
-    double* out = buf + (long)AF_ADJFR * nb + e;
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      const double* ad = m ? adB : adA;
+    __syncwarp();
+    if (site) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const double v = site ? ad[j] : 0.0;
-        const double sI = warp_sum(ca * v), sJ = warp_sum(cb * v), sK = warp_sum(cc * v), sC = warp_sum(v);
-        if (lane == 0) {
-          out[(long)(12 * m + j) * nb] = sI;
-          out[(long)(12 * m + 3 + j) * nb] = sJ;
-          out[(long)(12 * m + 6 + j) * nb] = sK;
-          out[(long)(12 * m + 9 + j) * nb] = sC;
-        }
+        sA[l * 3 + j] = adA[j];     // the sites themselves are no longer needed
+        sB[l * 3 + j] = adB[j];
       }
+    }
+    __syncwarp();
+    if (lane < 24) {
+      const int m = lane / 12, r = lane - 12 * m, w = r / 3, j = r - 3 * w;   // w: 0 I, 1 J, 2 K, 3 COM
+      const double* ad = m ? sB : sA;
+      double acc = 0.0;
+#pragma unroll 5
+      for (int k = 0; k < 25; ++k) acc += (w < 3 ? G.cc_abc[k][w] : 1.0) * ad[k * 3 + j];
+      buf[(long)(AF_ADJFR + lane) * nb + e] = acc;
     }
     if (lane == 0) buf[(long)AF_ERIG * nb + e] = (Esum + Eind) * kHar2Kcal;
     __syncwarp();
@@ -429,7 +574,7 @@ agrad_back_kernel(const CcpolGradTab* __restrict__ gt, int iemonomer, int icc, d
   }
 }
 
-size_t sapt_smem() { return (sizeof(CcpolDev) - PIMDK_RIGID_TABLE_BYTES + 15) / 16 * 16; }
+size_t sapt_smem() { return (sizeof(CcpolDev) - PIMDK_RIGID_TABLE_BYTES + 15) / 16 * 16 + (size_t)48 * kSaptThreads * sizeof(double); }
 size_t rigid_smem() {
   return (size_t)PIMDK_RIGID_TABLE_BYTES + (sizeof(CcpolGradTab) + 15) / 16 * 16 + (size_t)kRigWarps * kRigScratch * sizeof(double);
 }

@@ -2,7 +2,12 @@
 """Summarise an .ncu-rep that holds one `ncu --set full` capture of each kernel of the CCpol PES-gradient
 pipeline (read here, no GPU needed): per-kernel headline metrics, stall reasons, DRAM traffic and the SASS-level
 FP64 rate (2*DFMA + DMUL + DADD thread instructions, from the source page) against the DFMA peak.
-usage: ncu_pipeline_summary.py report.ncu-rep nbeads [out.md]"""
+usage: ncu_pipeline_summary.py report.ncu-rep nbeads [out.md] [--mode strict|fast|analytic --capture NAME]
+With --mode the per-bead counters (DRAM bytes, executed FP64 flop) are also written into profiles/ccpol_counters.json together
+with the hash of the kernel sources in the tree (bench.py reads them from there and refuses a stale entry)."""
+import json
+import os
+import re
 import csv
 import io
 import subprocess
@@ -18,11 +23,20 @@ def page(rep, *args):
 
 
 def main():
-    rep, nbeads = sys.argv[1], int(sys.argv[2])
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    opts = {}
+    av = sys.argv[1:]
+    for i, a in enumerate(av):
+        if a.startswith("--") and i + 1 < len(av):
+            opts[a[2:]] = av[i + 1]
+    args = [a for a in args if a not in opts.values()]
+    rep, nbeads = args[0], int(args[1])
     raw = page(rep, "--page", "raw")
     h = raw[0]
     kern = [dict(zip(h, r)) for r in raw[2:]]
-    names = [k["Kernel Name"].split("ccpol_")[-1].split("_kernel")[0] for k in kern]
+    prefix = "agrad" if opts.get("mode") == "analytic" else "ccpol"
+    kern = [k for k in kern if re.search(prefix + r"_(\w+?)_kernel", k["Kernel Name"])]
+    names = [re.search(prefix + r"_(\w+?)_kernel", k["Kernel Name"]).group(1) for k in kern]
     rows = [
         ("duration [ms]", "gpu__time_duration.sum"),
         ("registers/thread", "launch__registers_per_thread"),
@@ -63,7 +77,7 @@ def main():
     tot_ms = sum(float(k["gpu__time_duration.sum"]) for k in kern)
     flops, fracs, dram = [], [], 0.0
     for k, nm in zip(kern, names):
-        src = page(rep, "--page", "source", "--print-source", "sass", "-k", "regex:ccpol_%s_kernel" % nm)
+        src = page(rep, "--page", "source", "--print-source", "sass", "-k", "regex:%s_%s_kernel" % (prefix, nm))
         hh = src[1]
         te, so = hh.index("Predicated-On Thread Instructions Executed"), hh.index("Source")
         c = Counter()
@@ -89,8 +103,25 @@ def main():
         sum(flops) / nbeads, 100 * sum(flops) / cyc_tot / PEAK_FLOP_PER_CYCLE, PEAK_FLOP_PER_CYCLE)
     text += "\nDRAM traffic of the pass (read + write, all stages): %.3f GB = %.0f bytes per bead-gradient\n" % (dram / 1e9, dram / nbeads)
     print(text)
-    if len(sys.argv) > 3:
-        open(sys.argv[3], "w").write(text)
+    if len(args) > 2:
+        open(args[2], "w").write(text)
+    if "mode" in opts:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        from bench import ccpol_source_hash
+
+        path = os.path.join(root, "profiles", "ccpol_counters.json")
+        try:
+            d = json.load(open(path))
+        except Exception:
+            d = {}
+        d[opts["mode"]] = {"dram_bytes_per_bead": dram / nbeads, "sass_flop_per_bead": sum(flops) / nbeads,
+                           "pass_ms_ncu": tot_ms, "beads": nbeads, "capture": opts.get("capture", os.path.basename(rep)),
+                           "source_sha256": ccpol_source_hash(opts["mode"]),
+                           "how": "ncu --set full --clock-control none --import-source on, one pass; dram__bytes_read.sum + "
+                                  "dram__bytes_write.sum and 2*DFMA+DMUL+DADD thread instructions (source page), all kernels of the pipeline"}
+        json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+        print("wrote", path)
 
 
 if __name__ == "__main__":
