@@ -98,6 +98,11 @@ module pimdk
      integer(c_int) function pimdk_set_andersen_carry(enable) bind(C, name="pimdk_set_andersen_carry")
        import; integer(c_int64_t), value :: enable
      end function
+     ! dHdrlimit (pimd_par.f90:45,88; verletmodule.f90:404-409): outlier guard of propagate_pimd_pile with re-initialisation
+     integer(c_int) function pimdk_set_dhdrlimit(limit, npath, lampath, path, splinepath, ntraj, xi) bind(C, name="pimdk_set_dhdrlimit")
+       import; real(c_double), value :: limit; integer(c_int64_t), value :: npath, ntraj
+       real(c_double) :: lampath(*), path(*), splinepath(*), xi(*)
+     end function
      ! multi-GPU: the library's NCCL communicator and the one collective of the path (replaces MPI_Gather, pimd_par.f90:389)
      integer(c_int) function pimdk_comm_unique_id(id) bind(C, name="pimdk_comm_unique_id")
        import; character(kind=c_char) :: id(*)
@@ -155,8 +160,8 @@ module mcmod_mass
   logical::                        potforcepresent=.true.
   character, allocatable::         label(:)
   character(len=20)::              basename
-  ! which in-repo surface this plugin stands for: "ccpol8sf" (mcmod_waterdimer_ccpol.f90), "2dtest" (mcmod_2dtest.f90)
-  ! or "1d" (mcmod_1d.f90); set before V_init (the reference has one mcmod_<PES>.f90 per surface and picks at link time)
+  ! which in-repo surface this plugin stands for: "ccpol8sf" (mcmod_waterdimer_ccpol.f90), "2dtest" (mcmod_2dtest.f90),
+  ! "1d" (mcmod_1d.f90) or "so2" (mcmod_so2.f90); set before V_init (the reference has one mcmod_<PES>.f90 per surface and picks at link time)
   character(len=16)::              pimdk_pes_name = "ccpol8sf"
 contains
   subroutine V_init(iproc)
@@ -218,7 +223,7 @@ end module mcmod_mass
 !   restart = 2  x, p, dHdr and restartnmc are read from the files first (pimd_par.f90:356-370), then as restart = 1
 subroutine pimdk_propagate_tasks(thermostat, ncalcs, first_gid, iproc, startpoint, endpoints, gradpoints, xipoints, &
      lampath, path, splinepath, npath, mass, label, betan, tau, dt, gamma, NMC, imin, Noutput, cayley, seed, &
-     restart, integrand)
+     restart, dHdrlimit, integrand)
   use iso_c_binding
   use pimdk
   use mcmod_mass, only: n, ndim, natom
@@ -227,7 +232,7 @@ subroutine pimdk_propagate_tasks(thermostat, ncalcs, first_gid, iproc, startpoin
   logical :: cayley
   double precision :: startpoint(ndim,natom), endpoints(ncalcs,ndim,natom), gradpoints(ncalcs,ndim,natom)
   double precision :: xipoints(ncalcs), lampath(npath), path(npath,ndim,natom), splinepath(npath,ndim,natom)
-  double precision :: mass(natom), betan, tau, dt, gamma, integrand(ncalcs)
+  double precision :: mass(natom), betan, tau, dt, gamma, dHdrlimit, integrand(ncalcs)
   character :: label(natom)
   double precision, allocatable :: x(:,:,:,:), p(:,:,:,:), b(:,:,:), dbdl(:,:,:), dHdr(:), sums(:)
   integer(c_int64_t), allocatable, target :: gid(:)
@@ -237,6 +242,8 @@ subroutine pimdk_propagate_tasks(thermostat, ncalcs, first_gid, iproc, startpoin
      b(:,:,ii) = endpoints(ii,:,:); dbdl(:,:,ii) = gradpoints(ii,:,:); gid(ii) = first_gid + ii - 1
   end do
   call pimdk_check(pimdk_nm_setup(int(n,c_int64_t), int(ndim,c_int64_t), int(natom,c_int64_t), mass, betan, tau))
+  ! outlier guard of propagate_pimd_pile (verletmodule.f90:404-409); dHdrlimit < 0 (default -1) switches it off
+  call pimdk_check(pimdk_set_dhdrlimit(dHdrlimit, int(npath,c_int64_t), lampath, path, splinepath, int(ncalcs,c_int64_t), xipoints))
   done = 0
   sums(:) = 0.0d0
   if (restart .lt. 2) then

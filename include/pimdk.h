@@ -72,8 +72,9 @@ int pimdk_set_gemm(pimdk_int kind);
 /* ---- PES plugin: module mcmod_mass -------------------------------------------------------
  * pimdk_pes_select  = V_init  (mcmod_1d.f90:8, mcmod_2dtest.f90:11, mcmod_waterdimer_ccpol.f90:9
  *                     -> init_ccpol(3,1,1,0), main_CCpol-8sf.f:1-173)
- *   name: "1d" | "2dtest" | "ccpol8sf".  pes_params (optional): "1d": {Vheight, x0};
- *   "2dtest": {a0, b0, rho0}; "ccpol8sf": {iemonomer (default 1), isurf (default 3; 1..10 select the surfaces of
+ *   name: "1d" | "2dtest" | "so2" | "ccpol8sf".  pes_params (optional): "1d": {Vheight, x0};
+ *   "2dtest": {a0, b0, rho0}; "so2" (mcmod_so2.f90:10-48, the harmonic ring V = omegaforce**2/2 (r - r0)**2 in two
+ *   dimensions): {omegaforce (default 10000), r0 (default 20)}; "ccpol8sf": {iemonomer (default 1), isurf (default 3; 1..10 select the surfaces of
  *   init_ccpol, main_CCpol-8sf.f:14-107: SAPT data file, Eckart or Radau embedding, potparts or potparts_old,
  *   with or without the CCpol-8s correction)}.
  * pimdk_pes_set_v0  = assignment to module variable V0 (pimd_par.f90:166, rpi_ser.f90:95)
@@ -183,6 +184,14 @@ int pimdk_set_restart(pimdk_int restart, pimdk_int restartnmc);
  * number of trajectories; PIMDK_EINVAL otherwise) instead of starting at count = 0 with a new Poisson interval.
  * enable = 0 (default): every call starts its clocks like a fresh propagate_pimd_nm. */
 int pimdk_set_andersen_carry(pimdk_int enable);
+/* dHdrlimit of namelist MCDATA (pimd_par.f90:45, 88; verletmodule.f90:404-409, propagate_pimd_pile only): a step whose
+ * estimator contribution has |contr| >= limit is not added to dHdr, and the ring polymer is re-initialised on the spot by
+ * init_path(xi, ...) — beads back on the spline path at the trajectory's xi, fresh momenta (RNG stream 0 at that step).
+ * The guard therefore needs what init_path needs: the spline path and xi(ntraj) of the trajectories of the following
+ * propagate calls (same order, same count).  limit < 0 (the reference's default, -1) switches the guard off; the other
+ * arguments are then ignored.  Andersen calls ignore the limit, like propagate_pimd_nm. */
+int pimdk_set_dhdrlimit(double limit, pimdk_int npath, const double* lampath, const double* path, const double* splinepath,
+                        pimdk_int ntraj, const double* xi);
 int pimdk_get_dhdr_sums(pimdk_int ntraj, double* sums);
 /* index (0-based, into the last call's batch) of the first trajectory that tripped the NaN trap, or -1 */
 pimdk_int pimdk_last_nan_trajectory(void);

@@ -139,6 +139,7 @@ int orc_pes_select(const char* name) {
   std::string s(name);
   if (s == "1d") { g_pes = Pes(); g_pes.init_1d(); return 0; }
   if (s == "2dtest") { g_pes = Pes(); g_pes.init_2d(); return 0; }
+  if (s == "so2") { g_pes = Pes(); g_pes.init_so2(); return 0; }
   if (s == "ccpol8sf") {
     if (!g_tab_loaded) { g_err = "tables not loaded"; return 1; }
     g_pes = Pes();
@@ -150,6 +151,7 @@ int orc_pes_select(const char* name) {
 }
 void orc_pes_set_dims(int ndim, int natom) { g_pes.ndim = ndim; g_pes.natom = natom; }
 void orc_pes_set_V0(double v0) { g_pes.V0 = v0; }
+void orc_pes_set_so2(double omegaforce, double r0) { g_pes.omegaforce = omegaforce; g_pes.r0 = r0; }
 double orc_V(const double* x) { return g_pes.V(x); }
 void orc_Vprime(double* x, double* grad) { g_pes.Vprime(x, grad); }
 void orc_Vdoubleprime(double* x, double* hess) { g_pes.Vdoubleprime(x, hess); }
@@ -202,6 +204,17 @@ int orc_propagate(int thermostat, double* x, double* p, const double* dbdl, long
   g_v.nan_trap = false;
   ORC_TRY(*dHdr = (thermostat == 1) ? g_v.propagate_pimd_nm(x, p, dbdl) : g_v.propagate_pimd_pile(x, p, dbdl);
           if (g_v.nan_trap) throw std::runtime_error("NaN in propagation"))
+}
+// dHdrlimit and the path init_path re-initialises from (verletmodule.f90:404-409); limit < 0 switches the guard off
+void orc_set_dhdrlimit(double limit, double xi, const double* lampath, const double* path, const double* splinepath, int npath) {
+  g_v.dHdrlimit = limit;
+  g_v.rp_xi = xi;
+  if (limit >= 0.0) {
+    const size_t nd = (size_t)g_v.ndim * g_v.natom;
+    g_v.rp_lam.assign(lampath, lampath + npath);
+    g_v.rp_path.assign(path, path + npath * nd);
+    g_v.rp_spl.assign(splinepath, splinepath + npath * nd);
+  }
 }
 int orc_poisson(unsigned long long seed, unsigned long long step, unsigned int gid, double lambda) {
   return poisson_norm(seed, step, gid, lambda);

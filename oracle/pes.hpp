@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
 // CPU restatement of the three in-scope `module mcmod_mass` plugins:
-//   mcmod_1d.f90:8-58, mcmod_2dtest.f90:11-61, mcmod_waterdimer_ccpol.f90:9-77.
+//   mcmod_1d.f90:8-58, mcmod_2dtest.f90:11-61, mcmod_waterdimer_ccpol.f90:9-77, mcmod_so2.f90:10-84.
 // x and grad are Fortran (ndim,natom) column-major: index = (atom)*ndim + dim.
 #pragma once
 #include <cmath>
@@ -12,7 +12,7 @@
 
 namespace oracle {
 
-enum PesKind { PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3 };
+enum PesKind { PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4 };
 
 struct Pes {
   PesKind kind = PES_1D;
@@ -24,6 +24,8 @@ struct Pes {
   int m = 6;
   double a0 = 2.0, b0 = 0.2, rho0 = 3.0;
   double wx[6], wy[6];
+  // so2 (mcmod_so2.f90:10-14)
+  double omegaforce = 10000.0, r0 = 20.0;
   // CCpol
   const CcpolTables* tab = nullptr;
   long potcount = 0;
@@ -47,6 +49,14 @@ struct Pes {
       wy[k - 1] = rho0 * std::sin((double)k * 2.0 * pi / (double)m);
     }
     V0 = 0.0;  // never initialised by the reference: static storage -> 0
+  }
+  void init_so2() {
+    kind = PES_SO2;
+    ndim = 2;
+    natom = 1;
+    omegaforce = 10000.0;
+    r0 = 20.0;
+    V0 = 0.0;
   }
   void init_ccpol(const CcpolTables* t) {
     kind = PES_CCPOL;
@@ -74,6 +84,11 @@ struct Pes {
           answer = answer - 0.5 * pimdk_exp(-a0 * (dx * dx + dy * dy));
           answer = answer - 0.5 * pimdk_exp(-b0 * (dx * dx + dy * dy));
         }
+        return answer - V0;
+      }
+      case PES_SO2: {  // mcmod_so2.f90:22-31
+        double r = std::sqrt(x[0] * x[0] + x[1] * x[1]);
+        double answer = 0.5 * (omegaforce * omegaforce) * ((r - r0) * (r - r0));
         return answer - V0;
       }
       case PES_CCPOL: {  // mcmod_waterdimer_ccpol.f90:18-37
@@ -110,6 +125,12 @@ struct Pes {
         }
         grad[0] = g1;
         grad[1] = g2;
+        return;
+      }
+      case PES_SO2: {  // mcmod_so2.f90:42-44
+        double r = std::sqrt(x[0] * x[0] + x[1] * x[1]);
+        grad[0] = (omegaforce * omegaforce) * x[0] * (1.0 - r0 / r);
+        grad[1] = (omegaforce * omegaforce) * x[1] * (1.0 - r0 / r);
         return;
       }
       case PES_CCPOL: {  // mcmod_waterdimer_ccpol.f90:40-58
@@ -153,6 +174,15 @@ struct Pes {
         H(0, 0, 1, 0) = (d2vdu2 * dudy + dvdu) * dudx;
         H(1, 0, 1, 0) = (d2vdu2 * dudy + dvdu) * dudy;
       }
+      return;
+    }
+    if (kind == PES_SO2) {  // mcmod_so2.f90:76-82, literally (the diagonal (1 - r0/r) term is not in the reference)
+      double r = std::sqrt(x[0] * x[0] + x[1] * x[1]);
+      double w2 = omegaforce * omegaforce, r3 = r * r * r;
+      H(0, 0, 0, 0) = x[0] * x[0] * w2 * r0 / r3;
+      H(0, 0, 1, 0) = x[0] * x[1] * w2 * r0 / r3;
+      H(1, 0, 0, 0) = x[0] * x[1] * w2 * r0 / r3;
+      H(1, 0, 1, 0) = x[1] * x[1] * w2 * r0 / r3;
       return;
     }
     const double eps = (kind == PES_CCPOL) ? 1e-5 : 1e-4;

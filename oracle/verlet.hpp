@@ -317,7 +317,7 @@ struct Verlet {
 
   // init_path, verletmodule.f90:32-119 (readhess=.false.).  path(npath,ndim,natom) + splines.
   void init_path(double xi, const double* lampath, const double* path, const double* splinepath, int npath,
-                 double* x, double* p) {
+                 double* x, double* p, uint64_t step = 0) {
     std::vector<double> ya(npath), y2(npath);
     for (int i = 1; i <= ndim; ++i)
       for (int j = 1; j <= natom; ++j) {
@@ -327,7 +327,7 @@ struct Verlet {
           x[IX(k, i, j)] = splint(lampath, path + off, splinepath + off, npath, xieff);
         }
       }
-    sample_momenta(p, STREAM_INIT, 0);
+    sample_momenta(p, STREAM_INIT, step);
   }
 
   // estimator contribution, verletmodule.f90:397-403
@@ -339,13 +339,24 @@ struct Verlet {
     return c;
   }
 
-  // propagate_pimd_pile, verletmodule.f90:372-416 (restart<2, dHdrlimit<0, iprint=.false.)
+  // propagate_pimd_pile, verletmodule.f90:372-416 (restart<2, iprint=.false.)
+  // dHdrlimit (namelist MCDATA, pimd_par.f90:45,88) and what init_path needs for the outlier re-initialisation :404-409
+  double dHdrlimit = -1.0, rp_xi = 0.0;
+  std::vector<double> rp_lam, rp_path, rp_spl;
   double propagate_pimd_pile(double* x, double* p, const double* dbdl) {
     setup_pile();
     double dHdr = 0.0;
     for (long ii = 1; ii <= NMC; ++ii) {
       time_step_pile(x, p, (uint64_t)ii);
-      if (ii > imin) dHdr = dHdr + contr(x, dbdl);
+      if (ii > imin) {
+        const double c = contr(x, dbdl);
+        if (std::fabs(c) < dHdrlimit || dHdrlimit < 0.0) {
+          dHdr = dHdr + c;
+        } else {   // "Over limit ... reinitialize path": the contribution is dropped, the momenta are drawn afresh
+                   // (RNG contract: stream 0 at the current step; the initial init_path used step 0)
+          init_path(rp_xi, rp_lam.data(), rp_path.data(), rp_spl.data(), (int)rp_lam.size(), x, p, (uint64_t)ii);
+        }
+      }
     }
     return dHdr / (double)(NMC - imin);
   }

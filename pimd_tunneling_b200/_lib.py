@@ -51,6 +51,7 @@ _SIGS = {
     "pimdk_propagate_dev": [_i64, _i64, _pd, _pd, _pd, _pd, _pd, _dbl, _dbl, _i64, _i64, _i64, _i64, _u64, _pi, _pd],
     "pimdk_set_restart": [_i64, _i64],
     "pimdk_set_andersen_carry": [_i64],
+    "pimdk_set_dhdrlimit": [_dbl, _i64, _pd, _pd, _pd, _i64, _pd],
     "pimdk_set_propagate_chunk": [_i64],
     "pimdk_get_dhdr_sums": [_i64, _pd],
     "pimdk_ti_partial_sums": [_i64, _pd, _pi, _i64, _i64, _dbl, _pd],

@@ -47,7 +47,8 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
                    const double* __restrict__ dbdl, double dt, long NMC, long imin, double lambda, uint64_t seed,
                    const int64_t* __restrict__ gid, double* __restrict__ dHdr, int* __restrict__ flags, long step0,
                    int keep_sum, double* __restrict__ dHsum, int* __restrict__ clk_count, int* __restrict__ clk_kick,
-                   int carry) {
+                   int carry, double dhdrlimit, int npath, const double* __restrict__ lampath, const double* __restrict__ rpath,
+                   const double* __restrict__ rspl, const double* __restrict__ xis) {
   extern __shared__ __align__(16) double sm[];
   const int n = nm.n;
   double* Ts = sm;                                   // transmatrix, n x n
@@ -141,9 +142,10 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
   // estimator (verletmodule.f90:397-403): the lane that owns the last bead
   const int last_lane = (n - 1) & 31, last_s = (n - 1) >> 5;
   double acc = keep_sum ? dHdr[traj] : 0.0;   // restart = 2 continues the running sum (verletmodule.f90:200,388)
-  auto estimator = [&]() {
-    if (lane != last_lane) return;
+  // estimator; returns true (warp-uniform) when the dHdrlimit guard drops the contribution (verletmodule.f90:404-409)
+  auto estimator = [&](bool guard) -> bool {
     double contr = 0.0;
+    if (lane == last_lane) {
     for (int j = 0; j < ndim; ++j)
       for (int k = 0; k < NDOF / ndim; ++k) {
         const int d = k * ndim + j;
@@ -155,14 +157,47 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
             if (dd == d && s == last_s) xl = r.x[dd][s];
         contr = contr + nm.mass[k] * (-xl) * dbdl[traj * NDOF + d];
       }
-    acc = acc + contr;
+    }
+    bool over = false;
+    if (guard) {
+      const double c = __shfl_sync(0xffffffffu, contr, last_lane);
+      over = !(fabs(c) < dhdrlimit || dhdrlimit < 0.0);
+    }
+    if (lane == last_lane && !over) acc = acc + contr;
+    return over;
+  };
+  // init_path again (verletmodule.f90:39-48, 102-115): beads on the spline, momenta drawn in normal-mode space (stream 0 at
+  // the current step), Q = T x - beadvec
+  auto reinit = [&](uint64_t step) {
+#pragma unroll
+    for (int d = 0; d < NDOF; ++d) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int k = lane + 32 * s;
+        if (k < n) {
+          const double xv = (double)k * xis[traj] / (double)(n - 1);
+          r.x[d][s] = splint_at(lampath, rpath + (long)d * npath, rspl + (long)d * npath, npath, xv);
+          const double z = normal_at(seed, STREAM_INIT, step, g, (uint64_t)d * n + k);
+          r.P[d][s] = (0.0 + nm.stdev * z) * nm.sigp[(d / ndim) * n + k];
+          vec[k] = r.x[d][s];
+        }
+      }
+      __syncwarp();
+      warp_matvec<S>(Ts, vec, n, lane, r.Q[d]);
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int k = lane + 32 * s;
+        if (k < n) r.Q[d][s] = r.Q[d][s] - beadvec_at(nm, a, b, traj, d, k);
+      }
+    }
   };
 
   if (thermostat == 2) {  // time_step_pile (:423-435)
     for (long ii = 1; ii <= NMC; ++ii) {
       kick_and_rotate(true, 2, (uint64_t)(ii + step0));
       to_beads();
-      if (ii > imin) estimator();
+      if (ii > imin && estimator(dhdrlimit >= 0.0)) reinit((uint64_t)(ii + step0));
     }
   } else {                // propagate_pimd_nm (:190-250) / time_step_nm (:291-302)
     // collision clock: fresh (:199-202) or continued from the previous call of a run cut into segments
@@ -194,7 +229,7 @@ fused_small_kernel(NmTables nm, int pes_kind, SimplePesParams pp, int thermostat
       to_beads();
       kick_and_rotate(false, 1, (uint64_t)(ii + step0));
       to_beads();
-      if (ii > imin) estimator();
+      if (ii > imin) estimator(false);   // propagate_pimd_nm has no dHdrlimit guard (verletmodule.f90:236-244)
     }
     if (lane == 0 && clk_count) {
       clk_count[traj] = count;
@@ -232,14 +267,16 @@ template <int NDOF, int S>
 cudaError_t launch_t(const NmTables& nm, int kind, const SimplePesParams& pp, int thermostat, long ntraj, double* x,
                      double* p, const double* a, const double* b, const double* dbdl, double dt, long NMC, long imin,
                      double lambda, uint64_t seed, const int64_t* gid, double* dHdr, int* flags, long step0, int keep_sum,
-                     double* dHsum, int* clk_count, int* clk_kick, int carry, cudaStream_t st) {
+                     double* dHsum, int* clk_count, int* clk_kick, int carry, double dhdrlimit, int npath, const double* lampath,
+                     const double* rpath, const double* rspl, const double* xis, cudaStream_t st) {
   const size_t smem = ((size_t)nm.n * nm.n + (size_t)kWarpsPerBlock * nm.n) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(fused_small_kernel<NDOF, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned blocks = (unsigned)((ntraj + kWarpsPerBlock - 1) / kWarpsPerBlock);
   fused_small_kernel<NDOF, S><<<blocks, kWarpsPerBlock * 32, smem, st>>>(nm, kind, pp, thermostat, ntraj, x, p, a, b, dbdl,
                                                                         dt, NMC, imin, lambda, seed, gid, dHdr, flags, step0,
-                                                                        keep_sum, dHsum, clk_count, clk_kick, carry);
+                                                                        keep_sum, dHsum, clk_count, clk_kick, carry, dhdrlimit, npath,
+                                                                        lampath, rpath, rspl, xis);
   return cudaGetLastError();
 }
 
@@ -247,8 +284,8 @@ cudaError_t launch_t(const NmTables& nm, int kind, const SimplePesParams& pp, in
 
 bool fused_small_supported(PesKind kind, int n, int ndim, int natom) {
   const int ndof = ndim * natom;
-  if (kind != PES_1D && kind != PES_2DTEST) return false;
-  if (kind == PES_2DTEST && ndof != 2) return false;
+  if (kind != PES_1D && kind != PES_2DTEST && kind != PES_SO2) return false;
+  if ((kind == PES_2DTEST || kind == PES_SO2) && ndof != 2) return false;
   return n >= 2 && n <= 128 && (ndof == 1 || ndof == 2);
 }
 
@@ -256,12 +293,14 @@ cudaError_t launch_fused_small(const NmTables& nm, PesKind kind, const SimplePes
                                double* x, double* p, const double* a, const double* b, const double* dbdl, double dt,
                                long NMC, long imin, double lambda, uint64_t seed, const int64_t* gid, double* dHdr,
                                int* flags, long step0, int keep_sum, double* dHsum, int* clk_count, int* clk_kick, int carry,
-                               cudaStream_t st) {
+                               double dhdrlimit, int npath, const double* lampath, const double* rpath, const double* rspl,
+                               const double* xis, cudaStream_t st) {
   const int S = (nm.n + 31) / 32;
 #define PIMDK_FUSED_CASE(ND, SS)                                                                                        \
   if (nm.ndof == ND && S == SS)                                                                                         \
     return launch_t<ND, SS>(nm, (int)kind, pp, thermostat, ntraj, x, p, a, b, dbdl, dt, NMC, imin, lambda, seed, gid, \
-                            dHdr, flags, step0, keep_sum, dHsum, clk_count, clk_kick, carry, st);
+                            dHdr, flags, step0, keep_sum, dHsum, clk_count, clk_kick, carry, dhdrlimit, npath, lampath, rpath, rspl,   \
+                            xis, st);
   PIMDK_FUSED_CASE(1, 1) PIMDK_FUSED_CASE(1, 2) PIMDK_FUSED_CASE(1, 3) PIMDK_FUSED_CASE(1, 4)
   PIMDK_FUSED_CASE(2, 1) PIMDK_FUSED_CASE(2, 2) PIMDK_FUSED_CASE(2, 3) PIMDK_FUSED_CASE(2, 4)
 #undef PIMDK_FUSED_CASE

@@ -49,6 +49,16 @@ simple_hessian_kernel(int kind, SimplePesParams P, int ndim, int natom, GeomLayo
     H[3] = h22;  // hess(2,1,2,1)
     return;
   }
+  if (kind == PES_SO2) {   // mcmod_so2.f90:76-82, as written there (x(i)*x(j)*omegaforce**2*r0/r**3: no diagonal (1 - r0/r) term)
+    const double x1 = x[base], x2 = x[base + L.stride_dof];
+    const double r = sqrt(x1 * x1 + x2 * x2);
+    const double w2 = P.omegaforce * P.omegaforce, r3 = r * r * r;
+    H[0] = x1 * x1 * w2 * P.r0 / r3;
+    H[1] = x1 * x2 * w2 * P.r0 / r3;
+    H[2] = x1 * x2 * w2 * P.r0 / r3;
+    H[3] = x2 * x2 * w2 * P.r0 / r3;
+    return;
+  }
   const double eps = 1e-4;
   double xx[kMaxSimpleDof], gp[kMaxSimpleDof], gm[kMaxSimpleDof], e;
   for (int d = 0; d < nd; ++d) xx[d] = x[base + d * L.stride_dof];

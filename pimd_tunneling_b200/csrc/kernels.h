@@ -22,10 +22,11 @@ struct GeomLayout {
   }
 };
 
-enum PesKind { PES_NONE = 0, PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3 };
+enum PesKind { PES_NONE = 0, PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4 };
 
-struct SimplePesParams {  // mcmod_1d.f90:9-12, mcmod_2dtest.f90:16-24
+struct SimplePesParams {  // mcmod_1d.f90:9-12, mcmod_2dtest.f90:16-24, mcmod_so2.f90:10-14
   double Vheight, x0;
+  double omegaforce, r0;   // so2: harmonic ring V = omegaforce**2/2 (r - r0)**2
   double a0, b0;
   double wx[6], wy[6];
   double V0;
@@ -117,6 +118,12 @@ cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const do
                                    const double* BV = nullptr);
 cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* dbdl, double* dHdr, long ntraj,
                              cudaStream_t st);
+// dHdrlimit (verletmodule.f90:404-409): estimator with the outlier guard, and init_path again for the marked trajectories
+cudaError_t launch_estimator_limit(const NmTables& nm, const double* x, const double* dbdl, double* dHdr, long ntraj, double limit,
+                                   int* reinit, cudaStream_t st);
+cudaError_t launch_reinit(const NmTables& nm, int npath, const double* lampath, const double* path, const double* spl,
+                          const double* xi, double* x, double* P, double* Q, const double* a, const double* b, long ntraj,
+                          uint64_t seed, uint64_t step, const int64_t* gid, const int* reinit, cudaStream_t st);
 cudaError_t launch_scale(double* v, double s, long n, cudaStream_t st);
 
 // ---- fused warp-per-ring-polymer propagation for small systems (fused_small.cu) ----
@@ -125,7 +132,8 @@ cudaError_t launch_fused_small(const NmTables& nm, PesKind kind, const SimplePes
                                double* x, double* p, const double* a, const double* b, const double* dbdl, double dt,
                                long NMC, long imin, double lambda, uint64_t seed, const int64_t* gid, double* dHdr,
                                int* flags, long step0, int keep_sum, double* dHsum, int* clk_count, int* clk_kick, int carry,
-                               cudaStream_t st);
+                               double dhdrlimit, int npath, const double* lampath, const double* path, const double* spl,
+                               const double* xi, cudaStream_t st);
 
 // ---- second derivatives (hess_kernels.cu): Vdoubleprime, UMhessian (instantonmod.f90:155-217) ----
 cudaError_t launch_simple_hessian(PesKind kind, const SimplePesParams& P, int ndim, int natom, GeomLayout L, double* x,

@@ -583,6 +583,61 @@ estimator_modes_kernel(NmTables nm, const double* __restrict__ Q, const double* 
   }
 }
 
+// ---- dHdrlimit (verletmodule.f90:404-409, propagate_pimd_pile only) -----------------------------------------------
+// estimator with the outlier guard: |contr| < limit is added; otherwise the contribution is dropped and the trajectory is
+// marked for re-initialisation (init_path again: beads back on the spline path, fresh momenta)
+__global__ void estimator_limit_kernel(NmTables nm, const double* __restrict__ x, const double* __restrict__ dbdl,
+                                       double* __restrict__ dHdr, long ntraj, double limit, int* __restrict__ reinit) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntraj) return;
+  const double* xt = x + t * (long)nm.ndof * nm.n;
+  double contr = 0.0;
+  for (int j = 0; j < nm.ndim; ++j)
+    for (int k = 0; k < nm.natom; ++k) {
+      const int dof = k * nm.ndim + j;
+      contr = contr + nm.mass[k] * (-xt[(long)dof * nm.n + (nm.n - 1)]) * dbdl[t * nm.ndof + dof];
+    }
+  const bool keep = fabs(contr) < limit || limit < 0.0;
+  if (keep) dHdr[t] = dHdr[t] + contr;
+  reinit[t] = keep ? 0 : 1;
+}
+// init_path (verletmodule.f90:39-48, 102-115) for the marked trajectories: x on the spline, momenta drawn directly in
+// normal-mode space (the state lives there: p = T P), RNG stream 0 at the current step
+__global__ void __launch_bounds__(256)
+reinit_kernel(NmTables nm, int npath, const double* __restrict__ lampath, const double* __restrict__ path,
+              const double* __restrict__ spl, const double* __restrict__ xi, double* __restrict__ x, double* __restrict__ P,
+              long rows, uint64_t seed, uint64_t step, const int64_t* __restrict__ gid, const int* __restrict__ reinit) {
+  const long row = blockIdx.x;
+  if (row >= rows) return;
+  const long traj = row / nm.ndof;
+  if (!reinit[traj]) return;
+  const int dof = (int)(row - traj * nm.ndof);
+  const int n = nm.n;
+  const uint32_t g = gid ? (uint32_t)gid[traj] : (uint32_t)traj;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const double xv = (double)k * xi[traj] / (double)(n - 1);
+    x[row * n + k] = splint_at(lampath, path + (long)dof * npath, spl + (long)dof * npath, npath, xv);
+    const double z = normal_at(seed, STREAM_INIT, step, g, (uint64_t)dof * n + k);
+    P[row * n + k] = (0.0 + nm.stdev * z) * nm.sigp[(dof / nm.ndim) * n + k];
+  }
+}
+// Q = T x - beadvec for the marked trajectories (same fma chain, j ascending, as the transform kernels)
+__global__ void __launch_bounds__(256)
+reinit_q_kernel(NmTables nm, const double* __restrict__ x, const double* __restrict__ a, const double* __restrict__ b,
+                double* __restrict__ Q, long rows, const int* __restrict__ reinit) {
+  const long row = blockIdx.x;
+  if (row >= rows) return;
+  const long traj = row / nm.ndof;
+  if (!reinit[traj]) return;
+  const int dof = (int)(row - traj * nm.ndof);
+  const int n = nm.n;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) acc = fma(x[row * n + j], nm.T[(long)j * n + k], acc);
+    Q[row * n + k] = acc - beadvec_at(nm, a, b, traj, dof, k);
+  }
+}
+
 __global__ void scale_kernel(double* v, double s, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = v[i] / s;
@@ -733,6 +788,21 @@ cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const do
     if (e != cudaSuccess) return e;
   }
   estimator_modes_kernel<<<(unsigned)((ntraj + tpc - 1) / tpc), kEmThreads, smem, st>>>(nm, Q, a, b, dbdl, dHdr, ntraj, BV);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_estimator_limit(const NmTables& nm, const double* x, const double* dbdl, double* dHdr, long ntraj, double limit,
+                                   int* reinit, cudaStream_t st) {
+  estimator_limit_kernel<<<(unsigned)((ntraj + 127) / 128), 128, 0, st>>>(nm, x, dbdl, dHdr, ntraj, limit, reinit);
+  return cudaGetLastError();
+}
+cudaError_t launch_reinit(const NmTables& nm, int npath, const double* lampath, const double* path, const double* spl,
+                          const double* xi, double* x, double* P, double* Q, const double* a, const double* b, long ntraj,
+                          uint64_t seed, uint64_t step, const int64_t* gid, const int* reinit, cudaStream_t st) {
+  const long rows = ntraj * (long)nm.ndof;
+  if (rows > 0x7fffffffL) return cudaErrorInvalidValue;
+  reinit_kernel<<<(unsigned)rows, 256, 0, st>>>(nm, npath, lampath, path, spl, xi, x, P, rows, seed, step, gid, reinit);
+  reinit_q_kernel<<<(unsigned)rows, 256, 0, st>>>(nm, x, a, b, Q, rows, reinit);
   return cudaGetLastError();
 }
 

@@ -1,5 +1,5 @@
-// Bead energy and gradient of the 1D and 2D model surfaces: mcmod_1d.f90:20,31-32 and
-// mcmod_2dtest.f90:33-39,48-58, in the reference's operation order (compile with -fmad=false).  Shared by the
+// Bead energy and gradient of the model surfaces: mcmod_1d.f90:20,31-32, mcmod_2dtest.f90:33-39,48-58 and
+// mcmod_so2.f90:17-48 (harmonic ring), in the reference's operation order (compile with -fmad=false).  Shared by the
 // streamed kernel (pes_simple.cu) and the fused warp-per-ring-polymer kernel (fused_small.cu).
 #pragma once
 #include "../../include/pimdk_detmath.h"
@@ -25,6 +25,17 @@ __device__ __forceinline__ void simple_pes_eval(int kind, const SimplePesParams&
       }
     }
     if (want_v) *v = s;
+  } else if (kind == PES_SO2) {
+    // mcmod_so2.f90:22-23: r = sqrt(x**2 + y**2); V = 0.5*omegaforce**2*(r-r0)**2 - V0
+    // :42-44: grad = omegaforce**2 * x * (1 - r0/r)
+    const double x1 = x[0], x2 = x[MAXDOF > 1 ? 1 : 0];
+    const double r = sqrt(x1 * x1 + x2 * x2);
+    const double w2 = P.omegaforce * P.omegaforce;
+    if (want_v) *v = 0.5 * w2 * ((r - P.r0) * (r - P.r0)) - P.V0;
+    if (want_g) {
+      g[0] = w2 * x1 * (1.0 - P.r0 / r);
+      if (MAXDOF > 1) g[1] = w2 * x2 * (1.0 - P.r0 / r);
+    }
   } else {
     const double x1 = x[0], x2 = x[MAXDOF > 1 ? 1 : 0];
     double answer = 0.0, g1 = 0.0, g2 = 0.0;

@@ -17,6 +17,7 @@
 #include "../../include/pimdk.h"
 #include "ccpol_grad.cuh"
 #include "kernels.h"
+#include "nm_device.cuh"
 
 using namespace pimdk;
 
@@ -83,6 +84,9 @@ struct Ctx {
   long sums_n = 0;                   // trajectories in wDhSum (running sums of the last propagate call)
   bool andersen_carry = false;       // pimdk_set_andersen_carry: the next Andersen call continues the collision clocks
   long clock_n = 0;                  // trajectories whose (count, rkick) the last Andersen call left in wCount / wKick
+  double dhdrlimit = -1.0;           // pimdk_set_dhdrlimit (namelist dHdrlimit, pimd_par.f90:88): < 0 = no outlier guard
+  int rp_npath = 0;                  // spline path and per-trajectory xi for the re-initialisation (wPath, wXi)
+  long rp_ntraj = 0;
   long chunk_traj = 0;               // pimdk_set_propagate_chunk: trajectories per chunk of the host-buffer propagate (0 = automatic)
   long sum_off = 0, sum_total = 0;   // chunked host-buffer propagate: this chunk's offset into wDhSum / whole batch
   cudaStream_t copy_stream = nullptr; // host<->device copies of the chunked propagate, overlapped with compute
@@ -103,7 +107,7 @@ struct Ctx {
   std::vector<double> mass, lam, beadmass, T;
   DevBuf dT, dsA, dsB, dlamb2, dmass, dtabs;  // dtabs: 8 per-call (natom,n) tables
   // workspaces
-  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wX2, wPp2, wUmIn, wUmOut, wHgp, wHgm, wHess, wBand, wDense, wEig, wWork, wSums, wBV;
+  DevBuf wCc, wP, wQ, wG, wGn, wV, wX, wAux, wCount, wKick, wFlags, wGid, wA, wB, wDbdl, wDhdr, wPp, wMisc, wDhSum, wX2, wPp2, wUmIn, wUmOut, wHgp, wHgm, wHess, wBand, wDense, wEig, wWork, wSums, wBV, wPath, wXi, wReinit;
   PinBuf hUm;
   // profiling
   bool profiling = false;
@@ -328,26 +332,7 @@ __global__ void init_path_kernel(int n, int ndof, int npath, const double* __res
     const int dof = (int)(r % ndof);
     const long traj = r / ndof;
     const double xv = (double)k * xi[traj] / (double)(n - 1);
-    // locate
-    const bool ascnd = lampath[npath - 1] >= lampath[0];
-    int jl = 0, ju = npath + 1;
-    while (ju - jl > 1) {
-      const int jm = (ju + jl) / 2;
-      if (ascnd == (xv >= lampath[jm - 1])) jl = jm;
-      else ju = jm;
-    }
-    int loc = jl;
-    if (xv == lampath[0]) loc = 1;
-    else if (xv == lampath[npath - 1]) loc = npath - 1;
-    int klo = loc < npath - 1 ? loc : npath - 1;
-    if (klo < 1) klo = 1;
-    const int khi = klo + 1;
-    const double* ya = path + (long)dof * npath;
-    const double* y2 = spl + (long)dof * npath;
-    const double h = lampath[khi - 1] - lampath[klo - 1];
-    const double aa = (lampath[khi - 1] - xv) / h, bb = (xv - lampath[klo - 1]) / h;
-    x[e] = aa * ya[klo - 1] + bb * ya[khi - 1] +
-           ((aa * aa * aa - aa) * y2[klo - 1] + (bb * bb * bb - bb) * y2[khi - 1]) * (h * h) / 6.0;
+    x[e] = splint_at(lampath, path + (long)dof * npath, spl + (long)dof * npath, npath, xv);
   }
 }
 
@@ -461,7 +446,7 @@ int pimdk_finalize(void) {
   DevBuf* bufs[] = {&g.dtab, &g.dgtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
                     &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wX2, &g.wPp2, &g.wUmIn, &g.wUmOut, &g.wHgp, &g.wHgm, &g.wHess, &g.wBand,
-                    &g.wDense, &g.wEig, &g.wWork, &g.wSums, &g.wBV};
+                    &g.wDense, &g.wEig, &g.wWork, &g.wSums, &g.wBV, &g.wPath, &g.wXi, &g.wReinit};
   for (DevBuf* b : bufs) b->release();
   g.hUm.release();
   if (nc.comm) {
@@ -479,6 +464,9 @@ int pimdk_finalize(void) {
   g.inited = false;
   g.andersen_carry = false;
   g.clock_n = 0;
+  g.dhdrlimit = -1.0;
+  g.rp_npath = 0;
+  g.rp_ntraj = 0;
   g.nm_ready = false;
   g.pes = PES_NONE;
   g.tab_loaded = false;
@@ -538,6 +526,17 @@ int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
     g.sp.ndof = 2;
     return PIMDK_OK;
   }
+  if (s == "so2") {  // mcmod_so2.f90:10-15: harmonic ring, omegaforce = 10000, r0 = 20
+    g.pes = PES_SO2;
+    g.ndim = 2;
+    g.natom = 1;
+    g.sp = SimplePesParams{};
+    g.sp.omegaforce = np > 0 ? pp[0] : 10000.0;
+    g.sp.r0 = np > 1 ? pp[1] : 20.0;
+    g.sp.V0 = 0.0;
+    g.sp.ndof = 2;
+    return PIMDK_OK;
+  }
   if (s == "ccpol8sf") {  // mcmod_waterdimer_ccpol.f90:9-16 -> init_ccpol(3,1,1,0)
     const int iemon = np > 0 ? (int)pp[0] : 1;
     const int isurf = np > 1 ? (int)pp[1] : 3;
@@ -556,7 +555,7 @@ int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
     g.natom = 6;
     return PIMDK_OK;
   }
-  return fail(PIMDK_EINVAL, "unknown PES '%s' (1d, 2dtest, ccpol8sf)", s.c_str());
+  return fail(PIMDK_EINVAL, "unknown PES '%s' (1d, 2dtest, so2, ccpol8sf)", s.c_str());
 }
 
 int pimdk_pes_info(pimdk_int* ndim, pimdk_int* natom) {
@@ -572,7 +571,7 @@ int pimdk_pes_set_v0(double v0) {
     g.hdev.V0 = v0;
     return upload_ccpol_dev();
   }
-  if (g.pes == PES_2DTEST) g.sp.V0 = v0;  // mcmod_1d's V ignores V0 (mcmod_1d.f90:20)
+  if (g.pes == PES_2DTEST || g.pes == PES_SO2) g.sp.V0 = v0;  // mcmod_1d's V ignores V0 (mcmod_1d.f90:20)
   return PIMDK_OK;
 }
 
@@ -1088,6 +1087,19 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
     }
   }
   if (!traj_gid && ntraj > 0x100000000LL) return fail(PIMDK_EINVAL, "more than 2^32 trajectories need explicit ids below 2^32");
+  // dHdrlimit (verletmodule.f90:404-409): propagate_pimd_pile only
+  const bool guard = thermostat == PIMDK_THERMOSTAT_PILE && g.dhdrlimit >= 0.0;
+  const double* rp_lam = nullptr; const double* rp_path = nullptr; const double* rp_spl = nullptr; const double* rp_xi = nullptr;
+  if (guard) {
+    if (g.rp_ntraj != clock_total)
+      return fail(PIMDK_EINVAL, "dHdrlimit >= 0: pimdk_set_dhdrlimit was given xi for %ld trajectories, the call has %ld", g.rp_ntraj, clock_total);
+    const size_t np_ = (size_t)g.rp_npath, npd = np_ * (size_t)(g.nm_ndim * g.nm_natom);
+    rp_lam = g.wPath.as<double>();
+    rp_path = rp_lam + np_;
+    rp_spl = rp_path + npd;
+    rp_xi = g.wXi.as<double>() + clock_off;
+    CU(g.wReinit.ensure(sizeof(int) * ntraj));
+  }
   NmTables nm = nm_tables_base();
   rc = build_step_tables(&nm, dt, gamma, (int)cayley);
   if (rc) return rc;
@@ -1105,7 +1117,8 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
     {
       Scope s("fused");
       CU(launch_fused_small(nm, g.pes, g.sp, (int)thermostat, ntraj, x, p, a, b, dbdl, dt, NMC, imin, (double)Noutput, seed,
-                            dgid, dHdr, g.wFlags.as<int>(), step0, keep_sum, dsum, clk_count, clk_kick, carry ? 1 : 0, g.stream));
+                            dgid, dHdr, g.wFlags.as<int>(), step0, keep_sum, dsum, clk_count, clk_kick, carry ? 1 : 0,
+                            guard ? g.dhdrlimit : -1.0, g.rp_npath, rp_lam, rp_path, rp_spl, rp_xi, g.stream));
     }
     rc = check_flags(false);
     g.last_nan_traj = -1;
@@ -1152,7 +1165,13 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
         Scope s("gemm");
         CU(back_transform());
       }
-      if (ii > imin) {
+      if (ii > imin && guard) {
+        Scope s("estimator", 3);
+        int* reinit = g.wReinit.as<int>();
+        CU(launch_estimator_limit(nm, x, dbdl, dHdr, ntraj, g.dhdrlimit, reinit, g.stream));
+        CU(launch_reinit(nm, g.rp_npath, rp_lam, rp_path, rp_spl, rp_xi, x, P, Q, a, b, ntraj, seed, (uint64_t)(ii + step0), dgid,
+                         reinit, g.stream));
+      } else if (ii > imin) {
         Scope s("estimator");
         CU(launch_estimator(nm, x, dbdl, dHdr, ntraj, g.stream));
       }
@@ -1359,6 +1378,30 @@ pimdk_int pimdk_last_nan_trajectory(void) { return g.last_nan_traj; }
 int pimdk_set_propagate_chunk(pimdk_int ntraj_per_chunk) {
   if (ntraj_per_chunk < 0) return fail(PIMDK_EINVAL, "chunk size must be >= 0 (0 = automatic)");
   g.chunk_traj = (long)ntraj_per_chunk;
+  return PIMDK_OK;
+}
+
+int pimdk_set_dhdrlimit(double limit, pimdk_int npath, const double* lampath, const double* path, const double* splinepath,
+                        pimdk_int ntraj, const double* xi) {
+  NEED_INIT();
+  g.dhdrlimit = limit;
+  if (!(limit >= 0.0)) {
+    g.dhdrlimit = -1.0;
+    return PIMDK_OK;
+  }
+  if (!g.nm_ready) return fail(PIMDK_EINVAL, "pimdk_nm_setup has not been called");
+  if (npath < 2 || ntraj < 1 || !lampath || !path || !splinepath || !xi) return fail(PIMDK_EINVAL, "dHdrlimit >= 0 needs the spline path and xi of every trajectory");
+  const size_t np_ = (size_t)npath, npd = np_ * (size_t)(g.nm_ndim * g.nm_natom);
+  CU(g.wPath.ensure((np_ + 2 * npd) * sizeof(double)));
+  CU(g.wXi.ensure((size_t)ntraj * sizeof(double)));
+  double* d = g.wPath.as<double>();
+  CU(cudaMemcpyAsync(d, lampath, np_ * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d + np_, path, npd * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d + np_ + npd, splinepath, npd * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(g.wXi.p, xi, (size_t)ntraj * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  g.rp_npath = (int)npath;
+  g.rp_ntraj = (long)ntraj;
   return PIMDK_OK;
 }
 

@@ -9,7 +9,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, f64, hptr, lib
 
-_SHAPES = {"1d": (1, 1), "2dtest": (2, 1), "ccpol8sf": (3, 6)}
+_SHAPES = {"1d": (1, 1), "2dtest": (2, 1), "so2": (2, 1), "ccpol8sf": (3, 6)}
 
 
 class McmodMass:
@@ -20,11 +20,11 @@ class McmodMass:
     atom1, atom2, atom3 = 1, 2, 3
 
     def __init__(self, name, params=None, n=0, isurf=None, iemonomer=None):
-        """params: "1d" {Vheight, x0}; "2dtest" {a0, b0, rho0}; "ccpol8sf" {iemonomer, isurf} — the first two arguments
+        """params: "1d" {Vheight, x0}; "2dtest" {a0, b0, rho0}; "so2" {omegaforce, r0} (mcmod_so2.f90); "ccpol8sf" {iemonomer, isurf} — the first two arguments
         of init_ccpol(isurf, iemon, iembedang, ixyz) (main_CCpol-8sf.f:1; the plugin calls init_ccpol(3,1,1,0)), also
         settable by keyword."""
         if name not in _SHAPES:
-            raise ValueError("unknown PES %r (1d, 2dtest, ccpol8sf)" % name)
+            raise ValueError("unknown PES %r (1d, 2dtest, so2, ccpol8sf)" % name)
         self.name = name
         if name == "ccpol8sf" and (isurf is not None or iemonomer is not None):
             p0 = [1.0, 3.0] if params is None else (list(np.asarray(params, dtype=np.float64)) + [3.0])[:2]

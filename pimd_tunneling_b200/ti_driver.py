@@ -94,10 +94,6 @@ def run_ti(pes_name, mc, well1, well2, mass, path_points=None, rank=0, world=1, 
     rank.  With world > 1 (torch.distributed initialised) the estimator sums are all-reduced.
     The path: `path_file` (the reference's path.xyz, read like read_path with mc.xunit, mc.instapath, mc.centre) or
     `path_points` (frames already in bohr) or, with neither, the straight line between the wells."""
-    if mc.dHdrlimit >= 0.0 and mc.thermostat == PILE:
-        # verletmodule.f90:404-409 (propagate_pimd_pile only; propagate_pimd_nm ignores the limit): an over-limit
-        # contribution is skipped and the path re-initialised.  Silently summing the outliers would change the statistics.
-        raise NotImplementedError("dHdrlimit >= 0 (outlier re-initialisation, verletmodule.f90:404-409) is not offered")
     pes = McmodMass(pes_name).V_init()
     well1 = np.asfortranarray(well1, dtype=np.float64)
     well2 = np.asfortranarray(well2, dtype=np.float64)
@@ -143,6 +139,8 @@ def run_ti(pes_name, mc, well1, well2, mass, path_points=None, rank=0, world=1, 
         live = ~np.all(np.abs(b) < 1e-10, axis=(0, 1))
         out_dH = np.zeros(live.size)
         if live.any():
+            if mc.thermostat == PILE:   # dHdrlimit: verletmodule.f90:404-409 (propagate_pimd_nm ignores the limit)
+                vi.set_dhdrlimit(mc.dHdrlimit, xi[il[sl]][live], lam, path, spl)
             _, _, out_dH[live] = fn(np.asfortranarray(x[..., live]), np.asfortranarray(p[..., live]), startpoint,
                                     np.asfortranarray(b[..., live]), np.asfortranarray(dbdl[..., live]), traj_gid=gid[sl][live])
         dH[sl] = out_dH

@@ -30,6 +30,9 @@ class VerletInt:
         # 0 no restart files, 1 write them, 2 continue from them
         self.restart, self.restartnmc = 0, 0
         self.last_sums = None   # running (un-normalised) dHdr sums of the last propagate call
+        # dHdrlimit (module verletint, verletmodule.f90:18; namelist default -1): set_dhdrlimit() arms the outlier guard
+        self.dHdrlimit = -1.0
+        self._reinit = None
         self._ready = False
 
     # alloc_nm (verletmodule.f90:350-368): the reference seeds MT19937 from the clock; here the
@@ -143,6 +146,23 @@ class VerletInt:
                                             self.beta, self.seed, int(traj_gid), hptr(eta)))
         return xw, eta
 
+    def set_dhdrlimit(self, limit, xi=None, lampath=None, path=None, splinepath=None):
+        """dHdrlimit of the namelist (verletmodule.f90:404-409): an over-limit contribution is dropped and the path
+        re-initialised by init_path(xi, ...); needs the spline path and the xi of every trajectory of the next calls"""
+        self.dHdrlimit = float(limit)
+        self._reinit = None if limit < 0 else (f64(np.atleast_1d(np.asarray(xi, dtype=np.float64))), f64(np.asarray(lampath, dtype=np.float64)),
+                                               f64(path), f64(splinepath))
+        return self
+
+    def _arm_guard(self, ntraj):
+        if self.dHdrlimit >= 0.0:
+            xi, lam, path, spl = self._reinit
+            if xi.size != ntraj:
+                raise ValueError("dHdrlimit: xi for %d trajectories, the call has %d" % (xi.size, ntraj))
+            check(lib().pimdk_set_dhdrlimit(self.dHdrlimit, lam.size, hptr(lam), hptr(path), hptr(spl), ntraj, hptr(xi)))
+        else:
+            check(lib().pimdk_set_dhdrlimit(-1.0, 0, None, None, None, 0, None))
+
     def _propagate(self, thermostat, x, p, a, b, dbdl, traj_gid, dHdr0=None):
         self._need()
         x = np.asarray(x)
@@ -156,6 +176,7 @@ class VerletInt:
         dbdl = f64(np.asarray(dbdl, dtype=np.float64).reshape((self.ndim, self.natom, ntraj), order="F"))
         gid = None if traj_gid is None else np.ascontiguousarray(traj_gid, dtype=np.int64)
         check(lib().pimdk_set_restart(self.restart, self.restartnmc if self.restart == 2 else 0))
+        self._arm_guard(ntraj)
         if self.restart == 2:    # dHdr as read from the restart files is continued (verletmodule.f90:200,388)
             if dHdr0 is None:
                 raise ValueError("restart = 2 needs the running sums dHdr0 read from the restart files")

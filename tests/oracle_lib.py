@@ -143,7 +143,7 @@ class Oracle:
         if name == "ccpol8sf":
             self.load_ccpol()
         self._chk(self.L.orc_pes_select(name.encode()))
-        shapes = {"1d": (1, 1), "2dtest": (2, 1), "ccpol8sf": (3, 6)}
+        shapes = {"1d": (1, 1), "2dtest": (2, 1), "so2": (2, 1), "ccpol8sf": (3, 6)}
         self.ndim, self.natom = shapes[name]
         if ndim:
             self.ndim, self.natom = ndim, natom
@@ -152,6 +152,21 @@ class Oracle:
 
     def set_V0(self, v0):
         self.L.orc_pes_set_V0(float(v0))
+
+    def set_dhdrlimit(self, limit, xi=0.0, lampath=None, path=None, splinepath=None):
+        """dHdrlimit and the path init_path re-initialises from (verletmodule.f90:404-409); call after nm_setup"""
+        self.L.orc_set_dhdrlimit.argtypes = [ctypes.c_double, ctypes.c_double, _P, _P, _P, ctypes.c_int]
+        if limit < 0:
+            self.L.orc_set_dhdrlimit(float(limit), 0.0, None, None, None, 0)
+            return
+        lam = np.ascontiguousarray(lampath, dtype=np.float64)
+        pth = np.asfortranarray(path, dtype=np.float64)
+        spl = np.asfortranarray(splinepath, dtype=np.float64)
+        self.L.orc_set_dhdrlimit(float(limit), float(xi), _p(lam), _p(pth), _p(spl), lam.size)
+
+    def set_so2(self, omegaforce, r0):
+        self.L.orc_pes_set_so2.argtypes = [ctypes.c_double, ctypes.c_double]
+        self.L.orc_pes_set_so2(float(omegaforce), float(r0))
 
     def pes_eval(self, x, energy=True, gradient=True):
         """x(ndim,natom,nbatch) F-order; returns (v, grad, x_after) — x_after carries the FD drift."""

@@ -15,7 +15,11 @@ import os
 import numpy as np
 import pytest
 
+import ctypes
+
 from oracle_lib import GOLDEN_GEOM_ANG, GOLDEN_VAL, GOLDEN_VALM, Oracle, thermal_dimer_geometries
+
+ctypes_P = ctypes.POINTER(ctypes.c_double)
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -1174,3 +1178,86 @@ def test_ccpol_analytic_mode_surfaces_and_propagation(pk, orc):
     finally:
         check(lib().pimdk_set_mode(0))
     assert relmax(x_an, x_fd) < 1e-9 and relmax(p_an, p_fd) < 1e-6 and np.abs(d_an - d_fd).max() <= 1e-8 * np.abs(d_fd).max()
+
+
+# ---------------------------------------------------------------- a further in-repo surface: mcmod_so2 (row N4) -----
+def test_so2_surface_bit_exact_and_propagation(pk, orc):
+    """mcmod_so2.f90 (harmonic ring, analytic gradient, closed-form Hessian) behind pimdk_pes_select("so2"): V, Vprime and
+    Vdoubleprime bit-exact against the oracle; propagation (fused kernel at n = 16, streamed path at n = 160, both
+    thermostats) within 1e-10."""
+    orc.select("so2")
+    rng = np.random.default_rng(7)
+    for params in (None, [3.0, 2.5]):
+        pes = pk.McmodMass("so2", params=params).V_init()
+        om, r0 = (10000.0, 20.0) if params is None else params
+        orc.set_so2(om, r0)
+        x = np.asfortranarray(rng.normal(size=(2, 1, 513)) * (8.0 if params is None else 1.5) + 1.0)
+        v, g = pes.eval_batch(x)
+        vo, go, _ = orc.pes_eval(x)
+        assert np.array_equal(v, vo) and np.array_equal(g, go)
+        h = pes.Vdoubleprime_batch(np.array(x[:, :, :40], order="F"))
+        for k in range(40):
+            ho = np.empty((2, 1, 2, 1), order="F")
+            xk = np.array(x[:, :, k], order="F")
+            orc.L.orc_Vdoubleprime(xk.ctypes.data_as(ctypes_P), ho.ctypes.data_as(ctypes_P))
+            assert np.array_equal(h[..., k], ho)
+    pes = pk.McmodMass("so2", params=[3.0, 2.5]).V_init()
+    orc.set_so2(3.0, 2.5)
+    a = np.asfortranarray(np.array([[2.5], [0.0]]))
+    b = np.asfortranarray(np.array([[2.5 * np.cos(1.0)], [2.5 * np.sin(1.0)]]))
+    for n, thermostat, nout in ((16, 2, 100000), (16, 1, 6), (160, 2, 100000), (160, 1, 9)):
+        vi = pk.VerletInt(pes, n, [1.0], 10.0, dt=1e-3, NMC=30, Noutput=nout, seed=3).init_nm()
+        x, p, bt, dbdl, _ = _traj_inputs(pes, n, 3, a, b, 0.05, [1.0])
+        gid = np.arange(3, dtype=np.int64) + 40
+        fn = vi.propagate_pimd_pile if thermostat == 2 else vi.propagate_pimd_nm
+        xg, pg, dg = fn(x, p, a, bt, dbdl, traj_gid=gid)
+        for t in range(3):
+            orc.nm_setup(n, [1.0], vi.betan, 1.0, 1.0, 1e-3, False, True)
+            orc.init_nm(a, bt[..., t])
+            orc.set_rng(3, int(gid[t]))
+            xo, po, do = orc.propagate(thermostat, x[..., t], p[..., t], dbdl[..., t], 30, 0, nout)
+            assert relmax(xg[..., t], xo) < RTOL and relmax(pg[..., t], po) < RTOL and abs(dg[t] - do) <= RTOL * abs(do)
+    orc.select("ccpol8sf")
+
+
+@pytest.mark.parametrize("name,n", [("2dtest", 16), ("2dtest", 160), ("1d", 24)])
+def test_dhdrlimit_outlier_reinitialisation(pk, orc, name, n):
+    """dHdrlimit (pimd_par.f90:45,88; verletmodule.f90:404-409): an over-limit estimator contribution is dropped and the ring
+    polymer re-initialised by init_path.  The limit is set inside the range the contribution actually takes, so that some
+    trajectories trip it several times; fused kernel (n <= 128) and streamed path against the oracle, 1e-10; and the
+    Andersen thermostat ignores the limit like propagate_pimd_nm."""
+    from pimd_tunneling_b200 import path as P
+
+    mass = [1.0]
+    pes = pk.McmodMass(name).V_init()
+    orc.select(name)
+    a, b = _wells(name)
+    ntraj, steps = 5, 40
+    vi = pk.VerletInt(pes, n, mass, 10.0, dt=1e-3, NMC=steps, seed=808).init_nm()
+    x, p, bt, dbdl, (lam, path, spl, xi) = _traj_inputs(pes, n, ntraj, a, b, 0.05, mass)
+    gid = np.arange(ntraj, dtype=np.int64) + 1
+    x0, p0 = vi.init_path(xi, lam, path, spl, traj_gid=gid)
+    x_ref, p_ref, d_ref = vi.propagate_pimd_pile(x0, p0, a, bt, dbdl, traj_gid=gid)
+    # contribution of the initial state: a limit just above the smallest |contr| trips for the others
+    contr0 = np.abs(np.einsum("k,jkt,jkt->t", np.asarray(mass), -x0[n - 1], dbdl))
+    limit = float(np.sort(contr0)[1] * 1.0001)
+    vi.set_dhdrlimit(limit, xi, lam, path, spl)
+    try:
+        xg, pg, dg = vi.propagate_pimd_pile(x0, p0, a, bt, dbdl, traj_gid=gid)
+        xa, pa, da = vi.propagate_pimd_nm(x0, p0, a, bt, dbdl, traj_gid=gid)
+    finally:
+        vi.set_dhdrlimit(-1.0)
+    xb, pb, db = vi.propagate_pimd_nm(x0, p0, a, bt, dbdl, traj_gid=gid)
+    assert np.array_equal(xa, xb) and np.array_equal(da, db)          # Andersen: no guard
+    assert not np.array_equal(dg, d_ref)                                # the guard did act
+    tripped = 0
+    for t in range(ntraj):
+        orc.nm_setup(n, mass, vi.betan, 1.0, 1.0, 1e-3, False, True)
+        orc.init_nm(a, bt[..., t])
+        orc.set_rng(808, int(gid[t]))
+        orc.set_dhdrlimit(limit, float(xi[t]), lam, path, spl)
+        xo, po, do = orc.propagate(2, x0[..., t], p0[..., t], dbdl[..., t], steps, 0, 100000)
+        assert relmax(xg[..., t], xo) < RTOL and relmax(pg[..., t], po) < RTOL
+        assert abs(dg[t] - do) <= RTOL * max(abs(do), np.abs(d_ref).max())
+        tripped += int(abs(dg[t] - d_ref[t]) > 1e-12 * abs(d_ref[t]))
+    assert 1 <= tripped <= ntraj

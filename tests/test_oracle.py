@@ -390,3 +390,26 @@ def test_analytic_gradient_mathematics_matches_dual_numbers(orc, isurf, iemon):
             # the value is a sum of ~1e3 kcal/mol of cancelling electrostatic terms: absolute tolerance
             assert abs(v2 - v.value) <= 1e-9 and np.abs(g2 - g).max() <= 1e-10 * np.abs(g).max()
     orc.load_ccpol(3, 1)
+
+
+def test_so2_ring_surface_restatement(orc):
+    """mcmod_so2.f90:10-84: V = omegaforce**2/2 (r - r0)**2 on a ring; gradient against a central difference; the Hessian
+    literally as written there (x_i x_j omegaforce**2 r0 / r**3, without the diagonal (1 - r0/r) term)"""
+    orc.select("so2")
+    orc.set_so2(3.0, 2.5)
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        x = rng.normal(size=(2, 1)) * 2.0 + 0.5
+        r = np.hypot(x[0, 0], x[1, 0])
+        v, g, _ = orc.pes_eval(x.reshape(2, 1, 1))
+        assert abs(v[0] - 0.5 * 9.0 * (r - 2.5) ** 2) <= 1e-14 * max(1.0, abs(v[0]))
+        e = 1e-6
+        for d in range(2):
+            xp, xm = x.copy(), x.copy()
+            xp[d, 0] += e
+            xm[d, 0] -= e
+            fd = (orc.pes_eval(xp.reshape(2, 1, 1))[0][0] - orc.pes_eval(xm.reshape(2, 1, 1))[0][0]) / (2 * e)
+            assert abs(fd - g[d, 0, 0]) < 1e-7 * max(1.0, abs(fd))
+    orc.set_so2(10000.0, 20.0)   # the reference's own parameters: minimum on the ring r = 20
+    assert orc.pes_eval(np.array([[12.0], [16.0]]).reshape(2, 1, 1))[0][0] == 0.0
+    orc.select("ccpol8sf")
