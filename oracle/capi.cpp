@@ -140,6 +140,7 @@ int orc_pes_select(const char* name) {
   if (s == "1d") { g_pes = Pes(); g_pes.init_1d(); return 0; }
   if (s == "2dtest") { g_pes = Pes(); g_pes.init_2d(); return 0; }
   if (s == "so2") { g_pes = Pes(); g_pes.init_so2(); return 0; }
+  if (s == "watmeth") { g_pes = Pes(); g_pes.init_watmeth(); return 0; }
   if (s == "ccpol8sf") {
     if (!g_tab_loaded) { g_err = "tables not loaded"; return 1; }
     g_pes = Pes();
@@ -236,6 +237,8 @@ int orc_spline(const double* x, const double* y, int n, double yp1, double ypn, 
 double orc_splint(const double* xa, const double* ya, const double* y2a, int n, double x) {
   return splint(xa, ya, y2a, n, x);
 }
+// gammp of watermethane.f90:411-430 (Numerical Recipes, EPS = 3e-7), for the accuracy check against scipy
+double orc_wm_gammp(double a, double x) { return WaterMethane::gammp(a, x); }
 double orc_splin_grad(const double* xa, const double* ya, const double* y2a, int n, double x) {
   return splin_grad(xa, ya, y2a, n, x);
 }

@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
 // CPU restatement of the three in-scope `module mcmod_mass` plugins:
-//   mcmod_1d.f90:8-58, mcmod_2dtest.f90:11-61, mcmod_waterdimer_ccpol.f90:9-77, mcmod_so2.f90:10-84.
+//   mcmod_1d.f90:8-58, mcmod_2dtest.f90:11-61, mcmod_waterdimer_ccpol.f90:9-77, mcmod_so2.f90:10-84,
+//   mcmod_watmeth.f90:10-62 (watmeth.hpp).
 // x and grad are Fortran (ndim,natom) column-major: index = (atom)*ndim + dim.
 #pragma once
 #include <cmath>
@@ -9,10 +10,11 @@
 
 #include "ccpol_impl.hpp"
 #include "tables.hpp"
+#include "watmeth.hpp"
 
 namespace oracle {
 
-enum PesKind { PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4 };
+enum PesKind { PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4, PES_WATMETH = 5 };
 
 struct Pes {
   PesKind kind = PES_1D;
@@ -58,6 +60,14 @@ struct Pes {
     r0 = 20.0;
     V0 = 0.0;
   }
+  // water-methane (mcmod_watmeth.f90:10-13)
+  WaterMethane wm;
+  void init_watmeth() {
+    kind = PES_WATMETH;
+    ndim = 3;
+    natom = 17;
+    V0 = 0.0;
+  }
   void init_ccpol(const CcpolTables* t) {
     kind = PES_CCPOL;
     ndim = 3;
@@ -91,6 +101,8 @@ struct Pes {
         double answer = 0.5 * (omegaforce * omegaforce) * ((r - r0) * (r - r0));
         return answer - V0;
       }
+      case PES_WATMETH:  // mcmod_watmeth.f90:15-27 (V0 is not subtracted)
+        return wm.wmrb(x);
       case PES_CCPOL: {  // mcmod_waterdimer_ccpol.f90:18-37
         const double ang = 0.529177;
         double xtemp[18];
@@ -133,6 +145,9 @@ struct Pes {
         grad[1] = (omegaforce * omegaforce) * x[1] * (1.0 - r0 / r);
         return;
       }
+      case PES_WATMETH:  // mcmod_watmeth.f90:30-40
+        wm.wmrb_grad(x, grad);
+        return;
       case PES_CCPOL: {  // mcmod_waterdimer_ccpol.f90:40-58
         const double eps = 1e-4;
         for (int i = 0; i < ndim; ++i)

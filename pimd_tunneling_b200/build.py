@@ -23,6 +23,7 @@ UNITS = [
     ("ccpol_kernels.cu", "ccpol_fast.o", ["-fmad=true", "-DPIMDK_CCPOL_STRICT=0"]),
     ("ccpol_grad_kernels.cu", "ccpol_grad.o", ["-fmad=true"]),
     ("pes_simple.cu", "pes_simple.o", ["-fmad=false"]),
+    ("watmeth_kernels.cu", "watmeth.o", ["-fmad=false"]),
     ("nm_kernels.cu", "nm_kernels.o", ["-fmad=false"]),
     ("fused_small.cu", "fused_small.o", ["-fmad=false"]),
     ("um_kernels.cu", "um_kernels.o", ["-fmad=false"]),

@@ -22,7 +22,7 @@ struct GeomLayout {
   }
 };
 
-enum PesKind { PES_NONE = 0, PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4 };
+enum PesKind { PES_NONE = 0, PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4, PES_WATMETH = 5 };
 
 struct SimplePesParams {  // mcmod_1d.f90:9-12, mcmod_2dtest.f90:16-24, mcmod_so2.f90:10-14
   double Vheight, x0;
@@ -54,6 +54,12 @@ long ccpol_analytic_launches(long ngeom, int icc, size_t work_bytes);
 cudaError_t launch_ccpol_analytic(const CcpolDev* tab, const agrad::CcpolGradTab* gt, int iemonomer, int icc, double V0, GeomLayout L,
                                   const double* x, double* v, double* grad, long ngeom, int* flags, double* work, size_t work_bytes,
                                   int num_sms, cudaStream_t st);
+
+// ---- water-methane rigid-body surface (watmeth_kernels.cu; watermethane.f90 / mcmod_watmeth.f90) ----
+struct WatMethTab;
+cudaError_t launch_watmeth(const WatMethTab* tab, GeomLayout L, const double* x, double* v, double* grad, long ngeom, int* flags,
+                           cudaStream_t st);
+cudaError_t launch_watmeth_hessian(const WatMethTab* tab, GeomLayout L, double* x, double* hess, long ngeom, cudaStream_t st);
 
 // ---- 1D / 2D model surfaces (pes_simple.cu) ----
 cudaError_t launch_simple_pes(PesKind kind, const SimplePesParams& P, GeomLayout L, const double* x, double* v,

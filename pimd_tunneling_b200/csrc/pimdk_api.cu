@@ -18,6 +18,7 @@
 #include "ccpol_grad.cuh"
 #include "kernels.h"
 #include "nm_device.cuh"
+#include "watmeth.cuh"
 
 using namespace pimdk;
 
@@ -99,7 +100,7 @@ struct Ctx {
   CcpolHost htab;
   CcpolDev hdev;
   agrad::CcpolGradTab hgrad;   // rigid-body coefficients and sweep tables of the analytic-gradient mode
-  DevBuf dtab, dgtab;
+  DevBuf dtab, dgtab, dwm;   // dwm: WatMethTab
   // normal modes
   bool nm_ready = false;
   int n = 0, nm_ndim = 0, nm_natom = 0;
@@ -244,6 +245,9 @@ int pes_eval_dev(GeomLayout L, double* x, double* v, double* grad, long ngeom, i
               : launch_ccpol_strict(tab, g.hdev.iemonomer, g.hdev.iembed, g.hdev.icc, g.hdev.potparts_old, g.hdev.V0, L, x, vv, gg, ngeom, write_drift, flags,
                                     g.wCc.as<double>(), g.wCc.cap, g.stream));
     }
+  } else if (g.pes == PES_WATMETH) {
+    Scope s("pes");
+    CU(launch_watmeth(g.dwm.as<WatMethTab>(), L, x, v, grad, ngeom, flags, g.stream));
   } else {
     Scope s("pes");
     CU(launch_simple_pes(g.pes, g.sp, L, x, v, grad, ngeom, flags, g.stream));
@@ -443,7 +447,7 @@ int pimdk_finalize(void) {
   if (!g.inited) return PIMDK_OK;
   cudaStreamSynchronize(g.stream);
   resolve_spans();
-  DevBuf* bufs[] = {&g.dtab, &g.dgtab, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
+  DevBuf* bufs[] = {&g.dtab, &g.dgtab, &g.dwm, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
                     &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wX2, &g.wPp2, &g.wUmIn, &g.wUmOut, &g.wHgp, &g.wHgm, &g.wHess, &g.wBand,
                     &g.wDense, &g.wEig, &g.wWork, &g.wSums, &g.wBV, &g.wPath, &g.wXi, &g.wReinit};
@@ -537,6 +541,17 @@ int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
     g.sp.ndof = 2;
     return PIMDK_OK;
   }
+  if (s == "watmeth") {  // mcmod_watmeth.f90:10-13 + the unit conversions of wmrb (watermethane.f90:279-287)
+    WatMethTab t;
+    build_watmeth_tab(&t);
+    CU(g.dwm.ensure(sizeof(WatMethTab)));
+    CU(cudaMemcpyAsync(g.dwm.p, &t, sizeof(WatMethTab), cudaMemcpyHostToDevice, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    g.pes = PES_WATMETH;
+    g.ndim = 3;
+    g.natom = kWmSites;
+    return PIMDK_OK;
+  }
   if (s == "ccpol8sf") {  // mcmod_waterdimer_ccpol.f90:9-16 -> init_ccpol(3,1,1,0)
     const int iemon = np > 0 ? (int)pp[0] : 1;
     const int isurf = np > 1 ? (int)pp[1] : 3;
@@ -555,7 +570,7 @@ int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
     g.natom = 6;
     return PIMDK_OK;
   }
-  return fail(PIMDK_EINVAL, "unknown PES '%s' (1d, 2dtest, so2, ccpol8sf)", s.c_str());
+  return fail(PIMDK_EINVAL, "unknown PES '%s' (1d, 2dtest, so2, watmeth, ccpol8sf)", s.c_str());
 }
 
 int pimdk_pes_info(pimdk_int* ndim, pimdk_int* natom) {
@@ -724,6 +739,11 @@ static int pes_hessian_dev(GeomLayout L, double* x, double* hess, long ngeom, in
   if (g.pes == PES_NONE) return fail(PIMDK_EINVAL, "no PES selected (pimdk_pes_select)");
   if (ngeom <= 0) return PIMDK_OK;
   const int nd = ndim * natom;
+  if (g.pes == PES_WATMETH) {
+    Scope s("hess");
+    CU(launch_watmeth_hessian(g.dwm.as<WatMethTab>(), L, x, hess, ngeom, g.stream));
+    return PIMDK_OK;
+  }
   if (g.pes != PES_CCPOL) {
     if (nd > 4) return fail(PIMDK_EINVAL, "Vdoubleprime of the model surfaces supports ndim*natom <= 4");
     Scope s("hess");

@@ -143,7 +143,7 @@ class Oracle:
         if name == "ccpol8sf":
             self.load_ccpol()
         self._chk(self.L.orc_pes_select(name.encode()))
-        shapes = {"1d": (1, 1), "2dtest": (2, 1), "so2": (2, 1), "ccpol8sf": (3, 6)}
+        shapes = {"1d": (1, 1), "2dtest": (2, 1), "so2": (2, 1), "watmeth": (3, 17), "ccpol8sf": (3, 6)}
         self.ndim, self.natom = shapes[name]
         if ndim:
             self.ndim, self.natom = ndim, natom
@@ -282,6 +282,36 @@ class Oracle:
     def splin_grad(self, xa, ya, y2a, x):
         return self.L.orc_splin_grad(_p(np.ascontiguousarray(xa)), _p(np.ascontiguousarray(ya)),
                                      _p(np.ascontiguousarray(y2a)), len(xa), float(x))
+
+
+# rigid-body site coordinates of the water-methane surface as its header gives them (watermethane.f90:9-28), bohr:
+# water H H Q D D T T O, methane H H H H C M M M M (each monomer about its own origin)
+WATMETH_WATER = np.array([[0.0, 1.45365, -1.12169], [0.0, -1.45365, -1.12169], [0.0, 0.0, -0.04490], [0.0, 0.70785, 0.34527],
+                          [0.0, -0.70785, 0.34527], [0.60787, 0.0, 0.35218], [-0.60787, 0.0, 0.35218], [0.0, 0.0, 0.0]])
+WATMETH_METHANE = np.array([[0.0, 0.0, 2.07704], [1.95825, 0.0, -0.69235], [-0.97913, 1.69590, -0.69235], [-0.97913, -1.69590, -0.69235],
+                            [0.0, 0.0, 0.0], [0.0, 0.0, 1.03852], [0.97913, 0.0, -0.34617], [-0.48956, 0.84795, -0.34617],
+                            [-0.48956, -0.84795, -0.34617]])
+
+
+def watmeth_geometries(nbatch, seed=0, rmin=5.5, rmax=9.0):
+    """x(3,17,nbatch): the two rigid bodies, each randomly rotated, centres rmin..rmax bohr apart along a random direction"""
+    rng = np.random.default_rng(seed)
+
+    def rot():
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        a, b, c, d = q
+        return np.array([[a * a + b * b - c * c - d * d, 2 * (b * c - a * d), 2 * (b * d + a * c)],
+                         [2 * (b * c + a * d), a * a - b * b + c * c - d * d, 2 * (c * d - a * b)],
+                         [2 * (b * d - a * c), 2 * (c * d + a * b), a * a - b * b - c * c + d * d]])
+
+    x = np.empty((3, 17, nbatch), order="F")
+    for k in range(nbatch):
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        x[:, :8, k] = (WATMETH_WATER @ rot().T).T
+        x[:, 8:, k] = (WATMETH_METHANE @ rot().T).T + (u * rng.uniform(rmin, rmax))[:, None]
+    return x
 
 
 def thermal_dimer_geometries(nbatch, seed=0, sigma=0.05):

@@ -1261,3 +1261,39 @@ def test_dhdrlimit_outlier_reinitialisation(pk, orc, name, n):
         assert abs(dg[t] - do) <= RTOL * max(abs(do), np.abs(d_ref).max())
         tripped += int(abs(dg[t] - d_ref[t]) > 1e-12 * abs(d_ref[t]))
     assert 1 <= tripped <= ntraj
+
+
+def test_water_methane_surface_bit_exact(pk, orc):
+    """mcmod_watmeth.f90 + watermethane.f90 (wmrb, wmrb_grad: 63 Tang-Toennies site pairs with Numerical Recipes' incomplete
+    gamma function) behind pimdk_pes_select("watmeth"): V, Vprime, Vdoubleprime bit-exact against the oracle on rigid-body
+    geometries (ragged batch), and two PILE steps of a small ring polymer within 1e-10."""
+    from oracle_lib import watmeth_geometries
+
+    pes = pk.McmodMass("watmeth").V_init()
+    orc.select("watmeth")
+    x = watmeth_geometries(301, seed=9)
+    v, g = pes.eval_batch(x)
+    vo, go, _ = orc.pes_eval(x)
+    assert np.array_equal(v, vo) and np.array_equal(g, go)
+    pes.set_V0(0.5)                                   # mcmod_watmeth.f90:15-27: V does not subtract V0
+    assert np.array_equal(pes.V_batch(x[:, :, :3]), vo[:3])
+    xs = np.array(x[:, :, :2], order="F")
+    h = pes.Vdoubleprime_batch(xs)
+    for k in range(2):
+        xk = np.array(x[:, :, k], order="F")
+        ho = np.empty((3, 17, 3, 17), order="F")
+        orc.L.orc_Vdoubleprime(xk.ctypes.data_as(ctypes_P), ho.ctypes.data_as(ctypes_P))
+        assert np.array_equal(h[..., k], ho) and np.array_equal(xs[:, :, k], xk)
+    mass = [1837.0] * 17
+    a, b = np.asfortranarray(x[:, :, 0]), np.asfortranarray(x[:, :, 1])
+    n, ntraj, steps = 8, 2, 2
+    vi = pk.VerletInt(pes, n, mass, 800.0, dt=1e-3, NMC=steps, seed=4).init_nm()
+    xx, pp, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, 0.002, mass)
+    xg, pg, dg = vi.propagate_pimd_pile(xx, pp, a, bt, dbdl)
+    for t in range(ntraj):
+        orc.nm_setup(n, mass, vi.betan, 1.0, 1.0, 1e-3, False, True)
+        orc.init_nm(a, bt[..., t])
+        orc.set_rng(4, t)
+        xo, po, do = orc.propagate(2, xx[..., t], pp[..., t], dbdl[..., t], steps, 0, 100000)
+        assert relmax(xg[..., t], xo) < RTOL and relmax(pg[..., t], po) < RTOL and abs(dg[t] - do) <= RTOL * abs(do)
+    orc.select("ccpol8sf")

@@ -4,6 +4,8 @@ import json
 import math
 import os
 
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -412,4 +414,33 @@ def test_so2_ring_surface_restatement(orc):
             assert abs(fd - g[d, 0, 0]) < 1e-7 * max(1.0, abs(fd))
     orc.set_so2(10000.0, 20.0)   # the reference's own parameters: minimum on the ring r = 20
     assert orc.pes_eval(np.array([[12.0], [16.0]]).reshape(2, 1, 1))[0][0] == 0.0
+    orc.select("ccpol8sf")
+
+
+def test_water_methane_surface_restatement(orc):
+    """watermethane.f90 (wmrb / wmrb_grad, Numerical Recipes gammp with EPS = 3e-7) behind mcmod_watmeth.f90: the
+    incomplete gamma function against scipy to its own tolerance; the analytic gradient against a central difference of V
+    (limited by that same 3e-7); rigid-motion invariance; a bound state of the right size (the paper's well is ~1 kcal/mol)."""
+    from scipy.special import gammainc
+
+    from oracle_lib import watmeth_geometries
+    orc.L.orc_wm_gammp.restype = ctypes.c_double
+    orc.L.orc_wm_gammp.argtypes = [ctypes.c_double, ctypes.c_double]
+    for a in (7.0, 9.0, 11.0):
+        for xx in (0.0, 0.3, 2.0, a - 0.5, a + 0.99, a + 1.01, 15.0, 40.0):
+            assert abs(orc.L.orc_wm_gammp(a, xx) - gammainc(a, xx)) < 1e-6
+    orc.select("watmeth")
+    x = watmeth_geometries(24, seed=5)
+    v, g, _ = orc.pes_eval(x)
+    assert np.isfinite(v).all() and v.min() < -5e-4 and v.min() > -1e-2     # Hartree: a well of the order of 1 kcal/mol
+    assert np.abs(g.sum(axis=1)).max() <= 1e-12 * np.abs(g).max()           # no net force on the pair of rigid bodies
+    assert np.abs(g[:, 7, :]).max() == 0.0                                  # the water O site carries no interaction
+    e = 1e-4
+    for k in range(4):
+        for (d, s) in ((0, 0), (2, 3), (1, 12), (2, 16)):
+            xp, xm = x[:, :, k:k + 1].copy(order="F"), x[:, :, k:k + 1].copy(order="F")
+            xp[d, s, 0] += e
+            xm[d, s, 0] -= e
+            fd = (orc.pes_eval(xp)[0][0] - orc.pes_eval(xm)[0][0]) / (2 * e)
+            assert abs(fd - g[d, s, k]) < 2e-5 * np.abs(g[:, :, k]).max() + 1e-9
     orc.select("ccpol8sf")
