@@ -109,7 +109,10 @@ cudaError_t launch_add(const double* x, const double* y, double* z, long total, 
 cudaError_t launch_nm_update(const NmTables& nm, double* P, double* Q, const double* G, double dt, long ntraj,
                              int do_kick, int nrot, int do_langevin, uint64_t seed, uint64_t step,
                              const int64_t* gid, int* flags, cudaStream_t st, const double* BV = nullptr,
-                             double* QB = nullptr /* receives Q + BV */);
+                             double* QB = nullptr /* receives Q + BV */,
+                             int andersen = 0 /* 1: resample fired trajectories first; 2: advance the collision clocks */,
+                             int* count = nullptr, int* rkick = nullptr, double lambda = 0.0);
+bool nm_update_fuses_andersen(const NmTables& nm, long ntraj);
 // Andersen: P <- N(0, sqrt(1/betan))*sqrt(beadmass) for trajectories whose counter fired; updates counters.
 cudaError_t launch_andersen(const NmTables& nm, double* P, long ntraj, uint64_t seed, uint64_t step, double lambda,
                             const int64_t* gid, int* count, int* rkick, cudaStream_t st);

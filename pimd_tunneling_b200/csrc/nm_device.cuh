@@ -37,7 +37,7 @@ __device__ __forceinline__ double splint_at(const double* __restrict__ lampath, 
 }
 
 // ---- elementwise normal-mode update -------------------------------------------------------
-enum { OP_KICK = 1, OP_ROT1 = 2, OP_LANGEVIN = 4, OP_ROT2 = 8 };
+enum { OP_KICK = 1, OP_ROT1 = 2, OP_LANGEVIN = 4, OP_ROT2 = 8, OP_ANDERSEN = 16, OP_CLOCK = 32 };
 
 __device__ __forceinline__ void rotate(const NmTables& nm, int ak, double& P, double& Q) {
   const double bm = nm.bmass[ak];

@@ -400,9 +400,9 @@ nm_update_kernel(NmTables nm, double* __restrict__ Pn, double* __restrict__ Qn, 
 __global__ void __launch_bounds__(256)
 nm_update2_kernel(NmTables nm, double* __restrict__ Pn, double* __restrict__ Qn, const double* __restrict__ G,
                   double dt, unsigned rows, int ops, uint64_t seed, uint64_t step, const int64_t* __restrict__ gid,
-                  int* __restrict__ flags, const double* __restrict__ BV, double* __restrict__ QB) {
+                  int* __restrict__ flags, const double* __restrict__ BV, double* __restrict__ QB, int* __restrict__ count,
+                  int* __restrict__ rkick, double lambda) {
   const int n = nm.n;
-  const unsigned half = (unsigned)n >> 1;
   const unsigned rpc = (2 * blockDim.x >= (unsigned)n) ? (2 * blockDim.x) / (unsigned)n : 1;   // rows per CTA pass
   const unsigned tl = (2 * threadIdx.x) / (unsigned)n;            // this thread's row within the pass (0 when n >= 512)
   const unsigned k_first = 2 * threadIdx.x - tl * (unsigned)n;
@@ -415,11 +415,29 @@ nm_update2_kernel(NmTables nm, double* __restrict__ Pn, double* __restrict__ Qn,
     const int akb = (dof / nm.ndim) * n;
     const uint32_t g = gid ? (uint32_t)gid[traj] : traj;
     const size_t base = (size_t)row * n;
+    // Andersen (verletmodule.f90:204-234): OP_ANDERSEN, first kernel of the step, only READS the collision clock — a
+    // trajectory whose clock fires gets fresh momenta before the rotation; OP_CLOCK, second kernel of the step (stream
+    // order: every read of the first is done), advances the clock, one thread per trajectory
+    const bool fire = (ops & OP_ANDERSEN) && (count[traj] + 1 >= rkick[traj]);
+    if ((ops & OP_CLOCK) && dof == 0 && k_first == 0) {
+      int c = count[traj] + 1;
+      if (c >= rkick[traj]) {
+        c = 0;
+        rkick[traj] = poisson_norm(seed, step, g, lambda);
+      }
+      count[traj] = c;
+    }
     for (unsigned k = k_first; k < (unsigned)n; k += 2 * blockDim.x) {
       const size_t e = base + k;
       double2 P = *reinterpret_cast<const double2*>(Pn + e);
       double2 Q = *reinterpret_cast<const double2*>(Qn + e);
       const int ak = akb + (int)k;
+      if (fire) {
+        double z0, z1;
+        normal_pair_at(seed, STREAM_ANDERSEN, step, g, (uint64_t)(((unsigned)dof * (unsigned)n + k) >> 1), z0, z1);
+        P.x = (0.0 + nm.stdev * z0) * nm.sigp[ak];
+        P.y = (0.0 + nm.stdev * z1) * nm.sigp[ak + 1];
+      }
       if (ops & OP_KICK) {
         const double2 gg = *reinterpret_cast<const double2*>(G + e);
         P.x = P.x - gg.x * dt;
@@ -638,6 +656,59 @@ reinit_q_kernel(NmTables nm, const double* __restrict__ x, const double* __restr
   }
 }
 
+// The same estimator with a warp per 32 rows (no block-wide barriers in the mode loop): lanes stage 32 x 32 tiles of
+// Q + beadvec coalesced through warp-private shared memory, lane = row runs the fma chain (j ascending: the transform's
+// order, identical bits), the CTA's rows are whole trajectories, one barrier, then one thread per trajectory adds the ndof
+// terms in the reference's order.  Any ndof up to 256.
+constexpr int kEm2Threads = 256;
+__global__ void __launch_bounds__(kEm2Threads)
+estimator_modes2_kernel(NmTables nm, const double* __restrict__ Q, const double* __restrict__ BV, const double* __restrict__ dbdl,
+                        double* __restrict__ dHdr, long ntraj) {
+  extern __shared__ double em2_smem[];
+  const int n = nm.n, ndof = nm.ndof;
+  const int tpc = kEm2Threads / ndof;                 // trajectories per CTA
+  double* tcol = em2_smem;                            // T(:, n)
+  double* xl = tcol + n;                              // last-bead positions of the CTA's rows [kEm2Threads]
+  double* tiles = xl + kEm2Threads;                   // [8 warps][32][33]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long traj0 = (long)blockIdx.x * tpc;
+  const int nrow = (int)(((ntraj - traj0 < tpc) ? ntraj - traj0 : tpc) * ndof);
+  const long row0 = traj0 * ndof;
+  for (int m = threadIdx.x; m < n; m += kEm2Threads) tcol[m] = nm.T[(long)m * n + (n - 1)];
+  __syncthreads();
+  double* tile = tiles + warp * 32 * 33;
+  for (int r0 = warp * 32; r0 < nrow; r0 += 8 * 32) {
+    const int nr = nrow - r0 < 32 ? nrow - r0 : 32;
+    double acc = 0.0;
+    for (int m0 = 0; m0 < n; m0 += 32) {
+      __syncwarp();
+      const int m = m0 + lane;
+      for (int rr = 0; rr < nr; ++rr) {
+        const long off = (row0 + r0 + rr) * (long)n + m;
+        tile[rr * 33 + lane] = m < n ? Q[off] + BV[off] : 0.0;
+      }
+      __syncwarp();
+      if (lane < nr) {
+        const int mm = (n - m0 < 32) ? n - m0 : 32;
+        for (int q = 0; q < mm; ++q) acc = fma(tile[lane * 33 + q], tcol[m0 + q], acc);
+      }
+    }
+    if (lane < nr) xl[r0 + lane] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < nrow / ndof) {
+    const long t = traj0 + threadIdx.x;
+    const double* xt = xl + threadIdx.x * ndof;
+    double contr = 0.0;
+    for (int j = 0; j < nm.ndim; ++j)
+      for (int k = 0; k < nm.natom; ++k) {
+        const int d = k * nm.ndim + j;
+        contr = contr + nm.mass[k] * (-xt[d]) * dbdl[t * ndof + d];
+      }
+    dHdr[t] = dHdr[t] + contr;
+  }
+}
+
 __global__ void scale_kernel(double* v, double s, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = v[i] / s;
@@ -723,24 +794,29 @@ cudaError_t launch_add(const double* x, const double* y, double* z, long total, 
 
 cudaError_t launch_nm_update(const NmTables& nm, double* P, double* Q, const double* G, double dt, long ntraj,
                              int do_kick, int nrot, int do_langevin, uint64_t seed, uint64_t step,
-                             const int64_t* gid, int* flags, cudaStream_t st, const double* BV, double* QB) {
+                             const int64_t* gid, int* flags, cudaStream_t st, const double* BV, double* QB, int andersen,
+                             int* count, int* rkick, double lambda) {
   int ops = 0;
   if (do_kick) ops |= OP_KICK;
   if (nrot >= 1) ops |= OP_ROT1;
   if (do_langevin) ops |= OP_LANGEVIN;
   if (nrot >= 2) ops |= OP_ROT2;
+  if (andersen == 1) ops |= OP_ANDERSEN;
+  if (andersen == 2) ops |= OP_CLOCK;
   const long rows = ntraj * (long)nm.ndof;
   const long total = rows * nm.n;
   if ((nm.n & 1) == 0 && rows < 0xffffffffL) {
     const long rpc = 512 >= nm.n ? 512 / nm.n : 1;
     nm_update2_kernel<<<grid_for((rows + rpc - 1) / rpc, 1), 256, 0, st>>>(nm, P, Q, G, dt, (unsigned)rows, ops, seed, step, gid, flags,
-                                                                        QB ? BV : nullptr, QB);
+                                                                        QB ? BV : nullptr, QB, count, rkick, lambda);
     return cudaGetLastError();
   }
+  if (andersen) return cudaErrorInvalidValue;   // the fused Andersen forms exist in the paired kernel only (nm_update_fuses_andersen)
   nm_update_kernel<<<grid_for(total, 256), 256, 0, st>>>(nm, P, Q, G, dt, ntraj, ops, seed, step, gid, flags);
   if (QB) add_kernel<<<grid_for(total, 256), 256, 0, st>>>(Q, BV, QB, total);
   return cudaGetLastError();
 }
+bool nm_update_fuses_andersen(const NmTables& nm, long ntraj) { return (nm.n & 1) == 0 && ntraj * (long)nm.ndof < 0xffffffffL; }
 
 static void sample_momenta_any(const NmTables& nm, double* P, long ntraj, uint64_t seed, int stream, uint64_t step,
                                const int64_t* gid, const int* count, const int* rkick, cudaStream_t st) {
@@ -780,6 +856,21 @@ cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* 
 
 cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const double* a, const double* b,
                                    const double* dbdl, double* dHdr, long ntraj, cudaStream_t st, const double* BV) {
+  if (BV && nm.ndof <= kEm2Threads) {    // warp-per-32-rows form (needs the precomputed beadvec array)
+    const int tpc2 = kEm2Threads / nm.ndof;
+    const size_t smem2 = (size_t)(nm.n + kEm2Threads + 8 * 32 * 33) * sizeof(double);
+    static unsigned long long attr_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_mask & (1ull << (dev & 63)))) {
+      cudaError_t e = cudaFuncSetAttribute(estimator_modes2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_mask |= 1ull << (dev & 63);
+    }
+    if (smem2 > 160 * 1024) return cudaErrorInvalidValue;
+    estimator_modes2_kernel<<<(unsigned)((ntraj + tpc2 - 1) / tpc2), kEm2Threads, smem2, st>>>(nm, Q, BV, dbdl, dHdr, ntraj);
+    return cudaGetLastError();
+  }
   const int tpc = kEmRows / nm.ndof;     // (ndof <= 18 for every surface here)
   if (tpc < 1) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(nm.n + kEmRows * 33 + kEmRows) * sizeof(double);

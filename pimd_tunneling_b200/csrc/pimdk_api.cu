@@ -1199,12 +1199,17 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
   } else {
     int* count = clk_count;
     int* rkick = clk_kick;
+    const bool fuse_andersen = nm_update_fuses_andersen(nm, ntraj);
     if (!carry) {
       Scope s("update");
       CU(launch_andersen_init(ntraj, seed, (uint64_t)step0, (double)Noutput, dgid, count, rkick, g.stream));
     }
     for (pimdk_int ii = 1; ii <= NMC; ++ii) {
-      {
+      if (fuse_andersen) {   // resampling of the fired trajectories inside the first update kernel, clocks advanced by the second
+        Scope s("update");
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, BV, QB, 1, count,
+                            rkick, (double)Noutput));
+      } else {
         Scope s("update", 3);
         CU(launch_andersen(nm, P, ntraj, seed, (uint64_t)(ii + step0), (double)Noutput, dgid, count, rkick, g.stream));
         CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, BV, QB));
@@ -1221,7 +1226,8 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       }
       {
         Scope s("update");
-        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream));
+        CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, nullptr, nullptr,
+                            fuse_andersen ? 2 : 0, count, rkick, (double)Noutput));
       }
       if (ii > imin) {   // the estimator reads the last bead only: one contraction per (trajectory, dof), not a transform
         Scope s("estimator");
