@@ -656,59 +656,6 @@ reinit_q_kernel(NmTables nm, const double* __restrict__ x, const double* __restr
   }
 }
 
-// The same estimator with a warp per 32 rows (no block-wide barriers in the mode loop): lanes stage 32 x 32 tiles of
-// Q + beadvec coalesced through warp-private shared memory, lane = row runs the fma chain (j ascending: the transform's
-// order, identical bits), the CTA's rows are whole trajectories, one barrier, then one thread per trajectory adds the ndof
-// terms in the reference's order.  Any ndof up to 256.
-constexpr int kEm2Threads = 256;
-__global__ void __launch_bounds__(kEm2Threads)
-estimator_modes2_kernel(NmTables nm, const double* __restrict__ Q, const double* __restrict__ BV, const double* __restrict__ dbdl,
-                        double* __restrict__ dHdr, long ntraj) {
-  extern __shared__ double em2_smem[];
-  const int n = nm.n, ndof = nm.ndof;
-  const int tpc = kEm2Threads / ndof;                 // trajectories per CTA
-  double* tcol = em2_smem;                            // T(:, n)
-  double* xl = tcol + n;                              // last-bead positions of the CTA's rows [kEm2Threads]
-  double* tiles = xl + kEm2Threads;                   // [8 warps][32][33]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long traj0 = (long)blockIdx.x * tpc;
-  const int nrow = (int)(((ntraj - traj0 < tpc) ? ntraj - traj0 : tpc) * ndof);
-  const long row0 = traj0 * ndof;
-  for (int m = threadIdx.x; m < n; m += kEm2Threads) tcol[m] = nm.T[(long)m * n + (n - 1)];
-  __syncthreads();
-  double* tile = tiles + warp * 32 * 33;
-  for (int r0 = warp * 32; r0 < nrow; r0 += 8 * 32) {
-    const int nr = nrow - r0 < 32 ? nrow - r0 : 32;
-    double acc = 0.0;
-    for (int m0 = 0; m0 < n; m0 += 32) {
-      __syncwarp();
-      const int m = m0 + lane;
-      for (int rr = 0; rr < nr; ++rr) {
-        const long off = (row0 + r0 + rr) * (long)n + m;
-        tile[rr * 33 + lane] = m < n ? Q[off] + BV[off] : 0.0;
-      }
-      __syncwarp();
-      if (lane < nr) {
-        const int mm = (n - m0 < 32) ? n - m0 : 32;
-        for (int q = 0; q < mm; ++q) acc = fma(tile[lane * 33 + q], tcol[m0 + q], acc);
-      }
-    }
-    if (lane < nr) xl[r0 + lane] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < nrow / ndof) {
-    const long t = traj0 + threadIdx.x;
-    const double* xt = xl + threadIdx.x * ndof;
-    double contr = 0.0;
-    for (int j = 0; j < nm.ndim; ++j)
-      for (int k = 0; k < nm.natom; ++k) {
-        const int d = k * nm.ndim + j;
-        contr = contr + nm.mass[k] * (-xt[d]) * dbdl[t * ndof + d];
-      }
-    dHdr[t] = dHdr[t] + contr;
-  }
-}
-
 __global__ void scale_kernel(double* v, double s, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = v[i] / s;
@@ -856,22 +803,7 @@ cudaError_t launch_estimator(const NmTables& nm, const double* x, const double* 
 
 cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const double* a, const double* b,
                                    const double* dbdl, double* dHdr, long ntraj, cudaStream_t st, const double* BV) {
-  if (BV && nm.ndof <= kEm2Threads) {    // warp-per-32-rows form (needs the precomputed beadvec array)
-    const int tpc2 = kEm2Threads / nm.ndof;
-    const size_t smem2 = (size_t)(nm.n + kEm2Threads + 8 * 32 * 33) * sizeof(double);
-    static unsigned long long attr_mask = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(attr_mask & (1ull << (dev & 63)))) {
-      cudaError_t e = cudaFuncSetAttribute(estimator_modes2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      if (e != cudaSuccess) return e;
-      attr_mask |= 1ull << (dev & 63);
-    }
-    if (smem2 > 160 * 1024) return cudaErrorInvalidValue;
-    estimator_modes2_kernel<<<(unsigned)((ntraj + tpc2 - 1) / tpc2), kEm2Threads, smem2, st>>>(nm, Q, BV, dbdl, dHdr, ntraj);
-    return cudaGetLastError();
-  }
-  const int tpc = kEmRows / nm.ndof;     // (ndof <= 18 for every surface here)
+  const int tpc = kEmRows / nm.ndof;     // ndof <= 32 (the caller takes the full back-transform beyond that)
   if (tpc < 1) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(nm.n + kEmRows * 33 + kEmRows) * sizeof(double);
   if (smem > 48 * 1024) {

@@ -1229,9 +1229,14 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
         CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, nullptr, nullptr,
                             fuse_andersen ? 2 : 0, count, rkick, (double)Noutput));
       }
-      if (ii > imin) {   // the estimator reads the last bead only: one contraction per (trajectory, dof), not a transform
+      if (ii > imin && ndof <= 32) {   // the estimator reads the last bead only: one contraction per (trajectory, dof), not a transform
         Scope s("estimator");
         CU(launch_estimator_modes(nm, Q, a, b, dbdl, dHdr, ntraj, g.stream, BV));
+      } else if (ii > imin) {          // many-site surfaces (water-methane, 51 dof): the full back-transform, then the plain estimator
+        Scope s("estimator", use_bv ? 3 : 2);
+        if (use_bv) CU(launch_add(Q, BV, QB, (long)tot, g.stream));
+        CU(back_transform());
+        CU(launch_estimator(nm, x, dbdl, dHdr, ntraj, g.stream));
       }
     }
     {
