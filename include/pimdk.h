@@ -72,11 +72,13 @@ int pimdk_set_gemm(pimdk_int kind);
 /* ---- PES plugin: module mcmod_mass -------------------------------------------------------
  * pimdk_pes_select  = V_init  (mcmod_1d.f90:8, mcmod_2dtest.f90:11, mcmod_waterdimer_ccpol.f90:9
  *                     -> init_ccpol(3,1,1,0), main_CCpol-8sf.f:1-173)
- *   name: "1d" | "2dtest" | "so2" | "watmeth" | "ccpol8sf".  pes_params (optional): "1d": {Vheight, x0};
+ *   name: "1d" | "2dtest" | "so2" | "watmeth" | "malon" | "ccpol8sf".  pes_params (optional): "1d": {Vheight, x0};
  *   "2dtest": {a0, b0, rho0}; "so2" (mcmod_so2.f90:10-48, the harmonic ring V = omegaforce**2/2 (r - r0)**2 in two
  *   dimensions): {omegaforce (default 10000), r0 (default 20)}; "watmeth" (mcmod_watmeth.f90 + watermethane.f90 wmrb /
  *   wmrb_grad: rigid-body water-methane site-site surface, x(3,17) = sites H H Q D D T T O | H H H H C M M M M in bohr, analytic
- *   gradient, V0 not subtracted): no parameters; "ccpol8sf": {iemonomer (default 1), isurf (default 3; 1..10 select the surfaces of
+ *   gradient, V0 not subtracted): no parameters; "malon" (mcmod_malon.f90 + pes_malonaldehyde.f90 `pes`: Morse + 3549 Gaussians
+ *   over the 36 distances of x(3,9) = C C O C O H H H H in bohr, analytic gradient and Hessian, tables from
+ *   <data_dir>/malonaldehyde.tbl): no parameters; "ccpol8sf": {iemonomer (default 1), isurf (default 3; 1..10 select the surfaces of
  *   init_ccpol, main_CCpol-8sf.f:14-107: SAPT data file, Eckart or Radau embedding, potparts or potparts_old,
  *   with or without the CCpol-8s correction)}.
  * pimdk_pes_set_v0  = assignment to module variable V0 (pimd_par.f90:166, rpi_ser.f90:95)

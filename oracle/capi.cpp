@@ -33,6 +33,8 @@ extern "C" {
 const char* orc_last_error() { return g_err.c_str(); }
 
 // ---- CCpol tables -------------------------------------------------------------------------
+static Malonaldehyde g_mal;
+int orc_malon_load(const char* tbl) { ORC_TRY(g_mal.load(tbl)) }
 int orc_ccpol_load_text(const char* dir, int isurf, int iemon) {
   ORC_TRY(load_text(dir, isurf, iemon, g_tab); g_tab_loaded = true)
 }
@@ -141,6 +143,12 @@ int orc_pes_select(const char* name) {
   if (s == "2dtest") { g_pes = Pes(); g_pes.init_2d(); return 0; }
   if (s == "so2") { g_pes = Pes(); g_pes.init_so2(); return 0; }
   if (s == "watmeth") { g_pes = Pes(); g_pes.init_watmeth(); return 0; }
+  if (s == "malon") {
+    if (!g_mal.loaded) { g_err = "malonaldehyde tables not loaded (orc_malon_load)"; return 1; }
+    g_pes = Pes();
+    g_pes.init_malon(&g_mal);
+    return 0;
+  }
   if (s == "ccpol8sf") {
     if (!g_tab_loaded) { g_err = "tables not loaded"; return 1; }
     g_pes = Pes();

@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
 // CPU restatement of the three in-scope `module mcmod_mass` plugins:
 //   mcmod_1d.f90:8-58, mcmod_2dtest.f90:11-61, mcmod_waterdimer_ccpol.f90:9-77, mcmod_so2.f90:10-84,
-//   mcmod_watmeth.f90:10-62 (watmeth.hpp).
+//   mcmod_watmeth.f90:10-62 (watmeth.hpp), mcmod_malon.f90:10-72 (malon.hpp).
 // x and grad are Fortran (ndim,natom) column-major: index = (atom)*ndim + dim.
 #pragma once
 #include <cmath>
@@ -10,11 +10,12 @@
 
 #include "ccpol_impl.hpp"
 #include "tables.hpp"
+#include "malon.hpp"
 #include "watmeth.hpp"
 
 namespace oracle {
 
-enum PesKind { PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4, PES_WATMETH = 5 };
+enum PesKind { PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4, PES_WATMETH = 5, PES_MALON = 6 };
 
 struct Pes {
   PesKind kind = PES_1D;
@@ -68,6 +69,15 @@ struct Pes {
     natom = 17;
     V0 = 0.0;
   }
+  // malonaldehyde (mcmod_malon.f90:10-13: V_init does nothing; the fit lives in pes' DATA statements)
+  const Malonaldehyde* mal = nullptr;
+  void init_malon(const Malonaldehyde* t) {
+    kind = PES_MALON;
+    ndim = 3;
+    natom = 9;
+    mal = t;
+    V0 = 0.0;
+  }
   void init_ccpol(const CcpolTables* t) {
     kind = PES_CCPOL;
     ndim = 3;
@@ -103,6 +113,8 @@ struct Pes {
       }
       case PES_WATMETH:  // mcmod_watmeth.f90:15-27 (V0 is not subtracted)
         return wm.wmrb(x);
+      case PES_MALON:  // mcmod_malon.f90:15-23
+        return mal->energy(x) - V0;
       case PES_CCPOL: {  // mcmod_waterdimer_ccpol.f90:18-37
         const double ang = 0.529177;
         double xtemp[18];
@@ -147,6 +159,9 @@ struct Pes {
       }
       case PES_WATMETH:  // mcmod_watmeth.f90:30-40
         wm.wmrb_grad(x, grad);
+        return;
+      case PES_MALON:  // mcmod_malon.f90:26-40 (grad(i,j) = gradtemp(ndim*(j-1)+i): the same storage order)
+        mal->gradient(x, grad);
         return;
       case PES_CCPOL: {  // mcmod_waterdimer_ccpol.f90:40-58
         const double eps = 1e-4;
@@ -198,6 +213,19 @@ struct Pes {
       H(0, 0, 1, 0) = x[0] * x[1] * w2 * r0 / r3;
       H(1, 0, 0, 0) = x[0] * x[1] * w2 * r0 / r3;
       H(1, 0, 1, 0) = x[1] * x[1] * w2 * r0 / r3;
+      return;
+    }
+    if (kind == PES_MALON) {  // mcmod_malon.f90:43-70: the packed analytic Hessian spread to hess(i1,j1,i2,j2) and its transpose
+      std::vector<double> hp(nd * (nd + 1) / 2);
+      mal->hessian_packed(x, hp.data());
+      int ij = 0;
+      for (int d1 = 0; d1 < nd; ++d1)
+        for (int d2 = 0; d2 <= d1; ++d2) {
+          const int i1 = d1 % ndim, j1 = d1 / ndim, i2 = d2 % ndim, j2 = d2 / ndim;
+          H(i1, j1, i2, j2) = hp[ij];
+          H(i2, j2, i1, j1) = hp[ij];
+          ++ij;
+        }
       return;
     }
     const double eps = (kind == PES_CCPOL) ? 1e-5 : 1e-4;

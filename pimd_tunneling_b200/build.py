@@ -24,6 +24,8 @@ UNITS = [
     ("ccpol_grad_kernels.cu", "ccpol_grad.o", ["-fmad=true"]),
     ("pes_simple.cu", "pes_simple.o", ["-fmad=false"]),
     ("watmeth_kernels.cu", "watmeth.o", ["-fmad=false"]),
+    ("malon_kernels.cu", "malon.o", ["-fmad=false"]),
+    ("malon_tables.cpp", "malon_tables.o", []),
     ("nm_kernels.cu", "nm_kernels.o", ["-fmad=false"]),
     ("fused_small.cu", "fused_small.o", ["-fmad=false"]),
     ("um_kernels.cu", "um_kernels.o", ["-fmad=false"]),

@@ -22,7 +22,7 @@ struct GeomLayout {
   }
 };
 
-enum PesKind { PES_NONE = 0, PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4, PES_WATMETH = 5 };
+enum PesKind { PES_NONE = 0, PES_1D = 1, PES_2DTEST = 2, PES_CCPOL = 3, PES_SO2 = 4, PES_WATMETH = 5, PES_MALON = 6 };
 
 struct SimplePesParams {  // mcmod_1d.f90:9-12, mcmod_2dtest.f90:16-24, mcmod_so2.f90:10-14
   double Vheight, x0;
@@ -60,6 +60,12 @@ struct WatMethTab;
 cudaError_t launch_watmeth(const WatMethTab* tab, GeomLayout L, const double* x, double* v, double* grad, long ngeom, int* flags,
                            cudaStream_t st);
 cudaError_t launch_watmeth_hessian(const WatMethTab* tab, GeomLayout L, double* x, double* hess, long ngeom, cudaStream_t st);
+
+// ---- malonaldehyde surface (malon_kernels.cu; pes_malonaldehyde.f90 / mcmod_malon.f90) ----
+struct MalonTab;
+cudaError_t launch_malon(const MalonTab* tab, GeomLayout L, const double* x, double V0, double* v, double* grad, long ngeom, int* flags,
+                         cudaStream_t st);
+cudaError_t launch_malon_hessian(const MalonTab* tab, GeomLayout L, const double* x, double* hess, long ngeom, cudaStream_t st);
 
 // ---- 1D / 2D model surfaces (pes_simple.cu) ----
 cudaError_t launch_simple_pes(PesKind kind, const SimplePesParams& P, GeomLayout L, const double* x, double* v,

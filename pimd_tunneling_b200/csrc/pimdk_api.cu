@@ -18,6 +18,7 @@
 #include "ccpol_grad.cuh"
 #include "kernels.h"
 #include "nm_device.cuh"
+#include "malon.cuh"
 #include "watmeth.cuh"
 
 using namespace pimdk;
@@ -78,6 +79,7 @@ struct Ctx {
   int device = 0, num_sms = 148;
   cudaStream_t stream = 0;
   std::string data_dir = ".";
+  double malon_V0 = 0.0;   // module variable V0 of mcmod_malon
   std::string err;
   int mode = PIMDK_MODE_STRICT;
   bool fused = true;  // small systems: one persistent warp-per-ring-polymer kernel
@@ -100,7 +102,7 @@ struct Ctx {
   CcpolHost htab;
   CcpolDev hdev;
   agrad::CcpolGradTab hgrad;   // rigid-body coefficients and sweep tables of the analytic-gradient mode
-  DevBuf dtab, dgtab, dwm;   // dwm: WatMethTab
+  DevBuf dtab, dgtab, dwm, dmal;   // dwm: WatMethTab, dmal: MalonTab
   // normal modes
   bool nm_ready = false;
   int n = 0, nm_ndim = 0, nm_natom = 0;
@@ -248,6 +250,9 @@ int pes_eval_dev(GeomLayout L, double* x, double* v, double* grad, long ngeom, i
   } else if (g.pes == PES_WATMETH) {
     Scope s("pes");
     CU(launch_watmeth(g.dwm.as<WatMethTab>(), L, x, v, grad, ngeom, flags, g.stream));
+  } else if (g.pes == PES_MALON) {
+    Scope s("pes");
+    CU(launch_malon(g.dmal.as<MalonTab>(), L, x, g.malon_V0, v, grad, ngeom, flags, g.stream));
   } else {
     Scope s("pes");
     CU(launch_simple_pes(g.pes, g.sp, L, x, v, grad, ngeom, flags, g.stream));
@@ -447,7 +452,7 @@ int pimdk_finalize(void) {
   if (!g.inited) return PIMDK_OK;
   cudaStreamSynchronize(g.stream);
   resolve_spans();
-  DevBuf* bufs[] = {&g.dtab, &g.dgtab, &g.dwm, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
+  DevBuf* bufs[] = {&g.dtab, &g.dgtab, &g.dwm, &g.dmal, &g.dT, &g.dsA, &g.dsB, &g.dlamb2, &g.dmass, &g.dtabs, &g.wCc, &g.wP, &g.wQ, &g.wG, &g.wGn,
                     &g.wV, &g.wX, &g.wAux, &g.wCount, &g.wKick, &g.wFlags, &g.wGid, &g.wA, &g.wB, &g.wDbdl,
                     &g.wDhdr, &g.wPp, &g.wMisc, &g.wDhSum, &g.wX2, &g.wPp2, &g.wUmIn, &g.wUmOut, &g.wHgp, &g.wHgm, &g.wHess, &g.wBand,
                     &g.wDense, &g.wEig, &g.wWork, &g.wSums, &g.wBV, &g.wPath, &g.wXi, &g.wReinit};
@@ -552,6 +557,20 @@ int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
     g.natom = kWmSites;
     return PIMDK_OK;
   }
+  if (s == "malon") {  // mcmod_malon.f90:10-13: V_init does nothing, the fit is in pes' DATA statements (here: data/malonaldehyde.tbl)
+    std::vector<unsigned char> hb(sizeof(MalonTab));
+    MalonTab* t = reinterpret_cast<MalonTab*>(hb.data());
+    const char* m = load_malon_tab(g.data_dir.c_str(), t);
+    if (m[0]) return fail(PIMDK_EDATA, "%s", m);
+    CU(g.dmal.ensure(sizeof(MalonTab)));
+    CU(cudaMemcpyAsync(g.dmal.p, t, sizeof(MalonTab), cudaMemcpyHostToDevice, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    g.pes = PES_MALON;
+    g.ndim = 3;
+    g.natom = kMalAtoms;
+    g.malon_V0 = 0.0;
+    return PIMDK_OK;
+  }
   if (s == "ccpol8sf") {  // mcmod_waterdimer_ccpol.f90:9-16 -> init_ccpol(3,1,1,0)
     const int iemon = np > 0 ? (int)pp[0] : 1;
     const int isurf = np > 1 ? (int)pp[1] : 3;
@@ -570,7 +589,7 @@ int pimdk_pes_select(const char* name, const double* pp, pimdk_int np) {
     g.natom = 6;
     return PIMDK_OK;
   }
-  return fail(PIMDK_EINVAL, "unknown PES '%s' (1d, 2dtest, so2, watmeth, ccpol8sf)", s.c_str());
+  return fail(PIMDK_EINVAL, "unknown PES '%s' (1d, 2dtest, so2, watmeth, malon, ccpol8sf)", s.c_str());
 }
 
 int pimdk_pes_info(pimdk_int* ndim, pimdk_int* natom) {
@@ -587,6 +606,7 @@ int pimdk_pes_set_v0(double v0) {
     return upload_ccpol_dev();
   }
   if (g.pes == PES_2DTEST || g.pes == PES_SO2) g.sp.V0 = v0;  // mcmod_1d's V ignores V0 (mcmod_1d.f90:20)
+  if (g.pes == PES_MALON) g.malon_V0 = v0;                     // mcmod_malon.f90:21
   return PIMDK_OK;
 }
 
@@ -742,6 +762,11 @@ static int pes_hessian_dev(GeomLayout L, double* x, double* hess, long ngeom, in
   if (g.pes == PES_WATMETH) {
     Scope s("hess");
     CU(launch_watmeth_hessian(g.dwm.as<WatMethTab>(), L, x, hess, ngeom, g.stream));
+    return PIMDK_OK;
+  }
+  if (g.pes == PES_MALON) {   // mcmod_malon.f90:43-70: analytic (pes, iopt = 2)
+    Scope s("hess");
+    CU(launch_malon_hessian(g.dmal.as<MalonTab>(), L, x, hess, ngeom, g.stream));
     return PIMDK_OK;
   }
   if (g.pes != PES_CCPOL) {

@@ -9,7 +9,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, f64, hptr, lib
 
-_SHAPES = {"1d": (1, 1), "2dtest": (2, 1), "so2": (2, 1), "watmeth": (3, 17), "ccpol8sf": (3, 6)}
+_SHAPES = {"1d": (1, 1), "2dtest": (2, 1), "so2": (2, 1), "watmeth": (3, 17), "malon": (3, 9), "ccpol8sf": (3, 6)}
 
 
 class McmodMass:
@@ -24,7 +24,7 @@ class McmodMass:
         of init_ccpol(isurf, iemon, iembedang, ixyz) (main_CCpol-8sf.f:1; the plugin calls init_ccpol(3,1,1,0)), also
         settable by keyword."""
         if name not in _SHAPES:
-            raise ValueError("unknown PES %r (1d, 2dtest, so2, watmeth, ccpol8sf)" % name)
+            raise ValueError("unknown PES %r (1d, 2dtest, so2, watmeth, malon, ccpol8sf)" % name)
         self.name = name
         if name == "ccpol8sf" and (isurf is not None or iemonomer is not None):
             p0 = [1.0, 3.0] if params is None else (list(np.asarray(params, dtype=np.float64)) + [3.0])[:2]
@@ -38,6 +38,9 @@ class McmodMass:
         self.label = ["O", "H", "H", "O", "H", "H"] if name == "ccpol8sf" else ["X"] * self.natom
         if name == "watmeth":   # watermethane.f90:6-7
             self.label = list("HHQDDTTOHHHHCMMMM")
+        if name == "malon":     # pes_malonaldehyde.f90:12-21; mcmod_malon.f90:5 aligns on atoms 1, 2, 4
+            self.label = list("CCOCOHHHH")
+            self.atom1, self.atom2, self.atom3 = 1, 2, 4
         self.basename = ""
         self._selected = False
 

@@ -142,8 +142,10 @@ class Oracle:
     def select(self, name, ndim=None, natom=None):
         if name == "ccpol8sf":
             self.load_ccpol()
+        if name == "malon":
+            self._chk(self.L.orc_malon_load(os.path.join(DATA_DIR, "malonaldehyde.tbl").encode()))
         self._chk(self.L.orc_pes_select(name.encode()))
-        shapes = {"1d": (1, 1), "2dtest": (2, 1), "so2": (2, 1), "watmeth": (3, 17), "ccpol8sf": (3, 6)}
+        shapes = {"1d": (1, 1), "2dtest": (2, 1), "so2": (2, 1), "watmeth": (3, 17), "malon": (3, 9), "ccpol8sf": (3, 6)}
         self.ndim, self.natom = shapes[name]
         if ndim:
             self.ndim, self.natom = ndim, natom
@@ -320,3 +322,23 @@ def thermal_dimer_geometries(nbatch, seed=0, sigma=0.05):
     base = GOLDEN_GEOM_ANG / 0.529177
     x = base[None, :] + rng.normal(0.0, sigma, size=(nbatch, 18))
     return np.asfortranarray(x.T.reshape(3, 6, nbatch, order="F"))
+
+
+# ---- malonaldehyde (pes_malonaldehyde.f90) -----------------------------------------------------------------------
+# the minimum-energy structure the reference file lists in its header (pes_malonaldehyde.f90:12-21), Angstrom,
+# atom order C C O C O H H H H; the surface takes bohr
+MALON_MIN_ANG = np.array([[0.0035239647, 0.0, -1.1379095138], [1.1859410623, 0.0, -0.4671627095], [1.2951373352, 0.0, 0.8494123252],
+                          [-1.2326642069, 0.0, -0.3950488380], [-1.2836327508, 0.0, 0.8382056815], [-0.0071493753, 0.0, -2.2163348766],
+                          [0.3688205810, 0.0, 1.1962401614], [-2.1703435327, 0.0, -0.9688628849], [2.1404514581, 0.0, -0.9796660170]])
+MALON_BOHR = 0.52917721092
+MALON_MASS = np.array([12.0, 12.0, 15.9949, 12.0, 15.9949, 1.00783, 1.00783, 1.00783, 1.00783]) * 1822.888
+
+
+def malon_geometries(nbatch, seed=0, sigma=0.08):
+    """x(3,9,nbatch) F-order, bohr: the minimum-energy structure, randomly rotated, every coordinate displaced by N(0, sigma)"""
+    rng = np.random.default_rng(seed)
+    x = np.empty((3, 9, nbatch), order="F")
+    for k in range(nbatch):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        x[:, :, k] = (MALON_MIN_ANG / MALON_BOHR @ q.T).T + rng.normal(scale=sigma, size=(3, 9))
+    return x

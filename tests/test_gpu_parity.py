@@ -1297,3 +1297,43 @@ def test_water_methane_surface_bit_exact(pk, orc):
         xo, po, do = orc.propagate(2, xx[..., t], pp[..., t], dbdl[..., t], steps, 0, 100000)
         assert relmax(xg[..., t], xo) < RTOL and relmax(pg[..., t], po) < RTOL and abs(dg[t] - do) <= RTOL * abs(do)
     orc.select("ccpol8sf")
+
+
+def test_malonaldehyde_surface_bit_exact(pk, orc):
+    """mcmod_malon.f90 + pes_malonaldehyde.f90 (`pes`: 9 Morse terms and 3549 Gaussians over the 36 distances, analytic gradient
+    through the B matrix, analytic Hessian) behind pimdk_pes_select("malon"): V, Vprime, Vdoubleprime bit-exact against the
+    oracle (ragged batch, V0 subtracted), the reference's own minimum-energy structure gives V = 0, and two PILE steps of a
+    small ring polymer (27 degrees of freedom per bead, streamed path) stay within 1e-10."""
+    from oracle_lib import MALON_BOHR, MALON_MASS, MALON_MIN_ANG, malon_geometries
+
+    pes = pk.McmodMass("malon").V_init()
+    orc.select("malon")
+    x = malon_geometries(261, seed=7)
+    v, g = pes.eval_batch(x)
+    vo, go, _ = orc.pes_eval(x)
+    assert np.array_equal(v, vo) and np.array_equal(g, go)
+    xmin = np.asfortranarray((MALON_MIN_ANG / MALON_BOHR).T.reshape(3, 9, 1))
+    assert abs(pes.V_batch(xmin)[0]) < 1e-12                       # pes_malonaldehyde.f90:12-21: energy above equilibrium
+    pes.set_V0(0.125)                                              # mcmod_malon.f90:21
+    orc.set_V0(0.125)
+    assert np.array_equal(pes.V_batch(x[:, :, :5]), orc.pes_eval(x[:, :, :5], gradient=False)[0])
+    pes.set_V0(0.0)
+    orc.set_V0(0.0)
+    xs = np.array(x[:, :, :3], order="F")
+    h = pes.Vdoubleprime_batch(xs)
+    for k in range(3):
+        ho, _ = orc.Vdoubleprime(x[:, :, k])
+        assert np.array_equal(h[..., k], ho) and np.array_equal(xs[:, :, k], x[:, :, k])
+    mass = list(MALON_MASS)
+    a, b = np.asfortranarray(x[:, :, 0]), np.asfortranarray(x[:, :, 1])
+    n, ntraj, steps = 8, 2, 2
+    vi = pk.VerletInt(pes, n, mass, 800.0, dt=1e-3, NMC=steps, seed=4).init_nm()
+    xx, pp, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, 0.002, mass)
+    xg, pg, dg = vi.propagate_pimd_pile(xx, pp, a, bt, dbdl)
+    for t in range(ntraj):
+        orc.nm_setup(n, mass, vi.betan, 1.0, 1.0, 1e-3, False, True)
+        orc.init_nm(a, bt[..., t])
+        orc.set_rng(4, t)
+        xo, po, do = orc.propagate(2, xx[..., t], pp[..., t], dbdl[..., t], steps, 0, 100000)
+        assert relmax(xg[..., t], xo) < RTOL and relmax(pg[..., t], po) < RTOL and abs(dg[t] - do) <= RTOL * abs(do)
+    orc.select("ccpol8sf")

@@ -9,6 +9,8 @@ import ctypes
 import numpy as np
 import pytest
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 from oracle_lib import (GOLDEN_GEOM_ANG, GOLDEN_VAL, GOLDEN_VALM, REF_DATA, SAPT_FOR_SURF, Oracle,
                         thermal_dimer_geometries)
 
@@ -444,3 +446,56 @@ def test_water_methane_surface_restatement(orc):
             fd = (orc.pes_eval(xp)[0][0] - orc.pes_eval(xm)[0][0]) / (2 * e)
             assert abs(fd - g[d, s, k]) < 2e-5 * np.abs(g[:, :, k]).max() + 1e-9
     orc.select("ccpol8sf")
+
+
+def test_malonaldehyde_surface_restatement(orc):
+    """pes_malonaldehyde.f90 (`pes`, iopt 0/1/2) behind mcmod_malon.f90.  Reference-held known answer: the file's header lists
+    the minimum-energy structure (:12-21) and defines the energy as "above equilibrium" — V vanishes there and so does the
+    gradient (to the 10 printed decimals of the coordinates).  Then: analytic gradient against a central difference of V,
+    analytic Hessian against a central difference of the gradient, symmetry, rigid-motion invariance, V0."""
+    from oracle_lib import MALON_BOHR, MALON_MIN_ANG, malon_geometries
+    orc.select("malon")
+    xmin = np.asfortranarray((MALON_MIN_ANG / MALON_BOHR).T.reshape(3, 9, 1))
+    v, g, _ = orc.pes_eval(xmin)
+    assert abs(v[0]) < 1e-12 and np.abs(g).max() < 1e-8
+    x = malon_geometries(6, seed=2)
+    v, g, _ = orc.pes_eval(x)
+    assert (v > 0).all() and v.max() < 0.5                                   # Hartree above the minimum
+    assert np.abs(g.sum(axis=1)).max() <= 1e-12 * np.abs(g).max()           # translation invariance
+    e = 1e-5
+    x0 = np.array(x[:, :, 0], order="F")
+    num = np.zeros((3, 9))
+    for d in range(3):
+        for s in range(9):
+            xp, xm = x0.reshape(3, 9, 1).copy(order="F"), x0.reshape(3, 9, 1).copy(order="F")
+            xp[d, s, 0] += e
+            xm[d, s, 0] -= e
+            num[d, s] = (orc.pes_eval(xp, gradient=False)[0][0] - orc.pes_eval(xm, gradient=False)[0][0]) / (2 * e)
+    assert np.abs(num - g[:, :, 0]).max() < 1e-8 * np.abs(g[:, :, 0]).max()
+    h = orc.Vdoubleprime(x0.copy(order="F"))[0].reshape(27, 27, order="F")
+    assert np.array_equal(h, h.T)
+    numh = np.zeros((27, 27))
+    for d in range(27):
+        xp, xm = x0.reshape(-1, order="F").copy(), x0.reshape(-1, order="F").copy()
+        xp[d] += e
+        xm[d] -= e
+        gp = orc.pes_eval(xp.reshape(3, 9, 1, order="F"), energy=False)[1][:, :, 0].reshape(-1, order="F")
+        gm = orc.pes_eval(xm.reshape(3, 9, 1, order="F"), energy=False)[1][:, :, 0].reshape(-1, order="F")
+        numh[d] = (gp - gm) / (2 * e)
+    assert np.abs(numh - h).max() < 1e-8 * np.abs(h).max()
+    orc.set_V0(0.25)                                                         # mcmod_malon.f90:21: V = V - V0
+    assert orc.pes_eval(x[:, :, :1], gradient=False)[0][0] == v[0] - 0.25
+    orc.set_V0(0.0)
+    orc.select("ccpol8sf")
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/pes_malonaldehyde.f90"), reason="the reference tree is not on this box")
+def test_malonaldehyde_table_file_is_the_reference_data(tmp_path):
+    """pimd_tunneling_b200/data/malonaldehyde.tbl is exactly what tools/pack_malon_tables.py makes of the reference's DATA
+    statements (run where /root/reference exists; the GPU box only has the packed file)."""
+    import subprocess
+    import sys
+    out = tmp_path / "m.tbl"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "pack_malon_tables.py"), "/root/reference/pes_malonaldehyde.f90", str(out)],
+                   check=True, capture_output=True)
+    assert out.read_bytes() == open(os.path.join(ROOT, "pimd_tunneling_b200", "data", "malonaldehyde.tbl"), "rb").read()
