@@ -255,37 +255,27 @@ KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __
 // 128-thread CTAs at equal or higher occupancy are 11% slower and stall on instruction fetch).
 template <bool OLD>
 __global__ void __launch_bounds__(kSaptBlock, PIMDK_SAPT_MINB)
-KNAME(ccpol_sapt_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
+KNAME(ccpol_sapt_kernel)(const __grid_constant__ SaptParams T, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
-  // stage only the SAPT-5s'f members (param .. pairflags); T is a view whose leading (rigid) members are not backed
-  {
-    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + kRigidTableBytes);
-    int4* dst = reinterpret_cast<int4*>(smem);
-    for (int i = threadIdx.x; i < kSaptTableBytes / (int)sizeof(int4); i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-  }
-  const CcpolDev& T = *reinterpret_cast<const CcpolDev*>(smem - kRigidTableBytes);
   const long j = (long)blockIdx.x * kSaptBlock + threadIdx.x;
   if (j >= 2 * ne) return;
   const int which = j >= ne;    // 0: flexible geometry (val), 1: embedded rigid geometry (vall)
   const long e = which ? j - ne : j;
   GlobalSites S{buf + (long)(F_SITES + which * 2 * kSiteFields) * ne + e, ne};
   // the 8 sites of B are read once per site of A: keep them in shared memory, slot-major (conflict-free)
-  Scratch<kSaptBlock> sitesB{reinterpret_cast<double*>(smem + kSaptTableBytes) + threadIdx.x};
+  Scratch<kSaptBlock> sitesB{reinterpret_cast<double*>(smem) + threadIdx.x};
 #pragma unroll
   for (int k = 0; k < 24; ++k) sitesB[k] = S[24 + k];
   const double sa[3] = {S[48], S[49], S[50]};
   const double sb[3] = {S[51], S[52], S[53]};
-  Scratch<kSaptBlock> qb{reinterpret_cast<double*>(smem + kSaptTableBytes) + 24 * kSaptBlock + threadIdx.x};
+  Scratch<kSaptBlock> qb{reinterpret_cast<double*>(smem) + 24 * kSaptBlock + threadIdx.x};
   const double val = sapt_pair_sum<OLD>(T, S, sitesB, qb, sa, sb);
   buf[(which ? F_VALL : F_VAL) * ne + e] = val + buf[(F_FCIND + which) * ne + e];
 }
 
 // ---- stage 2a -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRigidBlock, PIMDK_RIGID_MINB)
-KNAME(ccpol_rigid_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf, int* __restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const CcpolDev& T = stage_tables<kRigidTableBytes>(tab, smem);  // only the CCpol-8s members are valid here
+KNAME(ccpol_rigid_kernel)(const __grid_constant__ RigidParams T, long ne, double* __restrict__ buf, int* __restrict__ flags) {
   const long e = (long)blockIdx.x * kRigidBlock + threadIdx.x;
   if (e >= ne) return;
   double rg[6][3];
@@ -398,11 +388,10 @@ __device__ __forceinline__ void sweep_block(const double* sA, const double* sB, 
 }
 
 __global__ void __launch_bounds__(kSweepBlock, PIMDK_SWEEP_MINB)
-KNAME(ccpol_sweep_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
+KNAME(ccpol_sweep_kernel)(const __grid_constant__ RigidParams T, long ne, double* __restrict__ buf) {
   pimdk_exp2_stage();
   extern __shared__ __align__(16) unsigned char smem[];
-  const CcpolDev& T = stage_tables<kRigidTableBytes>(tab, smem);
-  double* slots = reinterpret_cast<double*>(smem + kRigidTableBytes);
+  double* slots = reinterpret_cast<double*>(smem);
   int* queue = reinterpret_cast<int*>(slots + kSweepSlots * 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* sA = slots + lane;            // site s, coordinate c of A at sA[(s*3 + c) * 32]
@@ -490,10 +479,9 @@ KNAME(ccpol_combine_kernel)(int iemonomer, int icc, double V0, GeomLayout L, dou
   }
 }
 
-size_t sapt_smem() { return kSaptTableBytes + (size_t)(24 + 8) * kSaptBlock * sizeof(double); }
+size_t sapt_smem() { return (size_t)(24 + 8) * kSaptBlock * sizeof(double); }
 size_t dipind_smem() { return kSaptTableBytes; }
-size_t rigid_smem() { return kRigidTableBytes; }
-size_t sweep_smem() { return kRigidTableBytes + (size_t)kSweepSlots * 32 * sizeof(double) + 16; }
+size_t sweep_smem() { return (size_t)kSweepSlots * 32 * sizeof(double) + 16; }
 
 }  // namespace
 
@@ -528,6 +516,13 @@ inline long pass_geoms(long ngeom, int grad, size_t work_bytes, int* nbuf) {
 }
 }  // namespace
 
+// host copies of the two parameter blocks the kernels take by value; refreshed whenever the tables change
+namespace {
+SaptParams g_sapt;
+RigidParams g_rigid;
+}  // namespace
+void KNAME(ccpol_host_tables)(const CcpolDev* h) { fill_params(*h, &g_sapt, &g_rigid); }
+
 size_t KNAME(ccpol_work_bytes)(long ngeom, int grad) {
   const long cap = grad ? kGradPass : kEnergyPass;
   const long n = ngeom < cap ? ngeom : cap;
@@ -559,8 +554,6 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
     cudaError_t e = cudaFuncSetAttribute(KNAME(ccpol_sapt_kernel)<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sapt_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(KNAME(ccpol_sapt_kernel)<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sapt_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(KNAME(ccpol_rigid_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rigid_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(KNAME(ccpol_sweep_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem());
     if (e != cudaSuccess) return e;
@@ -601,11 +594,11 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
     KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, iembed, L, x, g0, ne, g, work);
     KNAME(ccpol_sites_kernel)<<<(unsigned)((4 * ne + 127) / 128), 128, 0, st>>>(tab, ne, work);
     KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, PIMDK_DIPIND_SPLIT ? 0 : dipind_smem(), st>>>(tab, ne, work);
-    if (potparts_old) KNAME(ccpol_sapt_kernel)<true><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
-    else KNAME(ccpol_sapt_kernel)<false><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(tab, ne, work);
+    if (potparts_old) KNAME(ccpol_sapt_kernel)<true><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(g_sapt, ne, work);
+    else KNAME(ccpol_sapt_kernel)<false><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(g_sapt, ne, work);
     if (icc) {   // CCpol-8s rigid model of the embedded monomers; surfaces 5..9 are SAPT-5s'f alone
-      KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, rigid_smem(), st>>>(tab, ne, work, flags);
-      KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + 31) / 32), kSweepBlock, sweep_smem(), st>>>(tab, ne, work);
+      KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, 0, st>>>(g_rigid, ne, work, flags);
+      KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + 31) / 32), kSweepBlock, sweep_smem(), st>>>(g_rigid, ne, work);
     }
     const long nt = g ? ne / 2 : ne;
     KNAME(ccpol_combine_kernel)<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(iemonomer, icc, V0, L, x, g0, ne, g, work, v, grad, write_drift, flags);

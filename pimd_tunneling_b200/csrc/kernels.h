@@ -38,6 +38,7 @@ struct SimplePesParams {  // mcmod_1d.f90:9-12, mcmod_2dtest.f90:16-24, mcmod_so
 // reference's in-place perturbation leaves it).  `work` is a staging buffer of ccpol_work_bytes().
 #define PIMDK_DECL_CCPOL(sfx)                                                                                       \
   size_t ccpol_work_bytes_##sfx(long ngeom, int grad);                                                              \
+  void ccpol_host_tables_##sfx(const CcpolDev* host_tables);   /* whenever the tables change, before the next launch */ \
   long ccpol_launches_##sfx(long ngeom, int grad, int icc, size_t work_bytes);                                                              \
   cudaError_t launch_ccpol_##sfx(const CcpolDev* tab, int iemonomer, int iembed, int icc, int potparts_old, \
                                  double V0, GeomLayout L, double* x, double* v, \

@@ -207,6 +207,8 @@ int ensure_ccpol_tables(int isurf) {
 }
 
 int upload_ccpol_dev() {
+  ccpol_host_tables_strict(&g.hdev);   // the pair-sum, rigid and sweep kernels take their tables as kernel parameters
+  ccpol_host_tables_fast(&g.hdev);
   CU(g.dtab.ensure(sizeof(CcpolDev)));
   CU(cudaMemcpyAsync(g.dtab.p, &g.hdev, sizeof(CcpolDev), cudaMemcpyHostToDevice, g.stream));
   CU(g.dgtab.ensure(sizeof(agrad::CcpolGradTab)));

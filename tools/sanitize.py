@@ -42,4 +42,18 @@ for n in (33, 200):
     check(lib().pimdk_set_propagate_chunk(2))
     vi.propagate_pimd_pile(x0, p0, a2, bt, dbdl); vi.propagate_pimd_nm(x0, p0, a2, bt, dbdl)
     check(lib().pimdk_set_propagate_chunk(0))
+# the further plugin surfaces (row N4): ragged batches, Hessians, a short streamed propagation each
+from oracle_lib import MALON_MASS, malon_geometries, watmeth_geometries
+for name, geoms, masses in (("malon", malon_geometries(37, seed=3), list(MALON_MASS)), ("watmeth", watmeth_geometries(37, seed=3), [1837.0] * 17)):
+    pz = pk.McmodMass(name).V_init()
+    pz.eval_batch(geoms)
+    pz.Vdoubleprime_batch(np.asfortranarray(geoms[..., :2].copy()))
+    az, bz = np.asfortranarray(geoms[..., 0]), np.asfortranarray(geoms[..., 1])
+    vz = pk.VerletInt(pz, 5, masses, 800.0, dt=1e-3, NMC=2, seed=2).init_nm()
+    xz = np.asfortranarray(np.repeat(np.repeat(az[None, ...], 5, axis=0)[..., None], 3, axis=-1))
+    pzz = np.zeros_like(xz, order="F")
+    btz = np.asfortranarray(np.repeat(bz[..., None], 3, axis=-1))
+    vz.propagate_pimd_pile(xz, pzz, az, btz, np.zeros_like(btz, order="F"))
+ps = pk.McmodMass("so2").V_init()
+ps.eval_batch(np.asfortranarray(np.random.default_rng(0).normal(size=(2, 1, 37)) + 14.0))
 pk.finalize(); print("sanitize workload done")
