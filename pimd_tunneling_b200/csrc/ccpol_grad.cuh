@@ -346,7 +346,8 @@ PIMDK_AG void flex_charge_adj(const double* pa, double s1, double s2, double s3,
 struct PairOut {
   double e, dr, dx[3], dy[3], dqa, dqb;
 };
-PIMDK_AG void sapt_pair_adj(const CcpolDev& T, int ia, int ib, double r, const double* sa, const double* sb, double qa,
+template <class Tab>
+PIMDK_AG void sapt_pair_adj(const Tab& T, int ia, int ib, double r, const double* sa, const double* sb, double qa,
                             double qb, PairOut& o) {
   const int ta = site_type(ia), tb = site_type(ib);
   const int pt = tb * kNType + ta;
@@ -468,7 +469,8 @@ PIMDK_AG void sapt_pair_adj(const CcpolDev& T, int ia, int ib, double r, const d
 // dipind, per-monomer part (proc_sapt5sf_new_ncd.f:1363-1470): dipole sum over the 8 sites and polarisability.
 // The sign of s3 flips cumulatively from site 3 on (:1400-1402): +, +, -, +, -, +, -, +.
 PIMDK_AG double dipind_sign(int i) { return (i >= 2 && (i & 1) == 0) ? -1.0 : 1.0; }
-PIMDK_AG void dipind_monomer(const CcpolDev& T, const double* sites, const double* s, double* dm, double& polis) {
+template <class Tab>
+PIMDK_AG void dipind_monomer(const Tab& T, const double* sites, const double* s, double* dm, double& polis) {
   dm[0] = dm[1] = dm[2] = 0.0;
   for (int i = 0; i < 8; ++i) {
     const double* pa = &T.param[site_type(i) * kNParam];
@@ -480,7 +482,8 @@ PIMDK_AG void dipind_monomer(const CcpolDev& T, const double* sites, const doubl
           pa[15] * s[0] * s[0] + pa[16] * s[1] * s[1] + pa[17] * s[2] * s[2];
 }
 // adjoint of the above: (adj_dm[3], adj_polis) -> += adj_sites[24], adj_s[3]
-PIMDK_AG void dipind_monomer_adj(const CcpolDev& T, const double* sites, const double* s, const double* adm, double apol,
+template <class Tab>
+PIMDK_AG void dipind_monomer_adj(const Tab& T, const double* sites, const double* s, const double* adm, double apol,
                                  double* asites, double* as) {
   for (int i = 0; i < 8; ++i) {
     const double* pa = &T.param[site_type(i) * kNParam];
@@ -542,7 +545,8 @@ PIMDK_AG double dipind_pair_adj(double par, const double* Oa, const double* Ob, 
 
 // poten (+ dipind) for one item: sites/s of A and B (Angstrom) -> energy (kcal/mol) and the adjoints
 //   adj[0..23] d/d sitesA, adj[24..47] d/d sitesB, adj[48..50] d/d sA, adj[51..53] d/d sB
-PIMDK_AG double sapt_item_adj(const CcpolDev& T, const double* sitesA, const double* sA, const double* sitesB, const double* sB,
+template <class Tab>
+PIMDK_AG double sapt_item_adj(const Tab& T, const double* sitesA, const double* sA, const double* sitesB, const double* sB,
                               double* adj) {
   for (int k = 0; k < 54; ++k) adj[k] = 0.0;
   // dipole-induction term

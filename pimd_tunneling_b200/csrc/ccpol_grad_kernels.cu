@@ -111,16 +111,10 @@ struct Slots {
   __device__ __forceinline__ double& operator[](int k) const { return p[k * STRIDE]; }
 };
 __global__ void __launch_bounds__(kSaptThreads, 1)
-agrad_sapt_kernel(const CcpolDev* __restrict__ tab, const CcpolGradTab* __restrict__ gt, long nb, double* __restrict__ buf) {
+agrad_sapt_kernel(const __grid_constant__ SaptParams T, const CcpolGradTab* __restrict__ gt, long nb, double* __restrict__ buf) {
+  // the SAPT-5s'f tables arrive as a kernel parameter: every read is warp-uniform, i.e. a constant-bank operand
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int kSaptTab = (int)((sizeof(CcpolDev) - PIMDK_RIGID_TABLE_BYTES + 15) / 16 * 16);
-  {  // the SAPT-5s'f members of the table (param .. pairflags) -> shared memory; T is a view whose leading members are not backed
-    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + PIMDK_RIGID_TABLE_BYTES);
-    int4* dst = reinterpret_cast<int4*>(smem);
-    for (int i = threadIdx.x; i < kSaptTab / 16; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-  }
-  const CcpolDev& T = *reinterpret_cast<const CcpolDev*>(smem - PIMDK_RIGID_TABLE_BYTES);
+  constexpr int kSaptTab = 0;
   const long j = (long)blockIdx.x * kSaptThreads + threadIdx.x;
   if (j >= 2 * nb) return;
   const int which = j >= nb;      // 0 flexible geometry, 1 embedded-rigid geometry
@@ -574,7 +568,8 @@ agrad_back_kernel(const CcpolGradTab* __restrict__ gt, int iemonomer, int icc, d
   }
 }
 
-size_t sapt_smem() { return (sizeof(CcpolDev) - PIMDK_RIGID_TABLE_BYTES + 15) / 16 * 16 + (size_t)48 * kSaptThreads * sizeof(double); }
+size_t sapt_smem() { return (size_t)48 * kSaptThreads * sizeof(double); }
+SaptParams g_sapt;   // host copy of the SAPT-5s'f tables, passed to agrad_sapt_kernel by value
 size_t rigid_smem() {
   return (size_t)PIMDK_RIGID_TABLE_BYTES + (sizeof(CcpolGradTab) + 15) / 16 * 16 + (size_t)kRigWarps * kRigScratch * sizeof(double);
 }
@@ -589,6 +584,11 @@ long ccpol_analytic_launches(long ngeom, int icc, size_t work_bytes) {
 }
 
 // v and/or grad for ngeom geometries; `work` holds at least one geometry's fields (a pass takes as many as fit)
+void ccpol_host_tables_analytic(const CcpolDev* h) {
+  RigidParams unused;
+  fill_params(*h, &g_sapt, &unused);
+}
+
 cudaError_t launch_ccpol_analytic(const CcpolDev* tab, const CcpolGradTab* gt, int iemonomer, int icc, double V0, GeomLayout L,
                                   const double* x, double* v, double* grad, long ngeom, int* flags, double* work, size_t work_bytes,
                                   int num_sms, cudaStream_t st) {
@@ -606,7 +606,7 @@ cudaError_t launch_ccpol_analytic(const CcpolDev* tab, const CcpolGradTab* gt, i
   for (long g0 = 0; g0 < ngeom; g0 += cap) {
     const long nb = ngeom - g0 < cap ? ngeom - g0 : cap;
     agrad_prep_kernel<<<(unsigned)((2 * nb + 127) / 128), 128, 0, st>>>(tab, gt, iemonomer, L, x, g0, nb, work);
-    agrad_sapt_kernel<<<(unsigned)((2 * nb + kSaptThreads - 1) / kSaptThreads), kSaptThreads, sapt_smem(), st>>>(tab, gt, nb, work);
+    agrad_sapt_kernel<<<(unsigned)((2 * nb + kSaptThreads - 1) / kSaptThreads), kSaptThreads, sapt_smem(), st>>>(g_sapt, gt, nb, work);
     if (icc) {
       long blocks = (nb + kRigWarps - 1) / kRigWarps;
       const long capb = (long)num_sms * 16;

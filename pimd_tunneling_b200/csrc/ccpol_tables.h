@@ -51,6 +51,55 @@ struct CcpolDev {
   uint8_t potparts_old;                      // ipotparts = 0: potparts_old (surfaces 8, 9)
   uint8_t pad1_[2];
 };
+// The tables as kernel parameters.  Every table read of the pair-sum, rigid and sweep kernels is warp-uniform; taken from
+// the constant bank it is an operand fetched through the uniform datapath (LDCU / c[0][..]) instead of a shared-memory load
+// with a vector-register address: no staging prologue, no barrier, fewer vector registers (the pair-sum kernel loses its
+// spills) and an idle load/store pipe.  Members carry CcpolDev's names so that the device functions below take either.
+struct SaptParams {      // SAPT-5s'f flexible model (22.3 KB of the 32 KB a kernel may take as parameters)
+  double param[kNParam * kNType];
+  double parab[kNParab * kNType * kNType];
+  alignas(16) double c[568];
+  int16_t itu_s[kNType * kNType], itu_a[kNType * kNType];
+  uint8_t pairflags[kNType * kNType];
+};
+struct RigidParams {     // CCpol-8s rigid model (3.6 KB)
+  double cc[144];
+  double params[134];
+  double sites[75];
+  double chrg[5];
+  double bin_beta[37];
+  uint32_t tbins[36];
+  uint8_t ind_charge[5];
+  uint8_t ind_d1[25];
+  uint8_t ind_d6[9], ind_d8[9], ind_d10[9], ind_c6[9], ind_c8[9], ind_c10[9];
+};
+template <class A, class B, int N>
+inline void copy_members(A (&dst)[N], const B (&src)[N]) {
+  for (int i = 0; i < N; ++i) dst[i] = src[i];
+}
+inline void fill_params(const CcpolDev& h, SaptParams* s, RigidParams* r) {
+  copy_members(s->param, h.param);
+  copy_members(s->parab, h.parab);
+  copy_members(s->c, h.c);
+  copy_members(s->itu_s, h.itu_s);
+  copy_members(s->itu_a, h.itu_a);
+  copy_members(s->pairflags, h.pairflags);
+  copy_members(r->cc, h.cc);
+  copy_members(r->params, h.params);
+  copy_members(r->sites, h.sites);
+  copy_members(r->chrg, h.chrg);
+  copy_members(r->bin_beta, h.bin_beta);
+  copy_members(r->tbins, h.tbins);
+  copy_members(r->ind_charge, h.ind_charge);
+  copy_members(r->ind_d1, h.ind_d1);
+  copy_members(r->ind_d6, h.ind_d6);
+  copy_members(r->ind_d8, h.ind_d8);
+  copy_members(r->ind_d10, h.ind_d10);
+  copy_members(r->ind_c6, h.ind_c6);
+  copy_members(r->ind_c8, h.ind_c8);
+  copy_members(r->ind_c10, h.ind_c10);
+}
+
 // bytes of the leading rigid-model block = offset of the first SAPT member (a multiple of 16)
 #define PIMDK_RIGID_TABLE_BYTES (offsetof(::pimdk::CcpolDev, param))
 

@@ -51,6 +51,7 @@ PIMDK_DECL_CCPOL(fast)
 // ---- CCpol analytic gradient (ccpol_grad_kernels.cu; opt-in mode PIMDK_MODE_ANALYTIC) ----
 namespace agrad { struct CcpolGradTab; }
 size_t ccpol_analytic_bytes_per_geom();
+void ccpol_host_tables_analytic(const CcpolDev* host_tables);   // whenever the tables change, before the next launch
 long ccpol_analytic_launches(long ngeom, int icc, size_t work_bytes);
 cudaError_t launch_ccpol_analytic(const CcpolDev* tab, const agrad::CcpolGradTab* gt, int iemonomer, int icc, double V0, GeomLayout L,
                                   const double* x, double* v, double* grad, long ngeom, int* flags, double* work, size_t work_bytes,

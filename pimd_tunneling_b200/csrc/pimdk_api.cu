@@ -209,6 +209,7 @@ int ensure_ccpol_tables(int isurf) {
 int upload_ccpol_dev() {
   ccpol_host_tables_strict(&g.hdev);   // the pair-sum, rigid and sweep kernels take their tables as kernel parameters
   ccpol_host_tables_fast(&g.hdev);
+  ccpol_host_tables_analytic(&g.hdev);
   CU(g.dtab.ensure(sizeof(CcpolDev)));
   CU(cudaMemcpyAsync(g.dtab.p, &g.hdev, sizeof(CcpolDev), cudaMemcpyHostToDevice, g.stream));
   CU(g.dgtab.ensure(sizeof(agrad::CcpolGradTab)));
