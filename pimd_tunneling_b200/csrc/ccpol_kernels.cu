@@ -48,7 +48,7 @@ namespace {
 #define PIMDK_RIGID_MINB 5
 #endif
 #ifndef PIMDK_SWEEP_MINB
-#define PIMDK_SWEEP_MINB 2
+#define PIMDK_SWEEP_MINB 3
 #endif
 constexpr int kSetupBlock = 128;
 #ifndef PIMDK_SAPT_BLOCK
@@ -57,8 +57,11 @@ constexpr int kSetupBlock = 128;
 constexpr int kSaptBlock = PIMDK_SAPT_BLOCK;
 
 constexpr int kRigidBlock = 128;
+// three CTAs of ten warps per SM (64 registers, no spills; possible since the tables left shared memory: 3 x 76.3 KB):
+// 1.976 ms per pass against 2.044 ms for two CTAs of twelve warps at 80 registers (352 x 3: 2.071, 384 x 3: 2.033, 288 x 3 and
+// 256 x 3: 2.05, 512 x 2 at 64 registers: 2.13; profiles/r2_sapt_split_and_param_tables.md)
 #ifndef PIMDK_SWEEP_BLOCK
-#define PIMDK_SWEEP_BLOCK 384
+#define PIMDK_SWEEP_BLOCK 320
 #endif
 constexpr int kSweepBlock = PIMDK_SWEEP_BLOCK;            // warps that share 32 energies in the U0 sweep
 // staging fields per energy: 18 flexible + 18 rigid coordinates, emon, val, vall, erigid, eind, a0u, then the
@@ -78,16 +81,6 @@ constexpr int kTabBytes = (int)((sizeof(CcpolDev) + 15) / 16 * 16);
 constexpr int kRigidTableBytes = (int)PIMDK_RIGID_TABLE_BYTES;
 constexpr int kSaptTableBytes = kTabBytes - kRigidTableBytes;
 static_assert(kRigidTableBytes % 16 == 0 && kSaptTableBytes % 16 == 0, "table blocks are staged in 16-byte granules");
-
-template <int BYTES>
-__device__ __forceinline__ const CcpolDev& stage_tables(const CcpolDev* __restrict__ g, unsigned char* smem) {
-  static_assert(BYTES % 16 == 0, "16-byte granules");
-  const int4* src = reinterpret_cast<const int4*>(g);
-  int4* dst = reinterpret_cast<int4*>(smem);
-  for (int i = threadIdx.x; i < BYTES / (int)sizeof(int4); i += blockDim.x) dst[i] = src[i];
-  __syncthreads();
-  return *reinterpret_cast<const CcpolDev*>(smem);
-}
 
 // ---- stage 0 ------------------------------------------------------------------------------------
 // grad = 1: energy e = 36*g + 2*c + s is the displaced geometry for component c (loop order i=dim outer,
@@ -253,22 +246,47 @@ KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __
 // FP64 code, more than the instruction cache, and every thread follows the same path through it; warps that
 // start together stay close enough in the code that one warp's instruction fetch serves the others (measured:
 // 128-thread CTAs at equal or higher occupancy are 11% slower and stall on instruction fetch).
+// PIMDK_SAPT_PARAM_TABLES: the SAPT-5s'f tables as a kernel parameter (strict build: 2.459 -> 2.315 ms per pass) or staged per
+// CTA into shared memory as in round 1 (fast build: with contraction on, ptxas schedules the parameter form worse, 2.55 against
+// 2.23 ms, so that build keeps the shared-memory form)
+#ifndef PIMDK_SAPT_PARAM_TABLES
+#define PIMDK_SAPT_PARAM_TABLES PIMDK_CCPOL_STRICT
+#endif
+#if PIMDK_SAPT_PARAM_TABLES
+#define PIMDK_SAPT_TABARG const __grid_constant__ SaptParams T
+#define PIMDK_SAPT_TABVAL g_sapt
+constexpr int kSaptSmemTab = 0;
+#else
+#define PIMDK_SAPT_TABARG const CcpolDev* __restrict__ tab
+#define PIMDK_SAPT_TABVAL tab
+constexpr int kSaptSmemTab = kSaptTableBytes;
+#endif
 template <bool OLD>
 __global__ void __launch_bounds__(kSaptBlock, PIMDK_SAPT_MINB)
-KNAME(ccpol_sapt_kernel)(const __grid_constant__ SaptParams T, long ne, double* __restrict__ buf) {
+KNAME(ccpol_sapt_kernel)(PIMDK_SAPT_TABARG, long ne, double* __restrict__ buf) {
   extern __shared__ __align__(16) unsigned char smem[];
+#if !PIMDK_SAPT_PARAM_TABLES
+  // stage only the SAPT-5s'f members (param .. pairflags); T is a view whose leading (rigid) members are not backed
+  {
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + kRigidTableBytes);
+    int4* dst = reinterpret_cast<int4*>(smem);
+    for (int i = threadIdx.x; i < kSaptTableBytes / (int)sizeof(int4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const CcpolDev& T = *reinterpret_cast<const CcpolDev*>(smem - kRigidTableBytes);
+#endif
   const long j = (long)blockIdx.x * kSaptBlock + threadIdx.x;
   if (j >= 2 * ne) return;
   const int which = j >= ne;    // 0: flexible geometry (val), 1: embedded rigid geometry (vall)
   const long e = which ? j - ne : j;
   GlobalSites S{buf + (long)(F_SITES + which * 2 * kSiteFields) * ne + e, ne};
   // the 8 sites of B are read once per site of A: keep them in shared memory, slot-major (conflict-free)
-  Scratch<kSaptBlock> sitesB{reinterpret_cast<double*>(smem) + threadIdx.x};
+  Scratch<kSaptBlock> sitesB{reinterpret_cast<double*>(smem + kSaptSmemTab) + threadIdx.x};
 #pragma unroll
   for (int k = 0; k < 24; ++k) sitesB[k] = S[24 + k];
   const double sa[3] = {S[48], S[49], S[50]};
   const double sb[3] = {S[51], S[52], S[53]};
-  Scratch<kSaptBlock> qb{reinterpret_cast<double*>(smem) + 24 * kSaptBlock + threadIdx.x};
+  Scratch<kSaptBlock> qb{reinterpret_cast<double*>(smem + kSaptSmemTab) + 24 * kSaptBlock + threadIdx.x};
   const double val = sapt_pair_sum<OLD>(T, S, sitesB, qb, sa, sb);
   buf[(which ? F_VALL : F_VAL) * ne + e] = val + buf[(F_FCIND + which) * ne + e];
 }
@@ -479,7 +497,7 @@ KNAME(ccpol_combine_kernel)(int iemonomer, int icc, double V0, GeomLayout L, dou
   }
 }
 
-size_t sapt_smem() { return (size_t)(24 + 8) * kSaptBlock * sizeof(double); }
+size_t sapt_smem() { return kSaptSmemTab + (size_t)(24 + 8) * kSaptBlock * sizeof(double); }
 size_t dipind_smem() { return kSaptTableBytes; }
 size_t sweep_smem() { return (size_t)kSweepSlots * 32 * sizeof(double) + 16; }
 
@@ -594,8 +612,8 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
     KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, iembed, L, x, g0, ne, g, work);
     KNAME(ccpol_sites_kernel)<<<(unsigned)((4 * ne + 127) / 128), 128, 0, st>>>(tab, ne, work);
     KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, PIMDK_DIPIND_SPLIT ? 0 : dipind_smem(), st>>>(tab, ne, work);
-    if (potparts_old) KNAME(ccpol_sapt_kernel)<true><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(g_sapt, ne, work);
-    else KNAME(ccpol_sapt_kernel)<false><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(g_sapt, ne, work);
+    if (potparts_old) KNAME(ccpol_sapt_kernel)<true><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(PIMDK_SAPT_TABVAL, ne, work);
+    else KNAME(ccpol_sapt_kernel)<false><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(PIMDK_SAPT_TABVAL, ne, work);
     if (icc) {   // CCpol-8s rigid model of the embedded monomers; surfaces 5..9 are SAPT-5s'f alone
       KNAME(ccpol_rigid_kernel)<<<(unsigned)((ne + kRigidBlock - 1) / kRigidBlock), kRigidBlock, 0, st>>>(g_rigid, ne, work, flags);
       KNAME(ccpol_sweep_kernel)<<<(unsigned)((ne + 31) / 32), kSweepBlock, sweep_smem(), st>>>(g_rigid, ne, work);

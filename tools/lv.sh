@@ -1,7 +1,7 @@
 #!/bin/bash
 # lv.sh TAG [LIB]: per-kernel durations of one 32768-bead CCpol gradient pass -> gpurun_out/lv_TAG.csv (printed)
 TAG=$1; [ -n "$2" ] && export PIMDK_LIB=$2
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ccpol_ -s 8 -c 17 --csv --log-file gpurun_out/lv_$TAG.csv python tools/prof_ccpol.py 0 32768 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ccpol_ -s 8 -c 17 --csv --log-file gpurun_out/lv_$TAG.csv python tools/prof_ccpol.py ${MODE:-0} 32768 > /dev/null 2>&1
 python - <<PY
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/lv_$TAG.csv')) if len(r)>10 and r[0].isdigit()]
