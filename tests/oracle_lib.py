@@ -324,6 +324,27 @@ def thermal_dimer_geometries(nbatch, seed=0, sigma=0.05):
     return np.asfortranarray(x.T.reshape(3, 6, nbatch, order="F"))
 
 
+def random_dimer_geometries(nbatch, seed=0, rmin=4.2, rmax=14.0, sigma=0.12):
+    """water dimers (bohr, x(3,6,nbatch) F-order) over the whole range a ring polymer can reach: each monomer of the golden
+    geometry moved to its centre of mass, rotated at random and distorted by N(0, sigma) per coordinate, the second one
+    placed at a random direction rmin..rmax bohr away (close contacts on the repulsive wall up to the damped long range)"""
+    rng = np.random.default_rng(seed)
+    base = (GOLDEN_GEOM_ANG / 0.529177).reshape(6, 3)
+    m = np.array([15.9949146221, 1.0078250321, 1.0078250321])
+    x = np.empty((3, 6, nbatch), order="F")
+    for k in range(nbatch):
+        for mono in range(2):
+            a = base[3 * mono:3 * mono + 3]
+            a = a - (m[:, None] * a).sum(0) / m.sum()
+            q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            a = a @ q.T + rng.normal(scale=sigma, size=(3, 3))
+            if mono == 1:
+                d = rng.normal(size=3)
+                a = a + d / np.linalg.norm(d) * rng.uniform(rmin, rmax)
+            x[:, 3 * mono:3 * mono + 3, k] = a.T
+    return x
+
+
 # ---- malonaldehyde (pes_malonaldehyde.f90) -----------------------------------------------------------------------
 # the minimum-energy structure the reference file lists in its header (pes_malonaldehyde.f90:12-21), Angstrom,
 # atom order C C O C O H H H H; the surface takes bohr

@@ -17,7 +17,7 @@ import pytest
 
 import ctypes
 
-from oracle_lib import GOLDEN_GEOM_ANG, GOLDEN_VAL, GOLDEN_VALM, Oracle, thermal_dimer_geometries
+from oracle_lib import GOLDEN_GEOM_ANG, GOLDEN_VAL, GOLDEN_VALM, Oracle, random_dimer_geometries, thermal_dimer_geometries
 
 ctypes_P = ctypes.POINTER(ctypes.c_double)
 
@@ -94,6 +94,26 @@ def test_ccpol_far_separated_dimers_underflow_exactly(pk, orc):
     v, g = pes.eval_batch(x)
     vo, go, _ = orc.pes_eval(x)
     assert np.array_equal(v, vo) and np.array_equal(g, go), (np.abs(v - vo).max(), np.abs(g - go).max())
+
+
+@pytest.mark.parametrize("isurf,seed", [(3, 11), (3, 12), (1, 13), (10, 14)])
+def test_ccpol_random_orientations_and_separations_bit_exact(pk, orc, isurf, seed):
+    """Dimers in random relative orientations, 4.2 ... 14 bohr apart, monomers distorted by 0.12 bohr per coordinate: the
+    repulsive wall, the small-argument branch of the damping functions, every quadrant of the embedding's angles and
+    induction iterations of different lengths inside one warp — energies and finite-difference gradients bit for bit
+    (Radau surfaces 3 and 10, Eckart surface 1)."""
+    pes = pk.McmodMass("ccpol8sf", isurf=isurf).V_init()
+    orc.load_ccpol(isurf, 1)
+    orc.L.orc_pes_select(b"ccpol8sf")
+    orc.ndim, orc.natom = 3, 6
+    x = random_dimer_geometries(150, seed=seed)
+    v, g = pes.eval_batch(x)
+    vo, go, _ = orc.pes_eval(x)
+    assert np.isfinite(vo).all() and np.isfinite(go).all()
+    assert np.array_equal(v, vo) and np.array_equal(g, go), (np.abs(v - vo).max(), np.abs(g - go).max())
+    assert vo.max() - vo.min() > 1e-3        # the batch does span the wall and the long range (hartree)
+    pk.McmodMass("ccpol8sf").V_init()      # back to the plugin's surface
+    orc.load_ccpol(3, 1)
 
 
 @pytest.mark.parametrize("nbatch", [1, 7, 252, 1000])
