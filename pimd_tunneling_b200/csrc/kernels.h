@@ -100,6 +100,7 @@ enum GemmMode {
   GEMM_PLAIN = 0,       // Y = A T
   GEMM_SUB_BEADVEC = 1, // Y = A T - beadvec            (nmtransform_forward, bead>0)
   GEMM_ADD_BEADVEC = 2, // Y = (A + beadvec) T          (nmtransform_backward, bead>0)
+  GEMM_KICK_ROTATE = 3, // G = A T consumed in the epilogue: P <- P - dt G, rotate(P, Q)   (launch_nm_gemm_kick_rotate)
 };
 void set_nm_gemm_dmma(int on);
 // BV (optional): beadvec(k, dof) of every row, precomputed by launch_beadvec; with it (and n even) GEMM_PLAIN and
@@ -109,6 +110,13 @@ cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, d
                            const double* a /*(ndof)*/, const double* b /*(ndof,ntraj)*/, cudaStream_t st,
                            const double* BV = nullptr);
 bool nm_uses_beadvec_array(const NmTables& nm);
+// The forward transform of the gradient fused with the update that consumes it (step_v's kick + one step_nm rotation, and the
+// Andersen collision clocks when clock != 0): same arithmetic per element as launch_nm_gemm + launch_nm_update(do_kick = 1,
+// nrot = 1, no O-step), hence the same bits; the normal-mode gradient is never stored.
+bool nm_gemm_fuses_kick_rotate(const NmTables& nm, long rows);
+cudaError_t launch_nm_gemm_kick_rotate(const NmTables& nm, const double* g, long rows, double* P, double* Q, double dt, int clock,
+                                       uint64_t seed, uint64_t step, const int64_t* gid, int* flags, int* count, int* rkick,
+                                       double lambda, cudaStream_t st);
 cudaError_t launch_beadvec(const NmTables& nm, const double* a, const double* b, long rows, double* BV, cudaStream_t st);
 cudaError_t launch_add(const double* x, const double* y, double* z, long total, cudaStream_t st);
 

@@ -263,10 +263,26 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// MODE = GEMM_KICK_ROTATE (forward transform of the gradient fused with the update that consumes it): the epilogue does not
+// store G = g T but applies P <- P - dt G and the rotation of (P, Q) to the two modes its accumulator pair holds — exactly
+// nm_update2_kernel's arithmetic for ops = OP_KICK | OP_ROT1 (| OP_CLOCK), so the normal-mode gradient never travels and the
+// update kernel's launch is gone.  Y is not written.
+struct KickRotateArgs {
+  double* P;
+  double* Q;
+  double dt;
+  int clock;                 // advance the Andersen collision clocks (one thread per trajectory)
+  uint64_t seed, step;
+  const int64_t* gid;
+  int* flags;
+  int* count;
+  int* rkick;
+  double lambda;
+};
 template <int MODE, int NT>
 __global__ void __launch_bounds__(GT, NT == 4 ? 2 : 1)
 nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restrict__ Y, long rows,
-                    const double* __restrict__ E) {
+                    const double* __restrict__ E, KickRotateArgs U) {
   constexpr int TN = 16 * NT, LDB = TN + 4, STAGE = BM * LDA + DK * LDB;
   extern __shared__ __align__(16) double pipe_smem[];
   const int n = nm.n;
@@ -333,11 +349,39 @@ nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restric
   for (int i = 0; i < 4; ++i) {
     const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
     if (r >= rows) continue;
+    int akb = 0;
+    if (MODE == GEMM_KICK_ROTATE) {
+      const long traj = r / nm.ndof;
+      const int dof = (int)(r - traj * nm.ndof);
+      akb = (dof / nm.ndim) * n;
+      if (U.clock && dof == 0 && col0 == 0 && wn == 0 && (lane & 3) == 0) {   // the thread that holds mode 0 of the trajectory's first row
+        const uint32_t g = U.gid ? (uint32_t)U.gid[traj] : (uint32_t)traj;
+        int c = U.count[traj] + 1;
+        if (c >= U.rkick[traj]) {
+          c = 0;
+          U.rkick[traj] = poisson_norm(U.seed, U.step, g, U.lambda);
+        }
+        U.count[traj] = c;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int c = col0 + wn * 8 * NT + j * 8 + 2 * (lane & 3);
       if (c >= n) continue;          // n is even: c and c + 1 are inside or outside together
       double y0 = acc[i][j][0], y1 = acc[i][j][1];
+      if (MODE == GEMM_KICK_ROTATE) {
+        const size_t e = (size_t)r * n + c;
+        double2 P = *reinterpret_cast<const double2*>(U.P + e);
+        double2 Q = *reinterpret_cast<const double2*>(U.Q + e);
+        P.x = P.x - y0 * U.dt;
+        P.y = P.y - y1 * U.dt;
+        rotate(nm, akb + c, P.x, Q.x);
+        rotate(nm, akb + c + 1, P.y, Q.y);
+        if (P.x != P.x || P.y != P.y) atomicOr(U.flags, PIMDK_FLAG_NAN);
+        *reinterpret_cast<double2*>(U.P + e) = P;
+        *reinterpret_cast<double2*>(U.Q + e) = Q;
+        continue;
+      }
       if (MODE == GEMM_SUB_BEADVEC) {
         const double2 e = *reinterpret_cast<const double2*>(&E[r * n + c]);
         y0 = y0 - e.x;
@@ -692,12 +736,12 @@ cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, d
       attr_mask |= 1ull << (dev & 63);
     }
     if (g_gemm_dmma == 3) {
-      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV);
-      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV);
+      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{});
+      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{});
     } else {
       dim3 g4((nm.n + 63) / 64, (unsigned)((rows + BM - 1) / BM));
-      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV);
-      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV);
+      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{});
+      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{});
     }
     return cudaGetLastError();
   }
@@ -724,6 +768,26 @@ cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, d
     case GEMM_SUB_BEADVEC: nm_gemm_kernel<GEMM_SUB_BEADVEC><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
     case GEMM_ADD_BEADVEC: nm_gemm_kernel<GEMM_ADD_BEADVEC><<<grid, GT, 0, st>>>(nm, A, Y, rows, a, b); break;
   }
+  return cudaGetLastError();
+}
+
+// G = g T fused with P <- P - dt G, rotate (and the Andersen clocks): available where the pipelined tensor-core kernel is
+bool nm_gemm_fuses_kick_rotate(const NmTables& nm, long rows) { return g_gemm_dmma == 1 && (nm.n & 1) == 0 && rows > 0; }
+cudaError_t launch_nm_gemm_kick_rotate(const NmTables& nm, const double* g, long rows, double* P, double* Q, double dt, int clock,
+                                       uint64_t seed, uint64_t step, const int64_t* gid, int* flags, int* count, int* rkick,
+                                       double lambda, cudaStream_t st) {
+  if (!nm_gemm_fuses_kick_rotate(nm, rows)) return cudaErrorNotSupported;
+  static unsigned long long attr_mask = 0;   // the >48 KB dynamic shared memory opt-in is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_mask & (1ull << (dev & 63)))) {
+    cudaError_t e = cudaFuncSetAttribute(nm_gemm_pipe_kernel<GEMM_KICK_ROTATE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes<4>());
+    if (e != cudaSuccess) return e;
+    attr_mask |= 1ull << (dev & 63);
+  }
+  dim3 g4((nm.n + 63) / 64, (unsigned)((rows + BM - 1) / BM));
+  nm_gemm_pipe_kernel<GEMM_KICK_ROTATE, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(
+      nm, g, nullptr, rows, nullptr, KickRotateArgs{P, Q, dt, clock, seed, step, gid, flags, count, rkick, lambda});
   return cudaGetLastError();
 }
 

@@ -1248,11 +1248,15 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       }
       rc = pes_eval_dev(L, x, nullptr, G, (long)ntraj * n, 1);
       if (rc) return rc;
-      {
+      if (fuse_andersen && nm_gemm_fuses_kick_rotate(nm, rows)) {   // kick + rotation (+ clocks) in the transform's epilogue
         Scope s("gemm");
-        CU(launch_nm_gemm(nm, GEMM_PLAIN, G, Gn, rows, a, b, g.stream));
-      }
-      {
+        CU(launch_nm_gemm_kick_rotate(nm, G, rows, P, Q, dt, 1, seed, (uint64_t)(ii + step0), dgid, flags, count, rkick,
+                                      (double)Noutput, g.stream));
+      } else {
+        {
+          Scope s("gemm");
+          CU(launch_nm_gemm(nm, GEMM_PLAIN, G, Gn, rows, a, b, g.stream));
+        }
         Scope s("update");
         CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, nullptr, nullptr,
                             fuse_andersen ? 2 : 0, count, rkick, (double)Noutput));
