@@ -101,6 +101,7 @@ enum GemmMode {
   GEMM_SUB_BEADVEC = 1, // Y = A T - beadvec            (nmtransform_forward, bead>0)
   GEMM_ADD_BEADVEC = 2, // Y = (A + beadvec) T          (nmtransform_backward, bead>0)
   GEMM_KICK_ROTATE = 3, // G = A T consumed in the epilogue: P <- P - dt G, rotate(P, Q)   (launch_nm_gemm_kick_rotate)
+  GEMM_MODEL_PES = 4,   // Y = grad V(A T) of a 1D / two-coordinate model surface           (launch_nm_gemm_model_pes)
 };
 void set_nm_gemm_dmma(int on);
 // BV (optional): beadvec(k, dof) of every row, precomputed by launch_beadvec; with it (and n even) GEMM_PLAIN and
@@ -113,6 +114,11 @@ bool nm_uses_beadvec_array(const NmTables& nm);
 // The forward transform of the gradient fused with the update that consumes it (step_v's kick + one step_nm rotation, and the
 // Andersen collision clocks when clock != 0): same arithmetic per element as launch_nm_gemm + launch_nm_update(do_kick = 1,
 // nrot = 1, no O-step), hence the same bits; the normal-mode gradient is never stored.
+// The back-transform fused with the gradient of a model surface (mcmod_1d, mcmod_2dtest, mcmod_so2): grad = Vprime(A T), bead
+// positions never stored; the same simple_pes_eval per bead as launch_simple_pes, hence the same bits.
+bool nm_gemm_fuses_model_pes(const NmTables& nm, long rows, int kind);
+cudaError_t launch_nm_gemm_model_pes(const NmTables& nm, const double* A, long rows, int kind, const SimplePesParams& P, double* grad,
+                                     int* flags, cudaStream_t st);
 bool nm_gemm_fuses_kick_rotate(const NmTables& nm, long rows);
 cudaError_t launch_nm_gemm_kick_rotate(const NmTables& nm, const double* g, long rows, double* P, double* Q, double dt, int clock,
                                        uint64_t seed, uint64_t step, const int64_t* gid, int* flags, int* count, int* rkick,

@@ -9,6 +9,7 @@
 // so a (traj,dof) row is contiguous and the transform is a row-major GEMM against the symmetric T.
 #include "kernels.h"
 #include "nm_device.cuh"
+#include "pes_simple_device.cuh"
 #include "philox.cuh"
 
 namespace pimdk {
@@ -279,10 +280,20 @@ struct KickRotateArgs {
   int* rkick;
   double lambda;
 };
+// MODE = GEMM_MODEL_PES (back-transform fused with the gradient of a model surface): the epilogue turns the bead positions
+// its accumulators hold into the bead gradient and stores that; x itself is not written.  1D surface: every coordinate on its
+// own.  Two-coordinate surfaces (2D double well, SO2 ring): rows 2t and 2t + 1 are the two coordinates of trajectory t and sit
+// in lanes l and l ^ 4 of the accumulator layout; the even row's thread takes the bead of its first column, the odd row's thread
+// the bead of the second, each evaluates simple_pes_eval once and the two exchange the components (three shuffles per pair).
+struct ModelPesArgs {
+  int kind;
+  SimplePesParams P;
+  int* flags;
+};
 template <int MODE, int NT>
 __global__ void __launch_bounds__(GT, NT == 4 ? 2 : 1)
 nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restrict__ Y, long rows,
-                    const double* __restrict__ E, KickRotateArgs U) {
+                    const double* __restrict__ E, KickRotateArgs U, ModelPesArgs M) {
   constexpr int TN = 16 * NT, LDB = TN + 4, STAGE = BM * LDA + DK * LDB;
   extern __shared__ __align__(16) double pipe_smem[];
   const int n = nm.n;
@@ -345,6 +356,39 @@ nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restric
     }
   }
   cp_async_wait<0>();
+  if (MODE == GEMM_MODEL_PES) {   // every lane stays in the loops (shuffles); stores are predicated
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int c = col0 + wn * 8 * NT + j * 8 + 2 * (lane & 3);
+        const bool valid = r < rows && c < n;   // rows and n are even: a pair of rows / columns is inside or outside together
+        const double y0 = acc[i][j][0], y1 = acc[i][j][1];
+        double g0, g1;
+        if (M.kind == PES_1D) {
+          SimplePesParams P1 = M.P;
+          P1.ndof = 1;
+          simple_pes_eval<1>(M.kind, P1, &y0, nullptr, &g0, false, true);
+          simple_pes_eval<1>(M.kind, P1, &y1, nullptr, &g1, false, true);
+        } else {
+          const int dof = (int)(r & 1);
+          const double o0 = __shfl_xor_sync(0xffffffffu, y0, 4), o1 = __shfl_xor_sync(0xffffffffu, y1, 4);
+          const double xx[2] = {dof ? o1 : y0, dof ? y1 : o0};   // the bead of column c (even row) or c + 1 (odd row)
+          double gg[2];
+          simple_pes_eval<2>(M.kind, M.P, xx, nullptr, gg, false, true);
+          const double other = __shfl_xor_sync(0xffffffffu, dof ? gg[0] : gg[1], 4);   // the partner's row component of my bead
+          g0 = dof ? other : gg[0];
+          g1 = dof ? gg[1] : other;
+        }
+        if (valid) {
+          if (g0 != g0 || g1 != g1) atomicOr(M.flags, PIMDK_FLAG_NAN);
+          *reinterpret_cast<double2*>(&Y[r * n + c]) = make_double2(g0, g1);
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
@@ -736,12 +780,12 @@ cudaError_t launch_nm_gemm(const NmTables& nm, GemmMode mode, const double* A, d
       attr_mask |= 1ull << (dev & 63);
     }
     if (g_gemm_dmma == 3) {
-      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{});
-      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{});
+      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{}, ModelPesArgs{});
+      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 8><<<grid, GT, pipe_smem_bytes<8>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{}, ModelPesArgs{});
     } else {
       dim3 g4((nm.n + 63) / 64, (unsigned)((rows + BM - 1) / BM));
-      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{});
-      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{});
+      if (mode == GEMM_PLAIN) nm_gemm_pipe_kernel<GEMM_PLAIN, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{}, ModelPesArgs{});
+      else nm_gemm_pipe_kernel<GEMM_SUB_BEADVEC, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, Y, rows, BV, KickRotateArgs{}, ModelPesArgs{});
     }
     return cudaGetLastError();
   }
@@ -787,7 +831,29 @@ cudaError_t launch_nm_gemm_kick_rotate(const NmTables& nm, const double* g, long
   }
   dim3 g4((nm.n + 63) / 64, (unsigned)((rows + BM - 1) / BM));
   nm_gemm_pipe_kernel<GEMM_KICK_ROTATE, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(
-      nm, g, nullptr, rows, nullptr, KickRotateArgs{P, Q, dt, clock, seed, step, gid, flags, count, rkick, lambda});
+      nm, g, nullptr, rows, nullptr, KickRotateArgs{P, Q, dt, clock, seed, step, gid, flags, count, rkick, lambda}, ModelPesArgs{});
+  return cudaGetLastError();
+}
+
+// grad V(A T) of a model surface in the back-transform's epilogue (A = Q + beadvec): where the pipelined tensor-core kernel runs,
+// for the 1D surface (any number of coordinates) and for the two-coordinate surfaces
+bool nm_gemm_fuses_model_pes(const NmTables& nm, long rows, int kind) {
+  return g_gemm_dmma == 1 && (nm.n & 1) == 0 && rows > 0 && (kind == PES_1D || ((kind == PES_2DTEST || kind == PES_SO2) && nm.ndof == 2));
+}
+cudaError_t launch_nm_gemm_model_pes(const NmTables& nm, const double* A, long rows, int kind, const SimplePesParams& P, double* grad,
+                                     int* flags, cudaStream_t st) {
+  if (!nm_gemm_fuses_model_pes(nm, rows, kind)) return cudaErrorNotSupported;
+  static unsigned long long attr_mask = 0;   // the >48 KB dynamic shared memory opt-in is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_mask & (1ull << (dev & 63)))) {
+    cudaError_t e = cudaFuncSetAttribute(nm_gemm_pipe_kernel<GEMM_MODEL_PES, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes<4>());
+    if (e != cudaSuccess) return e;
+    attr_mask |= 1ull << (dev & 63);
+  }
+  dim3 g4((nm.n + 63) / 64, (unsigned)((rows + BM - 1) / BM));
+  nm_gemm_pipe_kernel<GEMM_MODEL_PES, 4><<<g4, GT, pipe_smem_bytes<4>(), st>>>(nm, A, grad, rows, nullptr, KickRotateArgs{},
+                                                                                ModelPesArgs{kind, P, flags});
   return cudaGetLastError();
 }
 

@@ -1242,20 +1242,29 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
         CU(launch_andersen(nm, P, ntraj, seed, (uint64_t)(ii + step0), (double)Noutput, dgid, count, rkick, g.stream));
         CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, BV, QB));
       }
-      {
+      // model surfaces: the bead gradient is formed in the back-transform's epilogue (positions never stored).  Q + beadvec
+      // lives in G's buffer, so the gradient goes to x's, which nothing else reads inside this loop.
+      const double* grad_src = G;
+      if (use_bv && nm_gemm_fuses_model_pes(nm, rows, (int)g.pes)) {
         Scope s("gemm");
-        CU(back_transform());
+        CU(launch_nm_gemm_model_pes(nm, QB, rows, (int)g.pes, g.sp, x, flags, g.stream));
+        grad_src = x;
+      } else {
+        {
+          Scope s("gemm");
+          CU(back_transform());
+        }
+        rc = pes_eval_dev(L, x, nullptr, G, (long)ntraj * n, 1);
+        if (rc) return rc;
       }
-      rc = pes_eval_dev(L, x, nullptr, G, (long)ntraj * n, 1);
-      if (rc) return rc;
       if (fuse_andersen && nm_gemm_fuses_kick_rotate(nm, rows)) {   // kick + rotation (+ clocks) in the transform's epilogue
         Scope s("gemm");
-        CU(launch_nm_gemm_kick_rotate(nm, G, rows, P, Q, dt, 1, seed, (uint64_t)(ii + step0), dgid, flags, count, rkick,
+        CU(launch_nm_gemm_kick_rotate(nm, grad_src, rows, P, Q, dt, 1, seed, (uint64_t)(ii + step0), dgid, flags, count, rkick,
                                       (double)Noutput, g.stream));
       } else {
         {
           Scope s("gemm");
-          CU(launch_nm_gemm(nm, GEMM_PLAIN, G, Gn, rows, a, b, g.stream));
+          CU(launch_nm_gemm(nm, GEMM_PLAIN, grad_src, Gn, rows, a, b, g.stream));
         }
         Scope s("update");
         CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, nullptr, nullptr,
