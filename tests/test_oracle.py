@@ -119,21 +119,29 @@ def test_detmath_accuracy():
         getattr(L, "dm_" + f).argtypes = [ctypes.c_double]
     L.dm_pow.restype = ctypes.c_double
     L.dm_pow.argtypes = [ctypes.c_double] * 2
-    rng = np.random.default_rng(1)
+    rng = np.random.default_rng(7)
 
     def ulps(got, exact):
         return float(abs(mp.mpf(got) - exact) / mp.mpf(np.spacing(abs(float(exact)))))
 
-    cases = [("exp", mp.exp, rng.uniform(-200, 50, 600), 1.0), ("log", mp.log, np.exp(rng.uniform(-30, 30, 600)), 2.0),
-             ("sin", mp.sin, rng.uniform(-7, 7, 600), 2.0), ("cos", mp.cos, rng.uniform(-7, 7, 600), 2.0),
-             ("acos", mp.acos, rng.uniform(-1, 1, 600), 2.0), ("tanh", mp.tanh, rng.uniform(-3, 3, 600), 4.0),
-             ("atan", mp.atan, np.concatenate([rng.uniform(-3, 3, 400), rng.uniform(-1e4, 1e4, 200)]), 3.0)]
+    # 10 000+ points per function over the ranges the kernels reach (exp down to the flush-to-zero edge and around 0, acos up to
+    # the end points, tanh and atan into their tails).  Tolerances sit just above the worst error found (in ulp: exp 0.99,
+    # log 1.29, sin 1.10, cos 1.28, acos 1.11, tanh 3.15, atan 2.92; pow 2.2 / 2.0 / 3.9 for the three exponents the path uses):
+    # oracle and kernels share this header, so this test is the only guard of the functions themselves.
+    N = 10000
+    cases = [("exp", mp.exp, np.concatenate([rng.uniform(-700, 50, N), rng.uniform(-1, 1, N // 2), rng.uniform(-1e-3, 1e-3, N // 4)]), 1.0),
+             ("log", mp.log, np.exp(rng.uniform(-30, 30, N)), 1.5),
+             ("sin", mp.sin, rng.uniform(-7, 7, N), 1.5), ("cos", mp.cos, rng.uniform(-7, 7, N), 1.5),
+             ("acos", mp.acos, np.concatenate([rng.uniform(-1, 1, N), 1 - np.exp(rng.uniform(-30, 0, N // 4)),
+                                               -1 + np.exp(rng.uniform(-30, 0, N // 4))]), 1.5),
+             ("tanh", mp.tanh, np.concatenate([rng.uniform(-3, 3, N), rng.uniform(-20, 20, N // 4)]), 3.5),
+             ("atan", mp.atan, np.concatenate([rng.uniform(-3, 3, N), rng.uniform(-1e4, 1e4, N // 2)]), 3.2)]
     for name, ref, xs, tol in cases:
         worst = max(ulps(getattr(L, "dm_" + name)(float(x)), ref(mp.mpf(float(x)))) for x in xs)
         assert worst < tol, (name, worst)
-    for y in (-1.5, -3.0, 0.66666666666666666):
-        worst = max(ulps(L.dm_pow(float(x), y), mp.power(mp.mpf(float(x)), mp.mpf(y))) for x in np.exp(rng.uniform(-8, 3, 400)))
-        assert worst < 6.0, (y, worst)
+    for y, tol in ((-1.5, 2.5), (-3.0, 2.5), (0.66666666666666666, 4.5)):
+        worst = max(ulps(L.dm_pow(float(x), y), mp.power(mp.mpf(float(x)), mp.mpf(y))) for x in np.exp(rng.uniform(-8, 3, N)))
+        assert worst < tol, (y, worst)
 
 
 def test_philox_known_answer(orc):
