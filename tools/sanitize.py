@@ -42,6 +42,15 @@ for n in (33, 200):
     check(lib().pimdk_set_propagate_chunk(2))
     vi.propagate_pimd_pile(x0, p0, a2, bt, dbdl); vi.propagate_pimd_nm(x0, p0, a2, bt, dbdl)
     check(lib().pimdk_set_propagate_chunk(0))
+# 1D surface on the streamed Andersen path: the transforms' fused epilogues (model-surface gradient; kick + rotation + clocks)
+pes1 = pk.McmodMass("1d").V_init()
+a1, b1, m1 = wells("1d")
+vi = pk.VerletInt(pes1, 130, m1, 10.0, NMC=3, Noutput=2, seed=4).init_nm()
+lam, path, spl = ti_path("1d", a1, b1)
+xi = np.linspace(0.1, 0.9, 3)
+x0, p0 = vi.init_path(xi, lam, path, spl)
+bt, dbdl = P.endpoints(lam, path, spl, xi)
+vi.propagate_pimd_nm(x0, p0, a1, bt, dbdl); vi.propagate_pimd_pile(x0, p0, a1, bt, dbdl)
 # the further plugin surfaces (row N4): ragged batches, Hessians, a short streamed propagation each
 from oracle_lib import MALON_MASS, malon_geometries, watmeth_geometries
 for name, geoms, masses in (("malon", malon_geometries(37, seed=3), list(MALON_MASS)), ("watmeth", watmeth_geometries(37, seed=3), [1837.0] * 17)):
