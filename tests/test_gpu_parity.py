@@ -425,6 +425,37 @@ def test_fused_small_system_kernel_equals_streamed_path(pk, name, n, mass, therm
         assert np.array_equal(u, v)
 
 
+@pytest.mark.parametrize("name,n,ntraj,mass", [("2dtest", 256, 70, [1.0]), ("2dtest", 130, 3, [1.0]), ("1d", 130, 67, [1.3]), ("so2", 64, 5, [1.0])])
+def test_transform_epilogues_equal_the_separate_kernels(pk, name, n, ntraj, mass):
+    """Andersen steps on the streamed path: with the tensor-core engine the back-transform forms the model surface's bead
+    gradient and the forward transform applies kick, rotation and collision clocks in their epilogues; with the FMA-pipe
+    engine (pimdk_set_gemm(0)) the same step runs as separate transform, PES and update kernels.  Same arithmetic per element,
+    so positions, momenta and estimator sums agree bit for bit (ragged row counts against the 128-row tiles, collisions on)."""
+    from pimd_tunneling_b200._lib import check, lib
+
+    if name == "so2":
+        pes = pk.McmodMass("so2", params=[3.0, 2.5]).V_init()
+        a = np.asfortranarray(np.array([[2.5], [0.0]]))
+        b = np.asfortranarray(np.array([[2.5 * np.cos(1.0)], [2.5 * np.sin(1.0)]]))
+    else:
+        pes = pk.McmodMass(name).V_init()
+        a, b = _wells(name)
+    vi = pk.VerletInt(pes, n, mass, 10.0, NMC=25, imin=3, Noutput=4, seed=77).init_nm()
+    x, p, bt, dbdl, _ = _traj_inputs(pes, n, ntraj, a, b, 0.05, mass)
+    gid = np.arange(ntraj, dtype=np.int64) * 5 + 1
+    out = []
+    check(lib().pimdk_set_fused(0))         # streamed path also where the small-system kernel would take over
+    try:
+        for kind in (1, 0):
+            check(lib().pimdk_set_gemm(kind))
+            out.append(vi.propagate_pimd_nm(x, p, a, bt, dbdl, traj_gid=gid))
+    finally:
+        check(lib().pimdk_set_gemm(1))
+        check(lib().pimdk_set_fused(1))
+    for u, v in zip(out[0], out[1]):
+        assert np.isfinite(u).all() and np.array_equal(u, v)
+
+
 def test_partition_invariance_and_imin(pk):
     """results depend on the global trajectory id only, not on how trajectories are batched/sharded"""
     pes = pk.McmodMass("2dtest").V_init()
