@@ -526,8 +526,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                          "kernel": "nm_gemm_pipe_kernel (FP64 tensor-core transform, cp.async 3-stage)",
                          "kernel_note": "Andersen steps on a model surface: the back-transform's launch also evaluates the bead gradient "
                                         "(24 exponentials per bead for the 2D well) and the forward transform's launch applies the kick, "
-                                        "the rotation and the collision clocks, both in the epilogue (no PES launch, one update launch "
-                                        "fewer), so the time counted here is not all transform; the plain transform alone runs at "
+                                        "the rotation and the collision clocks, both in the epilogue (no PES launch; the step's other update "
+                                        "runs inside the estimator kernel), so the time counted here is not all transform; the plain transform alone runs at "
                                         "22.7 TFLOP/s on this shape (profiles/r2_nm_gemm.md)",
                          "kernel_ms_per_step": gms / K, "kernel_launches": gl, "kernel_share_of_step": gms / ms_prof,
                          "flop_per_launch": 2.0 * rows_per_gpu * n * n,

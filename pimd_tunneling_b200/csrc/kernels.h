@@ -144,6 +144,12 @@ cudaError_t launch_andersen_init(long ntraj, uint64_t seed, uint64_t step0, doub
 cudaError_t launch_sample_momenta(const NmTables& nm, double* P, long ntraj, uint64_t seed, int stream, uint64_t step,
                                   const int64_t* gid, cudaStream_t st);
 // estimator: dHdr[traj] += sum_{dim,atom} mass*(-x(n,dim,atom))*dbdl(dim,atom,traj)   (verletmodule.f90:397-403)
+// Andersen steps with a beadvec array: the last-bead estimator of step i (do_est) and the first update of step i + 1 (do_upd:
+// resampling of the trajectories whose clock fires, rotation by dt/2, Q + beadvec into QB; `step` is that step's index) in one
+// kernel; the bits of launch_estimator_modes followed by launch_nm_update(do_kick = 0, nrot = 1, andersen = 1).
+cudaError_t launch_estimator_update(const NmTables& nm, double* P, double* Q, const double* BV, double* QB, const double* dbdl,
+                                    double* dHdr, long ntraj, int do_est, int do_upd, uint64_t seed, uint64_t step, const int64_t* gid,
+                                    int* flags, const int* count, const int* rkick, cudaStream_t st);
 cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const double* a, const double* b,
                                    const double* dbdl, double* dHdr, long ntraj, cudaStream_t st,
                                    const double* BV = nullptr);

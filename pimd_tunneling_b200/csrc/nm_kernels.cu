@@ -689,6 +689,124 @@ estimator_modes_kernel(NmTables nm, const double* __restrict__ Q, const double* 
   }
 }
 
+// The last-bead estimator of step i and the first update of step i + 1 in one kernel (Andersen steps, beadvec array present):
+// both walk the same rows' modes — the estimator to contract Q + beadvec with T's last column, the update to resample the
+// momenta of the trajectories whose collision clock fires, rotate (P, Q) by dt/2 and leave Q + beadvec for the back-transform.
+// The tile loop of estimator_modes_kernel carries the update along: the estimator takes Q as the step left it, the update then
+// overwrites it.  Per element the arithmetic of nm_update2_kernel (ops = OP_ANDERSEN | OP_ROT1), per row the chain of
+// estimator_modes_kernel: the same bits as the two kernels.
+// Warp 0 runs the rows' chains; warps 1..8 stage the 32-column tiles, one row each (two buffers: tile t + 1 is staged and updated while
+// the chains walk tile t, one barrier per tile).
+constexpr int kEuRows = 8, kEuThreads = 32 * (kEuRows + 1);   // small CTAs: the update needs the whole machine's warps
+__global__ void __launch_bounds__(kEuThreads)
+estimator_update_kernel(NmTables nm, double* __restrict__ Pn, double* __restrict__ Qn, const double* __restrict__ BV,
+                        double* __restrict__ QB, const double* __restrict__ dbdl, double* __restrict__ dHdr, long ntraj, int do_est,
+                        int do_upd, uint64_t seed, uint64_t step, const int64_t* __restrict__ gid, int* __restrict__ flags,
+                        const int* __restrict__ count, const int* __restrict__ rkick) {
+  extern __shared__ double em_smem[];
+  const int n = nm.n, ndof = nm.ndof;
+  double* tcol = em_smem;                 // T(:, n): n doubles
+  double* tile = em_smem + n;             // [2][kEuRows][33]
+  double* xl = tile + 2 * kEuRows * 33;   // last-bead positions of the CTA's rows
+  const int tpc = kEuRows / ndof;         // trajectories per CTA
+  const long traj0 = (long)blockIdx.x * tpc;
+  const int nrow = (int)(((ntraj - traj0 < tpc) ? ntraj - traj0 : tpc) * ndof);   // active rows
+  const long row0 = traj0 * ndof;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kStageWarps = kEuThreads / 32 - 1;
+  const int ntiles = (n + 31) / 32;
+  constexpr int kRowsPerWarp = (kEuRows + kStageWarps - 1) / kStageWarps;
+  // what a staging warp needs to know of its rows, once: first normal-mode table index, RNG id, collision flag
+  int akb_r[kRowsPerWarp], dofn_r[kRowsPerWarp];
+  uint32_t g_r[kRowsPerWarp];
+  bool fire_r[kRowsPerWarp];
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int rr = warp - 1 + i * kStageWarps;
+    akb_r[i] = dofn_r[i] = 0;
+    g_r[i] = 0;
+    fire_r[i] = false;
+    if (warp > 0 && rr < nrow) {
+      const int tl = rr / ndof, dof = rr - tl * ndof;
+      const long traj = traj0 + tl;
+      akb_r[i] = (dof / nm.ndim) * n;
+      dofn_r[i] = dof * n;
+      g_r[i] = gid ? (uint32_t)gid[traj] : (uint32_t)traj;
+      fire_r[i] = do_upd && count[traj] + 1 >= rkick[traj];   // Andersen collision at the start of the coming step (verletmodule.f90:204-234)
+    }
+  }
+  auto stage = [&](int t) {               // warps 1..: rows of tile t -> buffer t & 1, updated in place behind the read
+    double* buf = tile + (t & 1) * kEuRows * 33;
+    const int m = t * 32 + lane;
+    double Qv[kRowsPerWarp], Bv[kRowsPerWarp], Pv[kRowsPerWarp];
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; ++i) {          // every load of the warp's rows in flight before the first use
+      const int rr = warp - 1 + i * kStageWarps;
+      const bool ok = rr < nrow && m < n;
+      const size_t e = ok ? (size_t)(row0 + rr) * n + m : 0;
+      Qv[i] = ok ? Qn[e] : 0.0;
+      Bv[i] = ok ? BV[e] : 0.0;
+      Pv[i] = (ok && do_upd) ? Pn[e] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; ++i) {
+      const int rr = warp - 1 + i * kStageWarps;
+      if (rr >= nrow) continue;
+      double Q = Qv[i];
+      const double bv = Bv[i];
+      const double qb = Q + bv;
+      if (m < n && do_upd) {
+        const size_t e = (size_t)(row0 + rr) * n + m;
+        const int ak = akb_r[i] + m;
+        double P = Pv[i];
+        if (fire_r[i]) {
+          const double z = normal_at(seed, STREAM_ANDERSEN, step, g_r[i], (uint64_t)((unsigned)dofn_r[i] + (unsigned)m));
+          P = (0.0 + nm.stdev * z) * nm.sigp[ak];
+        }
+        rotate(nm, ak, P, Q);
+        if (P != P) atomicOr(flags, PIMDK_FLAG_NAN);
+        Pn[e] = P;
+        Qn[e] = Q;
+        QB[e] = Q + bv;
+      }
+      buf[rr * 33 + lane] = qb;
+    }
+  };
+  if (warp == 0) {
+    if (do_est)
+      for (int m = lane; m < n; m += 32) tcol[m] = nm.T[(long)m * n + (n - 1)];
+  } else {
+    stage(0);
+  }
+  double acc = 0.0;
+  for (int t = 0; t < ntiles; ++t) {
+    __syncthreads();                      // tile t is staged; the chains are done with the other buffer
+    if (warp == 0) {
+      if (do_est && lane < nrow) {
+        const double* buf = tile + (t & 1) * kEuRows * 33;
+        const int m0 = t * 32, mm = (n - m0 < 32) ? n - m0 : 32;
+        for (int q = 0; q < mm; ++q) acc = fma(buf[lane * 33 + q], tcol[m0 + q], acc);
+      }
+    } else if (t + 1 < ntiles) {
+      stage(t + 1);
+    }
+  }
+  if (!do_est) return;
+  if (warp == 0 && lane < kEuRows) xl[lane] = acc;
+  __syncthreads();
+  if (threadIdx.x < nrow / ndof) {
+    const long t = traj0 + threadIdx.x;
+    const double* xt = xl + threadIdx.x * ndof;
+    double contr = 0.0;
+    for (int j = 0; j < nm.ndim; ++j)
+      for (int k = 0; k < nm.natom; ++k) {
+        const int d = k * nm.ndim + j;
+        contr = contr + nm.mass[k] * (-xt[d]) * dbdl[t * ndof + d];
+      }
+    dHdr[t] = dHdr[t] + contr;
+  }
+}
+
 // ---- dHdrlimit (verletmodule.f90:404-409, propagate_pimd_pile only) -----------------------------------------------
 // estimator with the outlier guard: |contr| < limit is added; otherwise the contribution is dropped and the trajectory is
 // marked for re-initialisation (init_path again: beads back on the spline path, fresh momenta)
@@ -941,6 +1059,22 @@ cudaError_t launch_estimator_modes(const NmTables& nm, const double* Q, const do
     if (e != cudaSuccess) return e;
   }
   estimator_modes_kernel<<<(unsigned)((ntraj + tpc - 1) / tpc), kEmThreads, smem, st>>>(nm, Q, a, b, dbdl, dHdr, ntraj, BV);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_estimator_update(const NmTables& nm, double* P, double* Q, const double* BV, double* QB, const double* dbdl,
+                                    double* dHdr, long ntraj, int do_est, int do_upd, uint64_t seed, uint64_t step, const int64_t* gid,
+                                    int* flags, const int* count, const int* rkick, cudaStream_t st) {
+  const int tpc = kEuRows / nm.ndof;
+  if (tpc < 1 || !BV || !QB) return cudaErrorInvalidValue;
+  if (!do_est && !do_upd) return cudaSuccess;
+  const size_t smem = (size_t)(nm.n + 2 * kEuRows * 33 + kEuRows) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(estimator_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  estimator_update_kernel<<<(unsigned)((ntraj + tpc - 1) / tpc), kEuThreads, smem, st>>>(nm, P, Q, BV, QB, dbdl, dHdr, ntraj, do_est, do_upd,
+                                                                                       seed, step, gid, flags, count, rkick);
   return cudaGetLastError();
 }
 

@@ -1232,8 +1232,12 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
       Scope s("update");
       CU(launch_andersen_init(ntraj, seed, (uint64_t)step0, (double)Noutput, dgid, count, rkick, g.stream));
     }
+    // with a beadvec array the step's last kernel is the estimator of this step AND the first update of the next one
+    const bool fuse_eu = fuse_andersen && use_bv && ndof <= 8;   // (a CTA of the fused kernel owns whole trajectories: 8 rows)
     for (pimdk_int ii = 1; ii <= NMC; ++ii) {
-      if (fuse_andersen) {   // resampling of the fired trajectories inside the first update kernel, clocks advanced by the second
+      if (fuse_eu && ii > 1) {
+        // (done by the previous turn's estimator + update kernel)
+      } else if (fuse_andersen) {   // resampling of the fired trajectories inside the first update kernel, clocks advanced by the second
         Scope s("update");
         CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 0, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, BV, QB, 1, count,
                             rkick, (double)Noutput));
@@ -1270,7 +1274,11 @@ int pimdk_propagate_dev(pimdk_int thermostat, pimdk_int ntraj, double* x, double
         CU(launch_nm_update(nm, P, Q, Gn, dt, ntraj, 1, 1, 0, seed, (uint64_t)(ii + step0), dgid, flags, g.stream, nullptr, nullptr,
                             fuse_andersen ? 2 : 0, count, rkick, (double)Noutput));
       }
-      if (ii > imin && ndof <= 32) {   // the estimator reads the last bead only: one contraction per (trajectory, dof), not a transform
+      if (fuse_eu) {
+        Scope s("estimator");
+        CU(launch_estimator_update(nm, P, Q, BV, QB, dbdl, dHdr, ntraj, ii > imin, ii < NMC, seed, (uint64_t)(ii + 1 + step0), dgid, flags,
+                                   count, rkick, g.stream));
+      } else if (ii > imin && ndof <= 32) {   // the estimator reads the last bead only: one contraction per (trajectory, dof), not a transform
         Scope s("estimator");
         CU(launch_estimator_modes(nm, Q, a, b, dbdl, dHdr, ntraj, g.stream, BV));
       } else if (ii > imin) {          // many-site surfaces (water-methane, 51 dof): the full back-transform, then the plain estimator
