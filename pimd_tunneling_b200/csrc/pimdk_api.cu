@@ -1413,13 +1413,21 @@ int pimdk_propagate(pimdk_int thermostat, pimdk_int ntraj, double* x, double* p,
   const int ndof = g.nm_ndim * g.nm_natom;
   const size_t tot = (size_t)ntraj * ndof * g.n, nb = (size_t)ntraj * ndof;
   {
-    // automatic: chunks of >= 128 MB of state (x and p) and >= 256 trajectories; worth it from three chunks on
+    // automatic: about eight chunks per call, each at least 256 trajectories and at most 128 MB of state (x and p); worth it
+    // from three chunks on.  Only the first copy-in and the last copy-out are exposed, so a call of 1024 trajectories (C4 on 8
+    // GPUs) runs as four chunks rather than unpipelined, and 8192 trajectories keep chunks of 1024 (smaller ones cost more in
+    // per-chunk launches than they hide: 6.13 against 6.16 M bead-steps/s end to end at 256).
     long chunk = g.chunk_traj;
     if (chunk <= 0) {
       const size_t per_traj = 2 * (size_t)ndof * g.n * sizeof(double);
-      chunk = (long)(((size_t)128 << 20) / per_traj) + 1;
+      long cmax = (long)(((size_t)128 << 20) / per_traj) + 1;
+      if (cmax < 256) cmax = 256;
+      cmax = (cmax + 63) / 64 * 64;
+      // (the many-site surfaces only: 256 trajectories of a model surface would not fill the machine, those keep 128 MB chunks)
+      const bool heavy = g.pes == PES_CCPOL || g.pes == PES_WATMETH || g.pes == PES_MALON;
+      chunk = heavy ? ((long)ntraj / 8 + 63) / 64 * 64 : cmax;
       if (chunk < 256) chunk = 256;
-      chunk = (chunk + 63) / 64 * 64;
+      if (chunk > cmax) chunk = cmax;
     }
     if ((long)ntraj >= 3 * chunk)
       return propagate_chunked(thermostat, ntraj, chunk, x, p, a, b, dbdl, dt, gamma, NMC, imin, Noutput, cayley, seed,
