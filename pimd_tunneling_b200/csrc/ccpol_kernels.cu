@@ -68,12 +68,9 @@ constexpr int kSweepBlock = PIMDK_SWEEP_BLOCK;            // warps that share 32
 // SAPT-5s'f sites: 4 blocks (flexible A, flexible B, rigid A, rigid B) of 24 site coordinates + 3 symmetry coordinates
 constexpr int kSiteFields = 27;
 constexpr int kFrameFields = 24;                 // body frames of the two rigid monomers (ex, ey, ez, com) x 2
-// PIMDK_DIPIND_SPLIT: stage 1a also forms dipind's per-monomer dipole sum and polarisability (4 values per monomer
-// geometry, appended to the staging buffer), so that stage 1b reads 14 values per item instead of 54
-#ifndef PIMDK_DIPIND_SPLIT
-#define PIMDK_DIPIND_SPLIT 1
-#endif
-constexpr int kDipFields = PIMDK_DIPIND_SPLIT ? 16 : 0;
+// stage 1a also forms dipind's per-monomer dipole sum and polarisability (4 values per monomer geometry, appended to the
+// staging buffer), so that stage 1b reads 14 values per item instead of 54
+constexpr int kDipFields = 16;
 constexpr int kFields = 44 + 4 * kSiteFields + kFrameFields + kDipFields;
 enum { F_FLEX = 0, F_RIGID = 18, F_EMON = 36, F_VAL = 37, F_VALL = 38, F_ERIG = 39, F_EIND = 40, F_A0U = 41, F_FCIND = 42, F_SITES = 44, F_FRAME = 44 + 4 * kSiteFields,
        F_DIP = 44 + 4 * kSiteFields + kFrameFields };
@@ -131,12 +128,6 @@ KNAME(ccpol_setup_kernel)(int iemonomer, int iembed, GeomLayout L, const double*
 // ---- stage 1a -----------------------------------------------------------------------------------
 // set_sites (proc_sapt5sf_new_ncd.f:1574-1758) for the four monomer geometries of an energy (flexible A, B and
 // embedded-rigid A, B): thread = (energy, geometry block).  8 sites (Angstrom) + symmetry coordinates s1..s3.
-struct GlobalSlots {  // set_sites' output sink: slot k of this thread's block lives at p[k * stride]
-  double* p;
-  long stride;
-  __device__ __forceinline__ double& operator[](int k) const { return p[k * stride]; }
-};
-#if PIMDK_DIPIND_SPLIT
 struct TeeSlots {  // set_sites' sink that also keeps the values in registers for dipind's per-monomer part
   double* p;
   long stride;
@@ -148,7 +139,6 @@ struct TeeSlots {  // set_sites' sink that also keeps the values in registers fo
   };
   __device__ __forceinline__ Ref operator[](int k) const { return Ref{p + k * stride, loc + k}; }
 };
-#endif
 __global__ void __launch_bounds__(128)
 KNAME(ccpol_sites_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
   const long i = (long)blockIdx.x * 128 + threadIdx.x;
@@ -162,7 +152,6 @@ KNAME(ccpol_sites_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __r
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int k = 0; k < 3; ++k) c[a][k] = fast_div(buf[(f0 + a * 3 + k) * ne + e], a0);
-#if PIMDK_DIPIND_SPLIT
   double loc[24];
   TeeSlots out{buf + (long)(F_SITES + blk * kSiteFields) * ne + e, ne, loc};
   set_sites(c, out, 0, s);
@@ -176,19 +165,12 @@ KNAME(ccpol_sites_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __r
   dip[ne] = dm[1];
   dip[2 * ne] = dm[2];
   dip[3 * ne] = polis;
-#else
-  GlobalSlots out{buf + (long)(F_SITES + blk * kSiteFields) * ne + e, ne};
-  set_sites(c, out, 0, s);
-  out[24] = s[0];
-  out[25] = s[1];
-  out[26] = s[2];
-#endif
 }
 
 // ---- stage 1b -----------------------------------------------------------------------------------
-// dipind (proc_sapt5sf_new_ncd.f:1363-1533): thread = item (an energy's flexible or embedded-rigid geometry).
-// Kept apart from the site-pair kernel: it runs once per item but is 27 KB of code (cbrt, pow, damping), and
-// the pair kernel's loop has to stay inside the 32 KB instruction cache.
+// the pair part of dipind (proc_sapt5sf_new_ncd.f:1363-1533): thread = item (an energy's flexible or embedded-rigid
+// geometry); the per-monomer part ran in stage 1a.  Kept apart from the site-pair kernel: it runs once per item and is
+// 10 KB of code (cbrt, pow, damping) that the pair kernel's loop should not have to fetch around.
 struct GlobalSites {  // slot k of the item in the staging buffer: sites of A, s of A, sites of B, s of B
   const double* p;
   long stride;
@@ -200,7 +182,6 @@ struct GlobalSites {  // slot k of the item in the staging buffer: sites of A, s
 };
 __global__ void __launch_bounds__(128, PIMDK_DIPIND_MINB)
 KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __restrict__ buf) {
-#if PIMDK_DIPIND_SPLIT
   const long j = (long)blockIdx.x * 128 + threadIdx.x;
   if (j >= 2 * ne) return;
   const int which = j >= ne;
@@ -218,24 +199,6 @@ KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __
     dmb[k] = __ldg(dipB + k * ne);
   }
   buf[(F_FCIND + which) * ne + e] = dipind_pair(__ldg(&tab->parab[10 - 1]), Oa, Ob, dma, dmb, __ldg(dipA + 3 * ne), __ldg(dipB + 3 * ne));
-#else
-  extern __shared__ __align__(16) unsigned char smem[];
-  {
-    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(tab) + kRigidTableBytes);
-    int4* dst = reinterpret_cast<int4*>(smem);
-    for (int i = threadIdx.x; i < kSaptTableBytes / (int)sizeof(int4); i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-  }
-  const CcpolDev& T = *reinterpret_cast<const CcpolDev*>(smem - kRigidTableBytes);
-  const long j = (long)blockIdx.x * 128 + threadIdx.x;
-  if (j >= 2 * ne) return;
-  const int which = j >= ne;
-  const long e = which ? j - ne : j;
-  GlobalSites S{buf + (long)(F_SITES + which * 2 * kSiteFields) * ne + e, ne};
-  const double sa[3] = {__ldg(S.p + 24 * ne), __ldg(S.p + 25 * ne), __ldg(S.p + 26 * ne)};
-  const double sb[3] = {__ldg(S.p + 51 * ne), __ldg(S.p + 52 * ne), __ldg(S.p + 53 * ne)};
-  buf[(F_FCIND + which) * ne + e] = dipind(T, S, sa, sb);
-#endif
 }
 
 // ---- stage 1c -----------------------------------------------------------------------------------
@@ -498,7 +461,6 @@ KNAME(ccpol_combine_kernel)(int iemonomer, int icc, double V0, GeomLayout L, dou
 }
 
 size_t sapt_smem() { return kSaptSmemTab + (size_t)(24 + 8) * kSaptBlock * sizeof(double); }
-size_t dipind_smem() { return kSaptTableBytes; }
 size_t sweep_smem() { return (size_t)kSweepSlots * 32 * sizeof(double) + 16; }
 
 }  // namespace
@@ -611,7 +573,7 @@ cudaError_t KNAME(launch_ccpol)(const CcpolDev* tab, int iemonomer, int iembed, 
     work = work_a + (size_t)slice * kGradPass * (geom_bytes(1) / sizeof(double));
     KNAME(ccpol_setup_kernel)<<<(unsigned)((ne + kSetupBlock - 1) / kSetupBlock), kSetupBlock, 0, st>>>(iemonomer, iembed, L, x, g0, ne, g, work);
     KNAME(ccpol_sites_kernel)<<<(unsigned)((4 * ne + 127) / 128), 128, 0, st>>>(tab, ne, work);
-    KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, PIMDK_DIPIND_SPLIT ? 0 : dipind_smem(), st>>>(tab, ne, work);
+    KNAME(ccpol_dipind_kernel)<<<(unsigned)((2 * ne + 127) / 128), 128, 0, st>>>(tab, ne, work);
     if (potparts_old) KNAME(ccpol_sapt_kernel)<true><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(PIMDK_SAPT_TABVAL, ne, work);
     else KNAME(ccpol_sapt_kernel)<false><<<(unsigned)((2 * ne + kSaptBlock - 1) / kSaptBlock), kSaptBlock, sapt_smem(), st>>>(PIMDK_SAPT_TABVAL, ne, work);
     if (icc) {   // CCpol-8s rigid model of the embedded monomers; surfaces 5..9 are SAPT-5s'f alone
