@@ -356,7 +356,7 @@ nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restric
     }
   }
   cp_async_wait<0>();
-  if (MODE == GEMM_MODEL_PES) {   // every lane stays in the loops (shuffles); stores are predicated
+  if constexpr (MODE == GEMM_MODEL_PES) {   // every lane stays in the loops (shuffles); stores are predicated
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
@@ -387,8 +387,7 @@ nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restric
         }
       }
     }
-    return;
-  }
+  } else {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
@@ -433,6 +432,7 @@ nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restric
       }
       *reinterpret_cast<double2*>(&Y[r * n + c]) = make_double2(y0, y1);
     }
+  }
   }
 }
 
