@@ -1,4 +1,4 @@
-// CCpol-8sf batched energy and finite-difference gradient (sm_100a): a four-stage kernel pipeline.
+// CCpol-8sf batched energy and finite-difference gradient (sm_100a): a pipeline of seven kernels per pass.
 // Compiled twice by the build: -fmad=false -DPIMDK_CCPOL_STRICT=1 (bit-faithful to the oracle's
 // operation order; default at run time) and -fmad=true -DPIMDK_CCPOL_STRICT=0 ("fast").
 //
@@ -6,15 +6,17 @@
 // (verletmodule.f90:572-573) and by UM/UMprime (instantonmod.f90:26,79).
 //
 //   stage 0  setup    thread = energy   displaced geometry (Vprime's in-place +eps/-2eps/+eps walk), COM
-//                                       alignment, Radau embedding, PJT2 monomers   -> 36 coordinates + emon
-//   stage 1  sapt     thread = (energy, flexible|rigid geometry)   SAPT-5s'f site-site sum + dipole induction
-//   stage 2a rigid    thread = energy   CCpol-8s: iterated induction (indN_iter), damped electrostatics, dispersion
-//   stage 2b sweep    8 lanes = energy  CCpol-8s: U0's 625-pair exponential sweep; each lane owns whole bins of
-//                                       aj(144) and walks them in the reference's pair order (registers ->
-//                                       shared memory, no local memory); lane 0 then forms Erigid
+//                                       alignment, Radau or Eckart embedding, PJT2 monomers -> 36 coordinates + emon
+//   stage 1a sites    thread = (energy, monomer geometry)   set_sites + the per-monomer part of dipind
+//   stage 1b dipind   thread = item (energy x {flexible, rigid})   the pair part of dipind
+//   stage 1c sapt     thread = item     SAPT-5s'f 8 x 8 site-pair sum
+//   stage 2a rigid    thread = energy   CCpol-8s: frames, iterated induction (indN_iter), damped electrostatics, dispersion
+//   stage 2b sweep    CTA = 32 energies x 10 warps (lane = energy, warp = bin)   CCpol-8s: U0's 625-pair exponential
+//                                       sweep, each bin walked in the reference's pair order; warp 0 then forms Erigid
 //   stage 3  combine  thread = (geometry, component)   V+ and V-  -> central difference, drift write-back
-// Staging buffers are structure-of-arrays [field][energy] so every stage reads and writes coalesced;
-// 320 B per energy against ~1e5 FP64 operations.  Each stage has its own register budget / occupancy.
+// Staging buffers are structure-of-arrays [field][energy] so every stage reads and writes coalesced (1.5 KB per
+// energy against ~6e4 FP64 operations).  Each stage has its own register budget / occupancy.  The pair-sum, rigid and
+// sweep kernels take their parameter tables as kernel parameters (constant bank): every table read in them is warp-uniform.
 #if PIMDK_CCPOL_STRICT
 #define PIMDK_CCPOL_NS ccpol_strict_impl
 #else
@@ -204,8 +206,8 @@ KNAME(ccpol_dipind_kernel)(const CcpolDev* __restrict__ tab, long ne, double* __
 // ---- stage 1c -----------------------------------------------------------------------------------
 // poten's 8 x 8 site-pair sum (proc_sapt5sf_new_ncd.f:130-213) + dipind: thread = item.  Sites and symmetry
 // coordinates come from stage 1a through the staging buffer ([slot][item]: coalesced, L1-resident for the
-// CTA's lifetime), so the kernel needs no per-thread shared-memory scratch; parameter tables in shared memory
-// (every read warp-uniform -> broadcast).  One 512-thread CTA per SM: the pair loop is ~45 KB of straight-line
+// CTA's lifetime); parameter tables in the constant bank (every read is warp-uniform: LDCU into a uniform register or a
+// c[0][..] operand).  One 512-thread CTA per SM: the pair loop is ~45 KB of straight-line
 // FP64 code, more than the instruction cache, and every thread follows the same path through it; warps that
 // start together stay close enough in the code that one warp's instruction fetch serves the others (measured:
 // 128-thread CTAs at equal or higher occupancy are 11% slower and stall on instruction fetch).
