@@ -325,7 +325,7 @@ def test_transform_engines_give_identical_bits(pk):
     from pimd_tunneling_b200._lib import check, hptr, lib
 
     rng = np.random.default_rng(17)
-    for n, nvec in ((64, 5), (129, 300), (512, 1000), (250, 131)):
+    for n, nvec in ((64, 5), (129, 300), (512, 1000), (250, 131), (256, 8192), (200, 57)):
         pes = pk.McmodMass("1d").V_init()
         vi = pk.VerletInt(pes, n, [1.0], 10.0).init_nm()
         v = np.asfortranarray(rng.normal(size=(n, nvec)))
