@@ -290,70 +290,6 @@ struct ModelPesArgs {
   SimplePesParams P;
   int* flags;
 };
-// What a thread does with one accumulator pair (row r, columns c and c + 1; n even): store, subtract beadvec and store,
-// kick + rotate, or model-surface gradient.  Called by every lane for every pair (the model-surface form shuffles).
-template <int MODE>
-__device__ __forceinline__ void gemm_epilogue_pair(const NmTables& nm, long r, int c, double y0, double y1, long rows,
-                                                   double* __restrict__ Y, const double* __restrict__ E, const KickRotateArgs& U,
-                                                   const ModelPesArgs& M) {
-  const int n = nm.n;
-  const bool valid = r < rows && c < n;   // rows of a trajectory / columns of a pair are inside or outside together
-  if constexpr (MODE == GEMM_MODEL_PES) {
-    double g0, g1;
-    if (M.kind == PES_1D) {
-      SimplePesParams P1 = M.P;
-      P1.ndof = 1;
-      simple_pes_eval<1>(M.kind, P1, &y0, nullptr, &g0, false, true);
-      simple_pes_eval<1>(M.kind, P1, &y1, nullptr, &g1, false, true);
-    } else {
-      const int dof = (int)(r & 1);
-      const double o0 = __shfl_xor_sync(0xffffffffu, y0, 4), o1 = __shfl_xor_sync(0xffffffffu, y1, 4);
-      const double xx[2] = {dof ? o1 : y0, dof ? y1 : o0};   // the bead of column c (even row) or c + 1 (odd row)
-      double gg[2];
-      simple_pes_eval<2>(M.kind, M.P, xx, nullptr, gg, false, true);
-      const double other = __shfl_xor_sync(0xffffffffu, dof ? gg[0] : gg[1], 4);   // the partner's row component of my bead
-      g0 = dof ? other : gg[0];
-      g1 = dof ? gg[1] : other;
-    }
-    if (valid) {
-      if (g0 != g0 || g1 != g1) atomicOr(M.flags, PIMDK_FLAG_NAN);
-      *reinterpret_cast<double2*>(&Y[r * n + c]) = make_double2(g0, g1);
-    }
-  } else if constexpr (MODE == GEMM_KICK_ROTATE) {
-    if (!valid) return;
-    const long traj = r / nm.ndof;
-    const int dof = (int)(r - traj * nm.ndof);
-    const int akb = (dof / nm.ndim) * n;
-    if (U.clock && dof == 0 && c == 0) {   // the thread that holds mode 0 of the trajectory's first row
-      const uint32_t g = U.gid ? (uint32_t)U.gid[traj] : (uint32_t)traj;
-      int cnt = U.count[traj] + 1;
-      if (cnt >= U.rkick[traj]) {
-        cnt = 0;
-        U.rkick[traj] = poisson_norm(U.seed, U.step, g, U.lambda);
-      }
-      U.count[traj] = cnt;
-    }
-    const size_t e = (size_t)r * n + c;
-    double2 P = *reinterpret_cast<const double2*>(U.P + e);
-    double2 Q = *reinterpret_cast<const double2*>(U.Q + e);
-    P.x = P.x - y0 * U.dt;
-    P.y = P.y - y1 * U.dt;
-    rotate(nm, akb + c, P.x, Q.x);
-    rotate(nm, akb + c + 1, P.y, Q.y);
-    if (P.x != P.x || P.y != P.y) atomicOr(U.flags, PIMDK_FLAG_NAN);
-    *reinterpret_cast<double2*>(U.P + e) = P;
-    *reinterpret_cast<double2*>(U.Q + e) = Q;
-  } else {
-    if (!valid) return;
-    if (MODE == GEMM_SUB_BEADVEC) {
-      const double2 e = *reinterpret_cast<const double2*>(&E[r * n + c]);
-      y0 = y0 - e.x;
-      y1 = y1 - e.y;
-    }
-    *reinterpret_cast<double2*>(&Y[r * n + c]) = make_double2(y0, y1);
-  }
-}
-
 template <int MODE, int NT>
 __global__ void __launch_bounds__(GT, NT == 4 ? 2 : 1)
 nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restrict__ Y, long rows,
@@ -420,12 +356,83 @@ nm_gemm_pipe_kernel(NmTables nm, const double* __restrict__ A, double* __restric
     }
   }
   cp_async_wait<0>();
+  if constexpr (MODE == GEMM_MODEL_PES) {   // every lane stays in the loops (shuffles); stores are predicated
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int c = col0 + wn * 8 * NT + j * 8 + 2 * (lane & 3);
+        const bool valid = r < rows && c < n;   // rows and n are even: a pair of rows / columns is inside or outside together
+        const double y0 = acc[i][j][0], y1 = acc[i][j][1];
+        double g0, g1;
+        if (M.kind == PES_1D) {
+          SimplePesParams P1 = M.P;
+          P1.ndof = 1;
+          simple_pes_eval<1>(M.kind, P1, &y0, nullptr, &g0, false, true);
+          simple_pes_eval<1>(M.kind, P1, &y1, nullptr, &g1, false, true);
+        } else {
+          const int dof = (int)(r & 1);
+          const double o0 = __shfl_xor_sync(0xffffffffu, y0, 4), o1 = __shfl_xor_sync(0xffffffffu, y1, 4);
+          const double xx[2] = {dof ? o1 : y0, dof ? y1 : o0};   // the bead of column c (even row) or c + 1 (odd row)
+          double gg[2];
+          simple_pes_eval<2>(M.kind, M.P, xx, nullptr, gg, false, true);
+          const double other = __shfl_xor_sync(0xffffffffu, dof ? gg[0] : gg[1], 4);   // the partner's row component of my bead
+          g0 = dof ? other : gg[0];
+          g1 = dof ? gg[1] : other;
+        }
+        if (valid) {
+          if (g0 != g0 || g1 != g1) atomicOr(M.flags, PIMDK_FLAG_NAN);
+          *reinterpret_cast<double2*>(&Y[r * n + c]) = make_double2(g0, g1);
+        }
+      }
+    }
+  } else {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long r = row0 + wm * 32 + i * 8 + (lane >> 2);
+    if (r >= rows) continue;
+    int akb = 0;
+    if (MODE == GEMM_KICK_ROTATE) {
+      const long traj = r / nm.ndof;
+      const int dof = (int)(r - traj * nm.ndof);
+      akb = (dof / nm.ndim) * n;
+      if (U.clock && dof == 0 && col0 == 0 && wn == 0 && (lane & 3) == 0) {   // the thread that holds mode 0 of the trajectory's first row
+        const uint32_t g = U.gid ? (uint32_t)U.gid[traj] : (uint32_t)traj;
+        int c = U.count[traj] + 1;
+        if (c >= U.rkick[traj]) {
+          c = 0;
+          U.rkick[traj] = poisson_norm(U.seed, U.step, g, U.lambda);
+        }
+        U.count[traj] = c;
+      }
+    }
 #pragma unroll
-    for (int j = 0; j < NT; ++j)
-      gemm_epilogue_pair<MODE>(nm, r, col0 + wn * 8 * NT + j * 8 + 2 * (lane & 3), acc[i][j][0], acc[i][j][1], rows, Y, E, U, M);
+    for (int j = 0; j < NT; ++j) {
+      const int c = col0 + wn * 8 * NT + j * 8 + 2 * (lane & 3);
+      if (c >= n) continue;          // n is even: c and c + 1 are inside or outside together
+      double y0 = acc[i][j][0], y1 = acc[i][j][1];
+      if (MODE == GEMM_KICK_ROTATE) {
+        const size_t e = (size_t)r * n + c;
+        double2 P = *reinterpret_cast<const double2*>(U.P + e);
+        double2 Q = *reinterpret_cast<const double2*>(U.Q + e);
+        P.x = P.x - y0 * U.dt;
+        P.y = P.y - y1 * U.dt;
+        rotate(nm, akb + c, P.x, Q.x);
+        rotate(nm, akb + c + 1, P.y, Q.y);
+        if (P.x != P.x || P.y != P.y) atomicOr(U.flags, PIMDK_FLAG_NAN);
+        *reinterpret_cast<double2*>(U.P + e) = P;
+        *reinterpret_cast<double2*>(U.Q + e) = Q;
+        continue;
+      }
+      if (MODE == GEMM_SUB_BEADVEC) {
+        const double2 e = *reinterpret_cast<const double2*>(&E[r * n + c]);
+        y0 = y0 - e.x;
+        y1 = y1 - e.y;
+      }
+      *reinterpret_cast<double2*>(&Y[r * n + c]) = make_double2(y0, y1);
+    }
+  }
   }
 }
 
