@@ -1198,6 +1198,25 @@ def test_ccpol_analytic_gradient_mode(pk, orc, nbatch):
         assert np.abs(g[:, :, k] - go).max() <= 1e-10 * np.abs(go).max()
 
 
+def test_ccpol_analytic_gradient_random_orientations(pk, orc):
+    """the analytic-gradient mode over the whole range a ring polymer reaches (random relative orientations, 4.2 ... 14 bohr,
+    distorted monomers; repulsive wall included): against the oracle's dual-number gradient, 1e-10 of max|grad|"""
+    from pimd_tunneling_b200._lib import check, lib
+
+    pes = pk.McmodMass("ccpol8sf").V_init()
+    orc.select("ccpol8sf")
+    x = random_dimer_geometries(48, seed=21)
+    check(lib().pimdk_set_mode(2))
+    try:
+        v, g = pes.eval_batch(x)
+    finally:
+        check(lib().pimdk_set_mode(0))
+    for k in range(x.shape[2]):
+        vo, go = orc.ccpol_analytic_gradient(x[:, :, k])
+        assert abs(v[k] - vo) <= 1e-12 * max(1.0, abs(vo))
+        assert np.abs(g[:, :, k] - go).max() <= 1e-10 * np.abs(go).max()
+
+
 def test_ccpol_analytic_mode_surfaces_and_propagation(pk, orc):
     """the mode covers the Radau-embedded potparts surfaces (3 and 10) and refuses the others; a propagation in this mode
     stays within the finite-difference truncation error of the default over a few steps"""
